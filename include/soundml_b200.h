@@ -1,0 +1,203 @@
+/* soundml_b200.h — C ABI of libsoundml_b200.so
+ *
+ * The B200-native replacement for the arithmetic under SoundML's spectral hot
+ * path: framing -> window -> batched rFFT -> |X|^p -> mel projection, plus the
+ * polyphase resampler / FIR.  Plain C: opaque plan handles, raw pointers and
+ * sizes, int status codes.  This is exactly what the reference's OCaml layer
+ * would bind through dune `foreign_stubs` (see INTEGRATION.md and ocaml/).
+ *
+ * Reference seams each entry point replaces (paths inside gabyfle/SoundML):
+ *   smb_stft_*            Stft.Config.create / frames / transform /
+ *                         power_spectrum    soundml/lib/stft.ml:61-111,217-223,
+ *                                           632-666,670-691  (Nx.stft, Nx.magnitude)
+ *   smb_mel_*             Mel.Config.create / filterbank / apply
+ *                                           soundml/lib/mel.ml:119-164,198-231 (Nx.matmul)
+ *   smb_mel_spectrogram   Soundml.mel_spectrogram   soundml/lib/soundml.ml:12-24
+ *   smb_window_make       Window.make               soundml/lib/window.ml:374-401
+ *   smb_resample_*        Resample.Config.create / output_frames / apply
+ *                                           soundml/lib/resample.ml:872-1051,1913-1936
+ *                         and the C executor it calls,
+ *                         soundml_resample_step     soundml/lib/resample_stubs.c:232-297
+ *   smb_fir_apply         the resampler's direct stage at L = M = 1
+ *                         (SURVEY.md 8a "FIR note"; resample_stubs.c:127-143)
+ *
+ * Conventions
+ *   - Tensors are C-contiguous, time axis last, leading axes flattened to
+ *     `batch` (the reference flattens the same way: stft.ml:637, resample.ml:1921).
+ *   - Spectral outputs are [batch, bins | n_mels, frames], frames contiguous.
+ *   - `mem` says where x/out live: SMB_MEM_DEVICE pointers are used in place and
+ *     the call only enqueues work on the plan's stream; SMB_MEM_HOST pointers
+ *     (pageable or pinned) are staged through device buffers owned by the plan
+ *     and the call returns after the result has landed in `out`.
+ *   - Every function returns SMB_OK or an error code; smb_last_error() gives
+ *     the message (thread-local).  SMB_EINVAL carries the reference's
+ *     Invalid_argument wording; SMB_ECUDA is a runtime failure (OCaml Failure).
+ *   - Plans are single-owner, like the reference's kernels ("not domain-safe",
+ *     stft.mli:436-437): do not share one plan across threads.
+ *   - There is no CPU fallback: compute entry points fail with SMB_ECUDA when
+ *     no sm_100 device is usable.
+ */
+#ifndef SOUNDML_B200_H
+#define SOUNDML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SMB_OK = 0, SMB_EINVAL = 1, SMB_ECUDA = 2, SMB_ENOMEM = 3 };
+enum { SMB_MEM_DEVICE = 0, SMB_MEM_HOST = 1 };
+enum { SMB_F32 = 0, SMB_F64 = 1 };
+
+/* Omitted optional integer argument (OCaml ?hop, ?win_length). */
+#define SMB_DEFAULT INT32_MIN
+
+/* Window.t (window.ml:22-33); `param` is beta / std / taper where it applies. */
+enum {
+  SMB_WINDOW_HANN = 0, SMB_WINDOW_HAMMING, SMB_WINDOW_BLACKMAN,
+  SMB_WINDOW_BLACKMAN_HARRIS, SMB_WINDOW_NUTTALL, SMB_WINDOW_BARTLETT,
+  SMB_WINDOW_KAISER, SMB_WINDOW_GAUSSIAN, SMB_WINDOW_TUKEY, SMB_WINDOW_FLAT_TOP,
+  SMB_WINDOW_RECTANGULAR
+};
+enum { SMB_ALIGN_CENTERED = 0, SMB_ALIGN_LEFT = 1, SMB_ALIGN_RIGHT = 2 };
+enum { SMB_PAD_REFLECT = 0, SMB_PAD_CONSTANT = 1, SMB_PAD_EDGE = 2 };
+enum { SMB_SCALE_NONE = 0, SMB_SCALE_MAGNITUDE = 1, SMB_SCALE_PSD = 2 };
+enum { SMB_MEL_SLANEY = 0, SMB_MEL_HTK = 1 };
+enum { SMB_NORM_SLANEY = 0, SMB_NORM_NONE = 1 };
+enum { SMB_QUALITY_FAST = 0, SMB_QUALITY_HIGH = 1, SMB_QUALITY_BEST = 2, SMB_QUALITY_CUSTOM = 3 };
+enum { SMB_EXEC_DIRECT = 0, SMB_EXEC_OLS = 1, SMB_EXEC_GEMM = 2 };
+/* Kernel selection for the STFT family (testing / benchmarking). */
+enum { SMB_PATH_AUTO = 0, SMB_PATH_GENERIC = 1, SMB_PATH_FAST = 2 };
+
+typedef struct smb_stft_plan smb_stft_plan;
+typedef struct smb_mel_plan smb_mel_plan;
+typedef struct smb_resample_plan smb_resample_plan;
+typedef struct smb_fir_plan smb_fir_plan;
+
+const char* smb_last_error(void);
+const char* smb_version(void);
+
+/* ---- device and buffers ------------------------------------------------- */
+int smb_device_count(int* count);
+int smb_set_device(int device);
+int smb_device_alloc(void** ptr, size_t bytes);
+int smb_device_free(void* ptr);
+int smb_host_alloc_pinned(void** ptr, size_t bytes);
+int smb_host_free_pinned(void* ptr);
+int smb_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
+int smb_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
+int smb_device_synchronize(void);
+/* Number of kernels this library has launched in the calling process. */
+int64_t smb_kernel_launch_count(void);
+
+/* ---- host-side design (no GPU needed) ------------------------------------ */
+/* Window.make Nx.float64 ~periodic kind n -> out[n]. */
+int smb_window_make(int kind, double param, int periodic, int64_t n, double* out);
+
+/* ---- STFT ---------------------------------------------------------------- */
+/* Stft.Config.create ?window ?win_length ?hop ?alignment ?pad ?scale ~fft_size. */
+int smb_stft_plan_create(smb_stft_plan** plan, int64_t fft_size, int64_t hop,
+                         int64_t win_length, int window_kind, double window_param,
+                         int alignment, int pad_kind, double pad_value, int scale);
+/* Same, with the analysis window (fft_size doubles, already centred and
+ * scaled) supplied by the caller — what an OCaml Stft.Config.t already holds. */
+int smb_stft_plan_create_with_window(smb_stft_plan** plan, int64_t fft_size,
+                                     int64_t hop, int alignment, int pad_kind,
+                                     double pad_value, const double* analysis_window);
+int smb_stft_plan_destroy(smb_stft_plan* plan);
+/* Run this plan's kernels on an existing CUDA stream (cudaStream_t); NULL
+ * restores the plan's own stream. */
+int smb_stft_plan_set_stream(smb_stft_plan* plan, void* cuda_stream);
+int smb_stft_plan_set_path(smb_stft_plan* plan, int path);
+int smb_stft_plan_sync(smb_stft_plan* plan);
+int64_t smb_stft_fft_size(const smb_stft_plan* plan);
+int64_t smb_stft_hop(const smb_stft_plan* plan);
+int64_t smb_stft_bins(const smb_stft_plan* plan);
+/* Stft.frames c ~n; -1 and SMB_EINVAL message on n < 0. */
+int64_t smb_stft_frames(const smb_stft_plan* plan, int64_t n);
+int smb_stft_analysis_window(const smb_stft_plan* plan, double* out);
+/* Source index each padded position reads (-1 = constant fill): the framing
+ * contract of Stft.pad_signal, exposed so index parity can be checked bit for
+ * bit.  out has n + left_width + right_width entries. */
+int smb_stft_source_indices(const smb_stft_plan* plan, int64_t n, int64_t* out,
+                            int64_t* padded_len);
+
+/* Stft.transform: x [batch, n] (dtype) -> out [batch, bins, frames] complex
+ * (interleaved re, im; complex64 for SMB_F32, complex128 for SMB_F64). */
+int smb_stft_transform(smb_stft_plan* plan, const void* x, int64_t batch, int64_t n,
+                       int dtype, void* out, int mem);
+/* Stft.power_spectrum ?power: out [batch, bins, frames] real. */
+int smb_stft_power_spectrum(smb_stft_plan* plan, const void* x, int64_t batch,
+                            int64_t n, int dtype, double power, void* out, int mem);
+
+/* ---- mel ----------------------------------------------------------------- */
+/* Mel.Config.create; f_max = NaN means "Nyquist" (the OCaml default). */
+int smb_mel_plan_create(smb_mel_plan** plan, int64_t n_mels, int64_t sample_rate,
+                        int64_t fft_size, double f_min, double f_max, int scale,
+                        int norm);
+/* Same, with the [n_mels, bins] float64 weights supplied by the caller. */
+int smb_mel_plan_create_with_weights(smb_mel_plan** plan, int64_t n_mels,
+                                     int64_t fft_size, const double* weights);
+int smb_mel_plan_destroy(smb_mel_plan* plan);
+int smb_mel_plan_set_stream(smb_mel_plan* plan, void* cuda_stream);
+int64_t smb_mel_n_mels(const smb_mel_plan* plan);
+int64_t smb_mel_bins(const smb_mel_plan* plan);
+/* Mel.filterbank Nx.float64: out [n_mels, bins]. */
+int smb_mel_filterbank(const smb_mel_plan* plan, double* out);
+/* Mel.apply: s [batch, bins, frames] -> out [batch, n_mels, frames]. */
+int smb_mel_apply(smb_mel_plan* plan, const void* s, int64_t batch, int64_t frames,
+                  int dtype, void* out, int mem);
+/* Soundml.mel_spectrogram stft mel ?power x: x [batch, n] ->
+ * out [batch, n_mels, frames].  The power spectrogram never reaches HBM on the
+ * fused path. */
+int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x,
+                        int64_t batch, int64_t n, int dtype, double power, void* out,
+                        int mem);
+
+/* ---- resampler ------------------------------------------------------------ */
+/* Resample.Config.create ?quality ~sample_rate ~target; attenuation/passband
+ * are read only for SMB_QUALITY_CUSTOM. */
+int smb_resample_plan_create(smb_resample_plan** plan, int64_t sample_rate,
+                             int64_t target, int quality, double attenuation,
+                             double passband);
+int smb_resample_plan_destroy(smb_resample_plan* plan);
+int smb_resample_plan_set_stream(smb_resample_plan* plan, void* cuda_stream);
+int smb_resample_plan_sync(smb_resample_plan* plan);
+/* Config.pp one-liner, e.g. "resample(44100 -> 16000 Hz, quality=high, ...)". */
+int smb_resample_describe(const smb_resample_plan* plan, char* buf, size_t cap);
+int64_t smb_resample_l(const smb_resample_plan* plan);
+int64_t smb_resample_m(const smb_resample_plan* plan);
+int64_t smb_resample_latency(const smb_resample_plan* plan);
+int smb_resample_num_stages(const smb_resample_plan* plan);
+/* Stage i: factors, group delay K, executor tag, OLS geometry (0 if none). */
+int smb_resample_stage_info(const smb_resample_plan* plan, int stage, int64_t* l,
+                            int64_t* m, int64_t* k, int* exec, int64_t* ols_n,
+                            int64_t* ols_b, int64_t* ols_delta);
+/* Stage prototype (2*K*L + 1 doubles); returns the length through *len when
+ * out is NULL. */
+int smb_resample_stage_prototype(const smb_resample_plan* plan, int stage,
+                                 double* out, int64_t* len);
+/* Config.output_frames c ~n = ceil(n*L/M); -1 on error. */
+int64_t smb_resample_output_frames(const smb_resample_plan* plan, int64_t n);
+/* Resample.apply: x [batch, n] f32 -> out [batch, output_frames(n)] f32. */
+int smb_resample_apply(smb_resample_plan* plan, const float* x, int64_t batch,
+                       int64_t n, float* out, int mem);
+
+/* ---- FIR ------------------------------------------------------------------ */
+/* y[c,i] = sum_t h[t] * x[c, i + (taps-1)/2 - t], zeros outside, taps odd.
+ * method: SMB_EXEC_DIRECT or SMB_EXEC_OLS (overlap-save on the rFFT kernels). */
+int smb_fir_plan_create(smb_fir_plan** plan, const double* h, int64_t taps);
+int smb_fir_plan_destroy(smb_fir_plan* plan);
+int smb_fir_plan_set_stream(smb_fir_plan* plan, void* cuda_stream);
+int smb_fir_apply(smb_fir_plan* plan, const float* x, int64_t batch, int64_t n,
+                  float* out, int method, int mem);
+/* Kaiser-windowed sinc lowpass, the resampler's design_prototype at L = 1
+ * (resample.ml:145-163): taps = 2K+1, cutoff in Nyquist units. */
+int smb_fir_design_lowpass(int64_t k, double cutoff, double attenuation, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOUNDML_B200_H */

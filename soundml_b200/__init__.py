@@ -1,0 +1,61 @@
+"""soundml_b200 — B200-native spectral hot path of SoundML.
+
+The flat API mirrors ``soundml/lib/soundml.ml``: ``mel_spectrogram`` and
+``resample``, with the ``stft``, ``mel``, ``window`` and ``resample`` modules
+underneath.  All arithmetic runs in ``libsoundml_b200.so`` (hand-written CUDA
+for sm_100a behind the C ABI in ``include/soundml_b200.h``).
+"""
+import numpy as np
+
+from . import _lib, mel, stft, window
+from . import resample as _resample_mod
+from ._lib import SoundmlError
+
+Stft = stft
+Mel = mel
+Window = window
+Resample = _resample_mod
+Fir = _resample_mod.Fir
+
+__all__ = ["Stft", "Mel", "Window", "Resample", "Fir", "mel_spectrogram", "resample",
+           "kernel_launch_count", "SoundmlError"]
+
+
+def mel_spectrogram(stft_config, mel_config, x, power=2.0):
+    """``Soundml.mel_spectrogram stft mel ?power x`` (soundml.ml:12-24):
+    ``[..., n]`` -> ``[..., n_mels, frames]``.  For fft 2048 float32 this is
+    one fused kernel; the power spectrogram never reaches device memory."""
+    if x.ndim < 1:
+        raise ValueError("power_spectrum: cannot analyse a rank-zero tensor "
+                         "(the time axis must exist)")
+    x = _lib.contiguous(x)
+    ptr, mem, dtype = _lib.describe(x)
+    n = int(x.shape[-1])
+    lead = tuple(int(d) for d in x.shape[:-1])
+    batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    # fft-size agreement is checked by the library before anything else
+    # (soundml.ml:12-20); an empty result keeps the broadcast shape.
+    if stft_config.fft_size != mel_config.fft_size:
+        _lib.check(_lib.lib.smb_mel_spectrogram(stft_config._h, mel_config._h, None, 0, 0,
+                                                dtype, float(power), None, mem))
+    count = stft.frames(stft_config, n)
+    out = _lib.empty_like_kind(x, lead + (mel_config.n_mels, count))
+    if batch == 0 or count == 0:
+        return out
+    stream = _lib.current_stream(x)
+    if stream is not None:
+        _lib.check(_lib.lib.smb_stft_plan_set_stream(stft_config._h, stream))
+    _lib.check(_lib.lib.smb_mel_spectrogram(stft_config._h, mel_config._h, ptr, batch, n, dtype,
+                                            float(power), _lib.out_pointer(out), mem))
+    return out
+
+
+def resample(x, *, sample_rate, target, quality="high"):
+    """``Soundml.resample ?quality ~sample_rate ~target x`` (soundml.ml:113-114)."""
+    return _resample_mod.apply(
+        _resample_mod.Config.create(sample_rate=sample_rate, target=target, quality=quality), x)
+
+
+def kernel_launch_count():
+    """Kernels this process has launched through the library."""
+    return int(_lib.lib.smb_kernel_launch_count())

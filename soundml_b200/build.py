@@ -1,0 +1,77 @@
+"""Build libsoundml_b200.so in-tree with nvcc for sm_100a.
+
+    python -m soundml_b200.build          # rebuild if sources are newer
+
+nvcc cross-compiles without a GPU.  The shared library lands next to this file
+(``soundml_b200/libsoundml_b200.so``): git-ignored, but it travels with the
+tree to the GPU box.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libsoundml_b200.so")
+
+CUDA_SOURCES = ["api.cu", "kernels_generic.cu", "stft2048.cu", "resample_kernels.cu"]
+HOST_SOURCES = ["host_design.cpp"]
+HEADERS = ["host_design.h", "kernels.h", os.path.join("..", "..", "include", "soundml_b200.h")]
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fPIC,-Wall",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libsoundml_b200.so")
+    return nvcc
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    built = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HOST_SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA translation unit for sm_100a and link the library."""
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src in CUDA_SOURCES + HOST_SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+            "-c", os.path.join(CSRC, src), "-o", obj]
+        if src.endswith(".cpp"):
+            cmd.insert(1, "-x")
+            cmd.insert(2, "cu")
+        _run(cmd, verbose)
+        objs.append(obj)
+    _run([nvcc, "-shared", "-o", LIB] + objs + ["-cudart", "static"], verbose)
+    return LIB
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError(f"build failed: {' '.join(cmd)}")
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

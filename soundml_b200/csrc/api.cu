@@ -1,0 +1,886 @@
+// C ABI of libsoundml_b200.so (see include/soundml_b200.h).
+//
+// Plans own: the host-side design (window / weights / filter banks, double),
+// its device copies, a CUDA stream, and staging buffers for host-memory calls.
+// Preconditions are checked in the reference's order and with its messages
+// (SMB_EINVAL = Invalid_argument); CUDA failures are SMB_ECUDA.  There is no
+// CPU execution path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/soundml_b200.h"
+#include "host_design.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string t_error;
+
+struct cuda_failure : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess)
+    throw cuda_failure(smb::format("soundml_b200: %s failed: %s", what, cudaGetErrorString(e)));
+}
+#define CK(call) cuda_check((call), #call)
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return SMB_OK;
+  } catch (const smb::invalid_argument& e) {
+    t_error = e.what();
+    return SMB_EINVAL;
+  } catch (const cuda_failure& e) {
+    t_error = e.what();
+    return SMB_ECUDA;
+  } catch (const std::bad_alloc&) {
+    t_error = "soundml_b200: out of host memory";
+    return SMB_ENOMEM;
+  } catch (const std::exception& e) {
+    t_error = e.what();
+    return SMB_ECUDA;
+  }
+}
+
+void require_device() {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw cuda_failure(
+        "soundml_b200: no CUDA device is available (this library has no CPU fallback)");
+}
+
+// A device buffer that only ever grows.
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  void* ensure(size_t bytes) {
+    if (bytes > cap) {
+      if (ptr) cudaFree(ptr);
+      ptr = nullptr;
+      cap = 0;
+      CK(cudaMalloc(&ptr, bytes));
+      cap = bytes;
+    }
+    return ptr;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+T* upload(const std::vector<T>& v) {
+  T* d = nullptr;
+  if (v.empty()) return d;
+  CK(cudaMalloc(&d, v.size() * sizeof(T)));
+  CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+struct StreamOwner {
+  cudaStream_t own = nullptr, use = nullptr;
+  void create() {
+    CK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+    use = own;
+  }
+  void set(void* external) { use = external ? (cudaStream_t)external : own; }
+  void destroy() {
+    if (own) cudaStreamDestroy(own);
+    own = use = nullptr;
+  }
+};
+
+size_t dtype_size(int dtype) {
+  if (dtype == SMB_F32) return 4;
+  if (dtype == SMB_F64) return 8;
+  throw smb::invalid_argument("soundml_b200: dtype must be SMB_F32 or SMB_F64");
+}
+
+const double kTwoPi = 6.283185307179586476925286766559;
+
+}  // namespace
+
+// ============================ plan types =====================================
+
+struct smb_stft_plan {
+  smb::StftGeometry geom;
+  std::vector<double> window;        // analysis window, fft doubles
+  bool device_ready = false;
+  int device = 0, sm_count = 0, path = SMB_PATH_AUTO;
+  StreamOwner stream;
+  double* d_window64 = nullptr;
+  double2* d_twiddle64 = nullptr;
+  float* d_window32 = nullptr;       // fast path tables (fft 2048 only)
+  float2* d_tw_pass = nullptr;
+  float2* d_tw_post = nullptr;
+  DeviceBuffer in, out, tmp;
+
+  void ensure_device() {
+    if (device_ready) return;
+    require_device();
+    CK(cudaGetDevice(&device));
+    CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    stream.create();
+    d_window64 = upload(window);
+    const int64_t n = geom.fft;
+    std::vector<double2> tw((size_t)n);
+    for (int64_t j = 0; j < n; ++j) {
+      const double a = kTwoPi * double(j) / double(n);
+      tw[(size_t)j] = make_double2(std::cos(a), -std::sin(a));
+    }
+    d_twiddle64 = upload(tw);
+    if (n == 2048) {
+      std::vector<float> w32((size_t)n);
+      for (int64_t j = 0; j < n; ++j) w32[(size_t)j] = (float)window[(size_t)j];
+      d_window32 = upload(w32);
+      std::vector<float2> pass(1024), post(512);
+      for (int k1 = 0; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+          const double a = kTwoPi * double(k1 * n2) / 1024.0;
+          pass[(size_t)(k1 * 32 + n2)] = make_float2((float)std::cos(a), (float)-std::sin(a));
+        }
+      for (int j = 0; j < 16; ++j)
+        for (int l = 0; l < 32; ++l) {
+          const double a = kTwoPi * double(l + 32 * j) / 2048.0;
+          post[(size_t)(j * 32 + l)] = make_float2((float)std::cos(a), (float)-std::sin(a));
+        }
+      d_tw_pass = upload(pass);
+      d_tw_post = upload(post);
+    }
+    device_ready = true;
+  }
+  smb::FrameGeom frame_geom(int64_t n) const {
+    smb::FrameGeom g;
+    g.n = n;
+    g.frames = geom.frames(n);
+    g.fft = (int)geom.fft;
+    g.hop = (int)geom.hop;
+    g.left = (int)geom.left_width();
+    g.pad = geom.pad;
+    g.pad_value = geom.pad_value;
+    return g;
+  }
+  ~smb_stft_plan() {
+    if (!device_ready) return;
+    cudaFree(d_window64);
+    cudaFree(d_twiddle64);
+    cudaFree(d_window32);
+    cudaFree(d_tw_pass);
+    cudaFree(d_tw_post);
+    in.release();
+    out.release();
+    tmp.release();
+    stream.destroy();
+  }
+};
+
+struct smb_mel_plan {
+  int64_t n_mels = 0, fft = 0, bins = 0, sample_rate = 0;
+  double f_min = 0, f_max = 0;
+  int scale = 0, norm = 0;
+  std::vector<double> weights;       // [n_mels][bins]
+  std::vector<int> band_lo, band_hi;
+  // sparse form for the fused kernel
+  std::vector<unsigned short> cols;
+  std::vector<float> vals;
+  std::vector<smb::MelSched> sched;
+  std::vector<int> round_iters, round_width;
+  bool device_ready = false;
+  StreamOwner stream;
+  double* d_weights = nullptr;
+  int *d_band_lo = nullptr, *d_band_hi = nullptr;
+  unsigned short* d_cols = nullptr;
+  float* d_vals = nullptr;
+  smb::MelSched* d_sched = nullptr;
+  int *d_round_iters = nullptr, *d_round_width = nullptr;
+  DeviceBuffer in, out;
+
+  void finish_host() {
+    band_lo.assign((size_t)n_mels, 0);
+    band_hi.assign((size_t)n_mels, 0);
+    std::vector<int> start((size_t)n_mels + 1, 0);
+    for (int64_t m = 0; m < n_mels; ++m) {
+      int lo = (int)bins, hi = 0;
+      for (int64_t k = 0; k < bins; ++k)
+        if (weights[(size_t)(m * bins + k)] != 0.0) {
+          lo = std::min(lo, (int)k);
+          hi = (int)k + 1;
+          if (bins <= 65536) {
+            cols.push_back((unsigned short)k);
+            vals.push_back((float)weights[(size_t)(m * bins + k)]);
+          }
+        }
+      if (hi == 0) lo = 0;
+      band_lo[(size_t)m] = lo;
+      band_hi[(size_t)m] = hi;
+      start[(size_t)m + 1] = (int)cols.size();
+    }
+    // Lane schedule: a filter with `len` nonzeros is split over the smallest
+    // power-of-two number of adjacent lanes that brings each lane to <= 16
+    // terms; rounds hold filters of one width so the shuffle reduction is
+    // uniform.
+    struct Item { int m, len, width; };
+    std::vector<Item> items;
+    for (int64_t m = 0; m < n_mels; ++m) {
+      const int len = start[(size_t)m + 1] - start[(size_t)m];
+      int width = 1;
+      while (width < 32 && (len + width - 1) / width > 16) width *= 2;
+      items.push_back({(int)m, len, width});
+    }
+    std::stable_sort(items.begin(), items.end(),
+                     [](const Item& a, const Item& b) { return a.width > b.width; });
+    size_t i = 0;
+    while (i < items.size()) {
+      const int width = items[i].width;
+      std::vector<smb::MelSched> round(32, smb::MelSched{0, 0, -1});
+      int lane = 0, iters = 0;
+      while (i < items.size() && items[i].width == width && lane + width <= 32) {
+        const Item& it = items[i];
+        const int chunk = (it.len + width - 1) / width;
+        for (int j = 0; j < width; ++j) {
+          const int begin = std::min(it.len, j * chunk);
+          const int cnt = std::min(chunk, it.len - begin);
+          round[(size_t)(lane + j)] =
+              smb::MelSched{start[(size_t)it.m] + begin, (short)cnt, (short)it.m};
+          iters = std::max(iters, cnt);
+        }
+        lane += width;
+        ++i;
+      }
+      sched.insert(sched.end(), round.begin(), round.end());
+      round_iters.push_back(iters);
+      round_width.push_back(width);
+    }
+  }
+  void ensure_device() {
+    if (device_ready) return;
+    require_device();
+    stream.create();
+    d_weights = upload(weights);
+    d_band_lo = upload(band_lo);
+    d_band_hi = upload(band_hi);
+    d_cols = upload(cols);
+    d_vals = upload(vals);
+    d_sched = upload(sched);
+    d_round_iters = upload(round_iters);
+    d_round_width = upload(round_width);
+    device_ready = true;
+  }
+  ~smb_mel_plan() {
+    if (!device_ready) return;
+    cudaFree(d_weights);
+    cudaFree(d_band_lo);
+    cudaFree(d_band_hi);
+    cudaFree(d_cols);
+    cudaFree(d_vals);
+    cudaFree(d_sched);
+    cudaFree(d_round_iters);
+    cudaFree(d_round_width);
+    in.release();
+    out.release();
+    stream.destroy();
+  }
+};
+
+struct smb_resample_plan {
+  smb::ResamplePlan plan;
+  bool device_ready = false;
+  StreamOwner stream;
+  std::vector<float*> d_bank;        // per stage, [l][2k+1] float32
+  DeviceBuffer in, out, mid;
+  void ensure_device() {
+    if (device_ready) return;
+    require_device();
+    stream.create();
+    for (const auto& s : plan.stages) {
+      std::vector<float> b(s.bank.size());
+      for (size_t i = 0; i < b.size(); ++i) b[i] = (float)s.bank[i];   // cast at prepare
+      d_bank.push_back(upload(b));
+    }
+    device_ready = true;
+  }
+  ~smb_resample_plan() {
+    if (!device_ready) return;
+    for (float* p : d_bank) cudaFree(p);
+    in.release();
+    out.release();
+    mid.release();
+    stream.destroy();
+  }
+};
+
+struct smb_fir_plan {
+  std::vector<double> h;
+  int64_t k = 0;
+  bool device_ready = false;
+  StreamOwner stream;
+  float* d_bank = nullptr;
+  DeviceBuffer in, out;
+  void ensure_device() {
+    if (device_ready) return;
+    require_device();
+    stream.create();
+    std::vector<float> b(h.size());
+    for (size_t s = 0; s < h.size(); ++s) b[s] = (float)h[h.size() - 1 - s];  // row reversed
+    d_bank = upload(b);
+    device_ready = true;
+  }
+  ~smb_fir_plan() {
+    if (!device_ready) return;
+    cudaFree(d_bank);
+    in.release();
+    out.release();
+    stream.destroy();
+  }
+};
+
+// ============================ entry points ===================================
+
+extern "C" {
+
+const char* smb_last_error(void) { return t_error.c_str(); }
+const char* smb_version(void) { return "soundml_b200 0.1 (sm_100a)"; }
+
+int smb_device_count(int* count) {
+  return guarded([&] {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) c = 0;
+    *count = c;
+  });
+}
+int smb_set_device(int device) { return guarded([&] { CK(cudaSetDevice(device)); }); }
+int smb_device_alloc(void** ptr, size_t bytes) {
+  return guarded([&] { require_device(); CK(cudaMalloc(ptr, bytes ? bytes : 1)); });
+}
+int smb_device_free(void* ptr) { return guarded([&] { CK(cudaFree(ptr)); }); }
+int smb_host_alloc_pinned(void** ptr, size_t bytes) {
+  return guarded([&] { require_device(); CK(cudaMallocHost(ptr, bytes ? bytes : 1)); });
+}
+int smb_host_free_pinned(void* ptr) { return guarded([&] { CK(cudaFreeHost(ptr)); }); }
+int smb_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+  return guarded([&] { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); });
+}
+int smb_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+  return guarded([&] { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); });
+}
+int smb_device_synchronize(void) { return guarded([&] { CK(cudaDeviceSynchronize()); }); }
+int64_t smb_kernel_launch_count(void) { return smb::g_launch_count; }
+
+int smb_window_make(int kind, double param, int periodic, int64_t n, double* out) {
+  return guarded([&] {
+    std::vector<double> w = smb::window_make("make", kind, param, periodic != 0, n);
+    std::memcpy(out, w.data(), w.size() * sizeof(double));
+  });
+}
+
+// ---- STFT --------------------------------------------------------------------
+
+int smb_stft_plan_create(smb_stft_plan** plan, int64_t fft_size, int64_t hop,
+                         int64_t win_length, int window_kind, double window_param,
+                         int alignment, int pad_kind, double pad_value, int scale) {
+  return guarded([&] {
+    *plan = nullptr;
+    smb::StftGeometry g;
+    g.fft = fft_size;
+    g.hop = hop;
+    g.win_length = win_length;
+    g.alignment = alignment;
+    g.pad = pad_kind;
+    g.pad_value = pad_value;
+    g.scale = scale;
+    std::vector<double> w = smb::stft_analysis_window(g, window_kind, window_param);
+    smb_stft_plan* p = new smb_stft_plan;
+    p->geom = g;
+    p->window = std::move(w);
+    *plan = p;
+  });
+}
+
+int smb_stft_plan_create_with_window(smb_stft_plan** plan, int64_t fft_size, int64_t hop,
+                                     int alignment, int pad_kind, double pad_value,
+                                     const double* analysis_window) {
+  return guarded([&] {
+    *plan = nullptr;
+    smb::StftGeometry g;
+    g.fft = fft_size;
+    g.hop = hop == SMB_DEFAULT ? std::max<int64_t>(1, fft_size / 4) : hop;
+    g.win_length = fft_size;
+    g.alignment = alignment;
+    g.pad = pad_kind;
+    g.pad_value = pad_value;
+    smb::stft_validate_geometry(g);
+    smb_stft_plan* p = new smb_stft_plan;
+    p->geom = g;
+    p->window.assign(analysis_window, analysis_window + fft_size);
+    *plan = p;
+  });
+}
+
+int smb_stft_plan_destroy(smb_stft_plan* plan) {
+  return guarded([&] { delete plan; });
+}
+int smb_stft_plan_set_stream(smb_stft_plan* plan, void* s) {
+  return guarded([&] { plan->ensure_device(); plan->stream.set(s); });
+}
+int smb_stft_plan_set_path(smb_stft_plan* plan, int path) {
+  return guarded([&] {
+    if (path < SMB_PATH_AUTO || path > SMB_PATH_FAST)
+      throw smb::invalid_argument("set_path: unknown path");
+    plan->path = path;
+  });
+}
+int smb_stft_plan_sync(smb_stft_plan* plan) {
+  return guarded([&] { if (plan->device_ready) CK(cudaStreamSynchronize(plan->stream.use)); });
+}
+int64_t smb_stft_fft_size(const smb_stft_plan* plan) { return plan->geom.fft; }
+int64_t smb_stft_hop(const smb_stft_plan* plan) { return plan->geom.hop; }
+int64_t smb_stft_bins(const smb_stft_plan* plan) { return plan->geom.bins(); }
+int64_t smb_stft_frames(const smb_stft_plan* plan, int64_t n) {
+  int64_t r = -1;
+  guarded([&] { r = plan->geom.frames(n); });
+  return r;
+}
+int smb_stft_analysis_window(const smb_stft_plan* plan, double* out) {
+  return guarded([&] {
+    std::memcpy(out, plan->window.data(), plan->window.size() * sizeof(double));
+  });
+}
+int smb_stft_source_indices(const smb_stft_plan* plan, int64_t n, int64_t* out,
+                            int64_t* padded_len) {
+  return guarded([&] {
+    if (n < 1) throw smb::invalid_argument("source_indices: n must be at least 1");
+    const int64_t left = plan->geom.left_width(), right = plan->geom.right_width();
+    if (padded_len) *padded_len = n + left + right;
+    if (!out) return;
+    for (int64_t q = 0; q < n + left + right; ++q) {
+      const int64_t s = q - left;
+      int64_t idx;
+      if (s >= 0 && s < n) idx = s;
+      else if (plan->geom.pad == smb::kReflect) idx = smb::reflect_index(n, s);
+      else if (plan->geom.pad == smb::kEdge) idx = s < 0 ? 0 : n - 1;
+      else idx = -1;
+      out[q] = idx;
+    }
+  });
+}
+
+}  // extern "C"
+
+namespace {
+
+enum SpecKind { kSpecComplex, kSpecPower };
+
+void check_signal(const char* op, int64_t batch, int64_t n) {
+  if (n < 0)
+    throw smb::invalid_argument(smb::format(
+        "%s: cannot analyse a signal of length %lld (length must be non-negative)", op,
+        (long long)n));
+  if (batch < 0) throw smb::invalid_argument(smb::format("%s: negative batch", op));
+}
+
+bool want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int out_kind,
+               const smb_mel_plan* mel) {
+  if (p->path == SMB_PATH_GENERIC) return false;
+  const bool ok = dtype == SMB_F32 && g.fft == 2048 &&
+                  smb::stft2048_supports(g, out_kind, mel ? (int)mel->n_mels : 0,
+                                         mel ? (int)mel->cols.size() : 0,
+                                         mel ? (int)mel->round_iters.size() : 0) &&
+                  (!mel || mel->bins == 1025);
+  if (!ok && p->path == SMB_PATH_FAST)
+    throw smb::invalid_argument(
+        "soundml_b200: the fused fft-2048 kernel does not cover this geometry");
+  return ok;
+}
+
+// x (device) -> spectrum (device).  kind: complex or |X|^power.
+void run_spectrum(smb_stft_plan* p, const void* dx, int64_t batch, const smb::FrameGeom& g,
+                  int dtype, SpecKind kind, double power, void* dout) {
+  cudaStream_t st = p->stream.use;
+  const int fast_kind = kind == kSpecComplex ? smb::kFastComplex : smb::kFastPower;
+  if (want_fast(p, dtype, g, fast_kind, nullptr)) {
+    smb::Stft2048Args a{};
+    a.x = (const float*)dx;
+    a.out = (float*)dout;
+    a.batch = batch;
+    a.g = g;
+    a.window = p->d_window32;
+    a.tw_pass = p->d_tw_pass;
+    a.tw_post = p->d_tw_post;
+    a.power = (float)power;
+    CK(smb::launch_stft2048(a, fast_kind, p->sm_count, st));
+  } else {
+    CK(smb::launch_stft_generic(dx, dtype, batch, g, p->d_window64, p->d_twiddle64,
+                                kind == kSpecComplex ? smb::kModeComplex : smb::kModePower,
+                                power, dout, st));
+  }
+}
+
+void spectrum_call(const char* op, smb_stft_plan* p, const void* x, int64_t batch, int64_t n,
+                   int dtype, SpecKind kind, double power, void* out, int mem) {
+  check_signal(op, batch, n);
+  const size_t esz = dtype_size(dtype);
+  const smb::FrameGeom g = p->frame_geom(n);
+  const size_t out_elems =
+      (size_t)batch * (size_t)p->geom.bins() * (size_t)g.frames * (kind == kSpecComplex ? 2 : 1);
+  if (batch == 0 || g.frames == 0) return;       // frameless spectrum: nothing to write
+  p->ensure_device();
+  cudaStream_t st = p->stream.use;
+  if (mem == SMB_MEM_DEVICE) {
+    run_spectrum(p, x, batch, g, dtype, kind, power, out);
+    return;
+  }
+  if (mem != SMB_MEM_HOST) throw smb::invalid_argument("soundml_b200: unknown memory kind");
+  const size_t in_bytes = (size_t)batch * (size_t)n * esz;
+  void* din = p->in.ensure(in_bytes);
+  void* dout = p->out.ensure(out_elems * esz);
+  CK(cudaMemcpyAsync(din, x, in_bytes, cudaMemcpyHostToDevice, st));
+  run_spectrum(p, din, batch, g, dtype, kind, power, dout);
+  CK(cudaMemcpyAsync(out, dout, out_elems * esz, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+}
+
+void run_mel_apply(smb_mel_plan* m, const void* ds, int64_t batch, int64_t frames, int dtype,
+                   void* dout, cudaStream_t st) {
+  CK(smb::launch_mel_apply(ds, dtype, batch, (int)m->bins, frames, (int)m->n_mels, m->d_weights,
+                           m->d_band_lo, m->d_band_hi, dout, st));
+}
+
+}  // namespace
+
+extern "C" {
+
+int smb_stft_transform(smb_stft_plan* plan, const void* x, int64_t batch, int64_t n,
+                       int dtype, void* out, int mem) {
+  return guarded([&] {
+    spectrum_call("transform", plan, x, batch, n, dtype, kSpecComplex, 1.0, out, mem);
+  });
+}
+
+int smb_stft_power_spectrum(smb_stft_plan* plan, const void* x, int64_t batch, int64_t n,
+                            int dtype, double power, void* out, int mem) {
+  return guarded([&] {
+    spectrum_call("power_spectrum", plan, x, batch, n, dtype, kSpecPower, power, out, mem);
+  });
+}
+
+// ---- mel ---------------------------------------------------------------------
+
+int smb_mel_plan_create(smb_mel_plan** plan, int64_t n_mels, int64_t sample_rate,
+                        int64_t fft_size, double f_min, double f_max, int scale, int norm) {
+  return guarded([&] {
+    *plan = nullptr;
+    double fmax_used = 0.0;
+    std::vector<double> w =
+        smb::mel_weights(n_mels, sample_rate, fft_size, f_min, f_max, scale, norm, &fmax_used);
+    smb_mel_plan* p = new smb_mel_plan;
+    p->n_mels = n_mels;
+    p->fft = fft_size;
+    p->bins = fft_size / 2 + 1;
+    p->sample_rate = sample_rate;
+    p->f_min = f_min;
+    p->f_max = fmax_used;
+    p->scale = scale;
+    p->norm = norm;
+    p->weights = std::move(w);
+    p->finish_host();
+    *plan = p;
+  });
+}
+
+int smb_mel_plan_create_with_weights(smb_mel_plan** plan, int64_t n_mels, int64_t fft_size,
+                                     const double* weights) {
+  return guarded([&] {
+    *plan = nullptr;
+    if (n_mels < 1)
+      throw smb::invalid_argument(smb::format(
+          "create: cannot build %lld mel bands (n_mels must be at least 1)", (long long)n_mels));
+    if (fft_size < 1)
+      throw smb::invalid_argument(smb::format(
+          "create: cannot use an FFT of size %lld (fft_size must be at least 1)",
+          (long long)fft_size));
+    smb_mel_plan* p = new smb_mel_plan;
+    p->n_mels = n_mels;
+    p->fft = fft_size;
+    p->bins = fft_size / 2 + 1;
+    p->weights.assign(weights, weights + n_mels * p->bins);
+    p->finish_host();
+    *plan = p;
+  });
+}
+
+int smb_mel_plan_destroy(smb_mel_plan* plan) { return guarded([&] { delete plan; }); }
+int smb_mel_plan_set_stream(smb_mel_plan* plan, void* s) {
+  return guarded([&] { plan->ensure_device(); plan->stream.set(s); });
+}
+int64_t smb_mel_n_mels(const smb_mel_plan* plan) { return plan->n_mels; }
+int64_t smb_mel_bins(const smb_mel_plan* plan) { return plan->bins; }
+int smb_mel_filterbank(const smb_mel_plan* plan, double* out) {
+  return guarded([&] {
+    std::memcpy(out, plan->weights.data(), plan->weights.size() * sizeof(double));
+  });
+}
+
+int smb_mel_apply(smb_mel_plan* plan, const void* s, int64_t batch, int64_t frames, int dtype,
+                  void* out, int mem) {
+  return guarded([&] {
+    if (batch < 0 || frames < 0) throw smb::invalid_argument("apply: negative extent");
+    const size_t esz = dtype_size(dtype);
+    if (batch == 0 || frames == 0) return;       // zero-size: nothing to reduce (mel.ml:221-227)
+    plan->ensure_device();
+    cudaStream_t st = plan->stream.use;
+    if (mem == SMB_MEM_DEVICE) {
+      run_mel_apply(plan, s, batch, frames, dtype, out, st);
+      return;
+    }
+    if (mem != SMB_MEM_HOST) throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    const size_t in_bytes = (size_t)batch * plan->bins * frames * esz;
+    const size_t out_bytes = (size_t)batch * plan->n_mels * frames * esz;
+    void* din = plan->in.ensure(in_bytes);
+    void* dout = plan->out.ensure(out_bytes);
+    CK(cudaMemcpyAsync(din, s, in_bytes, cudaMemcpyHostToDevice, st));
+    run_mel_apply(plan, din, batch, frames, dtype, dout, st);
+    CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batch,
+                        int64_t n, int dtype, double power, void* out, int mem) {
+  return guarded([&] {
+    // soundml.ml:12-20
+    if (stft->geom.fft != mel->fft)
+      throw smb::invalid_argument(smb::format(
+          "mel_spectrogram: cannot project a %lld-point STFT through a filterbank built for "
+          "an FFT of size %lld (the two configurations must agree on fft_size)",
+          (long long)stft->geom.fft, (long long)mel->fft));
+    check_signal("power_spectrum", batch, n);
+    const size_t esz = dtype_size(dtype);
+    const smb::FrameGeom g = stft->frame_geom(n);
+    if (batch == 0 || g.frames == 0) return;
+    stft->ensure_device();
+    mel->ensure_device();
+    cudaStream_t st = stft->stream.use;
+    const size_t in_bytes = (size_t)batch * (size_t)n * esz;
+    const size_t out_bytes = (size_t)batch * mel->n_mels * g.frames * esz;
+    const void* din = x;
+    void* dout = out;
+    if (mem == SMB_MEM_HOST) {
+      void* stage = stft->in.ensure(in_bytes);
+      dout = stft->out.ensure(out_bytes);
+      CK(cudaMemcpyAsync(stage, x, in_bytes, cudaMemcpyHostToDevice, st));
+      din = stage;
+    } else if (mem != SMB_MEM_DEVICE) {
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    }
+    if (want_fast(stft, dtype, g, smb::kFastMel, mel)) {
+      smb::Stft2048Args a{};
+      a.x = (const float*)din;
+      a.out = (float*)dout;
+      a.batch = batch;
+      a.g = g;
+      a.window = stft->d_window32;
+      a.tw_pass = stft->d_tw_pass;
+      a.tw_post = stft->d_tw_post;
+      a.n_mels = (int)mel->n_mels;
+      a.nnz = (int)mel->cols.size();
+      a.rounds = (int)mel->round_iters.size();
+      a.cols = mel->d_cols;
+      a.vals = mel->d_vals;
+      a.sched = mel->d_sched;
+      a.round_iters = mel->d_round_iters;
+      a.round_width = mel->d_round_width;
+      a.power = (float)power;
+      CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
+    } else {
+      // two kernels through a plan-owned power spectrogram
+      const size_t spec_bytes = (size_t)batch * stft->geom.bins() * g.frames * esz;
+      void* spec = stft->tmp.ensure(spec_bytes);
+      CK(smb::launch_stft_generic(din, dtype, batch, g, stft->d_window64, stft->d_twiddle64,
+                                  smb::kModePower, power, spec, st));
+      run_mel_apply(mel, spec, batch, g.frames, dtype, dout, st);
+    }
+    if (mem == SMB_MEM_HOST) {
+      CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  });
+}
+
+// ---- resampler ----------------------------------------------------------------
+
+int smb_resample_plan_create(smb_resample_plan** plan, int64_t sample_rate, int64_t target,
+                             int quality, double attenuation, double passband) {
+  return guarded([&] {
+    *plan = nullptr;
+    smb::ResamplePlan rp = smb::resample_plan(sample_rate, target, quality, attenuation, passband);
+    smb_resample_plan* p = new smb_resample_plan;
+    p->plan = std::move(rp);
+    *plan = p;
+  });
+}
+int smb_resample_plan_destroy(smb_resample_plan* plan) { return guarded([&] { delete plan; }); }
+int smb_resample_plan_set_stream(smb_resample_plan* plan, void* s) {
+  return guarded([&] { plan->ensure_device(); plan->stream.set(s); });
+}
+int smb_resample_plan_sync(smb_resample_plan* plan) {
+  return guarded([&] { if (plan->device_ready) CK(cudaStreamSynchronize(plan->stream.use)); });
+}
+int smb_resample_describe(const smb_resample_plan* plan, char* buf, size_t cap) {
+  return guarded([&] {
+    const std::string s = plan->plan.describe();
+    if (cap == 0) return;
+    const size_t n = std::min(cap - 1, s.size());
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  });
+}
+int64_t smb_resample_l(const smb_resample_plan* plan) { return plan->plan.l; }
+int64_t smb_resample_m(const smb_resample_plan* plan) { return plan->plan.m; }
+int64_t smb_resample_latency(const smb_resample_plan* plan) { return plan->plan.latency; }
+int smb_resample_num_stages(const smb_resample_plan* plan) { return (int)plan->plan.stages.size(); }
+int smb_resample_stage_info(const smb_resample_plan* plan, int stage, int64_t* l, int64_t* m,
+                            int64_t* k, int* exec, int64_t* ols_n, int64_t* ols_b,
+                            int64_t* ols_delta) {
+  return guarded([&] {
+    if (stage < 0 || stage >= (int)plan->plan.stages.size())
+      throw smb::invalid_argument("stage_info: no such stage");
+    const smb::ResampleStage& s = plan->plan.stages[(size_t)stage];
+    if (l) *l = s.l;
+    if (m) *m = s.m;
+    if (k) *k = s.k;
+    if (exec) *exec = s.exec;
+    if (ols_n) *ols_n = s.ols_n;
+    if (ols_b) *ols_b = s.ols_b;
+    if (ols_delta) *ols_delta = s.ols_delta;
+  });
+}
+int smb_resample_stage_prototype(const smb_resample_plan* plan, int stage, double* out,
+                                 int64_t* len) {
+  return guarded([&] {
+    if (stage < 0 || stage >= (int)plan->plan.stages.size())
+      throw smb::invalid_argument("stage_prototype: no such stage");
+    const std::vector<double>& h = plan->plan.stages[(size_t)stage].proto;
+    if (len) *len = (int64_t)h.size();
+    if (out) std::memcpy(out, h.data(), h.size() * sizeof(double));
+  });
+}
+int64_t smb_resample_output_frames(const smb_resample_plan* plan, int64_t n) {
+  int64_t r = -1;
+  guarded([&] { r = plan->plan.output_frames(n); });
+  return r;
+}
+
+int smb_resample_apply(smb_resample_plan* plan, const float* x, int64_t batch, int64_t n,
+                       float* out, int mem) {
+  return guarded([&] {
+    if (batch < 0) throw smb::invalid_argument("apply: negative batch");
+    const smb::ResamplePlan& rp = plan->plan;
+    const int64_t total = rp.output_frames(n);
+    if (batch == 0 || n == 0 || total == 0) return;
+    plan->ensure_device();
+    cudaStream_t st = plan->stream.use;
+    const size_t in_bytes = (size_t)batch * n * 4, out_bytes = (size_t)batch * total * 4;
+    const float* din = x;
+    float* dout = out;
+    if (mem == SMB_MEM_HOST) {
+      float* stage = (float*)plan->in.ensure(in_bytes);
+      dout = (float*)plan->out.ensure(out_bytes);
+      CK(cudaMemcpyAsync(stage, x, in_bytes, cudaMemcpyHostToDevice, st));
+      din = stage;
+    } else if (mem != SMB_MEM_DEVICE) {
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    }
+    if (rp.identity()) {
+      CK(cudaMemcpyAsync(dout, din, in_bytes, cudaMemcpyDeviceToDevice, st));
+    } else if (rp.stages.size() == 1) {
+      const smb::ResampleStage& s = rp.stages[0];
+      CK(smb::launch_polyphase_direct(din, batch, n, plan->d_bank[0], (int)s.l, (int)s.m,
+                                      (int)s.k, total, dout, st));
+    } else {
+      // cascade (resample.ml:1819-1842): stage 1 emits its exact ceil tail,
+      // stage 2 runs over it with zeros beyond and is cut to output_frames.
+      const smb::ResampleStage& s1 = rp.stages[0];
+      const smb::ResampleStage& s2 = rp.stages[1];
+      const int64_t n1 = (n * s1.l + s1.m - 1) / s1.m;
+      float* mid = (float*)plan->mid.ensure((size_t)batch * n1 * 4);
+      CK(smb::launch_polyphase_direct(din, batch, n, plan->d_bank[0], (int)s1.l, (int)s1.m,
+                                      (int)s1.k, n1, mid, st));
+      CK(smb::launch_polyphase_direct(mid, batch, n1, plan->d_bank[1], (int)s2.l, (int)s2.m,
+                                      (int)s2.k, total, dout, st));
+    }
+    if (mem == SMB_MEM_HOST) {
+      CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  });
+}
+
+// ---- FIR ----------------------------------------------------------------------
+
+int smb_fir_plan_create(smb_fir_plan** plan, const double* h, int64_t taps) {
+  return guarded([&] {
+    *plan = nullptr;
+    if (taps < 1 || (taps % 2) == 0)
+      throw smb::invalid_argument(smb::format(
+          "fir: cannot use a %lld-tap filter (taps must be odd and at least 1, so the group "
+          "delay is integral)", (long long)taps));
+    smb_fir_plan* p = new smb_fir_plan;
+    p->h.assign(h, h + taps);
+    p->k = (taps - 1) / 2;
+    *plan = p;
+  });
+}
+int smb_fir_plan_destroy(smb_fir_plan* plan) { return guarded([&] { delete plan; }); }
+int smb_fir_plan_set_stream(smb_fir_plan* plan, void* s) {
+  return guarded([&] { plan->ensure_device(); plan->stream.set(s); });
+}
+int smb_fir_apply(smb_fir_plan* plan, const float* x, int64_t batch, int64_t n, float* out,
+                  int method, int mem) {
+  return guarded([&] {
+    if (batch < 0 || n < 0) throw smb::invalid_argument("fir: negative extent");
+    if (method != SMB_EXEC_DIRECT)
+      throw smb::invalid_argument("fir: only the direct method is available in this build");
+    if (batch == 0 || n == 0) return;
+    plan->ensure_device();
+    cudaStream_t st = plan->stream.use;
+    const size_t bytes = (size_t)batch * n * 4;
+    const float* din = x;
+    float* dout = out;
+    if (mem == SMB_MEM_HOST) {
+      float* stage = (float*)plan->in.ensure(bytes);
+      dout = (float*)plan->out.ensure(bytes);
+      CK(cudaMemcpyAsync(stage, x, bytes, cudaMemcpyHostToDevice, st));
+      din = stage;
+    } else if (mem != SMB_MEM_DEVICE) {
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    }
+    CK(smb::launch_polyphase_direct(din, batch, n, plan->d_bank, 1, 1, (int)plan->k, n, dout, st));
+    if (mem == SMB_MEM_HOST) {
+      CK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  });
+}
+int smb_fir_design_lowpass(int64_t k, double cutoff, double attenuation, double* out) {
+  return guarded([&] {
+    if (k < 1) throw smb::invalid_argument("fir: k must be at least 1");
+    if (!(cutoff > 0.0 && cutoff <= 1.0))
+      throw smb::invalid_argument("fir: cutoff must lie in (0, 1] Nyquist units");
+    std::vector<double> h = smb::design_prototype(1, k, cutoff, smb::kaiser_beta(attenuation));
+    std::memcpy(out, h.data(), h.size() * sizeof(double));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Launch wrappers of the CUDA kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace smb {
+
+// How a frame reads the signal: padded position q <-> source index q - left,
+// out-of-range indices resolved by `pad` (stft.ml:300-338).
+struct FrameGeom {
+  long long n;        // samples per signal
+  long long frames;   // frames per signal
+  int fft, hop, left, pad;
+  double pad_value;
+};
+
+enum SpecMode { kModeComplex = 0, kModePower = 1 };
+
+extern long long g_launch_count;   // kernels launched by this library
+
+// ---- generic path: any fft size, float64 interior ---------------------------
+// x [batch, n] (f32 or f64) -> out [batch, bins, frames]; complex mode writes
+// interleaved (re, im) in the input's precision, power mode writes |X|^power.
+// window: fft doubles on the device; twiddle: fft double2 (cos, -sin)(2 pi j / fft).
+cudaError_t launch_stft_generic(const void* x, int dtype, long long batch, FrameGeom g,
+                                const double* window, const double2* twiddle,
+                                int mode, double power, void* out, cudaStream_t st);
+
+// Mel.apply: s [batch, bins, frames] -> out [batch, n_mels, frames], float64
+// accumulation over each filter's nonzero band [band_lo[m], band_hi[m]).
+cudaError_t launch_mel_apply(const void* s, int dtype, long long batch, int bins,
+                             long long frames, int n_mels, const double* weights,
+                             const int* band_lo, const int* band_hi, void* out,
+                             cudaStream_t st);
+
+// ---- fast path: fft 2048, float32, fused frame+window+rFFT+|X|^p(+mel) -------
+struct MelSched {          // one entry per (round, lane) of the sparse mel product
+  int off;                 // first nonzero this lane sums
+  short cnt;               // how many
+  short filt;              // output filter, -1 = idle lane
+};
+enum FastOut { kFastComplex = 0, kFastPower = 1, kFastMel = 2 };
+struct Stft2048Args {
+  const float* x;          // [batch, n]
+  float* out;              // [batch, bins | n_mels, frames] (float2 for complex)
+  long long batch;
+  FrameGeom g;
+  const float* window;     // [2048]
+  const float2* tw_pass;   // [32][32]  W_1024^(k1*n2), index k1*32 + n2
+  const float2* tw_post;   // [16][32]  W_2048^(l + 32 j), index j*32 + l
+  // sparse mel (kFastMel only)
+  int n_mels, nnz, rounds;
+  const unsigned short* cols;
+  const float* vals;
+  const MelSched* sched;   // [rounds][32]
+  const int* round_iters;  // [rounds]
+  const int* round_width;  // [rounds]
+  float power;
+};
+// True when the fused kernel can take this geometry (hop small enough for the
+// shared-memory sample tile, mel tables small enough to be resident).
+bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int rounds);
+cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
+
+// ---- resampler / FIR ----------------------------------------------------------
+// One polyphase stage, direct form (resample_stubs.c:127-143):
+// out[c][i] = sum_s xz[c][(i*m)/l - k + s] * bank[(i*m) % l][s], zeros outside [0, n).
+cudaError_t launch_polyphase_direct(const float* x, long long batch, long long n,
+                                    const float* bank, int l, int m, int k,
+                                    long long n_out, float* out, cudaStream_t st);
+
+}  // namespace smb

@@ -1,0 +1,411 @@
+// Fused STFT kernel for fft_size = 2048, float32 audio (sm_100a).
+//
+//   framing + boundary extension + window -> real FFT 2048 -> |X|^p
+//   -> (optionally) sparse mel projection -> [batch, bins | n_mels, frames]
+//
+// replaces, for this geometry, Stft.analyse / magnitude_pow / Mel.apply
+// (stft.ml:356-364, 670-674; mel.ml:202-231) in one pass: the complex spectrum
+// and the power spectrogram never reach HBM on the mel path.
+//
+// Decomposition
+//   * One persistent CTA per SM, 16 warps in two independent groups of 8.  A
+//     group owns a tile of 8 consecutive frames of one signal: it stages the
+//     tile's (8-1)*hop + 2048 samples once (each sample is shared by up to four
+//     overlapping frames), then every warp transforms one frame.
+//   * Real FFT 2048 = complex FFT 1024 on z[n] = x[2n] + i x[2n+1], done as
+//     32 x 32: pass 1 (lane = n2) is a 32-point FFT held entirely in
+//     registers over the stride-32 samples, the twiddled result is transposed
+//     through a padded, warp-private shared buffer, pass 2 (lane = k1) is the
+//     second register FFT.  The even/odd split that turns Z into the real
+//     spectrum pairs bin k with 1024-k, which live in lanes l and 32-l: the
+//     partner values move by warp shuffle, each lane finishing 16 pairs.
+//   * Mel: the filterbank is >98 % zeros (each bin feeds at most two
+//     triangles), so the projection runs as a lane-balanced sparse product
+//     over the frame's power row in shared memory, in float32 FMAs.
+//   * Outputs are staged per tile so global writes run along the contiguous
+//     frame axis.
+#include "kernels.h"
+
+namespace smb {
+
+namespace {
+
+constexpr int kFft = 2048;
+constexpr int kHalf = 1024;              // complex points
+constexpr int kBins = 1025;
+constexpr int kTile = 8;                 // frames per group tile
+constexpr int kGroups = 2;
+constexpr int kGroupThreads = 256;
+constexpr int kRowStride = 2116;         // floats per warp region; == 4 mod 32
+constexpr int kExStride = 33;            // padded transpose row (complex)
+constexpr int kMaxMel = 128;
+
+__device__ constexpr float kW32C[32] = {
+    1.0f, 0.9807852804032304f, 0.9238795325112867f, 0.8314696123025452f,
+    0.7071067811865476f, 0.5555702330196023f, 0.38268343236508984f, 0.19509032201612833f,
+    0.0f, -0.1950903220161282f, -0.3826834323650897f, -0.555570233019602f,
+    -0.7071067811865475f, -0.8314696123025453f, -0.9238795325112867f, -0.9807852804032304f,
+    -1.0f, -0.9807852804032304f, -0.9238795325112868f, -0.8314696123025455f,
+    -0.7071067811865477f, -0.5555702330196022f, -0.38268343236509034f, -0.19509032201612866f,
+    0.0f, 0.1950903220161283f, 0.38268343236509f, 0.5555702330196018f,
+    0.7071067811865474f, 0.8314696123025452f, 0.9238795325112865f, 0.9807852804032303f};
+__device__ constexpr float kW32S[32] = {
+    0.0f, -0.19509032201612825f, -0.3826834323650898f, -0.5555702330196022f,
+    -0.7071067811865475f, -0.8314696123025452f, -0.9238795325112867f, -0.9807852804032304f,
+    -1.0f, -0.9807852804032304f, -0.9238795325112867f, -0.8314696123025455f,
+    -0.7071067811865476f, -0.5555702330196022f, -0.3826834323650899f, -0.1950903220161286f,
+    0.0f, 0.19509032201612836f, 0.38268343236508967f, 0.555570233019602f,
+    0.7071067811865475f, 0.8314696123025452f, 0.9238795325112865f, 0.9807852804032303f,
+    1.0f, 0.9807852804032304f, 0.9238795325112866f, 0.8314696123025455f,
+    0.7071067811865477f, 0.5555702330196022f, 0.3826834323650904f, 0.19509032201612872f};
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// v * W32^E with E a compile-time exponent: trivial rotations cost no multiply.
+template <int E>
+__device__ __forceinline__ float2 rot32(float2 v) {
+  if constexpr (E == 0) return v;
+  else if constexpr (E == 8) return make_float2(v.y, -v.x);
+  else if constexpr (E == 16) return make_float2(-v.x, -v.y);
+  else if constexpr (E == 24) return make_float2(-v.y, v.x);
+  else if constexpr (E == 4) {
+    const float r = 0.7071067811865476f;
+    return make_float2((v.x + v.y) * r, (v.y - v.x) * r);
+  } else if constexpr (E == 12) {
+    const float r = 0.7071067811865476f;
+    return make_float2((v.y - v.x) * r, -(v.x + v.y) * r);
+  } else {
+    constexpr float c = kW32C[E], s = kW32S[E];
+    return make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+  }
+}
+
+__device__ __forceinline__ void fft4(float2 a0, float2 a1, float2 a2, float2 a3,
+                                     float2& x0, float2& x1, float2& x2, float2& x3) {
+  const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3);
+  const float2 d = csub(a1, a3);
+  const float2 t3 = make_float2(d.y, -d.x);     // -i (a1 - a3)
+  x0 = cadd(t0, t2);
+  x2 = csub(t0, t2);
+  x1 = cadd(t1, t3);
+  x3 = csub(t1, t3);
+}
+
+// 8-point forward DFT of v[0..7], natural order in and out.
+__device__ __forceinline__ void fft8(float2 (&v)[8]) {
+  float2 e0, e1, e2, e3, o0, o1, o2, o3;
+  fft4(v[0], v[2], v[4], v[6], e0, e1, e2, e3);
+  fft4(v[1], v[3], v[5], v[7], o0, o1, o2, o3);
+  o1 = rot32<4>(o1);
+  o2 = rot32<8>(o2);
+  o3 = rot32<12>(o3);
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+template <int B>
+__device__ __forceinline__ void fft32_column(const float2 (&x)[32], float2 (&y)[32]) {
+  float2 r0, r1, r2, r3;
+  fft4(x[B], x[8 + B], x[16 + B], x[24 + B], r0, r1, r2, r3);
+  y[B * 4 + 0] = r0;
+  y[B * 4 + 1] = rot32<(B * 1) % 32>(r1);
+  y[B * 4 + 2] = rot32<(B * 2) % 32>(r2);
+  y[B * 4 + 3] = rot32<(B * 3) % 32>(r3);
+}
+
+template <int C>
+__device__ __forceinline__ void fft32_row(const float2 (&y)[32], float2 (&x)[32]) {
+  float2 v[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) v[b] = y[b * 4 + C];
+  fft8(v);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) x[C + 4 * d] = v[d];
+}
+
+// 32-point forward DFT in registers, natural order in and out:
+// n = 8a + b, k = c + 4d  ->  4-point DFTs over a, twiddle W32^(bc), 8-point over b.
+__device__ __forceinline__ void fft32(float2 (&x)[32]) {
+  float2 y[32];
+  fft32_column<0>(x, y); fft32_column<1>(x, y); fft32_column<2>(x, y); fft32_column<3>(x, y);
+  fft32_column<4>(x, y); fft32_column<5>(x, y); fft32_column<6>(x, y); fft32_column<7>(x, y);
+  fft32_row<0>(y, x); fft32_row<1>(y, x); fft32_row<2>(y, x); fft32_row<3>(y, x);
+}
+
+__device__ __forceinline__ long long src_index(const FrameGeom& g, long long q) {
+  long long s = q - g.left;
+  if (s >= 0 && s < g.n) return s;
+  if (g.pad == 0) {
+    if (g.n == 1) return 0;
+    const long long period = 2 * (g.n - 1);
+    long long r = s % period;
+    if (r < 0) r += period;
+    return r < g.n ? r : period - r;
+  }
+  if (g.pad == 2) return s < 0 ? 0 : g.n - 1;
+  return -1;
+}
+
+__device__ __forceinline__ void group_sync(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
+}
+
+struct Params {
+  Stft2048Args a;
+  int span_cap;              // floats reserved per group for samples
+  long long tiles_per_signal, total_tiles;
+};
+
+template <int OUT>
+__global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
+stft2048_kernel(const Params p) {
+  extern __shared__ __align__(16) float smem[];
+  float* sWindow = smem;                                        // 2048, pre-scaled by 1/2
+  float2* sTwPass = reinterpret_cast<float2*>(sWindow + kFft);  // [32][32]
+  float2* sTwPost = sTwPass + 1024;                             // [16][32]
+  float* sMelVals = reinterpret_cast<float*>(sTwPost + 512);    // nnz (padded to 4)
+  const int nnz_pad = (p.a.nnz + 3) & ~3;
+  unsigned short* sMelCols = reinterpret_cast<unsigned short*>(sMelVals + nnz_pad);
+  MelSched* sSched = reinterpret_cast<MelSched*>(sMelCols + ((nnz_pad + 7) & ~7));
+  float* groups_base = reinterpret_cast<float*>(sSched + p.a.rounds * 32);
+  const int group_floats = p.span_cap + kTile * kRowStride + kMaxMel * kTile;
+
+  const int tid = threadIdx.x;
+  const int group = tid / kGroupThreads;
+  const int gtid = tid % kGroupThreads;
+  const int warp = gtid >> 5;
+  const int lane = tid & 31;
+  float* sSamples = groups_base + group * group_floats;
+  float* sRows = sSamples + p.span_cap;
+  float* sMelOut = sRows + kTile * kRowStride;
+
+  for (int i = tid; i < kFft; i += blockDim.x) sWindow[i] = p.a.window[i] * 0.5f;
+  for (int i = tid; i < 1024; i += blockDim.x) sTwPass[i] = p.a.tw_pass[i];
+  for (int i = tid; i < 512; i += blockDim.x) sTwPost[i] = p.a.tw_post[i];
+  if (OUT == kFastMel) {
+    for (int i = tid; i < p.a.nnz; i += blockDim.x) {
+      sMelVals[i] = p.a.vals[i];
+      sMelCols[i] = p.a.cols[i];
+    }
+    for (int i = tid; i < p.a.rounds * 32; i += blockDim.x) sSched[i] = p.a.sched[i];
+  }
+  __syncthreads();
+
+  const FrameGeom g = p.a.g;
+  const long long slot = (long long)blockIdx.x * kGroups + group;
+  const long long stride = (long long)gridDim.x * kGroups;
+  float* row = sRows + warp * kRowStride;
+  float2* ex = reinterpret_cast<float2*>(row);
+
+  for (long long tile = slot; tile < p.total_tiles; tile += stride) {
+    const long long b = tile / p.tiles_per_signal;
+    const long long p0 = (tile % p.tiles_per_signal) * kTile;
+    const int nf = (int)min((long long)kTile, g.frames - p0);
+    const float* xs = p.a.x + b * g.n;
+
+    // ---- stage the tile's samples (padded stream positions q0 .. q0 + span)
+    const long long q0 = p0 * g.hop;
+    const int span = (nf - 1) * g.hop + kFft;
+    const long long s0 = q0 - g.left;
+    const bool interior = s0 >= 0 && s0 + span <= g.n;
+    if (interior && ((reinterpret_cast<size_t>(xs + s0) & 15) == 0)) {
+      const float4* src = reinterpret_cast<const float4*>(xs + s0);
+      float4* dst = reinterpret_cast<float4*>(sSamples);
+      const int n4 = span >> 2;
+      for (int i = gtid; i < n4; i += kGroupThreads) dst[i] = __ldg(src + i);
+      for (int i = (n4 << 2) + gtid; i < span; i += kGroupThreads) sSamples[i] = __ldg(xs + s0 + i);
+    } else if (interior) {
+      for (int i = gtid; i < span; i += kGroupThreads) sSamples[i] = __ldg(xs + s0 + i);
+    } else {
+      for (int i = gtid; i < span; i += kGroupThreads) {
+        const long long s = src_index(g, q0 + i);
+        sSamples[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
+      }
+    }
+    group_sync(group);
+
+    if (warp < nf) {
+      // ---- pass 1: lane = n2, registers = n1; z[n] = x[2n] + i x[2n+1], n = 32 n1 + n2
+      float2 a[32];
+      const float* fs = sSamples + warp * g.hop;
+      const float2* w2 = reinterpret_cast<const float2*>(sWindow);
+      if (((warp * g.hop) & 1) == 0) {
+        const float2* f2 = reinterpret_cast<const float2*>(fs);
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const float2 v = f2[32 * n1 + lane];
+          const float2 w = w2[32 * n1 + lane];
+          a[n1] = make_float2(v.x * w.x, v.y * w.y);
+        }
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const float vx = fs[64 * n1 + 2 * lane], vy = fs[64 * n1 + 2 * lane + 1];
+          const float2 w = w2[32 * n1 + lane];
+          a[n1] = make_float2(vx * w.x, vy * w.y);
+        }
+      }
+      fft32(a);                                   // a[k1] = Y[n2 = lane][k1]
+      // twiddle W1024^(k1 n2) and transpose through the padded buffer
+      ex[lane] = a[0];
+#pragma unroll
+      for (int k1 = 1; k1 < 32; ++k1) {
+        const float2 t = sTwPass[k1 * 32 + lane];
+        ex[k1 * kExStride + lane] =
+            make_float2(a[k1].x * t.x - a[k1].y * t.y, a[k1].x * t.y + a[k1].y * t.x);
+      }
+      __syncwarp();
+      // ---- pass 2: lane = k1, registers = n2  ->  a[k2] = Z'[k1 + 32 k2]
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) a[n2] = ex[lane * kExStride + n2];
+      __syncwarp();                               // the buffer becomes the output row
+      fft32(a);
+
+      // ---- real-spectrum split.  With Z' = Z/2 (window pre-scaled):
+      //   S = Z'[k] + conj Z'[N-k],  D = Z'[k] - conj Z'[N-k],  W = W2048^k
+      //   X[k] = S + W (-i D),   X[N-k] = conj(S - W (-i D))
+      const int partner = (32 - lane) & 31;
+      float2 r[16];
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        // lanes != 0 need the partner's register 31-k2; lane 0 pairs with itself
+        // through register (32-k2) mod 32.
+        const float2 own = a[31 - k2];
+        const float2 alt = a[(32 - k2) & 31];
+        const float sx = lane == 0 ? alt.x : own.x;
+        const float sy = lane == 0 ? alt.y : own.y;
+        r[k2].x = __shfl_sync(0xffffffffu, sx, partner);
+        r[k2].y = __shfl_sync(0xffffffffu, sy, partner);
+      }
+      float2* rowc = reinterpret_cast<float2*>(row);
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const float2 A = a[k2];
+        const float2 S = make_float2(A.x + r[k2].x, A.y - r[k2].y);
+        const float2 D = make_float2(A.x - r[k2].x, A.y + r[k2].y);
+        const float2 w = sTwPost[k2 * 32 + lane];
+        const float tr = w.x * D.y + w.y * D.x;
+        const float ti = w.y * D.y - w.x * D.x;
+        const float2 xk = make_float2(S.x + tr, S.y + ti);
+        const float2 xn = make_float2(S.x - tr, ti - S.y);
+        const int k = lane + 32 * k2, nk = kHalf - k;
+        if (OUT == kFastComplex) {
+          rowc[k] = xk;
+          rowc[nk] = xn;
+        } else {
+          float pk = xk.x * xk.x + xk.y * xk.y;
+          float pn = xn.x * xn.x + xn.y * xn.y;
+          if (p.a.power != 2.0f) {
+            if (p.a.power == 1.0f) { pk = sqrtf(pk); pn = sqrtf(pn); }
+            else { pk = powf(sqrtf(pk), p.a.power); pn = powf(sqrtf(pn), p.a.power); }
+          }
+          row[k] = pk;
+          row[nk] = pn;
+        }
+      }
+      if (lane == 0) {                            // k = 512 pairs with itself
+        const float2 xm = make_float2(2.0f * a[16].x, -2.0f * a[16].y);
+        if (OUT == kFastComplex) rowc[512] = xm;
+        else {
+          float pm = xm.x * xm.x + xm.y * xm.y;
+          if (p.a.power != 2.0f) pm = p.a.power == 1.0f ? sqrtf(pm) : powf(sqrtf(pm), p.a.power);
+          row[512] = pm;
+        }
+      }
+      if (OUT == kFastMel) {
+        __syncwarp();
+        // lane-balanced sparse product: a filter's nonzeros are split over
+        // `width` adjacent lanes and summed by shuffle.
+        for (int rd = 0; rd < p.a.rounds; ++rd) {
+          const MelSched s = sSched[rd * 32 + lane];
+          const int iters = __ldg(p.a.round_iters + rd);
+          const int width = __ldg(p.a.round_width + rd);
+          float acc = 0.0f;
+          for (int i = 0; i < iters; ++i)
+            if (i < s.cnt) acc = fmaf(sMelVals[s.off + i], row[sMelCols[s.off + i]], acc);
+          for (int o = 1; o < width; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (s.filt >= 0 && (lane & (width - 1)) == 0) sMelOut[s.filt * kTile + warp] = acc;
+        }
+      }
+    }
+    group_sync(group);
+
+    // ---- write the tile along the frame axis: [batch, rows, frames]
+    if (OUT == kFastMel) {
+      float* ob = p.a.out + b * p.a.n_mels * g.frames + p0;
+      for (int i = gtid; i < p.a.n_mels * nf; i += kGroupThreads) {
+        const int m = i / nf, f = i - m * nf;
+        ob[(long long)m * g.frames + f] = sMelOut[m * kTile + f];
+      }
+    } else if (OUT == kFastPower) {
+      float* ob = p.a.out + b * kBins * g.frames + p0;
+      for (int i = gtid; i < kBins * nf; i += kGroupThreads) {
+        const int k = i / nf, f = i - k * nf;
+        ob[(long long)k * g.frames + f] = sRows[f * kRowStride + k];
+      }
+    } else {
+      float2* ob = reinterpret_cast<float2*>(p.a.out) + b * kBins * g.frames + p0;
+      for (int i = gtid; i < kBins * nf; i += kGroupThreads) {
+        const int k = i / nf, f = i - k * nf;
+        ob[(long long)k * g.frames + f] =
+            reinterpret_cast<const float2*>(sRows + f * kRowStride)[k];
+      }
+    }
+    group_sync(group);
+  }
+}
+
+}  // namespace
+
+static size_t smem_layout(int nnz, int rounds, int span_cap) {
+  const int nnz_pad = (nnz + 3) & ~3;
+  size_t bytes = (size_t)(kFft + 2 * 1024 + 2 * 512) * 4;        // window, tw_pass, tw_post
+  bytes += (size_t)nnz_pad * 4 + (size_t)((nnz_pad + 7) & ~7) * 2; // mel vals, cols
+  bytes += (size_t)rounds * 32 * sizeof(MelSched);
+  bytes += (size_t)kGroups * (span_cap + kTile * kRowStride + kMaxMel * kTile) * 4;
+  return bytes;
+}
+
+static const size_t kSmemLimit = 232448;   // 227 KB opt-in maximum per CTA
+
+static int span_needed(const FrameGeom& g) {
+  return (((kTile - 1) * g.hop + kFft) + 3) & ~3;
+}
+
+bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int rounds) {
+  if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;
+  if (out_kind == kFastMel && (n_mels < 1 || n_mels > kMaxMel || nnz > 65536)) return false;
+  const bool mel = out_kind == kFastMel;
+  return smem_layout(mel ? nnz : 0, mel ? rounds : 0, span_needed(g)) <= kSmemLimit;
+}
+
+cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st) {
+  if (a.batch == 0 || a.g.frames == 0) return cudaSuccess;
+  Params p;
+  p.a = a;
+  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.rounds = 0; }
+  p.span_cap = span_needed(a.g);
+  p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
+  p.total_tiles = p.tiles_per_signal * a.batch;
+  const size_t smem = smem_layout(p.a.nnz, p.a.rounds, p.span_cap);
+  if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+  long long want = (p.total_tiles + kGroups - 1) / kGroups;
+  const int grid = (int)(want < sm_count ? want : sm_count);
+  cudaError_t e;
+#define SMB_LAUNCH2048(OUT)                                                                  \
+  e = cudaFuncSetAttribute(stft2048_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)smem);                                                        \
+  if (e != cudaSuccess) return e;                                                             \
+  stft2048_kernel<OUT><<<grid, kGroups * kGroupThreads, smem, st>>>(p);
+  if (out_kind == kFastMel) { SMB_LAUNCH2048(kFastMel) }
+  else if (out_kind == kFastPower) { SMB_LAUNCH2048(kFastPower) }
+  else { SMB_LAUNCH2048(kFastComplex) }
+#undef SMB_LAUNCH2048
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+}  // namespace smb

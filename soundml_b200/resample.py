@@ -1,0 +1,148 @@
+"""``Soundml.Resample`` mirror — Config and offline ``apply``
+(reference: soundml/lib/resample.ml:872-1051, 1913-1936) plus the FIR surface
+this build defines on the resampler's direct stage (FIR note)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+EXEC_NAMES = {0: "direct", 1: "ols", 2: "gemm"}
+
+
+class Config:
+    """``Resample.Config.t``.  Build with :meth:`create`."""
+
+    def __init__(self, handle, sample_rate, target, quality):
+        self._h = handle
+        self.sample_rate, self.target, self.quality = sample_rate, target, quality
+
+    @classmethod
+    def create(cls, *, sample_rate, target, quality="high"):
+        """``Resample.Config.create ?quality ~sample_rate ~target ()``
+        (resample.ml:872-1019).  ``quality`` is ``"fast"``, ``"high"``,
+        ``"best"`` or ``("custom", attenuation_db, passband)``."""
+        att = pb = 0.0
+        q = quality
+        if not isinstance(quality, str):
+            q, att, pb = quality[0], float(quality[1]), float(quality[2])
+        if q not in _lib.QUALITIES:
+            raise ValueError(f"create: unknown quality {q!r}")
+        h = C.c_void_p()
+        _lib.check(_lib.lib.smb_resample_plan_create(
+            C.byref(h), int(sample_rate), int(target), _lib.QUALITIES[q], att, pb))
+        return cls(h, sample_rate, target, quality)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.lib.smb_resample_plan_destroy(h)
+
+    l = property(lambda self: int(_lib.lib.smb_resample_l(self._h)))
+    m = property(lambda self: int(_lib.lib.smb_resample_m(self._h)))
+    latency = property(lambda self: int(_lib.lib.smb_resample_latency(self._h)))
+
+    def output_frames(self, n):
+        """``Config.output_frames c ~n`` = ceil(n*L/M) (resample.ml:1038-1051)."""
+        r = _lib.lib.smb_resample_output_frames(self._h, int(n))
+        if r < 0:
+            raise ValueError(_lib.last_error())
+        return int(r)
+
+    def pp(self):
+        """``Config.pp`` one-liner (resample.ml:1093-1137)."""
+        buf = C.create_string_buffer(512)
+        _lib.check(_lib.lib.smb_resample_describe(self._h, buf, 512))
+        return buf.value.decode()
+
+    def stages(self):
+        out = []
+        for i in range(_lib.lib.smb_resample_num_stages(self._h)):
+            l, m, k = C.c_int64(), C.c_int64(), C.c_int64()
+            ex = C.c_int()
+            on, ob, od = C.c_int64(), C.c_int64(), C.c_int64()
+            _lib.check(_lib.lib.smb_resample_stage_info(
+                self._h, i, C.byref(l), C.byref(m), C.byref(k), C.byref(ex),
+                C.byref(on), C.byref(ob), C.byref(od)))
+            out.append(dict(l=l.value, m=m.value, k=k.value, exec=EXEC_NAMES[ex.value],
+                            ols_n=on.value, ols_b=ob.value, ols_delta=od.value))
+        return out
+
+    def stage_prototype(self, i):
+        n = C.c_int64()
+        _lib.check(_lib.lib.smb_resample_stage_prototype(self._h, i, None, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.float64)
+        _lib.check(_lib.lib.smb_resample_stage_prototype(
+            self._h, i, out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
+        return out
+
+
+def _check(op, x):
+    if x.ndim < 1:
+        raise ValueError(f"{op}: cannot resample a rank-zero tensor (the time axis must exist)")
+    ptr, mem, dtype = _lib.describe(x)
+    if dtype != _lib.F32:
+        raise ValueError(f"{op}: this build's resampler carries float32 audio only")
+    return ptr, mem
+
+
+def apply(c, x):
+    """``Resample.apply c x`` (resample.ml:1913-1936): ``[..., n]`` ->
+    ``[..., ceil(n*L/M)]``."""
+    x = _lib.contiguous(x)
+    ptr, mem = _check("apply", x)
+    n = int(x.shape[-1])
+    lead = tuple(int(d) for d in x.shape[:-1])
+    batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    total = c.output_frames(n)
+    out = _lib.empty_like_kind(x, lead + (total,))
+    if batch == 0 or n == 0:
+        return out
+    stream = _lib.current_stream(x)
+    if stream is not None:
+        _lib.check(_lib.lib.smb_resample_plan_set_stream(c._h, stream))
+    _lib.check(_lib.lib.smb_resample_apply(c._h, ptr, batch, n, _lib.out_pointer(out), mem))
+    return out
+
+
+class Fir:
+    """Odd-length FIR with its group delay compensated:
+    ``y[i] = sum_t h[t] x[i + (taps-1)/2 - t]`` — the resampler's direct stage
+    at L = M = 1 (resample_stubs.c:127-143)."""
+
+    def __init__(self, taps):
+        h = np.ascontiguousarray(taps, dtype=np.float64)
+        self.taps = h
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib.smb_fir_plan_create(
+            C.byref(self._h), h.ctypes.data_as(C.POINTER(C.c_double)), int(h.shape[0])))
+
+    @classmethod
+    def lowpass(cls, *, k, cutoff, attenuation=126.0):
+        """Kaiser-windowed sinc of 2k+1 taps, ``design_prototype ~l:1``
+        (resample.ml:145-163); ``cutoff`` in Nyquist units."""
+        h = np.zeros(2 * int(k) + 1, dtype=np.float64)
+        _lib.check(_lib.lib.smb_fir_design_lowpass(
+            int(k), float(cutoff), float(attenuation), h.ctypes.data_as(C.POINTER(C.c_double))))
+        return cls(h)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.lib.smb_fir_plan_destroy(h)
+
+    def apply(self, x, method="direct"):
+        x = _lib.contiguous(x)
+        ptr, mem = _check("fir", x)
+        n = int(x.shape[-1])
+        lead = tuple(int(d) for d in x.shape[:-1])
+        batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
+        out = _lib.empty_like_kind(x, x.shape)
+        if batch == 0 or n == 0:
+            return out
+        stream = _lib.current_stream(x)
+        if stream is not None:
+            _lib.check(_lib.lib.smb_fir_plan_set_stream(self._h, stream))
+        code = {"direct": _lib.EXEC_DIRECT, "ols": _lib.EXEC_OLS}[method]
+        _lib.check(_lib.lib.smb_fir_apply(self._h, ptr, batch, n, _lib.out_pointer(out), code, mem))
+        return out

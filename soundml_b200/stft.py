@@ -1,0 +1,147 @@
+"""``Soundml.Stft`` mirror — analysis half (reference: soundml/lib/stft.ml:48-691).
+
+Same names, argument meaning and error behaviour as the OCaml module:
+``Config.create``, ``frames``, ``transform``, ``power_spectrum``, ``times``,
+``frequencies``.  The arithmetic runs in libsoundml_b200.so on the GPU; numpy
+arrays are treated as host buffers (copied in and out by the library), torch
+CUDA tensors are used in place on torch's current stream.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import window as _window
+
+
+class Config:
+    """``Stft.Config.t``.  Build with :meth:`create`."""
+
+    def __init__(self, handle, window, alignment, pad, pad_value, scale):
+        self._h = handle
+        self.window, self.alignment, self.pad = window, alignment, pad
+        self.pad_value, self.scale = pad_value, scale
+
+    @classmethod
+    def create(cls, *, fft_size, window="hann", win_length=None, hop=None,
+               alignment="centered", pad="reflect", scale="none"):
+        """``Stft.Config.create ?window ?win_length ?hop ?alignment ?pad ?scale
+        ~fft_size ()`` (stft.ml:61-111).  ``pad`` is ``"reflect"``, ``"edge"``
+        or ``("constant", v)``.  Raises ValueError with the reference's
+        Invalid_argument messages."""
+        kind, param = _window.parse(window)
+        pad_value = 0.0
+        if not isinstance(pad, str):
+            pad, pad_value = pad[0], float(pad[1])
+        for table, key, what in ((_lib.ALIGNMENTS, alignment, "alignment"),
+                                 (_lib.PADS, pad, "pad"), (_lib.SCALES, scale, "scale")):
+            if key not in table:
+                raise ValueError(f"create: unknown {what} {key!r}")
+        h = C.c_void_p()
+        _lib.check(_lib.lib.smb_stft_plan_create(
+            C.byref(h), int(fft_size),
+            _lib.DEFAULT if hop is None else int(hop),
+            _lib.DEFAULT if win_length is None else int(win_length),
+            kind, param, _lib.ALIGNMENTS[alignment], _lib.PADS[pad], pad_value,
+            _lib.SCALES[scale]))
+        return cls(h, window, alignment, pad, pad_value, scale)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.lib.smb_stft_plan_destroy(h)
+
+    fft_size = property(lambda self: int(_lib.lib.smb_stft_fft_size(self._h)))
+    hop = property(lambda self: int(_lib.lib.smb_stft_hop(self._h)))
+    bins = property(lambda self: int(_lib.lib.smb_stft_bins(self._h)))
+
+    @property
+    def analysis_window(self):
+        out = np.zeros(self.fft_size, dtype=np.float64)
+        _lib.check(_lib.lib.smb_stft_analysis_window(
+            self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def set_path(self, path):
+        """Testing hook: force the generic (double interior) or the fused
+        fft-2048 kernel.  ``"auto"`` picks the fused kernel when it applies."""
+        code = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC,
+                "fast": _lib.PATH_FAST}[path]
+        _lib.check(_lib.lib.smb_stft_plan_set_path(self._h, code))
+        return self
+
+    def source_indices(self, n):
+        """Source sample each padded position reads (-1 = constant fill): the
+        boundary-extension contract of ``pad_signal`` (stft.ml:318-338)."""
+        total = C.c_int64()
+        _lib.check(_lib.lib.smb_stft_source_indices(self._h, int(n), None, C.byref(total)))
+        out = np.zeros(total.value, dtype=np.int64)
+        _lib.check(_lib.lib.smb_stft_source_indices(
+            self._h, int(n), out.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(total)))
+        return out
+
+
+def frames(c, n):
+    """``Stft.frames c ~n`` (stft.ml:217-223)."""
+    r = _lib.lib.smb_stft_frames(c._h, int(n))
+    if r < 0:
+        raise ValueError(_lib.last_error())
+    return int(r)
+
+
+def _check_rank(op, x):
+    if x.ndim < 1:
+        raise ValueError(
+            f"{op}: cannot analyse a rank-zero tensor (the time axis must exist)")
+
+
+def _run(op, c, x, complex_out, power):
+    _check_rank(op, x)
+    x = _lib.contiguous(x)
+    n = int(x.shape[-1])
+    lead = tuple(int(d) for d in x.shape[:-1])
+    batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    count = frames(c, n)
+    out = _lib.empty_like_kind(x, lead + (c.bins, count), complex_out)
+    ptr, mem, dtype = _lib.describe(x)
+    if batch == 0 or count == 0:
+        return out
+    stream = _lib.current_stream(x)
+    if stream is not None:
+        _lib.check(_lib.lib.smb_stft_plan_set_stream(c._h, stream))
+    if complex_out:
+        _lib.check(_lib.lib.smb_stft_transform(c._h, ptr, batch, n, dtype,
+                                               _lib.out_pointer(out), mem))
+    else:
+        _lib.check(_lib.lib.smb_stft_power_spectrum(c._h, ptr, batch, n, dtype, float(power),
+                                                    _lib.out_pointer(out), mem))
+    return out
+
+
+def transform(c, x):
+    """``Stft.transform cdtype c x`` (stft.ml:632-650): ``[..., n]`` ->
+    complex ``[..., bins, frames]`` (complex64 for float32 audio)."""
+    return _run("transform", c, x, True, 1.0)
+
+
+def power_spectrum(c, x, power=2.0):
+    """``Stft.power_spectrum ?power c x`` (stft.ml:687-691)."""
+    return _run("power_spectrum", c, x, False, power)
+
+
+def times(c, sample_rate, n, dtype=np.float64):
+    """``Stft.times`` (stft.ml:245-254)."""
+    if sample_rate < 1:
+        raise ValueError(f"times: cannot use a sample rate of {sample_rate} Hz "
+                         "(sample_rate must be at least 1)")
+    count = frames(c, n)
+    return (np.arange(count, dtype=np.float64) * float(c.hop) / float(sample_rate)).astype(dtype)
+
+
+def frequencies(c, sample_rate, dtype=np.float64):
+    """``Stft.frequencies`` (stft.ml:256-261)."""
+    if sample_rate < 1:
+        raise ValueError(f"frequencies: cannot use a sample rate of {sample_rate} Hz "
+                         "(sample_rate must be at least 1)")
+    return (np.arange(c.bins, dtype=np.float64) *
+            (float(sample_rate) / float(c.fft_size))).astype(dtype)
