@@ -127,7 +127,7 @@ def transform(c, x, workers=1):
     fr = np.lib.stride_tricks.sliding_window_view(
         padded, c.fft_size, axis=-1)[..., ::c.hop, :]
     spec = scipy.fft.rfft(fr * c.analysis_window, axis=-1, workers=workers)
-    return np.swapaxes(spec, -1, -2).astype(cdtype)
+    return np.ascontiguousarray(np.swapaxes(spec, -1, -2)).astype(cdtype)
 
 
 def power_spectrum(c, x, power=2.0, workers=1):

@@ -21,7 +21,7 @@ __all__ = ["Stft", "Mel", "Window", "Resample", "Fir", "mel_spectrogram", "resam
            "kernel_launch_count", "SoundmlError"]
 
 
-def mel_spectrogram(stft_config, mel_config, x, power=2.0):
+def mel_spectrogram(stft_config, mel_config, x, power=2.0, out=None):
     """``Soundml.mel_spectrogram stft mel ?power x`` (soundml.ml:12-24):
     ``[..., n]`` -> ``[..., n_mels, frames]``.  For fft 2048 float32 this is
     one fused kernel; the power spectrogram never reaches device memory."""
@@ -39,7 +39,7 @@ def mel_spectrogram(stft_config, mel_config, x, power=2.0):
         _lib.check(_lib.lib.smb_mel_spectrogram(stft_config._h, mel_config._h, None, 0, 0,
                                                 dtype, float(power), None, mem))
     count = stft.frames(stft_config, n)
-    out = _lib.empty_like_kind(x, lead + (mel_config.n_mels, count))
+    out = _lib.empty_like_kind(x, lead + (mel_config.n_mels, count), out=out)
     if batch == 0 or count == 0:
         return out
     stream = _lib.current_stream(x)

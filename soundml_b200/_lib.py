@@ -160,18 +160,32 @@ def contiguous(x):
     return np.ascontiguousarray(x)
 
 
-def empty_like_kind(x, shape, complex_out=False):
-    """Output buffer of `shape` living where x lives."""
+def empty_like_kind(x, shape, complex_out=False, out=None):
+    """Output buffer of `shape` living where x lives.  A caller-supplied `out`
+    (the reference's destination-passing offline calls own their destination
+    too, resample.ml:1926-1935) must match in kind, dtype and shape."""
     import numpy as np
     if is_torch(x):
         import torch
         dt = x.dtype
         if complex_out:
             dt = torch.complex64 if x.dtype == torch.float32 else torch.complex128
+        if out is not None:
+            if not (is_torch(out) and out.is_cuda and out.dtype == dt and
+                    tuple(out.shape) == tuple(shape) and out.is_contiguous()):
+                raise ValueError("out: expected a contiguous CUDA tensor of "
+                                 f"shape {tuple(shape)} and dtype {dt}")
+            return out
         return torch.zeros(shape, dtype=dt, device=x.device)
     dt = x.dtype
     if complex_out:
         dt = np.complex64 if x.dtype == np.float32 else np.complex128
+    if out is not None:
+        if not (isinstance(out, np.ndarray) and out.dtype == dt and
+                tuple(out.shape) == tuple(shape) and out.flags["C_CONTIGUOUS"]):
+            raise ValueError(f"out: expected a C-contiguous array of shape {tuple(shape)} "
+                             f"and dtype {np.dtype(dt)}")
+        return out
     return np.zeros(shape, dtype=dt)
 
 

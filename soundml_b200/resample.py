@@ -86,7 +86,7 @@ def _check(op, x):
     return ptr, mem
 
 
-def apply(c, x):
+def apply(c, x, out=None):
     """``Resample.apply c x`` (resample.ml:1913-1936): ``[..., n]`` ->
     ``[..., ceil(n*L/M)]``."""
     x = _lib.contiguous(x)
@@ -95,7 +95,7 @@ def apply(c, x):
     lead = tuple(int(d) for d in x.shape[:-1])
     batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
     total = c.output_frames(n)
-    out = _lib.empty_like_kind(x, lead + (total,))
+    out = _lib.empty_like_kind(x, lead + (total,), out=out)
     if batch == 0 or n == 0:
         return out
     stream = _lib.current_stream(x)
@@ -131,13 +131,13 @@ class Fir:
         if h:
             _lib.lib.smb_fir_plan_destroy(h)
 
-    def apply(self, x, method="direct"):
+    def apply(self, x, method="direct", out=None):
         x = _lib.contiguous(x)
         ptr, mem = _check("fir", x)
         n = int(x.shape[-1])
         lead = tuple(int(d) for d in x.shape[:-1])
         batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
-        out = _lib.empty_like_kind(x, x.shape)
+        out = _lib.empty_like_kind(x, x.shape, out=out)
         if batch == 0 or n == 0:
             return out
         stream = _lib.current_stream(x)

@@ -95,14 +95,14 @@ def _check_rank(op, x):
             f"{op}: cannot analyse a rank-zero tensor (the time axis must exist)")
 
 
-def _run(op, c, x, complex_out, power):
+def _run(op, c, x, complex_out, power, out=None):
     _check_rank(op, x)
     x = _lib.contiguous(x)
     n = int(x.shape[-1])
     lead = tuple(int(d) for d in x.shape[:-1])
     batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
     count = frames(c, n)
-    out = _lib.empty_like_kind(x, lead + (c.bins, count), complex_out)
+    out = _lib.empty_like_kind(x, lead + (c.bins, count), complex_out, out=out)
     ptr, mem, dtype = _lib.describe(x)
     if batch == 0 or count == 0:
         return out
@@ -118,15 +118,15 @@ def _run(op, c, x, complex_out, power):
     return out
 
 
-def transform(c, x):
+def transform(c, x, out=None):
     """``Stft.transform cdtype c x`` (stft.ml:632-650): ``[..., n]`` ->
     complex ``[..., bins, frames]`` (complex64 for float32 audio)."""
-    return _run("transform", c, x, True, 1.0)
+    return _run("transform", c, x, True, 1.0, out)
 
 
-def power_spectrum(c, x, power=2.0):
+def power_spectrum(c, x, power=2.0, out=None):
     """``Stft.power_spectrum ?power c x`` (stft.ml:687-691)."""
-    return _run("power_spectrum", c, x, False, power)
+    return _run("power_spectrum", c, x, False, power, out)
 
 
 def times(c, sample_rate, n, dtype=np.float64):

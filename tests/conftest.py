@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """The product library, built on demand (nvcc cross-compiles without a GPU)."""
+    from soundml_b200 import build
+    build.build()
+    import soundml_b200
+    return soundml_b200
+
+
+@pytest.fixture(scope="session")
+def goldens():
+    from golden_util import Goldens
+    return Goldens()

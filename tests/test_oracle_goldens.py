@@ -1,0 +1,109 @@
+"""The oracle against every golden vector the reference commits for this path
+(SURVEY.md 8c).  CPU only.  Tolerances are the reference's own."""
+import numpy as np
+import pytest
+
+from golden_util import (F32_ATOL, F32_RTOL, F64_ATOL, F64_RTOL, MEL_SEED, STFT_SEED,
+                         WINDOW_ATOL, WINDOW_RTOL, assert_close, lcg_signal, window_spec)
+from oracle import mel_oracle, stft_oracle, window_oracle
+
+
+def _param(spec):
+    return spec[1] if not isinstance(spec, str) else 0.0
+
+
+def _name(spec):
+    return spec if isinstance(spec, str) else spec[0]
+
+
+def test_window_goldens(goldens):
+    n = 0
+    for key, stem, name, e in goldens.cases("window"):
+        p = e["params"]
+        spec = window_spec(p)
+        if stem == "cola":
+            assert window_oracle.cola(_name(spec), p["length"], p["hop"], _param(spec)) == e["expected"], key
+        else:
+            got = window_oracle.make(_name(spec), p["n"], p["periodic"], _param(spec))
+            assert_close(got, goldens.values(key), WINDOW_RTOL, WINDOW_ATOL, key)
+        n += 1
+    assert n == 325
+
+
+def test_stft_spectrum_goldens(goldens):
+    n = 0
+    for key, stem, name, e in goldens.cases("stft"):
+        if stem == "coordinates":
+            continue
+        p = e["params"]
+        c = stft_oracle.StftConfig(p["fft_size"], p["hop"], p["win_length"], alignment=p["alignment"])
+        x = lcg_signal(p["length"], STFT_SEED)
+        if p["dtype"] == "float32":
+            x = x.astype(np.float32)
+        if p["kind"] in ("magnitude", "power"):
+            got = stft_oracle.power_spectrum(c, x, 1.0 if p["kind"] == "magnitude" else 2.0)
+        else:
+            z = stft_oracle.transform(c, x)
+            got = z.real if p["kind"] == "real" else z.imag
+        rtol, atol = (F64_RTOL, F64_ATOL) if p["dtype"] == "float64" else (F32_RTOL, F32_ATOL)
+        assert_close(got, goldens.values(key), rtol, atol, key)
+        n += 1
+    assert n == 66
+
+
+def test_stft_coordinate_goldens(goldens):
+    for key, stem, name, e in goldens.cases("stft", "coordinates"):
+        p = e["params"]
+        if p["kind"] == "frequencies":
+            c = stft_oracle.StftConfig(p["fft_size"], p["hop"])
+            got = stft_oracle.frequencies(c, p["sample_rate"])
+        else:
+            c = stft_oracle.StftConfig(p["fft_size"], p["hop"], alignment=p["alignment"])
+            got = stft_oracle.times(c, p["sample_rate"], p["length"])
+        assert_close(got, goldens.values(key), 1e-12, 1e-15, key)
+
+
+def test_mel_filterbank_goldens(goldens):
+    for key, stem, name, e in goldens.cases("mel", "filterbank"):
+        p = e["params"]
+        c = mel_oracle.MelConfig(p["n_mels"], p["sample_rate"], p["fft_size"], p["f_min"],
+                                 p["f_max"], p["scale"], p["norm"])
+        assert_close(c.weights, goldens.values(key), F64_RTOL, F64_ATOL, key)
+
+
+def test_mel_spectrogram_goldens(goldens):
+    for key, stem, name, e in goldens.cases("mel", "mel_spectrogram"):
+        p = e["params"]
+        sc = stft_oracle.StftConfig(p["fft_size"], p["hop"], alignment=p["alignment"])
+        mc = mel_oracle.MelConfig(p["n_mels"], p["sample_rate"], p["fft_size"], p["f_min"],
+                                  p["f_max"], p["scale"], p["norm"])
+        x = lcg_signal(p["length"], MEL_SEED, p["envelope"])
+        if p["dtype"] == "float32":
+            x = x.astype(np.float32)
+        got = mel_oracle.mel_spectrogram(sc, mc, x, p["power"])
+        rtol, atol = (F64_RTOL, F64_ATOL) if p["dtype"] == "float64" else (F32_RTOL, F32_ATOL)
+        assert_close(got, goldens.values(key), rtol, atol, key)
+
+
+# frame-count table of soundml/test/stft/stft_grid.ml:125-143
+@pytest.mark.parametrize("fft,hop,alignment,expected", [
+    (16, 4, "centered", {0: 0, 1: 1, 2: 1, 7: 2, 16: 5, 17: 5, 61: 16}),
+    (16, 4, "left", {0: 0, 1: 0, 2: 0, 7: 0, 16: 1, 17: 1, 61: 12}),
+    (16, 4, "right", {0: 0, 1: 1, 2: 1, 7: 2, 16: 4, 17: 5, 61: 16}),
+])
+def test_frame_counts(fft, hop, alignment, expected):
+    c = stft_oracle.StftConfig(fft, hop, alignment=alignment)
+    for n, want in expected.items():
+        assert stft_oracle.frames(c, n) == want, (alignment, n)
+
+
+def test_reflect_index_matches_numpy_pad():
+    for n in (1, 2, 3, 5, 17):
+        x = np.arange(n, dtype=np.float64)
+        c = stft_oracle.StftConfig(16, 4)
+        padded = stft_oracle.pad_signal(c, x)
+        if n > 1:
+            want = np.pad(x, (8, 8), mode="reflect") if n > 8 else None
+            if want is not None:
+                assert np.array_equal(padded, want)
+        assert padded.shape[-1] == n + 16
