@@ -51,6 +51,9 @@ enum { SMB_OK = 0, SMB_EINVAL = 1, SMB_ECUDA = 2, SMB_ENOMEM = 3 };
 enum { SMB_MEM_DEVICE = 0, SMB_MEM_HOST = 1 };
 enum { SMB_F32 = 0, SMB_F64 = 1 };
 
+/* The stream a plan creates for itself (see smb_*_plan_set_stream). */
+#define SMB_STREAM_OWN ((void*)(intptr_t)-1)
+
 /* Omitted optional integer argument (OCaml ?hop, ?win_length). */
 #define SMB_DEFAULT INT32_MIN
 
@@ -107,8 +110,8 @@ int smb_stft_plan_create_with_window(smb_stft_plan** plan, int64_t fft_size,
                                      int64_t hop, int alignment, int pad_kind,
                                      double pad_value, const double* analysis_window);
 int smb_stft_plan_destroy(smb_stft_plan* plan);
-/* Run this plan's kernels on an existing CUDA stream (cudaStream_t); NULL
- * restores the plan's own stream. */
+/* Run this plan's kernels on an existing CUDA stream (cudaStream_t; NULL is the
+ * CUDA default stream); SMB_STREAM_OWN restores the plan's own stream. */
 int smb_stft_plan_set_stream(smb_stft_plan* plan, void* cuda_stream);
 int smb_stft_plan_set_path(smb_stft_plan* plan, int path);
 int smb_stft_plan_sync(smb_stft_plan* plan);

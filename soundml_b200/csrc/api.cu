@@ -95,7 +95,9 @@ struct StreamOwner {
     CK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
     use = own;
   }
-  void set(void* external) { use = external ? (cudaStream_t)external : own; }
+  // SMB_STREAM_OWN restores the plan's stream; anything else (NULL = the CUDA
+  // default stream) is used as given.
+  void set(void* external) { use = external == SMB_STREAM_OWN ? own : (cudaStream_t)external; }
   void destroy() {
     if (own) cudaStreamDestroy(own);
     own = use = nullptr;
@@ -192,76 +194,57 @@ struct smb_mel_plan {
   int scale = 0, norm = 0;
   std::vector<double> weights;       // [n_mels][bins]
   std::vector<int> band_lo, band_hi;
-  // sparse form for the fused kernel
-  std::vector<unsigned short> cols;
+  // band storage for the fused kernel: filter m keeps bins [lo, lo+len)
   std::vector<float> vals;
-  std::vector<smb::MelSched> sched;
-  std::vector<int> round_iters, round_width;
+  std::vector<smb::MelBand> bands;
+  std::vector<short> slot_filters, slot_begin;
   bool device_ready = false;
   StreamOwner stream;
   double* d_weights = nullptr;
   int *d_band_lo = nullptr, *d_band_hi = nullptr;
-  unsigned short* d_cols = nullptr;
   float* d_vals = nullptr;
-  smb::MelSched* d_sched = nullptr;
-  int *d_round_iters = nullptr, *d_round_width = nullptr;
+  smb::MelBand* d_bands = nullptr;
+  short *d_slot_filters = nullptr, *d_slot_begin = nullptr;
   DeviceBuffer in, out;
 
   void finish_host() {
     band_lo.assign((size_t)n_mels, 0);
     band_hi.assign((size_t)n_mels, 0);
-    std::vector<int> start((size_t)n_mels + 1, 0);
+    const bool small = bins <= 32767 && n_mels <= 32767;
     for (int64_t m = 0; m < n_mels; ++m) {
       int lo = (int)bins, hi = 0;
       for (int64_t k = 0; k < bins; ++k)
         if (weights[(size_t)(m * bins + k)] != 0.0) {
           lo = std::min(lo, (int)k);
           hi = (int)k + 1;
-          if (bins <= 65536) {
-            cols.push_back((unsigned short)k);
-            vals.push_back((float)weights[(size_t)(m * bins + k)]);
-          }
         }
       if (hi == 0) lo = 0;
       band_lo[(size_t)m] = lo;
       band_hi[(size_t)m] = hi;
-      start[(size_t)m + 1] = (int)cols.size();
-    }
-    // Lane schedule: a filter with `len` nonzeros is split over the smallest
-    // power-of-two number of adjacent lanes that brings each lane to <= 16
-    // terms; rounds hold filters of one width so the shuffle reduction is
-    // uniform.
-    struct Item { int m, len, width; };
-    std::vector<Item> items;
-    for (int64_t m = 0; m < n_mels; ++m) {
-      const int len = start[(size_t)m + 1] - start[(size_t)m];
-      int width = 1;
-      while (width < 32 && (len + width - 1) / width > 16) width *= 2;
-      items.push_back({(int)m, len, width});
-    }
-    std::stable_sort(items.begin(), items.end(),
-                     [](const Item& a, const Item& b) { return a.width > b.width; });
-    size_t i = 0;
-    while (i < items.size()) {
-      const int width = items[i].width;
-      std::vector<smb::MelSched> round(32, smb::MelSched{0, 0, -1});
-      int lane = 0, iters = 0;
-      while (i < items.size() && items[i].width == width && lane + width <= 32) {
-        const Item& it = items[i];
-        const int chunk = (it.len + width - 1) / width;
-        for (int j = 0; j < width; ++j) {
-          const int begin = std::min(it.len, j * chunk);
-          const int cnt = std::min(chunk, it.len - begin);
-          round[(size_t)(lane + j)] =
-              smb::MelSched{start[(size_t)it.m] + begin, (short)cnt, (short)it.m};
-          iters = std::max(iters, cnt);
-        }
-        lane += width;
-        ++i;
+      if (small) {
+        bands.push_back(smb::MelBand{(int)vals.size(), (short)lo, (short)(hi - lo)});
+        for (int k = lo; k < hi; ++k) vals.push_back((float)weights[(size_t)(m * bins + k)]);
       }
-      sched.insert(sched.end(), round.begin(), round.end());
-      round_iters.push_back(iters);
-      round_width.push_back(width);
+    }
+    // Filters go to 32 slots, longest first onto the lightest slot, so the
+    // threads of the tile-level product finish together.
+    const int slots = 32;
+    std::vector<std::vector<short>> lists((size_t)slots);
+    std::vector<long long> load((size_t)slots, 0);
+    std::vector<int> order((size_t)n_mels);
+    for (int64_t m = 0; m < n_mels; ++m) order[(size_t)m] = (int)m;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      return band_hi[(size_t)a] - band_lo[(size_t)a] > band_hi[(size_t)b] - band_lo[(size_t)b];
+    });
+    for (int m : order) {
+      const size_t s = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+      lists[s].push_back((short)m);
+      load[s] += (band_hi[(size_t)m] - band_lo[(size_t)m]) + 6;     // + per-filter overhead
+    }
+    slot_begin.assign((size_t)slots + 1, 0);
+    for (int s = 0; s < slots; ++s) {
+      slot_filters.insert(slot_filters.end(), lists[(size_t)s].begin(), lists[(size_t)s].end());
+      slot_begin[(size_t)s + 1] = (short)slot_filters.size();
     }
   }
   void ensure_device() {
@@ -271,11 +254,10 @@ struct smb_mel_plan {
     d_weights = upload(weights);
     d_band_lo = upload(band_lo);
     d_band_hi = upload(band_hi);
-    d_cols = upload(cols);
     d_vals = upload(vals);
-    d_sched = upload(sched);
-    d_round_iters = upload(round_iters);
-    d_round_width = upload(round_width);
+    d_bands = upload(bands);
+    d_slot_filters = upload(slot_filters);
+    d_slot_begin = upload(slot_begin);
     device_ready = true;
   }
   ~smb_mel_plan() {
@@ -283,11 +265,10 @@ struct smb_mel_plan {
     cudaFree(d_weights);
     cudaFree(d_band_lo);
     cudaFree(d_band_hi);
-    cudaFree(d_cols);
     cudaFree(d_vals);
-    cudaFree(d_sched);
-    cudaFree(d_round_iters);
-    cudaFree(d_round_width);
+    cudaFree(d_bands);
+    cudaFree(d_slot_filters);
+    cudaFree(d_slot_begin);
     in.release();
     out.release();
     stream.destroy();
@@ -494,10 +475,9 @@ bool want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int o
                const smb_mel_plan* mel) {
   if (p->path == SMB_PATH_GENERIC) return false;
   const bool ok = dtype == SMB_F32 && g.fft == 2048 &&
+                  (!mel || (mel->bins == 1025 && !mel->bands.empty())) &&
                   smb::stft2048_supports(g, out_kind, mel ? (int)mel->n_mels : 0,
-                                         mel ? (int)mel->cols.size() : 0,
-                                         mel ? (int)mel->round_iters.size() : 0) &&
-                  (!mel || mel->bins == 1025);
+                                         mel ? (int)mel->vals.size() : 0);
   if (!ok && p->path == SMB_PATH_FAST)
     throw smb::invalid_argument(
         "soundml_b200: the fused fft-2048 kernel does not cover this geometry");
@@ -694,13 +674,11 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
       a.tw_pass = stft->d_tw_pass;
       a.tw_post = stft->d_tw_post;
       a.n_mels = (int)mel->n_mels;
-      a.nnz = (int)mel->cols.size();
-      a.rounds = (int)mel->round_iters.size();
-      a.cols = mel->d_cols;
+      a.nnz = (int)mel->vals.size();
       a.vals = mel->d_vals;
-      a.sched = mel->d_sched;
-      a.round_iters = mel->d_round_iters;
-      a.round_width = mel->d_round_width;
+      a.bands = mel->d_bands;
+      a.slot_filters = mel->d_slot_filters;
+      a.slot_begin = mel->d_slot_begin;
       a.power = (float)power;
       CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
     } else {

@@ -34,10 +34,10 @@ cudaError_t launch_mel_apply(const void* s, int dtype, long long batch, int bins
                              cudaStream_t st);
 
 // ---- fast path: fft 2048, float32, fused frame+window+rFFT+|X|^p(+mel) -------
-struct MelSched {          // one entry per (round, lane) of the sparse mel product
-  int off;                 // first nonzero this lane sums
-  short cnt;               // how many
-  short filt;              // output filter, -1 = idle lane
+struct MelBand {           // one filter of the band-stored filterbank
+  int off;                 // first weight in vals
+  short lo;                // first bin of the band
+  short len;               // bins in the band (zero weights inside are kept)
 };
 enum FastOut { kFastComplex = 0, kFastPower = 1, kFastMel = 2 };
 struct Stft2048Args {
@@ -48,18 +48,17 @@ struct Stft2048Args {
   const float* window;     // [2048]
   const float2* tw_pass;   // [32][32]  W_1024^(k1*n2), index k1*32 + n2
   const float2* tw_post;   // [16][32]  W_2048^(l + 32 j), index j*32 + l
-  // sparse mel (kFastMel only)
-  int n_mels, nnz, rounds;
-  const unsigned short* cols;
-  const float* vals;
-  const MelSched* sched;   // [rounds][32]
-  const int* round_iters;  // [rounds]
-  const int* round_width;  // [rounds]
+  // band-stored mel filterbank (kFastMel only)
+  int n_mels, nnz;
+  const float* vals;           // [nnz] weights, filter by filter
+  const MelBand* bands;        // [n_mels]
+  const short* slot_filters;   // [n_mels] filters grouped by slot
+  const short* slot_begin;     // [33] slot s owns slot_filters[begin[s] .. begin[s+1])
   float power;
 };
 // True when the fused kernel can take this geometry (hop small enough for the
 // shared-memory sample tile, mel tables small enough to be resident).
-bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int rounds);
+bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz);
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
 
 // ---- resampler / FIR ----------------------------------------------------------

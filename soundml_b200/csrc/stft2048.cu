@@ -39,6 +39,7 @@ constexpr int kGroupThreads = 256;
 constexpr int kRowStride = 2116;         // floats per warp region; == 4 mod 32
 constexpr int kExStride = 33;            // padded transpose row (complex)
 constexpr int kMaxMel = 128;
+constexpr int kMelSlots = kGroupThreads / kTile;   // 32 filter slots per tile
 
 __device__ constexpr float kW32C[32] = {
     1.0f, 0.9807852804032304f, 0.9238795325112867f, 0.8314696123025452f,
@@ -159,18 +160,20 @@ struct Params {
   long long tiles_per_signal, total_tiles;
 };
 
-template <int OUT>
+template <int OUT, bool SQUARE>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 stft2048_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
   float* sWindow = smem;                                        // 2048, pre-scaled by 1/2
   float2* sTwPass = reinterpret_cast<float2*>(sWindow + kFft);  // [32][32]
   float2* sTwPost = sTwPass + 1024;                             // [16][32]
-  float* sMelVals = reinterpret_cast<float*>(sTwPost + 512);    // nnz (padded to 4)
+  float* sMelVals = reinterpret_cast<float*>(sTwPost + 512);    // band weights, filter by filter
   const int nnz_pad = (p.a.nnz + 3) & ~3;
-  unsigned short* sMelCols = reinterpret_cast<unsigned short*>(sMelVals + nnz_pad);
-  MelSched* sSched = reinterpret_cast<MelSched*>(sMelCols + ((nnz_pad + 7) & ~7));
-  float* groups_base = reinterpret_cast<float*>(sSched + p.a.rounds * 32);
+  MelBand* sBands = reinterpret_cast<MelBand*>(sMelVals + nnz_pad);      // [n_mels]
+  short* sSlotFilters = reinterpret_cast<short*>(sBands + p.a.n_mels);  // [n_mels]
+  short* sSlotBegin = sSlotFilters + ((p.a.n_mels + 7) & ~7);           // [kMelSlots + 1] (+pad)
+  float* groups_base = reinterpret_cast<float*>(
+      (reinterpret_cast<size_t>(sSlotBegin + 40) + 15) & ~(size_t)15);
   const int group_floats = p.span_cap + kTile * kRowStride + kMaxMel * kTile;
 
   const int tid = threadIdx.x;
@@ -186,11 +189,12 @@ stft2048_kernel(const Params p) {
   for (int i = tid; i < 1024; i += blockDim.x) sTwPass[i] = p.a.tw_pass[i];
   for (int i = tid; i < 512; i += blockDim.x) sTwPost[i] = p.a.tw_post[i];
   if (OUT == kFastMel) {
-    for (int i = tid; i < p.a.nnz; i += blockDim.x) {
-      sMelVals[i] = p.a.vals[i];
-      sMelCols[i] = p.a.cols[i];
+    for (int i = tid; i < p.a.nnz; i += blockDim.x) sMelVals[i] = p.a.vals[i];
+    for (int i = tid; i < p.a.n_mels; i += blockDim.x) {
+      sBands[i] = p.a.bands[i];
+      sSlotFilters[i] = p.a.slot_filters[i];
     }
-    for (int i = tid; i < p.a.rounds * 32; i += blockDim.x) sSched[i] = p.a.sched[i];
+    for (int i = tid; i <= kMelSlots; i += blockDim.x) sSlotBegin[i] = p.a.slot_begin[i];
   }
   __syncthreads();
 
@@ -298,7 +302,7 @@ stft2048_kernel(const Params p) {
         } else {
           float pk = xk.x * xk.x + xk.y * xk.y;
           float pn = xn.x * xn.x + xn.y * xn.y;
-          if (p.a.power != 2.0f) {
+          if (!SQUARE) {
             if (p.a.power == 1.0f) { pk = sqrtf(pk); pn = sqrtf(pn); }
             else { pk = powf(sqrtf(pk), p.a.power); pn = powf(sqrtf(pn), p.a.power); }
           }
@@ -311,27 +315,37 @@ stft2048_kernel(const Params p) {
         if (OUT == kFastComplex) rowc[512] = xm;
         else {
           float pm = xm.x * xm.x + xm.y * xm.y;
-          if (p.a.power != 2.0f) pm = p.a.power == 1.0f ? sqrtf(pm) : powf(sqrtf(pm), p.a.power);
+          if (!SQUARE) pm = p.a.power == 1.0f ? sqrtf(pm) : powf(sqrtf(pm), p.a.power);
           row[512] = pm;
-        }
-      }
-      if (OUT == kFastMel) {
-        __syncwarp();
-        // lane-balanced sparse product: a filter's nonzeros are split over
-        // `width` adjacent lanes and summed by shuffle.
-        for (int rd = 0; rd < p.a.rounds; ++rd) {
-          const MelSched s = sSched[rd * 32 + lane];
-          const int iters = __ldg(p.a.round_iters + rd);
-          const int width = __ldg(p.a.round_width + rd);
-          float acc = 0.0f;
-          for (int i = 0; i < iters; ++i)
-            if (i < s.cnt) acc = fmaf(sMelVals[s.off + i], row[sMelCols[s.off + i]], acc);
-          for (int o = 1; o < width; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-          if (s.filt >= 0 && (lane & (width - 1)) == 0) sMelOut[s.filt * kTile + warp] = acc;
         }
       }
     }
     group_sync(group);
+
+    if (OUT == kFastMel) {
+      // ---- mel projection over the tile's power rows.  Thread = (filter slot,
+      // frame): the 8 lanes of a slot share each weight (one broadcast read)
+      // and walk their own frame's row; a filter's band is contiguous bins.
+      const int f = gtid & (kTile - 1), slot = gtid >> 3;
+      const float* prow = sRows + f * kRowStride;
+      for (int q = sSlotBegin[slot]; q < sSlotBegin[slot + 1]; ++q) {
+        const int m = sSlotFilters[q];
+        const MelBand band = sBands[m];
+        const float* w = sMelVals + band.off;
+        const float* v = prow + band.lo;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int i = 0;
+        for (; i + 4 <= band.len; i += 4) {
+          a0 = fmaf(w[i], v[i], a0);
+          a1 = fmaf(w[i + 1], v[i + 1], a1);
+          a2 = fmaf(w[i + 2], v[i + 2], a2);
+          a3 = fmaf(w[i + 3], v[i + 3], a3);
+        }
+        for (; i < band.len; ++i) a0 = fmaf(w[i], v[i], a0);
+        sMelOut[m * kTile + f] = (a0 + a1) + (a2 + a3);
+      }
+      group_sync(group);
+    }
 
     // ---- write the tile along the frame axis: [batch, rows, frames]
     if (OUT == kFastMel) {
@@ -360,11 +374,12 @@ stft2048_kernel(const Params p) {
 
 }  // namespace
 
-static size_t smem_layout(int nnz, int rounds, int span_cap) {
+static size_t smem_layout(int nnz, int n_mels, int span_cap) {
   const int nnz_pad = (nnz + 3) & ~3;
   size_t bytes = (size_t)(kFft + 2 * 1024 + 2 * 512) * 4;        // window, tw_pass, tw_post
-  bytes += (size_t)nnz_pad * 4 + (size_t)((nnz_pad + 7) & ~7) * 2; // mel vals, cols
-  bytes += (size_t)rounds * 32 * sizeof(MelSched);
+  bytes += (size_t)nnz_pad * 4 + (size_t)n_mels * sizeof(MelBand); // band weights, descriptors
+  bytes += (size_t)(((n_mels + 7) & ~7) + 40) * 2;                 // slot lists
+  bytes = (bytes + 15) & ~(size_t)15;
   bytes += (size_t)kGroups * (span_cap + kTile * kRowStride + kMaxMel * kTile) * 4;
   return bytes;
 }
@@ -375,34 +390,35 @@ static int span_needed(const FrameGeom& g) {
   return (((kTile - 1) * g.hop + kFft) + 3) & ~3;
 }
 
-bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int rounds) {
+bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz) {
   if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;
   if (out_kind == kFastMel && (n_mels < 1 || n_mels > kMaxMel || nnz > 65536)) return false;
   const bool mel = out_kind == kFastMel;
-  return smem_layout(mel ? nnz : 0, mel ? rounds : 0, span_needed(g)) <= kSmemLimit;
+  return smem_layout(mel ? nnz : 0, mel ? n_mels : 0, span_needed(g)) <= kSmemLimit;
 }
 
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st) {
   if (a.batch == 0 || a.g.frames == 0) return cudaSuccess;
   Params p;
   p.a = a;
-  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.rounds = 0; }
+  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; }
   p.span_cap = span_needed(a.g);
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
   p.total_tiles = p.tiles_per_signal * a.batch;
-  const size_t smem = smem_layout(p.a.nnz, p.a.rounds, p.span_cap);
+  const size_t smem = smem_layout(p.a.nnz, p.a.n_mels, p.span_cap);
   if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
   long long want = (p.total_tiles + kGroups - 1) / kGroups;
   const int grid = (int)(want < sm_count ? want : sm_count);
   cudaError_t e;
-#define SMB_LAUNCH2048(OUT)                                                                  \
-  e = cudaFuncSetAttribute(stft2048_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           (int)smem);                                                        \
-  if (e != cudaSuccess) return e;                                                             \
-  stft2048_kernel<OUT><<<grid, kGroups * kGroupThreads, smem, st>>>(p);
-  if (out_kind == kFastMel) { SMB_LAUNCH2048(kFastMel) }
-  else if (out_kind == kFastPower) { SMB_LAUNCH2048(kFastPower) }
-  else { SMB_LAUNCH2048(kFastComplex) }
+#define SMB_LAUNCH2048(OUT, SQ)                                                              \
+  e = cudaFuncSetAttribute(stft2048_kernel<OUT, SQ>,                                         \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+  if (e != cudaSuccess) return e;                                                            \
+  stft2048_kernel<OUT, SQ><<<grid, kGroups * kGroupThreads, smem, st>>>(p);
+  const bool sq = a.power == 2.0f;
+  if (out_kind == kFastMel) { if (sq) { SMB_LAUNCH2048(kFastMel, true) } else { SMB_LAUNCH2048(kFastMel, false) } }
+  else if (out_kind == kFastPower) { if (sq) { SMB_LAUNCH2048(kFastPower, true) } else { SMB_LAUNCH2048(kFastPower, false) } }
+  else { SMB_LAUNCH2048(kFastComplex, true) }
 #undef SMB_LAUNCH2048
   ++g_launch_count;
   return cudaGetLastError();
