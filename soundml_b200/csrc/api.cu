@@ -197,14 +197,15 @@ struct smb_mel_plan {
   // band storage for the fused kernel: filter m keeps bins [lo, lo+len)
   std::vector<float> vals;
   std::vector<smb::MelBand> bands;
-  std::vector<short> slot_filters, slot_begin;
+  std::vector<short> mel_order;      // [8][mel_rounds][4]
+  int mel_rounds = 0;
   bool device_ready = false;
   StreamOwner stream;
   double* d_weights = nullptr;
   int *d_band_lo = nullptr, *d_band_hi = nullptr;
   float* d_vals = nullptr;
   smb::MelBand* d_bands = nullptr;
-  short *d_slot_filters = nullptr, *d_slot_begin = nullptr;
+  short* d_mel_order = nullptr;
   DeviceBuffer in, out;
 
   void finish_host() {
@@ -222,30 +223,41 @@ struct smb_mel_plan {
       band_lo[(size_t)m] = lo;
       band_hi[(size_t)m] = hi;
       if (small) {
-        bands.push_back(smb::MelBand{(int)vals.size(), (short)lo, (short)(hi - lo)});
-        for (int k = lo; k < hi; ++k) vals.push_back((float)weights[(size_t)(m * bins + k)]);
+        // stored band: widened to whole float4s of the 16-byte aligned power row
+        const int slo = lo & ~3, shi = (hi + 3) & ~3;
+        bands.push_back(smb::MelBand{(int)vals.size(), (short)slo, (short)(shi - slo)});
+        for (int k = slo; k < shi; ++k)
+          vals.push_back(k < bins ? (float)weights[(size_t)(m * bins + k)] : 0.0f);
       }
     }
-    // Filters go to 32 slots, longest first onto the lightest slot, so the
-    // threads of the tile-level product finish together.
-    const int slots = 32;
-    std::vector<std::vector<short>> lists((size_t)slots);
-    std::vector<long long> load((size_t)slots, 0);
+    if (!small) return;
+    // Schedule for the fused kernel: filters sorted by stored length are cut into
+    // quads (four lanes-groups of a warp run them in lockstep), quads go to the
+    // 8 warps longest-first onto the lightest warp.
     std::vector<int> order((size_t)n_mels);
     for (int64_t m = 0; m < n_mels; ++m) order[(size_t)m] = (int)m;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      return band_hi[(size_t)a] - band_lo[(size_t)a] > band_hi[(size_t)b] - band_lo[(size_t)b];
+      return bands[(size_t)a].len > bands[(size_t)b].len;
     });
-    for (int m : order) {
-      const size_t s = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
-      lists[s].push_back((short)m);
-      load[s] += (band_hi[(size_t)m] - band_lo[(size_t)m]) + 6;     // + per-filter overhead
+    const int warps = 8;
+    const int quads = (int)((n_mels + 3) / 4);
+    std::vector<std::vector<int>> lists((size_t)warps);
+    std::vector<long long> load((size_t)warps, 0);
+    for (int q = 0; q < quads; ++q) {
+      const size_t w = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+      lists[w].push_back(q);
+      load[w] += bands[(size_t)order[(size_t)q * 4]].len + 8;
     }
-    slot_begin.assign((size_t)slots + 1, 0);
-    for (int s = 0; s < slots; ++s) {
-      slot_filters.insert(slot_filters.end(), lists[(size_t)s].begin(), lists[(size_t)s].end());
-      slot_begin[(size_t)s + 1] = (short)slot_filters.size();
-    }
+    mel_rounds = 0;
+    for (const auto& l : lists) mel_rounds = std::max(mel_rounds, (int)l.size());
+    mel_order.assign((size_t)(warps * mel_rounds * 4), (short)-1);
+    for (int w = 0; w < warps; ++w)
+      for (size_t r = 0; r < lists[(size_t)w].size(); ++r)
+        for (int j = 0; j < 4; ++j) {
+          const size_t idx = (size_t)lists[(size_t)w][r] * 4 + (size_t)j;
+          if (idx < order.size())
+            mel_order[((size_t)w * mel_rounds + r) * 4 + (size_t)j] = (short)order[idx];
+        }
   }
   void ensure_device() {
     if (device_ready) return;
@@ -256,8 +268,7 @@ struct smb_mel_plan {
     d_band_hi = upload(band_hi);
     d_vals = upload(vals);
     d_bands = upload(bands);
-    d_slot_filters = upload(slot_filters);
-    d_slot_begin = upload(slot_begin);
+    d_mel_order = upload(mel_order);
     device_ready = true;
   }
   ~smb_mel_plan() {
@@ -267,8 +278,7 @@ struct smb_mel_plan {
     cudaFree(d_band_hi);
     cudaFree(d_vals);
     cudaFree(d_bands);
-    cudaFree(d_slot_filters);
-    cudaFree(d_slot_begin);
+    cudaFree(d_mel_order);
     in.release();
     out.release();
     stream.destroy();
@@ -477,7 +487,8 @@ bool want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int o
   const bool ok = dtype == SMB_F32 && g.fft == 2048 &&
                   (!mel || (mel->bins == 1025 && !mel->bands.empty())) &&
                   smb::stft2048_supports(g, out_kind, mel ? (int)mel->n_mels : 0,
-                                         mel ? (int)mel->vals.size() : 0);
+                                         mel ? (int)mel->vals.size() : 0,
+                                         mel ? mel->mel_rounds : 0);
   if (!ok && p->path == SMB_PATH_FAST)
     throw smb::invalid_argument(
         "soundml_b200: the fused fft-2048 kernel does not cover this geometry");
@@ -677,8 +688,8 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
       a.nnz = (int)mel->vals.size();
       a.vals = mel->d_vals;
       a.bands = mel->d_bands;
-      a.slot_filters = mel->d_slot_filters;
-      a.slot_begin = mel->d_slot_begin;
+      a.mel_rounds = mel->mel_rounds;
+      a.mel_order = mel->d_mel_order;
       a.power = (float)power;
       CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
     } else {

@@ -35,9 +35,9 @@ cudaError_t launch_mel_apply(const void* s, int dtype, long long batch, int bins
 
 // ---- fast path: fft 2048, float32, fused frame+window+rFFT+|X|^p(+mel) -------
 struct MelBand {           // one filter of the band-stored filterbank
-  int off;                 // first weight in vals
-  short lo;                // first bin of the band
-  short len;               // bins in the band (zero weights inside are kept)
+  int off;                 // first weight in vals (multiple of 4)
+  short lo;                // first bin of the stored band (multiple of 4)
+  short len;               // stored bins (multiple of 4; padding weights are zero)
 };
 enum FastOut { kFastComplex = 0, kFastPower = 1, kFastMel = 2 };
 struct Stft2048Args {
@@ -52,13 +52,13 @@ struct Stft2048Args {
   int n_mels, nnz;
   const float* vals;           // [nnz] weights, filter by filter
   const MelBand* bands;        // [n_mels]
-  const short* slot_filters;   // [n_mels] filters grouped by slot
-  const short* slot_begin;     // [33] slot s owns slot_filters[begin[s] .. begin[s+1])
+  int mel_rounds;              // filter quads each warp walks
+  const short* mel_order;      // [8 warps][mel_rounds][4] filter ids, -1 = none
   float power;
 };
 // True when the fused kernel can take this geometry (hop small enough for the
 // shared-memory sample tile, mel tables small enough to be resident).
-bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz);
+bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds);
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
 
 // ---- resampler / FIR ----------------------------------------------------------

@@ -39,7 +39,6 @@ constexpr int kGroupThreads = 256;
 constexpr int kRowStride = 2116;         // floats per warp region; == 4 mod 32
 constexpr int kExStride = 33;            // padded transpose row (complex)
 constexpr int kMaxMel = 128;
-constexpr int kMelSlots = kGroupThreads / kTile;   // 32 filter slots per tile
 
 __device__ constexpr float kW32C[32] = {
     1.0f, 0.9807852804032304f, 0.9238795325112867f, 0.8314696123025452f,
@@ -170,10 +169,9 @@ stft2048_kernel(const Params p) {
   float* sMelVals = reinterpret_cast<float*>(sTwPost + 512);    // band weights, filter by filter
   const int nnz_pad = (p.a.nnz + 3) & ~3;
   MelBand* sBands = reinterpret_cast<MelBand*>(sMelVals + nnz_pad);      // [n_mels]
-  short* sSlotFilters = reinterpret_cast<short*>(sBands + p.a.n_mels);  // [n_mels]
-  short* sSlotBegin = sSlotFilters + ((p.a.n_mels + 7) & ~7);           // [kMelSlots + 1] (+pad)
+  short* sMelOrder = reinterpret_cast<short*>(sBands + p.a.n_mels);     // [8 warps][rounds][4]
   float* groups_base = reinterpret_cast<float*>(
-      (reinterpret_cast<size_t>(sSlotBegin + 40) + 15) & ~(size_t)15);
+      (reinterpret_cast<size_t>(sMelOrder + kTile * p.a.mel_rounds * 4) + 15) & ~(size_t)15);
   const int group_floats = p.span_cap + kTile * kRowStride + kMaxMel * kTile;
 
   const int tid = threadIdx.x;
@@ -190,11 +188,8 @@ stft2048_kernel(const Params p) {
   for (int i = tid; i < 512; i += blockDim.x) sTwPost[i] = p.a.tw_post[i];
   if (OUT == kFastMel) {
     for (int i = tid; i < p.a.nnz; i += blockDim.x) sMelVals[i] = p.a.vals[i];
-    for (int i = tid; i < p.a.n_mels; i += blockDim.x) {
-      sBands[i] = p.a.bands[i];
-      sSlotFilters[i] = p.a.slot_filters[i];
-    }
-    for (int i = tid; i <= kMelSlots; i += blockDim.x) sSlotBegin[i] = p.a.slot_begin[i];
+    for (int i = tid; i < p.a.n_mels; i += blockDim.x) sBands[i] = p.a.bands[i];
+    for (int i = tid; i < kTile * p.a.mel_rounds * 4; i += blockDim.x) sMelOrder[i] = p.a.mel_order[i];
   }
   __syncthreads();
 
@@ -204,29 +199,35 @@ stft2048_kernel(const Params p) {
   float* row = sRows + warp * kRowStride;
   float2* ex = reinterpret_cast<float2*>(row);
 
+  bool prefetched = false;
   for (long long tile = slot; tile < p.total_tiles; tile += stride) {
     const long long b = tile / p.tiles_per_signal;
     const long long p0 = (tile % p.tiles_per_signal) * kTile;
     const int nf = (int)min((long long)kTile, g.frames - p0);
     const float* xs = p.a.x + b * g.n;
 
-    // ---- stage the tile's samples (padded stream positions q0 .. q0 + span)
-    const long long q0 = p0 * g.hop;
-    const int span = (nf - 1) * g.hop + kFft;
-    const long long s0 = q0 - g.left;
-    const bool interior = s0 >= 0 && s0 + span <= g.n;
-    if (interior && ((reinterpret_cast<size_t>(xs + s0) & 15) == 0)) {
-      const float4* src = reinterpret_cast<const float4*>(xs + s0);
-      float4* dst = reinterpret_cast<float4*>(sSamples);
-      const int n4 = span >> 2;
-      for (int i = gtid; i < n4; i += kGroupThreads) dst[i] = __ldg(src + i);
-      for (int i = (n4 << 2) + gtid; i < span; i += kGroupThreads) sSamples[i] = __ldg(xs + s0 + i);
-    } else if (interior) {
-      for (int i = gtid; i < span; i += kGroupThreads) sSamples[i] = __ldg(xs + s0 + i);
+    // ---- stage the tile's samples (padded stream positions q0 .. q0 + span),
+    // unless the previous iteration already prefetched them with cp.async.
+    if (prefetched) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
-      for (int i = gtid; i < span; i += kGroupThreads) {
-        const long long s = src_index(g, q0 + i);
-        sSamples[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
+      const long long q0 = p0 * g.hop;
+      const int span = (nf - 1) * g.hop + kFft;
+      const long long s0 = q0 - g.left;
+      const bool interior = s0 >= 0 && s0 + span <= g.n;
+      if (interior && ((reinterpret_cast<size_t>(xs + s0) & 15) == 0)) {
+        const float4* src = reinterpret_cast<const float4*>(xs + s0);
+        float4* dst = reinterpret_cast<float4*>(sSamples);
+        const int n4 = span >> 2;
+        for (int i = gtid; i < n4; i += kGroupThreads) dst[i] = __ldg(src + i);
+        for (int i = (n4 << 2) + gtid; i < span; i += kGroupThreads) sSamples[i] = __ldg(xs + s0 + i);
+      } else if (interior) {
+        for (int i = gtid; i < span; i += kGroupThreads) sSamples[i] = __ldg(xs + s0 + i);
+      } else {
+        for (int i = gtid; i < span; i += kGroupThreads) {
+          const long long s = src_index(g, q0 + i);
+          sSamples[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
+        }
       }
     }
     group_sync(group);
@@ -317,31 +318,62 @@ stft2048_kernel(const Params p) {
           float pm = xm.x * xm.x + xm.y * xm.y;
           if (!SQUARE) pm = p.a.power == 1.0f ? sqrtf(pm) : powf(sqrtf(pm), p.a.power);
           row[512] = pm;
+          row[1025] = row[1026] = row[1027] = 0.0f;   // float4 padding read by the mel bands
         }
       }
     }
     group_sync(group);
 
-    if (OUT == kFastMel) {
-      // ---- mel projection over the tile's power rows.  Thread = (filter slot,
-      // frame): the 8 lanes of a slot share each weight (one broadcast read)
-      // and walk their own frame's row; a filter's band is contiguous bins.
-      const int f = gtid & (kTile - 1), slot = gtid >> 3;
-      const float* prow = sRows + f * kRowStride;
-      for (int q = sSlotBegin[slot]; q < sSlotBegin[slot + 1]; ++q) {
-        const int m = sSlotFilters[q];
-        const MelBand band = sBands[m];
-        const float* w = sMelVals + band.off;
-        const float* v = prow + band.lo;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int i = 0;
-        for (; i + 4 <= band.len; i += 4) {
-          a0 = fmaf(w[i], v[i], a0);
-          a1 = fmaf(w[i + 1], v[i + 1], a1);
-          a2 = fmaf(w[i + 2], v[i + 2], a2);
-          a3 = fmaf(w[i + 3], v[i + 3], a3);
+    // ---- the sample buffer is free: start fetching the next tile's samples
+    // (cp.async, 16 bytes per request) under the mel / write-out phases.
+    prefetched = false;
+    {
+      const long long next = tile + stride;
+      if (next < p.total_tiles) {
+        const long long nb = next / p.tiles_per_signal;
+        const long long np0 = (next % p.tiles_per_signal) * kTile;
+        const int nnf = (int)min((long long)kTile, g.frames - np0);
+        const int nspan = (nnf - 1) * g.hop + kFft;
+        const long long ns0 = np0 * g.hop - g.left;
+        const float* nsrc = p.a.x + nb * g.n + ns0;
+        if (ns0 >= 0 && ns0 + nspan <= g.n && (reinterpret_cast<size_t>(nsrc) & 15) == 0) {
+          const unsigned base = (unsigned)__cvta_generic_to_shared(sSamples);
+          const int n4 = nspan >> 2;
+          for (int i = gtid; i < n4; i += kGroupThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + 16u * i),
+                         "l"(nsrc + 4 * i) : "memory");
+          for (int i = (n4 << 2) + gtid; i < nspan; i += kGroupThreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i),
+                         "l"(nsrc + i) : "memory");
+          prefetched = true;
         }
-        for (; i < band.len; ++i) a0 = fmaf(w[i], v[i], a0);
+      }
+    }
+
+    if (OUT == kFastMel) {
+      // ---- mel projection over the tile's power rows.  A warp takes four
+      // filters of near-equal band length at a time: lane = (filter j, frame f).
+      // Bands are stored padded to whole float4s (zero weights), rows are 16-byte
+      // aligned and kRowStride == 4 (mod 32), so the eight frames of one filter
+      // read one conflict-free 128-byte wavefront per float4 and share the weight.
+      const int f = lane & (kTile - 1), j = lane >> 3;
+      const float4* prow4 = reinterpret_cast<const float4*>(sRows + f * kRowStride);
+      for (int r = 0; r < p.a.mel_rounds; ++r) {
+        const int m = sMelOrder[(warp * p.a.mel_rounds + r) * 4 + j];
+        if (m < 0) continue;
+        const MelBand band = sBands[m];
+        const float4* w4 = reinterpret_cast<const float4*>(sMelVals + band.off);
+        const float4* v4 = prow4 + (band.lo >> 2);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const int n4 = band.len >> 2;
+#pragma unroll 2
+        for (int i = 0; i < n4; ++i) {
+          const float4 w = w4[i], v = v4[i];
+          a0 = fmaf(w.x, v.x, a0);
+          a1 = fmaf(w.y, v.y, a1);
+          a2 = fmaf(w.z, v.z, a2);
+          a3 = fmaf(w.w, v.w, a3);
+        }
         sMelOut[m * kTile + f] = (a0 + a1) + (a2 + a3);
       }
       group_sync(group);
@@ -374,11 +406,11 @@ stft2048_kernel(const Params p) {
 
 }  // namespace
 
-static size_t smem_layout(int nnz, int n_mels, int span_cap) {
+static size_t smem_layout(int nnz, int n_mels, int mel_rounds, int span_cap) {
   const int nnz_pad = (nnz + 3) & ~3;
   size_t bytes = (size_t)(kFft + 2 * 1024 + 2 * 512) * 4;        // window, tw_pass, tw_post
   bytes += (size_t)nnz_pad * 4 + (size_t)n_mels * sizeof(MelBand); // band weights, descriptors
-  bytes += (size_t)(((n_mels + 7) & ~7) + 40) * 2;                 // slot lists
+  bytes += (size_t)kTile * mel_rounds * 4 * 2;                     // warp -> filter schedule
   bytes = (bytes + 15) & ~(size_t)15;
   bytes += (size_t)kGroups * (span_cap + kTile * kRowStride + kMaxMel * kTile) * 4;
   return bytes;
@@ -390,22 +422,23 @@ static int span_needed(const FrameGeom& g) {
   return (((kTile - 1) * g.hop + kFft) + 3) & ~3;
 }
 
-bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz) {
+bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds) {
   if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;
   if (out_kind == kFastMel && (n_mels < 1 || n_mels > kMaxMel || nnz > 65536)) return false;
   const bool mel = out_kind == kFastMel;
-  return smem_layout(mel ? nnz : 0, mel ? n_mels : 0, span_needed(g)) <= kSmemLimit;
+  return smem_layout(mel ? nnz : 0, mel ? n_mels : 0, mel ? mel_rounds : 0, span_needed(g)) <=
+         kSmemLimit;
 }
 
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st) {
   if (a.batch == 0 || a.g.frames == 0) return cudaSuccess;
   Params p;
   p.a = a;
-  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; }
+  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; }
   p.span_cap = span_needed(a.g);
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
   p.total_tiles = p.tiles_per_signal * a.batch;
-  const size_t smem = smem_layout(p.a.nnz, p.a.n_mels, p.span_cap);
+  const size_t smem = smem_layout(p.a.nnz, p.a.n_mels, p.a.mel_rounds, p.span_cap);
   if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
   long long want = (p.total_tiles + kGroups - 1) / kGroups;
   const int grid = (int)(want < sm_count ? want : sm_count);
