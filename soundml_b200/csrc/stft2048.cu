@@ -170,8 +170,11 @@ stft2048_kernel(const Params p) {
   const int nnz_pad = (p.a.nnz + 3) & ~3;
   MelBand* sBands = reinterpret_cast<MelBand*>(sMelVals + nnz_pad);      // [n_mels]
   short* sMelOrder = reinterpret_cast<short*>(sBands + p.a.n_mels);     // [8 warps][rounds][4]
-  float* groups_base = reinterpret_cast<float*>(
-      (reinterpret_cast<size_t>(sMelOrder + kTile * p.a.mel_rounds * 4) + 15) & ~(size_t)15);
+  // offsets stay integers so every pointer keeps its shared-memory provenance
+  // (generic LD/ST would go through the slower generic path)
+  const int tables_bytes = (kFft + 2 * 1024 + 2 * 512 + nnz_pad) * 4 +
+                           p.a.n_mels * (int)sizeof(MelBand) + kTile * p.a.mel_rounds * 4 * 2;
+  float* groups_base = smem + (((tables_bytes + 15) & ~15) >> 2);
   const int group_floats = p.span_cap + kTile * kRowStride + kMaxMel * kTile;
 
   const int tid = threadIdx.x;
@@ -366,7 +369,7 @@ stft2048_kernel(const Params p) {
         const float4* v4 = prow4 + (band.lo >> 2);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         const int n4 = band.len >> 2;
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < n4; ++i) {
           const float4 w = w4[i], v = v4[i];
           a0 = fmaf(w.x, v.x, a0);
@@ -379,25 +382,26 @@ stft2048_kernel(const Params p) {
       group_sync(group);
     }
 
-    // ---- write the tile along the frame axis: [batch, rows, frames]
-    if (OUT == kFastMel) {
-      float* ob = p.a.out + b * p.a.n_mels * g.frames + p0;
-      for (int i = gtid; i < p.a.n_mels * nf; i += kGroupThreads) {
-        const int m = i / nf, f = i - m * nf;
-        ob[(long long)m * g.frames + f] = sMelOut[m * kTile + f];
-      }
-    } else if (OUT == kFastPower) {
-      float* ob = p.a.out + b * kBins * g.frames + p0;
-      for (int i = gtid; i < kBins * nf; i += kGroupThreads) {
-        const int k = i / nf, f = i - k * nf;
-        ob[(long long)k * g.frames + f] = sRows[f * kRowStride + k];
-      }
-    } else {
-      float2* ob = reinterpret_cast<float2*>(p.a.out) + b * kBins * g.frames + p0;
-      for (int i = gtid; i < kBins * nf; i += kGroupThreads) {
-        const int k = i / nf, f = i - k * nf;
-        ob[(long long)k * g.frames + f] =
-            reinterpret_cast<const float2*>(sRows + f * kRowStride)[k];
+    // ---- write the tile along the frame axis: [batch, rows, frames].  Eight
+    // consecutive lanes carry the eight frames of one output row (32 bytes).
+    {
+      const int f = gtid & (kTile - 1), r0 = gtid >> 3;
+      if (f < nf) {
+        if (OUT == kFastMel) {
+          float* ob = p.a.out + (b * p.a.n_mels) * g.frames + p0 + f;
+          for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile)
+            ob[(long long)m * g.frames] = sMelOut[m * kTile + f];
+        } else if (OUT == kFastPower) {
+          float* ob = p.a.out + (b * kBins) * g.frames + p0 + f;
+          const float* src = sRows + f * kRowStride;
+          for (int k = r0; k < kBins; k += kGroupThreads / kTile)
+            ob[(long long)k * g.frames] = src[k];
+        } else {
+          float2* ob = reinterpret_cast<float2*>(p.a.out) + (b * kBins) * g.frames + p0 + f;
+          const float2* src = reinterpret_cast<const float2*>(sRows + f * kRowStride);
+          for (int k = r0; k < kBins; k += kGroupThreads / kTile)
+            ob[(long long)k * g.frames] = src[k];
+        }
       }
     }
     group_sync(group);
