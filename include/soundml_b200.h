@@ -178,6 +178,10 @@ int smb_resample_num_stages(const smb_resample_plan* plan);
 int smb_resample_stage_info(const smb_resample_plan* plan, int stage, int64_t* l,
                             int64_t* m, int64_t* k, int* exec, int64_t* ols_n,
                             int64_t* ols_b, int64_t* ols_delta);
+/* Stage i design parameters: cutoff (Nyquist units of the interpolated rate)
+ * and Kaiser beta handed to design_prototype (resample.ml:145-163). */
+int smb_resample_stage_design(const smb_resample_plan* plan, int stage, double* fc,
+                              double* beta);
 /* Stage prototype (2*K*L + 1 doubles); returns the length through *len when
  * out is NULL. */
 int smb_resample_stage_prototype(const smb_resample_plan* plan, int stage,

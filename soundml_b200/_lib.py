@@ -35,7 +35,7 @@ class SoundmlError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m soundml_b200.build` "
+            f"{LIB_PATH} is missing: build it with `python soundml_b200/build.py` "
             "(there is no pure-Python or CPU fallback)")
     return C.CDLL(LIB_PATH)
 
@@ -95,6 +95,7 @@ SIGNATURES = {
     "smb_resample_latency": (_i64, [_vp]),
     "smb_resample_num_stages": (_int, [_vp]),
     "smb_resample_stage_info": (_int, [_vp, _int, _pi64, _pi64, _pi64, _pint, _pi64, _pi64, _pi64]),
+    "smb_resample_stage_design": (_int, [_vp, _int, _pd, _pd]),
     "smb_resample_stage_prototype": (_int, [_vp, _int, _pd, _pi64]),
     "smb_resample_output_frames": (_i64, [_vp, _i64]),
     "smb_resample_apply": (_int, [_vp, _vp, _i64, _i64, _vp, _int]),

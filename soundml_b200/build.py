@@ -1,6 +1,6 @@
 """Build libsoundml_b200.so in-tree with nvcc for sm_100a.
 
-    python -m soundml_b200.build          # rebuild if sources are newer
+    python soundml_b200/build.py          # rebuild if sources are newer
 
 nvcc cross-compiles without a GPU.  The shared library lands next to this file
 (``soundml_b200/libsoundml_b200.so``): git-ignored, but it travels with the

@@ -755,6 +755,15 @@ int smb_resample_stage_info(const smb_resample_plan* plan, int stage, int64_t* l
     if (ols_delta) *ols_delta = s.ols_delta;
   });
 }
+int smb_resample_stage_design(const smb_resample_plan* plan, int stage, double* fc,
+                              double* beta) {
+  return guarded([&] {
+    if (stage < 0 || stage >= (int)plan->plan.stages.size())
+      throw smb::invalid_argument("stage_design: no such stage");
+    if (fc) *fc = plan->plan.stages[(size_t)stage].fc;
+    if (beta) *beta = plan->plan.stages[(size_t)stage].beta;
+  });
+}
 int smb_resample_stage_prototype(const smb_resample_plan* plan, int stage, double* out,
                                  int64_t* len) {
   return guarded([&] {

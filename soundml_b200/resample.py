@@ -64,8 +64,11 @@ class Config:
             _lib.check(_lib.lib.smb_resample_stage_info(
                 self._h, i, C.byref(l), C.byref(m), C.byref(k), C.byref(ex),
                 C.byref(on), C.byref(ob), C.byref(od)))
+            fc, beta = C.c_double(), C.c_double()
+            _lib.check(_lib.lib.smb_resample_stage_design(self._h, i, C.byref(fc), C.byref(beta)))
             out.append(dict(l=l.value, m=m.value, k=k.value, exec=EXEC_NAMES[ex.value],
-                            ols_n=on.value, ols_b=ob.value, ols_delta=od.value))
+                            ols_n=on.value, ols_b=ob.value, ols_delta=od.value,
+                            fc=fc.value, beta=beta.value))
         return out
 
     def stage_prototype(self, i):

@@ -1,0 +1,139 @@
+"""CUDA resampler / FIR against the float64 oracle (``pytest -m gpu``).
+
+Tolerance: BASELINE.json's bar for FIR/resample output, max |got - ref| /
+max |ref| <= 1e-5 per signal (the reference's own surfaces differ by up to
+32 float32 units of peak, resample_gemm.ml:80-100).  Output lengths and the
+phase/index arithmetic are exact integers and must match exactly.
+"""
+import numpy as np
+import pytest
+
+from golden_util import peak_rel_err
+from oracle import resample_oracle as R
+from test_resample_oracle import RATE_PAIRS, oracle_stages
+
+pytestmark = pytest.mark.gpu
+
+RESAMPLE_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def sb(lib):
+    import torch
+    assert torch.cuda.is_available()
+    return lib
+
+
+def noise(shape, seed):
+    return np.random.default_rng(seed).uniform(-1, 1, shape).astype(np.float32)
+
+
+@pytest.mark.parametrize("sr,target", RATE_PAIRS)
+def test_apply_matches_oracle(sb, sr, target):
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
+    st = oracle_stages(cfg)
+    x = noise((3, 6000), sr * 7 + target)
+    got = sb.Resample.apply(cfg, x)
+    want = R.apply_plan(x, st, cfg.l, cfg.m)
+    assert got.dtype == np.float32 and got.shape == want.shape == (3, cfg.output_frames(6000))
+    for c in range(3):
+        assert peak_rel_err(got[c], want[c]) <= RESAMPLE_TOL, (sr, target, c)
+
+
+# resample_kernel.ml:28-52 — output length is ceil(n L / M), also for tiny inputs
+@pytest.mark.parametrize("sr,target,l,m", [(44100, 48000, 160, 147), (48000, 44100, 147, 160),
+                                            (44100, 16000, 160, 441), (44100, 22050, 1, 2),
+                                            (22050, 44100, 2, 1), (3, 2, 2, 3)])
+def test_output_lengths_and_short_inputs(sb, sr, target, l, m):
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
+    st = oracle_stages(cfg)
+    for n in [0, 1, 2, 3, 17, 100, 147, 160, 1000]:
+        x = noise((n,), n + 1)
+        y = sb.Resample.apply(cfg, x)
+        assert y.shape == (-(-n * l // m),)
+        if n:
+            want = R.apply_plan(x, st, cfg.l, cfg.m)
+            assert np.abs(y - want).max() <= RESAMPLE_TOL * max(np.abs(want).max(), 1e-3)
+
+
+@pytest.mark.parametrize("sr,target,quality,j,expected", [
+    (44100, 48000, "high", 294, 320), (48000, 44100, "high", 320, 294),
+    (44100, 22050, "high", 500, 250), (22050, 44100, "best", 250, 500),
+    (44100, 16000, "high", 882, 320), (48000, 8000, "high", 600, 100),
+    (8000, 48000, "high", 100, 600)])
+def test_impulse_landing(sb, sr, target, quality, j, expected):
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target, quality=quality)
+    x = np.zeros(1000, np.float32)
+    x[j] = 1.0
+    assert int(np.argmax(np.abs(sb.Resample.apply(cfg, x)))) == expected
+
+
+def test_channels_never_mix_and_match_standalone_calls(sb):
+    """resample_kernel.ml:199-237: leading axes are independent signals."""
+    cfg = sb.Resample.Config.create(sample_rate=44100, target=16000)
+    x = noise((2, 3, 5000), 3)
+    whole = sb.Resample.apply(cfg, x)
+    assert whole.shape == (2, 3, cfg.output_frames(5000))
+    for i in range(2):
+        for j in range(3):
+            assert np.array_equal(whole[i, j], sb.Resample.apply(cfg, x[i, j]))
+
+
+def test_identity_and_flat_api(sb):
+    x = noise((2, 777), 1)
+    cfg = sb.Resample.Config.create(sample_rate=48000, target=48000)
+    assert np.array_equal(sb.Resample.apply(cfg, x), x)
+    y = sb.resample(x, sample_rate=44100, target=22050)
+    assert y.shape == (2, 389)
+    with pytest.raises(ValueError, match="float32 audio only"):
+        sb.Resample.apply(cfg, x.astype(np.float64))
+
+
+def test_device_tensors(sb):
+    import torch
+    cfg = sb.Resample.Config.create(sample_rate=44100, target=16000)
+    x = noise((4, 44100), 9)
+    host = sb.Resample.apply(cfg, x)
+    dev = sb.Resample.apply(cfg, torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_tone_quality_44k_to_16k(sb):
+    """A passband tone comes through at unit gain and an out-of-band tone is
+    rejected by the designed stop band (resample_quality.ml Q3/Q4 in spirit)."""
+    cfg = sb.Resample.Config.create(sample_rate=44100, target=16000)
+    t = np.arange(88200) / 44100.0
+    keep = sb.Resample.apply(cfg, np.sin(2 * np.pi * 3000.0 * t).astype(np.float32))
+    mid = keep[4000:-4000]
+    assert abs(np.abs(mid).max() - 1.0) < 2e-3
+    gone = sb.Resample.apply(cfg, np.sin(2 * np.pi * 12000.0 * t).astype(np.float32))
+    assert np.abs(gone[4000:-4000]).max() < 1e-5           # < -100 dBFS in float32
+
+
+# ----------------------------------------------------------------- FIR ----
+
+@pytest.mark.parametrize("k", [1, 7, 50, 255])
+def test_fir_direct_matches_oracle(sb, k):
+    fir = sb.Fir.lowpass(k=k, cutoff=0.25)
+    assert fir.taps.shape == (2 * k + 1,)
+    np.testing.assert_allclose(fir.taps, R.design_prototype(1, k, 0.25, R.kaiser_beta(126.0)),
+                               rtol=1e-12, atol=1e-18)
+    x = noise((2, 2, 9000), k)
+    got = fir.apply(x)
+    want = R.fir_apply(x, fir.taps)
+    assert got.shape == x.shape
+    assert peak_rel_err(got, want) <= RESAMPLE_TOL
+    for n in (1, 2, k, 2 * k + 1):
+        xs = noise((n,), n)
+        assert peak_rel_err(fir.apply(xs), R.fir_apply(xs, fir.taps)) <= RESAMPLE_TOL
+
+
+def test_fir_arbitrary_taps_and_errors(sb):
+    h = np.array([0.25, 0.5, 0.25])
+    x = noise((100,), 4)
+    got = sb.Fir(h).apply(x)
+    want = np.convolve(x.astype(np.float64), h, mode="same")
+    assert peak_rel_err(got, want) <= RESAMPLE_TOL
+    with pytest.raises(ValueError, match="taps must be odd"):
+        sb.Fir(np.ones(4))
