@@ -1,0 +1,120 @@
+(* soundml_b200.ml — the OCaml side of the drop-in: externals over
+   libsoundml_b200.so and the three functions of the reference that change.
+
+   UNVERIFIED (no OCaml toolchain in the build container).  The intent is a
+   patch to soundml/lib that leaves every signature of stft.mli / mel.mli /
+   resample.mli / soundml.mli untouched:
+
+     Stft.power_spectrum   stft.ml:687-691   -> B200.power_spectrum
+     Stft.transform        stft.ml:632-650   -> B200.transform
+     Mel.apply             mel.ml:202-231    -> B200.mel_apply
+     Soundml.mel_spectrogram soundml.ml:22-24 -> B200.mel_spectrogram (fused)
+     Resample.apply        resample.ml:1913-1936 -> B200.resample_apply
+
+   Config.create stays in OCaml: the plan is built from the float64 window /
+   weights the config already owns, so the two sides cannot disagree. *)
+
+type stft_plan
+type mel_plan
+type resample_plan
+
+type ('a, 'b) ba = ('a, 'b, Bigarray.c_layout) Bigarray.Array1.t
+
+external stft_create :
+  int -> int -> int -> int -> float -> (float, Bigarray.float64_elt) ba -> stft_plan
+  = "soundml_b200_stft_create_bc" "soundml_b200_stft_create"
+
+external power_spectrum_c :
+  stft_plan -> (float, 'a) ba -> int -> int -> float -> (float, 'a) ba -> unit
+  = "soundml_b200_power_spectrum_bc" "soundml_b200_power_spectrum"
+
+external transform_c :
+  stft_plan -> (float, 'a) ba -> int -> int -> (Complex.t, 'c) ba -> unit
+  = "soundml_b200_transform"
+
+external mel_create : int -> int -> (float, Bigarray.float64_elt) ba -> mel_plan
+  = "soundml_b200_mel_create"
+
+external mel_apply_c : mel_plan -> (float, 'a) ba -> int -> int -> (float, 'a) ba -> unit
+  = "soundml_b200_mel_apply"
+
+external mel_spectrogram_c :
+  stft_plan -> mel_plan -> (float, 'a) ba -> int -> int -> float -> (float, 'a) ba -> unit
+  = "soundml_b200_mel_spectrogram_bc" "soundml_b200_mel_spectrogram"
+
+external resample_create : int -> int -> int -> float -> float -> resample_plan
+  = "soundml_b200_resample_create"
+
+external resample_apply_c :
+  resample_plan -> (float, Bigarray.float32_elt) ba -> int -> int
+  -> (float, Bigarray.float32_elt) ba -> unit
+  = "soundml_b200_resample_apply"
+
+(* The flat storage of a contiguous tensor, shared (resample.ml:94). *)
+let array1_of t = Nx_buffer.to_bigarray1 (Nx.to_buffer t)
+
+let leading_shape t =
+  let shape = Nx.shape t in
+  Array.sub shape 0 (Array.length shape - 1)
+
+let alignment_code = function `Centered -> 0 | `Left -> 1 | `Right -> 2
+
+let pad_code = function `Reflect -> (0, 0.) | `Constant v -> (1, v) | `Edge -> (2, 0.)
+
+(* One plan per configuration, created on first use (Config.t is immutable). *)
+let stft_plan_of (c : Stft.Config.t) =
+  let pad, pad_value = pad_code (Stft.Config.pad c) in
+  stft_create (Stft.Config.fft_size c) (Stft.Config.hop c)
+    (alignment_code (Stft.Config.alignment c))
+    pad pad_value
+    (array1_of (Stft.Config.analysis_window c))
+
+(* Replacement body of Stft.power_spectrum: same checks, same result shape
+   [...; bins; frames]; the arithmetic is the fused B200 kernel. *)
+let power_spectrum ?(power = 2.) c x =
+  let n = Nx.dim (Nx.ndim x - 1) x in
+  let lead = leading_shape x in
+  let batch = Array.fold_left ( * ) 1 lead in
+  let frames = Stft.frames c ~n in
+  let out = Nx.zeros (Nx.dtype x) (Array.append lead [|Stft.Config.bins c; frames|]) in
+  if batch > 0 && frames > 0 then
+    power_spectrum_c (stft_plan_of c) (array1_of (Nx.contiguous x)) batch n power
+      (array1_of out) ;
+  out
+
+let mel_spectrogram stft_config mel_config ?(power = 2.) x =
+  let n = Nx.dim (Nx.ndim x - 1) x in
+  let lead = leading_shape x in
+  let batch = Array.fold_left ( * ) 1 lead in
+  let frames = Stft.frames stft_config ~n in
+  let n_mels = Mel.Config.n_mels mel_config in
+  let out = Nx.zeros (Nx.dtype x) (Array.append lead [|n_mels; frames|]) in
+  ( if batch > 0 && frames > 0 then
+      let mel =
+        mel_create n_mels (Mel.Config.fft_size mel_config)
+          (array1_of (Mel.filterbank Nx.float64 mel_config))
+      in
+      mel_spectrogram_c (stft_plan_of stft_config) mel
+        (array1_of (Nx.contiguous x))
+        batch n power (array1_of out) ) ;
+  out
+
+let resample_apply ~sample_rate ~target ~quality x =
+  let q, att, pb =
+    match quality with
+    | `Fast -> (0, 0., 0.)
+    | `High -> (1, 0., 0.)
+    | `Best -> (2, 0., 0.)
+    | `Custom (att, pb) -> (3, att, pb)
+  in
+  let plan = resample_create sample_rate target q att pb in
+  let n = Nx.dim (Nx.ndim x - 1) x in
+  let lead = leading_shape x in
+  let batch = Array.fold_left ( * ) 1 lead in
+  let g = let rec gcd a b = if b = 0 then a else gcd b (a mod b) in gcd sample_rate target in
+  let l = target / g and m = sample_rate / g in
+  let total = if n <= 0 then 0 else (((n * l) - 1) / m) + 1 in
+  let out = Nx.zeros Nx.float32 (Array.append lead [|total|]) in
+  if batch > 0 && n > 0 then
+    resample_apply_c plan (array1_of (Nx.contiguous x)) batch n (array1_of out) ;
+  out

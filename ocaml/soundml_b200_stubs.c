@@ -1,0 +1,209 @@
+/* soundml_b200_stubs.c — OCaml foreign stubs over libsoundml_b200.so.
+ *
+ * UNVERIFIED: the build container has no OCaml toolchain (ocaml, dune, opam all
+ * absent), so this file has been reviewed by eye only; it follows the
+ * conventions of the reference's own stubs:
+ *   - Bigarray storage is shared, never copied      (resample.ml:94, resample_stubs.c:220-226)
+ *   - every pointer is extracted before the runtime lock is released and no
+ *     OCaml value is touched until it is re-acquired (resample_stubs.c:284-295)
+ *   - raises happen only while the lock is held     (resample_stubs.c:49-52)
+ *   - externals with more than five arguments get a bytecode twin
+ *                                                    (resample_stubs.c:410-422)
+ *   - handles are custom blocks whose finalizer is the GC backstop for an
+ *     explicit destroy                               (soundml_io_stubs.c:202-229)
+ * Precondition failures (SMB_EINVAL) become Invalid_argument with the
+ * reference's wording; CUDA/runtime failures become Failure.
+ */
+#include <stdint.h>
+#include <string.h>
+
+#include <caml/alloc.h>
+#include <caml/bigarray.h>
+#include <caml/custom.h>
+#include <caml/fail.h>
+#include <caml/memory.h>
+#include <caml/mlvalues.h>
+#include <caml/threads.h>
+
+#include "soundml_b200.h"
+
+static void smb_ml_raise(int status) {
+  if (status == SMB_OK) return;
+  if (status == SMB_EINVAL) caml_invalid_argument(smb_last_error());
+  if (status == SMB_ENOMEM) caml_raise_out_of_memory();
+  caml_failwith(smb_last_error());
+}
+
+/* ---- handles ------------------------------------------------------------- */
+#define HANDLE(v) (*((void **)Data_custom_val(v)))
+
+static void stft_finalize(value v) { if (HANDLE(v)) { smb_stft_plan_destroy(HANDLE(v)); HANDLE(v) = NULL; } }
+static void mel_finalize(value v) { if (HANDLE(v)) { smb_mel_plan_destroy(HANDLE(v)); HANDLE(v) = NULL; } }
+static void rs_finalize(value v) { if (HANDLE(v)) { smb_resample_plan_destroy(HANDLE(v)); HANDLE(v) = NULL; } }
+
+static struct custom_operations stft_ops = {"soundml_b200.stft", stft_finalize,
+  custom_compare_default, custom_hash_default, custom_serialize_default,
+  custom_deserialize_default, custom_compare_ext_default, custom_fixed_length_default};
+static struct custom_operations mel_ops = {"soundml_b200.mel", mel_finalize,
+  custom_compare_default, custom_hash_default, custom_serialize_default,
+  custom_deserialize_default, custom_compare_ext_default, custom_fixed_length_default};
+static struct custom_operations rs_ops = {"soundml_b200.resample", rs_finalize,
+  custom_compare_default, custom_hash_default, custom_serialize_default,
+  custom_deserialize_default, custom_compare_ext_default, custom_fixed_length_default};
+
+static value wrap(struct custom_operations *ops, void *h) {
+  value v = caml_alloc_custom(ops, sizeof(void *), 0, 1);
+  HANDLE(v) = h;
+  return v;
+}
+
+static int dtype_of(value ba) {
+  int kind = Caml_ba_array_val(ba)->flags & CAML_BA_KIND_MASK;
+  if (kind == CAML_BA_FLOAT32 || kind == CAML_BA_COMPLEX32) return SMB_F32;
+  if (kind == CAML_BA_FLOAT64 || kind == CAML_BA_COMPLEX64) return SMB_F64;
+  caml_invalid_argument("soundml_b200: unsupported dtype (float32 and float64 are carried)");
+}
+
+/* ---- Stft ------------------------------------------------------------------
+ * The OCaml Stft.Config.t already holds the float64 analysis window
+ * (stft.ml:57-59), so the plan is created from it.
+ * soundml_b200_stft_create : fft_size -> hop -> alignment -> pad_kind -> pad_value
+ *                            -> (float, float64_elt, c_layout) Array1.t -> stft_plan */
+CAMLprim value soundml_b200_stft_create(value v_fft, value v_hop, value v_align, value v_pad,
+                                        value v_pad_value, value v_window) {
+  CAMLparam1(v_window);
+  smb_stft_plan *h = NULL;
+  int st = smb_stft_plan_create_with_window(&h, Long_val(v_fft), Long_val(v_hop),
+                                            Int_val(v_align), Int_val(v_pad),
+                                            Double_val(v_pad_value),
+                                            (const double *)Caml_ba_data_val(v_window));
+  smb_ml_raise(st);
+  CAMLreturn(wrap(&stft_ops, h));
+}
+CAMLprim value soundml_b200_stft_create_bc(value *argv, int argn) {
+  (void)argn;
+  return soundml_b200_stft_create(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5]);
+}
+
+/* Stft.analyse replacement (stft.ml:356-364 + 670-674):
+ * soundml_b200_power_spectrum : stft_plan -> x:ba -> batch -> n -> power -> out:ba -> unit
+ * x and out are the flat storage of caller-allocated Nx tensors (host memory). */
+CAMLprim value soundml_b200_power_spectrum(value v_plan, value v_x, value v_batch, value v_n,
+                                           value v_power, value v_out) {
+  CAMLparam3(v_plan, v_x, v_out);
+  smb_stft_plan *h = HANDLE(v_plan);
+  const void *x = Caml_ba_data_val(v_x);
+  void *out = Caml_ba_data_val(v_out);
+  const int dtype = dtype_of(v_x);
+  const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
+  const double power = Double_val(v_power);
+  if ((int64_t)Caml_ba_array_val(v_x)->dim[0] < batch * n)
+    caml_failwith("soundml_b200: input extent disagrees with geometry");
+  if ((int64_t)Caml_ba_array_val(v_out)->dim[0] < batch * smb_stft_bins(h) * smb_stft_frames(h, n))
+    caml_failwith("soundml_b200: output extent disagrees with geometry");
+  caml_release_runtime_system();
+  int st = smb_stft_power_spectrum(h, x, batch, n, dtype, power, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value soundml_b200_power_spectrum_bc(value *argv, int argn) {
+  (void)argn;
+  return soundml_b200_power_spectrum(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5]);
+}
+
+/* Stft.transform: out is a complex Bigarray (complex32 for float32 audio). */
+CAMLprim value soundml_b200_transform(value v_plan, value v_x, value v_batch, value v_n,
+                                      value v_out) {
+  CAMLparam3(v_plan, v_x, v_out);
+  smb_stft_plan *h = HANDLE(v_plan);
+  const void *x = Caml_ba_data_val(v_x);
+  void *out = Caml_ba_data_val(v_out);
+  const int dtype = dtype_of(v_x);
+  const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
+  caml_release_runtime_system();
+  int st = smb_stft_transform(h, x, batch, n, dtype, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+
+/* ---- Mel ------------------------------------------------------------------- */
+CAMLprim value soundml_b200_mel_create(value v_n_mels, value v_fft, value v_weights) {
+  CAMLparam1(v_weights);
+  smb_mel_plan *h = NULL;
+  int st = smb_mel_plan_create_with_weights(&h, Long_val(v_n_mels), Long_val(v_fft),
+                                            (const double *)Caml_ba_data_val(v_weights));
+  smb_ml_raise(st);
+  CAMLreturn(wrap(&mel_ops, h));
+}
+
+/* Mel.apply (mel.ml:202-231): s [batch; bins; frames] -> out [batch; n_mels; frames] */
+CAMLprim value soundml_b200_mel_apply(value v_plan, value v_s, value v_batch, value v_frames,
+                                      value v_out) {
+  CAMLparam3(v_plan, v_s, v_out);
+  smb_mel_plan *h = HANDLE(v_plan);
+  const void *s = Caml_ba_data_val(v_s);
+  void *out = Caml_ba_data_val(v_out);
+  const int dtype = dtype_of(v_s);
+  const int64_t batch = Long_val(v_batch), frames = Long_val(v_frames);
+  caml_release_runtime_system();
+  int st = smb_mel_apply(h, s, batch, frames, dtype, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+
+/* Soundml.mel_spectrogram (soundml.ml:22-24), fused. */
+CAMLprim value soundml_b200_mel_spectrogram(value v_stft, value v_mel, value v_x, value v_batch,
+                                            value v_n, value v_power, value v_out) {
+  CAMLparam5(v_stft, v_mel, v_x, v_out, v_power);
+  smb_stft_plan *hs = HANDLE(v_stft);
+  smb_mel_plan *hm = HANDLE(v_mel);
+  const void *x = Caml_ba_data_val(v_x);
+  void *out = Caml_ba_data_val(v_out);
+  const int dtype = dtype_of(v_x);
+  const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
+  const double power = Double_val(v_power);
+  caml_release_runtime_system();
+  int st = smb_mel_spectrogram(hs, hm, x, batch, n, dtype, power, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value soundml_b200_mel_spectrogram_bc(value *argv, int argn) {
+  (void)argn;
+  return soundml_b200_mel_spectrogram(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5],
+                                      argv[6]);
+}
+
+/* ---- Resample ---------------------------------------------------------------
+ * quality: 0 fast, 1 high, 2 best, 3 custom (attenuation, passband). */
+CAMLprim value soundml_b200_resample_create(value v_sr, value v_target, value v_quality,
+                                            value v_att, value v_passband) {
+  CAMLparam0();
+  smb_resample_plan *h = NULL;
+  int st = smb_resample_plan_create(&h, Long_val(v_sr), Long_val(v_target), Int_val(v_quality),
+                                    Double_val(v_att), Double_val(v_passband));
+  smb_ml_raise(st);
+  CAMLreturn(wrap(&rs_ops, h));
+}
+
+/* Resample.apply (resample.ml:1913-1936): x [batch; n] -> out [batch; ceil(n L / M)] */
+CAMLprim value soundml_b200_resample_apply(value v_plan, value v_x, value v_batch, value v_n,
+                                           value v_out) {
+  CAMLparam3(v_plan, v_x, v_out);
+  smb_resample_plan *h = HANDLE(v_plan);
+  const float *x = (const float *)Caml_ba_data_val(v_x);
+  float *out = (float *)Caml_ba_data_val(v_out);
+  const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
+  if ((Caml_ba_array_val(v_x)->flags & CAML_BA_KIND_MASK) != CAML_BA_FLOAT32)
+    caml_invalid_argument("apply: the GPU resampler carries float32 audio");
+  if ((int64_t)Caml_ba_array_val(v_out)->dim[0] < batch * smb_resample_output_frames(h, n))
+    caml_failwith("soundml_b200: output extent disagrees with geometry");
+  caml_release_runtime_system();
+  int st = smb_resample_apply(h, x, batch, n, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
