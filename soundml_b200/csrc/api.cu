@@ -223,8 +223,11 @@ struct smb_mel_plan {
       band_lo[(size_t)m] = lo;
       band_hi[(size_t)m] = hi;
       if (small) {
-        // stored band: widened to whole float4s of the 16-byte aligned power row
-        const int slo = lo & ~3, shi = (hi + 3) & ~3;
+        // stored band: widened to whole float4s of the 16-byte aligned power row,
+        // an even number of them so the product loop unrolls by two cleanly
+        const int slo = lo & ~3;
+        int shi = (hi + 3) & ~3;
+        if (((shi - slo) >> 2) & 1) shi += 4;
         bands.push_back(smb::MelBand{(int)vals.size(), (short)slo, (short)(shi - slo)});
         for (int k = slo; k < shi; ++k)
           vals.push_back(k < bins ? (float)weights[(size_t)(m * bins + k)] : 0.0f);

@@ -36,8 +36,8 @@ constexpr int kBins = 1025;
 constexpr int kTile = 8;                 // frames per group tile
 constexpr int kGroups = 2;
 constexpr int kGroupThreads = 256;
-constexpr int kRowStride = 2116;         // floats per warp region; == 4 mod 32
-constexpr int kExStride = 33;            // padded transpose row (complex)
+constexpr int kRowStride = 2180;         // floats per warp region; == 4 mod 32, holds [32][34] complex
+constexpr int kExStride = 34;            // padded transpose row (complex): 16-byte rows, conflict-free
 constexpr int kMaxMel = 128;
 
 __device__ constexpr float kW32C[32] = {
@@ -159,13 +159,67 @@ struct Params {
   long long tiles_per_signal, total_tiles;
 };
 
+// Brings one tile's samples (padded stream positions p0*hop .. + span) into the
+// group's sample buffer.  Positions that map to real samples are fetched with
+// cp.async (16 bytes per request when source and destination are both 16-byte
+// aligned, else 8 or 4); border positions are resolved by the reference's
+// boundary rule (stft.ml:300-338) and stored directly.  Completion is awaited
+// by the caller (cp.async.wait_all + group barrier).
+__device__ __forceinline__ void stage_tile(const Params& p, long long tile, float* sSamples,
+                                           int gtid) {
+  const FrameGeom& g = p.a.g;
+  const long long b = tile / p.tiles_per_signal;
+  const long long p0 = (tile % p.tiles_per_signal) * kTile;
+  const int nf = (int)min((long long)kTile, g.frames - p0);
+  const int span = (nf - 1) * g.hop + kFft;
+  const long long q0 = p0 * g.hop;
+  const long long s0 = q0 - g.left;
+  const float* xs = p.a.x + b * g.n;
+  // [lo, hi): positions of the span that are real samples
+  const int lo = (int)max(0LL, min((long long)span, -s0));
+  const int hi = (int)max((long long)lo, min((long long)span, g.n - s0));
+  for (int i = gtid; i < lo; i += kGroupThreads) {
+    const long long s = src_index(g, q0 + i);
+    sSamples[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
+  }
+  for (int i = hi + gtid; i < span; i += kGroupThreads) {
+    const long long s = src_index(g, q0 + i);
+    sSamples[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
+  }
+  const float* src = xs + s0;                       // src + i is valid for i in [lo, hi)
+  const unsigned base = (unsigned)__cvta_generic_to_shared(sSamples);
+  const size_t addr = reinterpret_cast<size_t>(src);
+  if ((addr & 15) == 0) {
+    const int head = min(hi, (lo + 3) & ~3), tail = max(head, hi & ~3);
+    for (int i = lo + gtid; i < head; i += kGroupThreads)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
+    for (int i = head + 4 * gtid; i < tail; i += 4 * kGroupThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
+    for (int i = tail + gtid; i < hi; i += kGroupThreads)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
+  } else if ((addr & 7) == 0) {
+    const int head = min(hi, (lo + 1) & ~1), tail = max(head, hi & ~1);
+    for (int i = lo + gtid; i < head; i += kGroupThreads)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
+    for (int i = head + 2 * gtid; i < tail; i += 2 * kGroupThreads)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
+    for (int i = tail + gtid; i < hi; i += kGroupThreads)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
+  } else {
+    for (int i = lo + gtid; i < hi; i += kGroupThreads)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
+  }
+}
+
 template <int OUT, bool SQUARE>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 stft2048_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
-  float* sWindow = smem;                                        // 2048, pre-scaled by 1/2
-  float2* sTwPass = reinterpret_cast<float2*>(sWindow + kFft);  // [32][32]
-  float2* sTwPost = sTwPass + 1024;                             // [16][32]
+  // Constant tables are laid out so a lane fetches two of its values per
+  // 16-byte load: [pair][lane][2] (half the shared-memory instructions).
+  float* sWindow = smem;                                        // [16][32] x {w(n1), w(n1+1)} float2 pairs, x 1/2
+  float2* sTwPass = reinterpret_cast<float2*>(sWindow + kFft);  // [16][32][2]  W_1024^(k1 n2), k1 = 2 pair + {0,1}
+  float2* sTwPost = sTwPass + 1024;                             // [8][32][2]   W_2048^(l + 32 k2), k2 = 2 pair + {0,1}
   float* sMelVals = reinterpret_cast<float*>(sTwPost + 512);    // band weights, filter by filter
   const int nnz_pad = (p.a.nnz + 3) & ~3;
   MelBand* sBands = reinterpret_cast<MelBand*>(sMelVals + nnz_pad);      // [n_mels]
@@ -186,9 +240,19 @@ stft2048_kernel(const Params p) {
   float* sRows = sSamples + p.span_cap;
   float* sMelOut = sRows + kTile * kRowStride;
 
-  for (int i = tid; i < kFft; i += blockDim.x) sWindow[i] = p.a.window[i] * 0.5f;
-  for (int i = tid; i < 1024; i += blockDim.x) sTwPass[i] = p.a.tw_pass[i];
-  for (int i = tid; i < 512; i += blockDim.x) sTwPost[i] = p.a.tw_post[i];
+  for (int i = tid; i < kFft; i += blockDim.x) {
+    // source index j = 2 (32 n1 + l) + c  ->  ((n1/2) * 32 + l) * 4 + (n1 & 1) * 2 + c
+    const int c = i & 1, l = (i >> 1) & 31, n1 = i >> 6;
+    sWindow[(((n1 >> 1) * 32 + l) << 2) + ((n1 & 1) << 1) + c] = p.a.window[i] * 0.5f;
+  }
+  for (int i = tid; i < 1024; i += blockDim.x) {
+    const int l = i & 31, k1 = i >> 5;
+    sTwPass[(((k1 >> 1) * 32 + l) << 1) + (k1 & 1)] = p.a.tw_pass[i];
+  }
+  for (int i = tid; i < 512; i += blockDim.x) {
+    const int l = i & 31, k2 = i >> 5;
+    sTwPost[(((k2 >> 1) * 32 + l) << 1) + (k2 & 1)] = p.a.tw_post[i];
+  }
   if (OUT == kFastMel) {
     for (int i = tid; i < p.a.nnz; i += blockDim.x) sMelVals[i] = p.a.vals[i];
     for (int i = tid; i < p.a.n_mels; i += blockDim.x) sBands[i] = p.a.bands[i];
@@ -202,73 +266,65 @@ stft2048_kernel(const Params p) {
   float* row = sRows + warp * kRowStride;
   float2* ex = reinterpret_cast<float2*>(row);
 
-  bool prefetched = false;
+  if (slot < p.total_tiles) stage_tile(p, slot, sSamples, gtid);
   for (long long tile = slot; tile < p.total_tiles; tile += stride) {
     const long long b = tile / p.tiles_per_signal;
     const long long p0 = (tile % p.tiles_per_signal) * kTile;
     const int nf = (int)min((long long)kTile, g.frames - p0);
-    const float* xs = p.a.x + b * g.n;
 
-    // ---- stage the tile's samples (padded stream positions q0 .. q0 + span),
-    // unless the previous iteration already prefetched them with cp.async.
-    if (prefetched) {
-      asm volatile("cp.async.wait_all;" ::: "memory");
-    } else {
-      const long long q0 = p0 * g.hop;
-      const int span = (nf - 1) * g.hop + kFft;
-      const long long s0 = q0 - g.left;
-      const bool interior = s0 >= 0 && s0 + span <= g.n;
-      if (interior && ((reinterpret_cast<size_t>(xs + s0) & 15) == 0)) {
-        const float4* src = reinterpret_cast<const float4*>(xs + s0);
-        float4* dst = reinterpret_cast<float4*>(sSamples);
-        const int n4 = span >> 2;
-        for (int i = gtid; i < n4; i += kGroupThreads) dst[i] = __ldg(src + i);
-        for (int i = (n4 << 2) + gtid; i < span; i += kGroupThreads) sSamples[i] = __ldg(xs + s0 + i);
-      } else if (interior) {
-        for (int i = gtid; i < span; i += kGroupThreads) sSamples[i] = __ldg(xs + s0 + i);
-      } else {
-        for (int i = gtid; i < span; i += kGroupThreads) {
-          const long long s = src_index(g, q0 + i);
-          sSamples[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
-        }
-      }
-    }
+    // ---- the tile's samples were requested one iteration ago (or just above
+    // the loop): wait for this thread's copies, then for the group's.
+    asm volatile("cp.async.wait_all;" ::: "memory");
     group_sync(group);
 
     if (warp < nf) {
       // ---- pass 1: lane = n2, registers = n1; z[n] = x[2n] + i x[2n+1], n = 32 n1 + n2
       float2 a[32];
       const float* fs = sSamples + warp * g.hop;
-      const float2* w2 = reinterpret_cast<const float2*>(sWindow);
+      const float4* w4 = reinterpret_cast<const float4*>(sWindow);
       if (((warp * g.hop) & 1) == 0) {
         const float2* f2 = reinterpret_cast<const float2*>(fs);
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          const float2 v = f2[32 * n1 + lane];
-          const float2 w = w2[32 * n1 + lane];
-          a[n1] = make_float2(v.x * w.x, v.y * w.y);
+        for (int n1 = 0; n1 < 32; n1 += 2) {
+          const float2 v0 = f2[32 * n1 + lane], v1 = f2[32 * (n1 + 1) + lane];
+          const float4 w = w4[(n1 >> 1) * 32 + lane];
+          a[n1] = make_float2(v0.x * w.x, v0.y * w.y);
+          a[n1 + 1] = make_float2(v1.x * w.z, v1.y * w.w);
         }
       } else {
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          const float vx = fs[64 * n1 + 2 * lane], vy = fs[64 * n1 + 2 * lane + 1];
-          const float2 w = w2[32 * n1 + lane];
-          a[n1] = make_float2(vx * w.x, vy * w.y);
+        for (int n1 = 0; n1 < 32; n1 += 2) {
+          const float4 w = w4[(n1 >> 1) * 32 + lane];
+          a[n1] = make_float2(fs[64 * n1 + 2 * lane] * w.x, fs[64 * n1 + 2 * lane + 1] * w.y);
+          a[n1 + 1] = make_float2(fs[64 * (n1 + 1) + 2 * lane] * w.z,
+                                  fs[64 * (n1 + 1) + 2 * lane + 1] * w.w);
         }
       }
       fft32(a);                                   // a[k1] = Y[n2 = lane][k1]
       // twiddle W1024^(k1 n2) and transpose through the padded buffer
-      ex[lane] = a[0];
+      {
+        const float4* t4 = reinterpret_cast<const float4*>(sTwPass);
 #pragma unroll
-      for (int k1 = 1; k1 < 32; ++k1) {
-        const float2 t = sTwPass[k1 * 32 + lane];
-        ex[k1 * kExStride + lane] =
-            make_float2(a[k1].x * t.x - a[k1].y * t.y, a[k1].x * t.y + a[k1].y * t.x);
+        for (int k1 = 0; k1 < 32; k1 += 2) {
+          const float4 t = t4[(k1 >> 1) * 32 + lane];
+          ex[k1 * kExStride + lane] =
+              k1 == 0 ? a[0]
+                      : make_float2(a[k1].x * t.x - a[k1].y * t.y, a[k1].x * t.y + a[k1].y * t.x);
+          ex[(k1 + 1) * kExStride + lane] = make_float2(a[k1 + 1].x * t.z - a[k1 + 1].y * t.w,
+                                                        a[k1 + 1].x * t.w + a[k1 + 1].y * t.z);
+        }
       }
       __syncwarp();
       // ---- pass 2: lane = k1, registers = n2  ->  a[k2] = Z'[k1 + 32 k2]
+      {
+        const float4* e4 = reinterpret_cast<const float4*>(ex + lane * kExStride);
 #pragma unroll
-      for (int n2 = 0; n2 < 32; ++n2) a[n2] = ex[lane * kExStride + n2];
+        for (int n2 = 0; n2 < 32; n2 += 2) {
+          const float4 v = e4[n2 >> 1];
+          a[n2] = make_float2(v.x, v.y);
+          a[n2 + 1] = make_float2(v.z, v.w);
+        }
+      }
       __syncwarp();                               // the buffer becomes the output row
       fft32(a);
 
@@ -294,7 +350,7 @@ stft2048_kernel(const Params p) {
         const float2 A = a[k2];
         const float2 S = make_float2(A.x + r[k2].x, A.y - r[k2].y);
         const float2 D = make_float2(A.x - r[k2].x, A.y + r[k2].y);
-        const float2 w = sTwPost[k2 * 32 + lane];
+        const float2 w = sTwPost[(((k2 >> 1) * 32 + lane) << 1) + (k2 & 1)];
         const float tr = w.x * D.y + w.y * D.x;
         const float ti = w.y * D.y - w.x * D.x;
         const float2 xk = make_float2(S.x + tr, S.y + ti);
@@ -328,30 +384,8 @@ stft2048_kernel(const Params p) {
     group_sync(group);
 
     // ---- the sample buffer is free: start fetching the next tile's samples
-    // (cp.async, 16 bytes per request) under the mel / write-out phases.
-    prefetched = false;
-    {
-      const long long next = tile + stride;
-      if (next < p.total_tiles) {
-        const long long nb = next / p.tiles_per_signal;
-        const long long np0 = (next % p.tiles_per_signal) * kTile;
-        const int nnf = (int)min((long long)kTile, g.frames - np0);
-        const int nspan = (nnf - 1) * g.hop + kFft;
-        const long long ns0 = np0 * g.hop - g.left;
-        const float* nsrc = p.a.x + nb * g.n + ns0;
-        if (ns0 >= 0 && ns0 + nspan <= g.n && (reinterpret_cast<size_t>(nsrc) & 15) == 0) {
-          const unsigned base = (unsigned)__cvta_generic_to_shared(sSamples);
-          const int n4 = nspan >> 2;
-          for (int i = gtid; i < n4; i += kGroupThreads)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + 16u * i),
-                         "l"(nsrc + 4 * i) : "memory");
-          for (int i = (n4 << 2) + gtid; i < nspan; i += kGroupThreads)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i),
-                         "l"(nsrc + i) : "memory");
-          prefetched = true;
-        }
-      }
-    }
+    // under the mel / write-out phases.
+    if (tile + stride < p.total_tiles) stage_tile(p, tile + stride, sSamples, gtid);
 
     if (OUT == kFastMel) {
       // ---- mel projection over the tile's power rows.  A warp takes four
@@ -369,7 +403,7 @@ stft2048_kernel(const Params p) {
         const float4* v4 = prow4 + (band.lo >> 2);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         const int n4 = band.len >> 2;
-#pragma unroll 4
+#pragma unroll 2
         for (int i = 0; i < n4; ++i) {
           const float4 w = w4[i], v = v4[i];
           a0 = fmaf(w.x, v.x, a0);
