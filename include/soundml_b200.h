@@ -168,6 +168,11 @@ int smb_resample_plan_create(smb_resample_plan** plan, int64_t sample_rate,
 int smb_resample_plan_destroy(smb_resample_plan* plan);
 int smb_resample_plan_set_stream(smb_resample_plan* plan, void* cuda_stream);
 int smb_resample_plan_sync(smb_resample_plan* plan);
+/* Which kernel runs the stages: SMB_EXEC_OLS (default) follows the planner --
+ * overlap-save for the stages it tags "ols" when the transform lengths are
+ * powers of two, the direct polyphase kernel otherwise; SMB_EXEC_DIRECT forces
+ * the direct kernel everywhere.  Same designed filter either way. */
+int smb_resample_plan_set_executor(smb_resample_plan* plan, int exec);
 /* Config.pp one-liner, e.g. "resample(44100 -> 16000 Hz, quality=high, ...)". */
 int smb_resample_describe(const smb_resample_plan* plan, char* buf, size_t cap);
 int64_t smb_resample_l(const smb_resample_plan* plan);

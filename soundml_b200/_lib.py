@@ -89,6 +89,7 @@ SIGNATURES = {
     "smb_resample_plan_destroy": (_int, [_vp]),
     "smb_resample_plan_set_stream": (_int, [_vp, _vp]),
     "smb_resample_plan_sync": (_int, [_vp]),
+    "smb_resample_plan_set_executor": (_int, [_vp, _int]),
     "smb_resample_describe": (_int, [_vp, C.c_char_p, _sz]),
     "smb_resample_l": (_i64, [_vp]),
     "smb_resample_m": (_i64, [_vp]),

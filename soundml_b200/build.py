@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsoundml_b200.so")
 
-CUDA_SOURCES = ["api.cu", "kernels_generic.cu", "stft2048.cu", "resample_kernels.cu"]
+CUDA_SOURCES = ["api.cu", "kernels_generic.cu", "stft2048.cu", "resample_kernels.cu",
+                "ols_kernels.cu"]
 HOST_SOURCES = ["host_design.cpp"]
 HEADERS = ["host_design.h", "kernels.h", os.path.join("..", "..", "include", "soundml_b200.h")]
 

@@ -288,11 +288,54 @@ struct smb_mel_plan {
   }
 };
 
+// Device copies of one overlap-save plan.
+struct OlsDevice {
+  smb::OlsPlan plan;
+  float2* d_h = nullptr;
+  float2* d_tw = nullptr;
+  void upload_from(const smb::OlsPlan& p) {
+    plan = p;
+    if (!p.ok) return;
+    std::vector<float2> h(p.spectrum_re.size());
+    for (size_t i = 0; i < h.size(); ++i)
+      h[i] = make_float2((float)p.spectrum_re[i], (float)p.spectrum_im[i]);
+    d_h = upload(h);
+    const int64_t tn = std::max(p.n, p.w);
+    std::vector<float2> tw((size_t)(tn / 2));
+    for (int64_t j = 0; j < tn / 2; ++j) {
+      const double a = kTwoPi * double(j) / double(tn);
+      tw[(size_t)j] = make_float2((float)std::cos(a), (float)-std::sin(a));
+    }
+    d_tw = upload(tw);
+  }
+  void release() {
+    cudaFree(d_h);
+    cudaFree(d_tw);
+    d_h = d_tw = nullptr;
+  }
+  void run(const float* x, int64_t batch, int64_t n, int64_t n_out, float* out,
+           cudaStream_t st) const {
+    smb::OlsArgs a{};
+    a.x = x;
+    a.out = out;
+    a.n = n;
+    a.n_out = n_out;
+    a.blocks = plan.blocks_for(n_out);
+    a.L = (int)plan.l; a.M = (int)plan.m; a.K = (int)plan.k;
+    a.N = (int)plan.n; a.B = (int)plan.b; a.delta = (int)plan.delta; a.W = (int)plan.w;
+    a.H = d_h;
+    a.tw = d_tw;
+    CK(smb::launch_ols(a, batch, st));
+  }
+};
+
 struct smb_resample_plan {
   smb::ResamplePlan plan;
   bool device_ready = false;
   StreamOwner stream;
   std::vector<float*> d_bank;        // per stage, [l][2k+1] float32
+  std::vector<OlsDevice> ols;        // per stage; plan.ok only for OLS-tagged power-of-two stages
+  int executor = SMB_EXEC_OLS;       // SMB_EXEC_DIRECT forces the dot-product kernel everywhere
   DeviceBuffer in, out, mid;
   void ensure_device() {
     if (device_ready) return;
@@ -302,12 +345,27 @@ struct smb_resample_plan {
       std::vector<float> b(s.bank.size());
       for (size_t i = 0; i < b.size(); ++i) b[i] = (float)s.bank[i];   // cast at prepare
       d_bank.push_back(upload(b));
+      ols.emplace_back();
+      ols.back().upload_from(smb::ols_plan_for_stage(s));
     }
     device_ready = true;
+  }
+  // One stage over device buffers: overlap-save where the planner tagged it and
+  // the GPU plan exists, the direct polyphase kernel otherwise -- the same
+  // designed filter either way (resample.ml:495-497).
+  void run_stage(size_t i, const float* x, int64_t batch, int64_t n, int64_t n_out, float* out,
+                 cudaStream_t st) {
+    const smb::ResampleStage& s = plan.stages[i];
+    if (executor != SMB_EXEC_DIRECT && ols[i].plan.ok)
+      ols[i].run(x, batch, n, n_out, out, st);
+    else
+      CK(smb::launch_polyphase_direct(x, batch, n, d_bank[i], (int)s.l, (int)s.m, (int)s.k,
+                                      n_out, out, st));
   }
   ~smb_resample_plan() {
     if (!device_ready) return;
     for (float* p : d_bank) cudaFree(p);
+    for (OlsDevice& o : ols) o.release();
     in.release();
     out.release();
     mid.release();
@@ -321,6 +379,7 @@ struct smb_fir_plan {
   bool device_ready = false;
   StreamOwner stream;
   float* d_bank = nullptr;
+  OlsDevice ols;
   DeviceBuffer in, out;
   void ensure_device() {
     if (device_ready) return;
@@ -329,11 +388,13 @@ struct smb_fir_plan {
     std::vector<float> b(h.size());
     for (size_t s = 0; s < h.size(); ++s) b[s] = (float)h[h.size() - 1 - s];  // row reversed
     d_bank = upload(b);
+    ols.upload_from(smb::ols_plan_for_fir(h));
     device_ready = true;
   }
   ~smb_fir_plan() {
     if (!device_ready) return;
     cudaFree(d_bank);
+    ols.release();
     in.release();
     out.release();
     stream.destroy();
@@ -729,6 +790,13 @@ int smb_resample_plan_set_stream(smb_resample_plan* plan, void* s) {
 int smb_resample_plan_sync(smb_resample_plan* plan) {
   return guarded([&] { if (plan->device_ready) CK(cudaStreamSynchronize(plan->stream.use)); });
 }
+int smb_resample_plan_set_executor(smb_resample_plan* plan, int exec) {
+  return guarded([&] {
+    if (exec != SMB_EXEC_DIRECT && exec != SMB_EXEC_OLS)
+      throw smb::invalid_argument("set_executor: SMB_EXEC_DIRECT or SMB_EXEC_OLS");
+    plan->executor = exec;
+  });
+}
 int smb_resample_describe(const smb_resample_plan* plan, char* buf, size_t cap) {
   return guarded([&] {
     const std::string s = plan->plan.describe();
@@ -806,20 +874,15 @@ int smb_resample_apply(smb_resample_plan* plan, const float* x, int64_t batch, i
     if (rp.identity()) {
       CK(cudaMemcpyAsync(dout, din, in_bytes, cudaMemcpyDeviceToDevice, st));
     } else if (rp.stages.size() == 1) {
-      const smb::ResampleStage& s = rp.stages[0];
-      CK(smb::launch_polyphase_direct(din, batch, n, plan->d_bank[0], (int)s.l, (int)s.m,
-                                      (int)s.k, total, dout, st));
+      plan->run_stage(0, din, batch, n, total, dout, st);
     } else {
       // cascade (resample.ml:1819-1842): stage 1 emits its exact ceil tail,
       // stage 2 runs over it with zeros beyond and is cut to output_frames.
       const smb::ResampleStage& s1 = rp.stages[0];
-      const smb::ResampleStage& s2 = rp.stages[1];
       const int64_t n1 = (n * s1.l + s1.m - 1) / s1.m;
       float* mid = (float*)plan->mid.ensure((size_t)batch * n1 * 4);
-      CK(smb::launch_polyphase_direct(din, batch, n, plan->d_bank[0], (int)s1.l, (int)s1.m,
-                                      (int)s1.k, n1, mid, st));
-      CK(smb::launch_polyphase_direct(mid, batch, n1, plan->d_bank[1], (int)s2.l, (int)s2.m,
-                                      (int)s2.k, total, dout, st));
+      plan->run_stage(0, din, batch, n, n1, mid, st);
+      plan->run_stage(1, mid, batch, n1, total, dout, st);
     }
     if (mem == SMB_MEM_HOST) {
       CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
@@ -851,10 +914,13 @@ int smb_fir_apply(smb_fir_plan* plan, const float* x, int64_t batch, int64_t n, 
                   int method, int mem) {
   return guarded([&] {
     if (batch < 0 || n < 0) throw smb::invalid_argument("fir: negative extent");
-    if (method != SMB_EXEC_DIRECT)
-      throw smb::invalid_argument("fir: only the direct method is available in this build");
+    if (method != SMB_EXEC_DIRECT && method != SMB_EXEC_OLS)
+      throw smb::invalid_argument("fir: method must be SMB_EXEC_DIRECT or SMB_EXEC_OLS");
     if (batch == 0 || n == 0) return;
     plan->ensure_device();
+    if (method == SMB_EXEC_OLS && !plan->ols.plan.ok)
+      throw smb::invalid_argument(
+          "fir: this filter is too long for the overlap-save kernel (use the direct method)");
     cudaStream_t st = plan->stream.use;
     const size_t bytes = (size_t)batch * n * 4;
     const float* din = x;
@@ -867,7 +933,10 @@ int smb_fir_apply(smb_fir_plan* plan, const float* x, int64_t batch, int64_t n, 
     } else if (mem != SMB_MEM_DEVICE) {
       throw smb::invalid_argument("soundml_b200: unknown memory kind");
     }
-    CK(smb::launch_polyphase_direct(din, batch, n, plan->d_bank, 1, 1, (int)plan->k, n, dout, st));
+    if (method == SMB_EXEC_OLS)
+      plan->ols.run(din, batch, n, n, dout, st);
+    else
+      CK(smb::launch_polyphase_direct(din, batch, n, plan->d_bank, 1, 1, (int)plan->k, n, dout, st));
     if (mem == SMB_MEM_HOST) {
       CK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));

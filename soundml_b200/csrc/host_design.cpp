@@ -636,6 +636,91 @@ std::string bytes_pretty(double bytes) {        // resample.ml:530-538
 
 }  // namespace
 
+// ---- overlap-save plans -------------------------------------------------------
+
+static void fft_pow2(std::vector<double>& re, std::vector<double>& im) {
+  // in-place iterative radix-2, forward sign; plan creation only
+  const size_t n = re.size();
+  for (size_t i = 1, j = 0; i < n; ++i) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+  }
+  for (size_t len = 2; len <= n; len <<= 1) {
+    const double ang = -2.0 * kPi / double(len);
+    for (size_t i = 0; i < n; i += len)
+      for (size_t k = 0; k < len / 2; ++k) {
+        const double wr = std::cos(ang * double(k)), wi = std::sin(ang * double(k));
+        const size_t a = i + k, b = i + k + len / 2;
+        const double tr = re[b] * wr - im[b] * wi, ti = re[b] * wi + im[b] * wr;
+        re[b] = re[a] - tr; im[b] = im[a] - ti;
+        re[a] += tr; im[a] += ti;
+      }
+  }
+}
+
+static bool is_pow2(int64_t v) { return v >= 2 && (v & (v - 1)) == 0; }
+
+int64_t OlsPlan::hi(int64_t block) const {         // resample.ml:1313-1315
+  if (l > 1) return l * (block * b + n - 3 * k) - 1;
+  const int64_t num = block * b + n - 3 * k - delta - 1;
+  return num >= 0 ? num / m : -1;
+}
+
+int64_t OlsPlan::blocks_for(int64_t n_out) const {
+  if (n_out <= 0) return 0;
+  int64_t blk = 0;
+  // hi is affine in the block index: jump close, then settle
+  const int64_t per = l > 1 ? l * b : std::max<int64_t>(1, b / m);
+  blk = std::max<int64_t>(0, (n_out - 1) / per - 2);
+  while (hi(blk) < n_out - 1) ++blk;
+  return blk + 1;
+}
+
+static OlsPlan finish_ols(OlsPlan p, const std::vector<double>& proto) {
+  const int64_t len = p.l > 1 ? p.n * p.l : p.n;             // resample.ml:858
+  p.w = p.l > 1 ? p.n * p.l : p.n / p.m;
+  const int64_t longest = std::max(p.n, p.w);
+  if (!is_pow2(p.n) || !is_pow2(p.w) || longest > 16384 || (int64_t)proto.size() > len ||
+      p.b < 1 || (p.m > 1 && p.n % p.m != 0))
+    return p;
+  std::vector<double> re((size_t)len, 0.0), im((size_t)len, 0.0);
+  std::copy(proto.begin(), proto.end(), re.begin());          // padded at the tail
+  fft_pow2(re, im);
+  const double scale = (p.m > 1 ? 1.0 / double(p.m) : 1.0) / double(p.w);
+  const int64_t bins = (p.l > 1 ? p.w : p.n) / 2 + 1;
+  p.spectrum_re.resize((size_t)bins);
+  p.spectrum_im.resize((size_t)bins);
+  for (int64_t i = 0; i < bins; ++i) {
+    p.spectrum_re[(size_t)i] = re[(size_t)i] * scale;
+    p.spectrum_im[(size_t)i] = im[(size_t)i] * scale;
+  }
+  p.ok = true;
+  return p;
+}
+
+OlsPlan ols_plan_for_stage(const ResampleStage& s) {
+  OlsPlan p;
+  if (s.exec != kExecOls || (s.l > 1 && s.m > 1)) return p;
+  p.l = s.l; p.m = s.m; p.k = s.k;
+  p.n = s.ols_n; p.b = s.ols_b; p.delta = s.ols_delta;
+  return finish_ols(p, s.proto);
+}
+
+OlsPlan ols_plan_for_fir(const std::vector<double>& h) {
+  OlsPlan p;
+  p.k = ((int64_t)h.size() - 1) / 2;
+  int64_t n = 64;
+  while (n < 10 * p.k) n *= 2;                               // resample.ml:279-286
+  if (n > 16384) n = 16384;
+  p.n = n;
+  p.b = n - 2 * p.k;
+  p.delta = 0;
+  if (p.b < n / 4) return p;                                 // filter too long for one block
+  return finish_ols(p, h);
+}
+
 int64_t ResamplePlan::output_frames(int64_t n) const {   // resample.ml:1038-1051
   if (n < 0)
     throw invalid_argument(format(

@@ -88,6 +88,20 @@ double kaiser_numtaps(double att, double width);
 double bessel_i0_series(double x);
 std::vector<double> design_prototype(int64_t l, int64_t k, double fc, double beta);
 std::vector<double> bank_of_prototype(int64_t l, int64_t k, const std::vector<double>& h);
+// Overlap-save geometry and plan spectrum of a stage (resample.ml:279-300, 856-867).
+struct OlsPlan {
+  bool ok = false;
+  int64_t n = 0, b = 0, delta = 0, w = 0, l = 1, m = 1, k = 0;
+  std::vector<double> spectrum_re, spectrum_im;   // W/2+1 (xL) or N/2+1 bins, 1/M and 1/W folded in
+  int64_t blocks_for(int64_t n_out) const;         // blocks whose runs cover [0, n_out)
+  int64_t hi(int64_t block) const;                 // last output block `block` completes
+};
+// GPU-executable OLS plan for a stage, or ok = false when the transform lengths
+// are not powers of two / too long for one CTA (the direct kernel runs instead).
+OlsPlan ols_plan_for_stage(const ResampleStage& s);
+// FIR as an L = M = 1 stage: N = smallest power of two >= max(64, 10 K).
+OlsPlan ols_plan_for_fir(const std::vector<double>& h);
+
 ResamplePlan resample_plan(int64_t sample_rate, int64_t target, int quality,
                            double attenuation, double passband);
 

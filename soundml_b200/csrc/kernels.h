@@ -68,4 +68,16 @@ cudaError_t launch_polyphase_direct(const float* x, long long batch, long long n
                                     const float* bank, int l, int m, int k,
                                     long long n_out, float* out, cudaStream_t st);
 
+// Overlap-save stage (FIR, xL, /M) on half-length complex FFTs.
+struct OlsArgs {
+  const float* x;        // [batch, n]
+  float* out;            // [batch, n_out]
+  long long n, n_out, blocks;
+  int L, M, K, N, B, delta, W;
+  const float2* H;       // plan spectrum: W/2+1 bins (xL) or N/2+1 (otherwise), scales folded in
+  const float2* tw;      // exp(-2 pi i j / max(N, W)), j < max(N, W)/2
+};
+size_t ols_smem_bytes(int N, int W);
+cudaError_t launch_ols(const OlsArgs& a, long long batch, cudaStream_t st);
+
 }  // namespace smb

@@ -42,6 +42,13 @@ class Config:
     m = property(lambda self: int(_lib.lib.smb_resample_m(self._h)))
     latency = property(lambda self: int(_lib.lib.smb_resample_latency(self._h)))
 
+    def set_executor(self, name):
+        """``"planned"`` (default) follows the planner's executor tags where the
+        GPU has the kernel; ``"direct"`` forces the dot-product kernel."""
+        code = {"planned": _lib.EXEC_OLS, "direct": _lib.EXEC_DIRECT}[name]
+        _lib.check(_lib.lib.smb_resample_plan_set_executor(self._h, code))
+        return self
+
     def output_frames(self, n):
         """``Config.output_frames c ~n`` = ceil(n*L/M) (resample.ml:1038-1051)."""
         r = _lib.lib.smb_resample_output_frames(self._h, int(n))

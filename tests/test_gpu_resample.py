@@ -137,3 +137,39 @@ def test_fir_arbitrary_taps_and_errors(sb):
     assert peak_rel_err(got, want) <= RESAMPLE_TOL
     with pytest.raises(ValueError, match="taps must be odd"):
         sb.Fir(np.ones(4))
+
+
+# --------------------------------------------------- overlap-save executors ----
+
+@pytest.mark.parametrize("k", [7, 50, 255, 600])
+def test_fir_overlap_save_matches_oracle_and_direct(sb, k):
+    fir = sb.Fir.lowpass(k=k, cutoff=0.3)
+    x = noise((3, 20011), k + 100)
+    want = R.fir_apply(x, fir.taps)
+    ols = fir.apply(x, method="ols")
+    direct = fir.apply(x, method="direct")
+    assert ols.shape == x.shape
+    assert peak_rel_err(ols, want) <= RESAMPLE_TOL
+    assert peak_rel_err(ols, direct) <= RESAMPLE_TOL
+    for n in (1, 2, k, 2 * k + 1, 4097):
+        xs = noise((n,), n + 7)
+        assert peak_rel_err(fir.apply(xs, method="ols"), R.fir_apply(xs, fir.taps)) <= RESAMPLE_TOL
+
+
+@pytest.mark.parametrize("sr,target", [(44100, 22050), (22050, 44100), (48000, 8000), (8000, 48000),
+                                       (48000, 12000), (12000, 48000), (44100, 88200)])
+def test_planned_ols_stages_match_direct_and_oracle(sb, sr, target):
+    """Stages the planner tags for overlap-save (x2, x4, /2, /4) run the FFT
+    kernel by default; forcing the direct kernel must give the same signal."""
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
+    assert any(s["exec"] == "ols" for s in cfg.stages()), cfg.pp()
+    st = oracle_stages(cfg)
+    for n in (1, 37, 5000, 30000):
+        x = noise((2, n), n + sr)
+        want = R.apply_plan(x, st, cfg.l, cfg.m)
+        planned = sb.Resample.apply(cfg.set_executor("planned"), x)
+        direct = sb.Resample.apply(cfg.set_executor("direct"), x)
+        assert planned.shape == direct.shape == want.shape
+        scale = max(np.abs(want).max(), 1e-3)
+        assert np.abs(planned - want).max() / scale <= RESAMPLE_TOL, (sr, target, n)
+        assert np.abs(direct - want).max() / scale <= RESAMPLE_TOL, (sr, target, n)
