@@ -70,7 +70,7 @@ enum { SMB_SCALE_NONE = 0, SMB_SCALE_MAGNITUDE = 1, SMB_SCALE_PSD = 2 };
 enum { SMB_MEL_SLANEY = 0, SMB_MEL_HTK = 1 };
 enum { SMB_NORM_SLANEY = 0, SMB_NORM_NONE = 1 };
 enum { SMB_QUALITY_FAST = 0, SMB_QUALITY_HIGH = 1, SMB_QUALITY_BEST = 2, SMB_QUALITY_CUSTOM = 3 };
-enum { SMB_EXEC_DIRECT = 0, SMB_EXEC_OLS = 1, SMB_EXEC_GEMM = 2 };
+enum { SMB_EXEC_DIRECT = 0, SMB_EXEC_OLS = 1, SMB_EXEC_GEMM = 2, SMB_EXEC_PLANNED = 3 };
 /* Kernel selection for the STFT family (testing / benchmarking). */
 enum { SMB_PATH_AUTO = 0, SMB_PATH_GENERIC = 1, SMB_PATH_FAST = 2 };
 
@@ -168,10 +168,11 @@ int smb_resample_plan_create(smb_resample_plan** plan, int64_t sample_rate,
 int smb_resample_plan_destroy(smb_resample_plan* plan);
 int smb_resample_plan_set_stream(smb_resample_plan* plan, void* cuda_stream);
 int smb_resample_plan_sync(smb_resample_plan* plan);
-/* Which kernel runs the stages: SMB_EXEC_OLS (default) follows the planner --
- * overlap-save for the stages it tags "ols" when the transform lengths are
- * powers of two, the direct polyphase kernel otherwise; SMB_EXEC_DIRECT forces
- * the direct kernel everywhere.  Same designed filter either way. */
+/* Which kernel runs the stages: SMB_EXEC_PLANNED (default) follows the planner's
+ * tags -- overlap-save FFT blocks for "ols" stages (power-of-two lengths), the
+ * tcgen05 banded product for "gemm" stages (L <= 160), the direct polyphase
+ * kernel for everything else; SMB_EXEC_DIRECT forces the direct kernel
+ * everywhere.  Same designed filter either way. */
 int smb_resample_plan_set_executor(smb_resample_plan* plan, int exec);
 /* Config.pp one-liner, e.g. "resample(44100 -> 16000 Hz, quality=high, ...)". */
 int smb_resample_describe(const smb_resample_plan* plan, char* buf, size_t cap);

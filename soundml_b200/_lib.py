@@ -15,7 +15,7 @@ MEM_DEVICE, MEM_HOST = 0, 1
 F32, F64 = 0, 1
 DEFAULT = -(2 ** 31)
 PATH_AUTO, PATH_GENERIC, PATH_FAST = 0, 1, 2
-EXEC_DIRECT, EXEC_OLS, EXEC_GEMM = 0, 1, 2
+EXEC_DIRECT, EXEC_OLS, EXEC_GEMM, EXEC_PLANNED = 0, 1, 2, 3
 
 WINDOWS = {"hann": 0, "hamming": 1, "blackman": 2, "blackman_harris": 3,
            "nuttall": 4, "bartlett": 5, "kaiser": 6, "gaussian": 7, "tukey": 8,

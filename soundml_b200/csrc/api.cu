@@ -329,13 +329,55 @@ struct OlsDevice {
   }
 };
 
+// Device image of G for the tensor-core executor of one phase-rich stage.
+struct GemmDevice {
+  bool ok = false;
+  int n_pad = 0, chunks = 0, tmem_cols = 0;
+  float* d_images = nullptr;
+  void build(const smb::ResampleStage& s) {
+    const int64_t l = s.l, m = s.m, k = s.k, taps = 2 * k + 1;
+    n_pad = (int)((l + 15) / 16 * 16);
+    if (s.exec != smb::kExecGemm || 3 * n_pad > 512) return;
+    const int64_t p_len = taps + ((l - 1) * m) / l;          // gemm_bank, resample.ml:215-226
+    chunks = (int)((p_len + 31) / 32);
+    tmem_cols = 32;
+    while (tmem_cols < 3 * n_pad) tmem_cols *= 2;
+    std::vector<float> img((size_t)chunks * 2 * n_pad * 32, 0.0f);
+    for (int64_t r = 0; r < l; ++r) {
+      const int64_t d = (r * m) / l, ph = (r * m) % l;
+      for (int64_t t = 0; t < taps; ++t) {
+        const int64_t j = d + t;                               // row of G
+        const double g = s.bank[(size_t)(ph * taps + t)];
+        const float gf = (float)g;
+        uint32_t bits;
+        std::memcpy(&bits, &gf, 4);
+        bits &= 0xFFFFE000u;                                   // tf32 piece, exact
+        float hi;
+        std::memcpy(&hi, &bits, 4);
+        const float lo = (float)(g - (double)hi);
+        const int64_t ch = j / 32, kk = j % 32;
+        const size_t cell = (size_t)(r * 32 + ((((kk >> 2) ^ (r & 7)) << 2) | (kk & 3)));
+        img[((size_t)ch * 2 + 0) * n_pad * 32 + cell] = hi;
+        img[((size_t)ch * 2 + 1) * n_pad * 32 + cell] = lo;
+      }
+    }
+    d_images = upload(img);
+    ok = true;
+  }
+  void release() {
+    cudaFree(d_images);
+    d_images = nullptr;
+  }
+};
+
 struct smb_resample_plan {
   smb::ResamplePlan plan;
   bool device_ready = false;
   StreamOwner stream;
   std::vector<float*> d_bank;        // per stage, [l][2k+1] float32
   std::vector<OlsDevice> ols;        // per stage; plan.ok only for OLS-tagged power-of-two stages
-  int executor = SMB_EXEC_OLS;       // SMB_EXEC_DIRECT forces the dot-product kernel everywhere
+  std::vector<GemmDevice> gemm;      // per stage; ok only for GEMM-tagged stages with L <= 160
+  int executor = SMB_EXEC_PLANNED;   // SMB_EXEC_DIRECT forces the dot-product kernel everywhere
   DeviceBuffer in, out, mid;
   void ensure_device() {
     if (device_ready) return;
@@ -347,6 +389,8 @@ struct smb_resample_plan {
       d_bank.push_back(upload(b));
       ols.emplace_back();
       ols.back().upload_from(smb::ols_plan_for_stage(s));
+      gemm.emplace_back();
+      gemm.back().build(s);
     }
     device_ready = true;
   }
@@ -356,9 +400,21 @@ struct smb_resample_plan {
   void run_stage(size_t i, const float* x, int64_t batch, int64_t n, int64_t n_out, float* out,
                  cudaStream_t st) {
     const smb::ResampleStage& s = plan.stages[i];
-    if (executor != SMB_EXEC_DIRECT && ols[i].plan.ok)
+    if (executor != SMB_EXEC_DIRECT && ols[i].plan.ok) {
       ols[i].run(x, batch, n, n_out, out, st);
-    else
+    } else if (executor != SMB_EXEC_DIRECT && gemm[i].ok) {
+      smb::GemmResampleArgs a{};
+      a.x = x;
+      a.out = out;
+      a.n = n;
+      a.n_out = n_out;
+      a.l = (int)s.l; a.m = (int)s.m; a.k = (int)s.k;
+      a.n_pad = gemm[i].n_pad;
+      a.chunks = gemm[i].chunks;
+      a.tmem_cols = gemm[i].tmem_cols;
+      a.b_images = gemm[i].d_images;
+      CK(smb::launch_resample_gemm(a, batch, st));
+    } else
       CK(smb::launch_polyphase_direct(x, batch, n, d_bank[i], (int)s.l, (int)s.m, (int)s.k,
                                       n_out, out, st));
   }
@@ -366,6 +422,7 @@ struct smb_resample_plan {
     if (!device_ready) return;
     for (float* p : d_bank) cudaFree(p);
     for (OlsDevice& o : ols) o.release();
+    for (GemmDevice& g : gemm) g.release();
     in.release();
     out.release();
     mid.release();
@@ -792,8 +849,8 @@ int smb_resample_plan_sync(smb_resample_plan* plan) {
 }
 int smb_resample_plan_set_executor(smb_resample_plan* plan, int exec) {
   return guarded([&] {
-    if (exec != SMB_EXEC_DIRECT && exec != SMB_EXEC_OLS)
-      throw smb::invalid_argument("set_executor: SMB_EXEC_DIRECT or SMB_EXEC_OLS");
+    if (exec != SMB_EXEC_DIRECT && exec != SMB_EXEC_PLANNED)
+      throw smb::invalid_argument("set_executor: SMB_EXEC_DIRECT or SMB_EXEC_PLANNED");
     plan->executor = exec;
   });
 }

@@ -80,4 +80,18 @@ struct OlsArgs {
 size_t ols_smem_bytes(int N, int W);
 cudaError_t launch_ols(const OlsArgs& a, long long batch, cudaStream_t st);
 
+// Phase-rich polyphase stage as a banded tf32x3 product on tcgen05 (resample_gemm.cu).
+struct GemmResampleArgs {
+  const float* x;          // [batch, n]
+  float* out;              // [batch, n_out]
+  long long n, n_out;
+  int l, m, k;             // stage factors and group delay
+  int n_pad;               // l rounded up to a multiple of 16 (UMMA N)
+  int chunks;              // ceil(P / 32) K-chunks
+  int tmem_cols;           // power of two >= 3 * n_pad
+  const float* b_images;   // [chunks][hi, lo][n_pad][32] pre-swizzled K-major tiles of G
+};
+size_t resample_gemm_smem_bytes(int n_pad);
+cudaError_t launch_resample_gemm(const GemmResampleArgs& a, long long batch, cudaStream_t st);
+
 }  // namespace smb

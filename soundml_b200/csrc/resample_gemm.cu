@@ -1,0 +1,268 @@
+// Phase-rich polyphase stage as a banded matrix product on the 5th-generation
+// tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// The reference runs such stages (L >= 64 phases, e.g. 44.1 -> 16 kHz: L/M =
+// 160/441, 523 taps) as [R; P] x [P; L] through Nx.matmul
+// (resample.ml:430-476, 1608-1698, gemm_bank :207-226): block-row rho holds the
+// L outputs of one phase cycle and reads the P = 2K + 1 + floor((L-1) M / L)
+// consecutive inputs starting at rho*M - K; column r of G is the phase-(r M mod L)
+// bank row shifted down by floor(r M / L).  This is a true dense contraction
+// (3.8 TFLOP for BASELINE config 4), so it belongs on the tensor pipe:
+//
+//   D[128 rows x L] (TMEM, fp32)  +=  A[128 x 32] (smem)  *  B[L x 32]^T (smem)
+//
+// per K-chunk of 32 inputs, kind::tf32.  float32 accuracy (1e-5 of peak) is kept
+// by operand splitting: a = a_hi + a_lo, g = g_hi + g_lo with 11-bit pieces and
+// D += a_hi g_hi + a_hi g_lo + a_lo g_hi  (the dropped term is 2^-22).  The two
+// small terms go to their own accumulator and the main term alternates between
+// two accumulators per chunk, which keeps each accumulation chain short.
+//
+//   A: gathered by the CTA's threads (row = thread): 32 consecutive samples per
+//      row per chunk, split, written in the canonical K-major SWIZZLE_128B
+//      layout (16-byte chunk index XOR row mod 8).
+//   B: pre-split, pre-swizzled images of G built once per plan on the host; one
+//      cp.async.bulk (TMA) per split per chunk lands them with an mbarrier.
+//   MMA: one thread issues 4 K-steps x 3 products per chunk; tcgen05.commit
+//      releases the stage; two stages overlap the gather with the MMAs.
+//   Epilogue: tcgen05.ld (32 lanes x 16 columns per warp), sum of the three
+//      accumulators, row-contiguous stores (a row is L consecutive outputs).
+#include "kernels.h"
+
+#include <cstdint>
+
+namespace smb {
+
+namespace {
+
+constexpr int kRows = 128;            // block-rows per CTA (UMMA M)
+constexpr int kChunk = 32;            // tf32 elements per 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr int kABytes = kRows * 128;  // one split of the A chunk
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);         // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kRows, 1)
+resample_gemm_kernel(const GemmResampleArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  const int b_bytes = a.n_pad * 128;                      // one split of the B chunk
+  const int stage_bytes = 2 * kABytes + 2 * b_bytes;
+  __shared__ __align__(8) uint64_t bars[2 * kStages + 1];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const long long c = blockIdx.y;
+  const long long row0 = (long long)blockIdx.x * kRows;
+  const float* xs = a.x + c * a.n;
+  float* out = a.out + c * a.n_out;
+
+  const uint32_t bar_b = smem_u32(&bars[0]);              // [stage]: B bytes landed
+  const uint32_t bar_mma = smem_u32(&bars[kStages]);      // [stage]: MMAs reading the stage done
+  const uint32_t bar_done = smem_u32(&bars[2 * kStages]); // all MMAs done
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_b + 8 * s, 1);
+      mbar_init(bar_mma + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_slot)), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_slot;
+
+  // instruction descriptor: D f32, A/B tf32, both K-major, N = n_pad, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) |
+                         ((uint32_t)(kRows >> 4) << 24);
+  const uint32_t acc_main0 = tmem, acc_main1 = tmem + a.n_pad;
+  const uint32_t acc_corr = tmem + 2 * a.n_pad;
+  uint32_t used_main0 = 0, used_main1 = 0, used_corr = 0;   // meaningful on the issuing thread
+
+  // this thread's block-row reads x[rho*M - K + j], j in [0, P)
+  const long long rho = row0 + tid;
+  const long long first = rho * a.m - a.k;
+
+  for (int ch = 0; ch < a.chunks; ++ch) {
+    const int s = ch & 1;
+    uint8_t* stage = smem + s * stage_bytes;
+    if (ch >= kStages) mbar_wait(bar_mma + 8 * s, ((ch / kStages) - 1) & 1);
+    if (tid == 0) {
+      mbar_expect_tx(bar_b + 8 * s, 2 * b_bytes);
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.b_images) + (size_t)ch * 2 * b_bytes;
+      bulk_g2s(smem_u32(stage + 2 * kABytes), img, 2 * b_bytes, bar_b + 8 * s);
+    }
+    // gather + split this row's 32 samples, 4 at a time, into the swizzled tiles
+    {
+      const long long s0 = first + (long long)ch * kChunk;
+      const bool inside = s0 >= 0 && s0 + kChunk <= a.n;
+      float4* ahi = reinterpret_cast<float4*>(stage + tid * 128);
+      float4* alo = reinterpret_cast<float4*>(stage + kABytes + tid * 128);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const long long si = s0 + 4 * q + e;
+          v[e] = inside ? __ldg(xs + si) : ((si >= 0 && si < a.n) ? __ldg(xs + si) : 0.0f);
+        }
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); l.x = v[0] - h.x;
+        h.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); l.y = v[1] - h.y;
+        h.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); l.z = v[2] - h.z;
+        h.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); l.w = v[3] - h.w;
+        const int slot = q ^ (tid & 7);
+        ahi[slot] = h;
+        alo[slot] = l;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> async proxy
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(bar_b + 8 * s, (ch / kStages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(stage), a_lo = a_hi + kABytes;
+      const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + b_bytes;
+      const uint32_t acc = s ? acc_main1 : acc_main0;
+      uint32_t& used = s ? used_main1 : used_main0;
+#pragma unroll
+      for (int ks = 0; ks < kChunk / 8; ++ks) {
+        const uint32_t off = ks * 32;                               // 8 tf32 = 32 bytes along K
+        umma_tf32(acc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, used);
+        used = 1;
+        umma_tf32(acc_corr, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, used_corr);
+        used_corr = 1;
+        umma_tf32(acc_corr, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+      }
+      umma_commit(bar_mma + 8 * s);
+      if (ch == a.chunks - 1) umma_commit(bar_done);
+    }
+  }
+  mbar_wait(bar_done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // epilogue: thread = block-row, 16 columns at a time from the three accumulators
+  const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+  const long long o0 = rho * a.l;
+  const bool two_main = a.chunks > 1;
+  for (int col = 0; col < a.l; col += 16) {
+    float d0[16], d1[16], dc[16];
+    tmem_ld16(acc_main0 + lane_base + col, d0);
+    tmem_ld16(acc_corr + lane_base + col, dc);
+    if (two_main) tmem_ld16(acc_main1 + lane_base + col, d1);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const long long o = o0 + col + e;
+      if (col + e < a.l && o < a.n_out) {
+        const float main = two_main ? d0[e] + d1[e] : d0[e];
+        out[o] = main + dc[e];
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
+                 "r"(a.tmem_cols) : "memory");
+}
+
+}  // namespace
+
+size_t resample_gemm_smem_bytes(int n_pad) {
+  return (size_t)kStages * (2 * kABytes + 2 * (size_t)n_pad * 128) + 1024;
+}
+
+cudaError_t launch_resample_gemm(const GemmResampleArgs& a, long long batch, cudaStream_t st) {
+  if (batch == 0 || a.n_out == 0) return cudaSuccess;
+  const size_t smem = resample_gemm_smem_bytes(a.n_pad);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(resample_gemm_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long rows = (a.n_out + a.l - 1) / a.l;
+  const long long tiles = (rows + kRows - 1) / kRows;
+  for (long long b0 = 0; b0 < batch; b0 += 65535) {
+    const long long nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    GemmResampleArgs s = a;
+    s.x = a.x + b0 * a.n;
+    s.out = a.out + b0 * a.n_out;
+    dim3 grid((unsigned)tiles, (unsigned)nb);
+    resample_gemm_kernel<<<grid, kRows, smem, st>>>(s);
+    ++g_launch_count;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace smb

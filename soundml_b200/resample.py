@@ -45,7 +45,7 @@ class Config:
     def set_executor(self, name):
         """``"planned"`` (default) follows the planner's executor tags where the
         GPU has the kernel; ``"direct"`` forces the dot-product kernel."""
-        code = {"planned": _lib.EXEC_OLS, "direct": _lib.EXEC_DIRECT}[name]
+        code = {"planned": _lib.EXEC_PLANNED, "direct": _lib.EXEC_DIRECT}[name]
         _lib.check(_lib.lib.smb_resample_plan_set_executor(self._h, code))
         return self
 
