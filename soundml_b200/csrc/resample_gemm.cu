@@ -36,7 +36,7 @@ namespace {
 
 constexpr int kRows = 128;            // block-rows per CTA (UMMA M)
 constexpr int kChunk = 32;            // tf32 elements per 128-byte swizzle row
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 constexpr int kABytes = kRows * 128;  // one split of the A chunk
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -118,6 +118,7 @@ resample_gemm_kernel(const GemmResampleArgs a) {
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  const int lane = tid & 31;
   const long long c = blockIdx.y;
   const long long row0 = (long long)blockIdx.x * kRows;
   const float* xs = a.x + c * a.n;
@@ -151,12 +152,25 @@ resample_gemm_kernel(const GemmResampleArgs a) {
   const uint32_t acc_corr = tmem + 2 * a.n_pad;
   uint32_t used_main0 = 0, used_main1 = 0, used_corr = 0;   // meaningful on the issuing thread
 
-  // this thread's block-row reads x[rho*M - K + j], j in [0, P)
-  const long long rho = row0 + tid;
-  const long long first = rho * a.m - a.k;
+  const long long rho = row0 + tid;        // epilogue: thread = block-row
+
+  // A warp gathers 32 block-rows, lane = sample within the chunk, so every row
+  // is one coalesced 128-byte request.  The loads of chunk ch+1 are issued before
+  // chunk ch is handed to the tensor core, so global latency hides under the
+  // barrier waits and the MMAs.
+  float v[32];
+  auto load_chunk = [&](int ch) {
+    const long long col0 = (long long)ch * kChunk + lane - a.k;
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      const long long si = (row0 + warp * 32 + rr) * a.m + col0;
+      v[rr] = (si >= 0 && si < a.n) ? __ldg(xs + si) : 0.0f;
+    }
+  };
+  load_chunk(0);
 
   for (int ch = 0; ch < a.chunks; ++ch) {
-    const int s = ch & 1;
+    const int s = ch % kStages;
     uint8_t* stage = smem + s * stage_bytes;
     if (ch >= kStages) mbar_wait(bar_mma + 8 * s, ((ch / kStages) - 1) & 1);
     if (tid == 0) {
@@ -164,30 +178,21 @@ resample_gemm_kernel(const GemmResampleArgs a) {
       const uint8_t* img = reinterpret_cast<const uint8_t*>(a.b_images) + (size_t)ch * 2 * b_bytes;
       bulk_g2s(smem_u32(stage + 2 * kABytes), img, 2 * b_bytes, bar_b + 8 * s);
     }
-    // gather + split this row's 32 samples, 4 at a time, into the swizzled tiles
+    // split and store: element (row, k) lands at 16-byte chunk (k/4) XOR (row mod 8)
+    // of its 128-byte row (K-major SWIZZLE_128B)
     {
-      const long long s0 = first + (long long)ch * kChunk;
-      const bool inside = s0 >= 0 && s0 + kChunk <= a.n;
-      float4* ahi = reinterpret_cast<float4*>(stage + tid * 128);
-      float4* alo = reinterpret_cast<float4*>(stage + kABytes + tid * 128);
+      float* ahi = reinterpret_cast<float*>(stage);
+      float* alo = reinterpret_cast<float*>(stage + kABytes);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const long long si = s0 + 4 * q + e;
-          v[e] = inside ? __ldg(xs + si) : ((si >= 0 && si < a.n) ? __ldg(xs + si) : 0.0f);
-        }
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); l.x = v[0] - h.x;
-        h.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); l.y = v[1] - h.y;
-        h.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); l.z = v[2] - h.z;
-        h.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); l.w = v[3] - h.w;
-        const int slot = q ^ (tid & 7);
-        ahi[slot] = h;
-        alo[slot] = l;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int row = warp * 32 + rr;
+        const float h = __uint_as_float(__float_as_uint(v[rr]) & 0xFFFFE000u);
+        const int cell = row * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3));
+        ahi[cell] = h;
+        alo[cell] = v[rr] - h;
       }
     }
+    if (ch + 1 < a.chunks) load_chunk(ch + 1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> async proxy
     __syncthreads();
     if (tid == 0) {
@@ -195,8 +200,8 @@ resample_gemm_kernel(const GemmResampleArgs a) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(stage), a_lo = a_hi + kABytes;
       const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + b_bytes;
-      const uint32_t acc = s ? acc_main1 : acc_main0;
-      uint32_t& used = s ? used_main1 : used_main0;
+      const uint32_t acc = (ch & 1) ? acc_main1 : acc_main0;
+      uint32_t& used = (ch & 1) ? used_main1 : used_main0;
 #pragma unroll
       for (int ks = 0; ks < kChunk / 8; ++ks) {
         const uint32_t off = ks * 32;                               // 8 tf32 = 32 bytes along K
