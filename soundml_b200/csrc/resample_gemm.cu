@@ -17,15 +17,17 @@
 // small terms go to their own accumulator and the main term alternates between
 // two accumulators per chunk, which keeps each accumulation chain short.
 //
-//   A: gathered by the CTA's threads (row = thread): 32 consecutive samples per
-//      row per chunk, split, written in the canonical K-major SWIZZLE_128B
-//      layout (16-byte chunk index XOR row mod 8).
+//   A: gathered by four producer warps (a warp takes 32 block-rows, lane = sample
+//      within the chunk: one coalesced 128-byte request per row), split, written
+//      in the canonical K-major SWIZZLE_128B layout (16-byte chunk index XOR row
+//      mod 8); loads run two chunks ahead in registers.
 //   B: pre-split, pre-swizzled images of G built once per plan on the host; one
-//      cp.async.bulk (TMA) per split per chunk lands them with an mbarrier.
-//   MMA: one thread issues 4 K-steps x 3 products per chunk; tcgen05.commit
-//      releases the stage; two stages overlap the gather with the MMAs.
+//      cp.async.bulk (TMA) per chunk lands hi+lo with an mbarrier.
+//   MMA: a fifth warp's elected lane issues 4 K-steps x 3 products per chunk;
+//      tcgen05.commit releases the stage; three stages, mbarriers only.
 //   Epilogue: tcgen05.ld (32 lanes x 16 columns per warp), sum of the three
-//      accumulators, row-contiguous stores (a row is L consecutive outputs).
+//      accumulators, transposed through shared memory so global stores are
+//      row-contiguous (a block-row is L consecutive outputs).
 #include "kernels.h"
 
 #include <cstdint>
@@ -38,6 +40,7 @@ constexpr int kRows = 128;            // block-rows per CTA (UMMA M)
 constexpr int kChunk = 32;            // tf32 elements per 128-byte swizzle row
 constexpr int kStages = 3;
 constexpr int kABytes = kRows * 128;  // one split of the A chunk
+constexpr int kThreads = kRows + 32;  // 4 producer/epilogue warps + 1 TMA/MMA warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -105,7 +108,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(kRows, 1)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Warps 0-3: producers (gather + split + swizzled store of A) and, at the end,
+// the epilogue (a warp may only read its own 32 TMEM lanes).  Warp 4: loads the
+// B images by TMA and issues the MMAs.  Stages hand over through mbarriers only:
+//   a_full[s] (128 arrivals)  b_full[s] (TMA bytes)  ->  MMA  ->  empty[s] (commit)
+__global__ void __launch_bounds__(kThreads, 1)
 resample_gemm_kernel(const GemmResampleArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles
@@ -113,7 +124,7 @@ resample_gemm_kernel(const GemmResampleArgs a) {
                                              ~(uintptr_t)1023);
   const int b_bytes = a.n_pad * 128;                      // one split of the B chunk
   const int stage_bytes = 2 * kABytes + 2 * b_bytes;
-  __shared__ __align__(8) uint64_t bars[2 * kStages + 1];
+  __shared__ __align__(8) uint64_t bars[3 * kStages + 1];
   __shared__ uint32_t tmem_base_slot;
 
   const int tid = threadIdx.x;
@@ -124,18 +135,20 @@ resample_gemm_kernel(const GemmResampleArgs a) {
   const float* xs = a.x + c * a.n;
   float* out = a.out + c * a.n_out;
 
-  const uint32_t bar_b = smem_u32(&bars[0]);              // [stage]: B bytes landed
-  const uint32_t bar_mma = smem_u32(&bars[kStages]);      // [stage]: MMAs reading the stage done
-  const uint32_t bar_done = smem_u32(&bars[2 * kStages]); // all MMAs done
+  const uint32_t bar_a = smem_u32(&bars[0]);                // [stage]: A tile written
+  const uint32_t bar_b = smem_u32(&bars[kStages]);          // [stage]: B bytes landed
+  const uint32_t bar_empty = smem_u32(&bars[2 * kStages]);  // [stage]: MMAs reading the stage done
+  const uint32_t bar_done = smem_u32(&bars[3 * kStages]);   // all MMAs done
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_a + 8 * s, kRows);
       mbar_init(bar_b + 8 * s, 1);
-      mbar_init(bar_mma + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(&tmem_base_slot)), "r"(a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -144,45 +157,74 @@ resample_gemm_kernel(const GemmResampleArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_slot;
-
-  // instruction descriptor: D f32, A/B tf32, both K-major, N = n_pad, M = 128
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) |
-                         ((uint32_t)(kRows >> 4) << 24);
   const uint32_t acc_main0 = tmem, acc_main1 = tmem + a.n_pad;
   const uint32_t acc_corr = tmem + 2 * a.n_pad;
-  uint32_t used_main0 = 0, used_main1 = 0, used_corr = 0;   // meaningful on the issuing thread
 
-  const long long rho = row0 + tid;        // epilogue: thread = block-row
-
-  // A warp gathers 32 block-rows, lane = sample within the chunk, so every row
-  // is one coalesced 128-byte request.  The loads of chunk ch+1 are issued before
-  // chunk ch is handed to the tensor core, so global latency hides under the
-  // barrier waits and the MMAs.
-  float v[32];
-  auto load_chunk = [&](int ch) {
-    const long long col0 = (long long)ch * kChunk + lane - a.k;
+  if (warp == 4) {
+    // ===== B loader + MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      // instruction descriptor: D f32, A/B tf32, both K-major, N = n_pad, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
+                             ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+      uint32_t used_main0 = 0, used_main1 = 0, used_corr = 0;
+      const uint8_t* images = reinterpret_cast<const uint8_t*>(a.b_images);
+      auto load_b = [&](int ch) {
+        const int s = ch % kStages;
+        mbar_expect_tx(bar_b + 8 * s, 2 * b_bytes);
+        bulk_g2s(smem_u32(smem + s * stage_bytes + 2 * kABytes), images + (size_t)ch * 2 * b_bytes,
+                 2 * b_bytes, bar_b + 8 * s);
+      };
+      for (int ch = 0; ch < kStages && ch < a.chunks; ++ch) load_b(ch);
+      for (int ch = 0; ch < a.chunks; ++ch) {
+        const int s = ch % kStages;
+        const uint32_t parity = (ch / kStages) & 1;
+        mbar_wait(bar_a + 8 * s, parity);
+        mbar_wait(bar_b + 8 * s, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem + s * stage_bytes), a_lo = a_hi + kABytes;
+        const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + b_bytes;
+        const uint32_t acc = (ch & 1) ? acc_main1 : acc_main0;
+        uint32_t& used = (ch & 1) ? used_main1 : used_main0;
 #pragma unroll
-    for (int rr = 0; rr < 32; ++rr) {
-      const long long si = (row0 + warp * 32 + rr) * a.m + col0;
-      v[rr] = (si >= 0 && si < a.n) ? __ldg(xs + si) : 0.0f;
+        for (int ks = 0; ks < kChunk / 8; ++ks) {
+          const uint32_t off = ks * 32;                             // 8 tf32 = 32 bytes along K
+          umma_tf32(acc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, used);
+          used = 1;
+          umma_tf32(acc_corr, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, used_corr);
+          used_corr = 1;
+          umma_tf32(acc_corr, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+        }
+        umma_commit(bar_empty + 8 * s);
+        if (ch == a.chunks - 1) umma_commit(bar_done);
+        // refill this stage's B as soon as its MMAs have drained
+        if (ch + kStages < a.chunks) {
+          mbar_wait(bar_empty + 8 * s, parity);
+          load_b(ch + kStages);
+        }
+      }
     }
-  };
-  load_chunk(0);
-
-  for (int ch = 0; ch < a.chunks; ++ch) {
-    const int s = ch % kStages;
-    uint8_t* stage = smem + s * stage_bytes;
-    if (ch >= kStages) mbar_wait(bar_mma + 8 * s, ((ch / kStages) - 1) & 1);
-    if (tid == 0) {
-      mbar_expect_tx(bar_b + 8 * s, 2 * b_bytes);
-      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.b_images) + (size_t)ch * 2 * b_bytes;
-      bulk_g2s(smem_u32(stage + 2 * kABytes), img, 2 * b_bytes, bar_b + 8 * s);
-    }
-    // split and store: element (row, k) lands at 16-byte chunk (k/4) XOR (row mod 8)
-    // of its 128-byte row (K-major SWIZZLE_128B)
-    {
-      float* ahi = reinterpret_cast<float*>(stage);
-      float* alo = reinterpret_cast<float*>(stage + kABytes);
+    __syncwarp();
+  } else {
+    // ===== producers: a warp gathers 32 block-rows, lane = sample within the
+    // chunk, so every row is one coalesced 128-byte request.  Loads run two
+    // chunks ahead of the stores (registers), stores one to three chunks ahead
+    // of the tensor core (stages).
+    float v0[32], v1[32];
+    auto load_chunk = [&](int ch, float (&v)[32]) {
+      const long long col0 = (long long)ch * kChunk + lane - a.k;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const long long si = (row0 + warp * 32 + rr) * a.m + col0;
+        v[rr] = (ch < a.chunks && si >= 0 && si < a.n) ? __ldg(xs + si) : 0.0f;
+      }
+    };
+    auto store_chunk = [&](int ch, const float (&v)[32]) {
+      const int s = ch % kStages;
+      if (ch >= kStages) mbar_wait(bar_empty + 8 * s, ((ch / kStages) - 1) & 1);
+      // element (row, k) lands at 16-byte chunk (k/4) XOR (row mod 8) of its
+      // 128-byte row (K-major SWIZZLE_128B)
+      float* ahi = reinterpret_cast<float*>(smem + s * stage_bytes);
+      float* alo = ahi + kABytes / 4;
 #pragma unroll
       for (int rr = 0; rr < 32; ++rr) {
         const int row = warp * 32 + rr;
@@ -191,54 +233,69 @@ resample_gemm_kernel(const GemmResampleArgs a) {
         ahi[cell] = h;
         alo[cell] = v[rr] - h;
       }
-    }
-    if (ch + 1 < a.chunks) load_chunk(ch + 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> async proxy
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(bar_b + 8 * s, (ch / kStages) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(stage), a_lo = a_hi + kABytes;
-      const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + b_bytes;
-      const uint32_t acc = (ch & 1) ? acc_main1 : acc_main0;
-      uint32_t& used = (ch & 1) ? used_main1 : used_main0;
-#pragma unroll
-      for (int ks = 0; ks < kChunk / 8; ++ks) {
-        const uint32_t off = ks * 32;                               // 8 tf32 = 32 bytes along K
-        umma_tf32(acc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, used);
-        used = 1;
-        umma_tf32(acc_corr, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, used_corr);
-        used_corr = 1;
-        umma_tf32(acc_corr, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> async proxy
+      mbar_arrive(bar_a + 8 * s);
+    };
+    load_chunk(0, v0);
+    load_chunk(1, v1);
+    for (int ch = 0; ch < a.chunks; ch += 2) {
+      store_chunk(ch, v0);
+      load_chunk(ch + 2, v0);
+      if (ch + 1 < a.chunks) {
+        store_chunk(ch + 1, v1);
+        load_chunk(ch + 3, v1);
       }
-      umma_commit(bar_mma + 8 * s);
-      if (ch == a.chunks - 1) umma_commit(bar_done);
     }
-  }
-  mbar_wait(bar_done, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // epilogue: thread = block-row, 16 columns at a time from the three accumulators
-  const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
-  const long long o0 = rho * a.l;
-  const bool two_main = a.chunks > 1;
-  for (int col = 0; col < a.l; col += 16) {
-    float d0[16], d1[16], dc[16];
-    tmem_ld16(acc_main0 + lane_base + col, d0);
-    tmem_ld16(acc_corr + lane_base + col, dc);
-    if (two_main) tmem_ld16(acc_main1 + lane_base + col, d1);
+    // ===== epilogue: TMEM -> registers (thread = block-row) -> shared tile ->
+    // row-contiguous global stores (a block-row is L consecutive outputs)
+    mbar_wait(bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* tile = reinterpret_cast<float*>(smem);            // the stages are drained
+    const int pitch = a.n_pad + 4;
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    const bool two_main = a.chunks > 1;
+    for (int col = 0; col < a.n_pad; col += 16) {
+      float d0[16], d1[16], dc[16];
+      tmem_ld16(acc_main0 + lane_base + col, d0);
+      tmem_ld16(acc_corr + lane_base + col, dc);
+      if (two_main) tmem_ld16(acc_main1 + lane_base + col, d1);
+      float4* dst = reinterpret_cast<float4*>(tile + tid * pitch + col);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const long long o = o0 + col + e;
-      if (col + e < a.l && o < a.n_out) {
-        const float main = two_main ? d0[e] + d1[e] : d0[e];
-        out[o] = main + dc[e];
+      for (int e = 0; e < 16; e += 4) {
+        float4 o;
+        o.x = (two_main ? d0[e] + d1[e] : d0[e]) + dc[e];
+        o.y = (two_main ? d0[e + 1] + d1[e + 1] : d0[e + 1]) + dc[e + 1];
+        o.z = (two_main ? d0[e + 2] + d1[e + 2] : d0[e + 2]) + dc[e + 2];
+        o.w = (two_main ? d0[e + 3] + d1[e + 3] : d0[e + 3]) + dc[e + 3];
+        dst[e >> 2] = o;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kRows) : "memory");   // producers/epilogue warps only
+    const long long o_base = row0 * a.l;
+    const long long o_end = min(a.n_out, o_base + (long long)kRows * a.l);
+    if ((a.l & 3) == 0 && (reinterpret_cast<size_t>(out + o_base) & 15) == 0) {
+      const int per_row = a.l >> 2;
+      const long long total4 = (o_end - o_base) >> 2;           // whole float4s in range
+      for (long long j = tid; j < total4; j += kRows) {
+        const int row = (int)(j / per_row), c4 = (int)(j - (long long)row * per_row);
+        reinterpret_cast<float4*>(out + o_base)[j] =
+            *reinterpret_cast<const float4*>(tile + row * pitch + 4 * c4);
+      }
+      for (long long o = o_base + (total4 << 2) + tid; o < o_end; o += kRows) {
+        const long long rel = o - o_base;
+        out[o] = tile[(rel / a.l) * pitch + (rel % a.l)];
+      }
+    } else {
+      for (long long o = o_base + tid; o < o_end; o += kRows) {
+        const long long rel = o - o_base;
+        out[o] = tile[(rel / a.l) * pitch + (rel % a.l)];
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0)
+  if (warp == 4)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
                  "r"(a.tmem_cols) : "memory");
 }
@@ -264,7 +321,7 @@ cudaError_t launch_resample_gemm(const GemmResampleArgs& a, long long batch, cud
     s.x = a.x + b0 * a.n;
     s.out = a.out + b0 * a.n_out;
     dim3 grid((unsigned)tiles, (unsigned)nb);
-    resample_gemm_kernel<<<grid, kRows, smem, st>>>(s);
+    resample_gemm_kernel<<<grid, kThreads, smem, st>>>(s);
     ++g_launch_count;
   }
   return cudaGetLastError();
