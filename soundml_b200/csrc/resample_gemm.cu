@@ -40,7 +40,11 @@ constexpr int kRows = 128;            // block-rows per CTA (UMMA M)
 constexpr int kChunk = 32;            // tf32 elements per 128-byte swizzle row
 constexpr int kStages = 3;
 constexpr int kABytes = kRows * 128;  // one split of the A chunk
-constexpr int kThreads = kRows + 32;  // 4 producer/epilogue warps + 1 TMA/MMA warp
+constexpr int kProducerWarps = 8;      // warps 0-3 double as the epilogue
+constexpr int kProducers = kProducerWarps * 32;
+constexpr int kRowsPerWarp = kRows / kProducerWarps;
+constexpr int kMmaWarp = kProducerWarps;
+constexpr int kThreads = kProducers + 32;  // producer warps + 1 TMA/MMA warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -141,14 +145,14 @@ resample_gemm_kernel(const GemmResampleArgs a) {
   const uint32_t bar_done = smem_u32(&bars[3 * kStages]);   // all MMAs done
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar_a + 8 * s, kRows);
+      mbar_init(bar_a + 8 * s, kProducers);
       mbar_init(bar_b + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(&tmem_base_slot)), "r"(a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -160,7 +164,7 @@ resample_gemm_kernel(const GemmResampleArgs a) {
   const uint32_t acc_main0 = tmem, acc_main1 = tmem + a.n_pad;
   const uint32_t acc_corr = tmem + 2 * a.n_pad;
 
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     // ===== B loader + MMA issuer (one elected lane) =====
     if (lane == 0) {
       // instruction descriptor: D f32, A/B tf32, both K-major, N = n_pad, M = 128
@@ -209,27 +213,40 @@ resample_gemm_kernel(const GemmResampleArgs a) {
     // chunk, so every row is one coalesced 128-byte request.  Loads run two
     // chunks ahead of the stores (registers), stores one to three chunks ahead
     // of the tensor core (stages).
-    float v0[32], v1[32];
-    auto load_chunk = [&](int ch, float (&v)[32]) {
-      const long long col0 = (long long)ch * kChunk + lane - a.k;
+    float v0[kRowsPerWarp], v1[kRowsPerWarp];
+    const long long first_row = row0 + warp * kRowsPerWarp;
+    // x index of (row rr of this warp, this lane) in chunk 0; chunk ch adds 32 ch
+    const long long base0 = first_row * a.m + lane - a.k;
+    // the warp's whole footprint over all chunks is interior for most tiles:
+    // no per-element bounds checks then
+    const bool interior = first_row * a.m - a.k >= 0 &&
+                          (first_row + kRowsPerWarp - 1) * a.m - a.k + (long long)a.chunks * kChunk <= a.n;
+    auto load_chunk = [&](int ch, float (&v)[kRowsPerWarp]) {
+      if (ch >= a.chunks) return;
+      const long long b0 = base0 + (long long)ch * kChunk;
+      if (interior) {
+        const float* p = xs + b0;
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const long long si = (row0 + warp * 32 + rr) * a.m + col0;
-        v[rr] = (ch < a.chunks && si >= 0 && si < a.n) ? __ldg(xs + si) : 0.0f;
+        for (int rr = 0; rr < kRowsPerWarp; ++rr) v[rr] = __ldg(p + rr * a.m);
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+          const long long si = b0 + (long long)rr * a.m;
+          v[rr] = (si >= 0 && si < a.n) ? __ldg(xs + si) : 0.0f;
+        }
       }
     };
-    auto store_chunk = [&](int ch, const float (&v)[32]) {
+    auto store_chunk = [&](int ch, const float (&v)[kRowsPerWarp]) {
       const int s = ch % kStages;
       if (ch >= kStages) mbar_wait(bar_empty + 8 * s, ((ch / kStages) - 1) & 1);
       // element (row, k) lands at 16-byte chunk (k/4) XOR (row mod 8) of its
       // 128-byte row (K-major SWIZZLE_128B)
-      float* ahi = reinterpret_cast<float*>(smem + s * stage_bytes);
+      float* ahi = reinterpret_cast<float*>(smem + s * stage_bytes) + warp * kRowsPerWarp * 32;
       float* alo = ahi + kABytes / 4;
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const int row = warp * 32 + rr;
+      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
         const float h = __uint_as_float(__float_as_uint(v[rr]) & 0xFFFFE000u);
-        const int cell = row * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3));
+        const int cell = rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3));
         ahi[cell] = h;
         alo[cell] = v[rr] - h;
       }
@@ -246,6 +263,7 @@ resample_gemm_kernel(const GemmResampleArgs a) {
         load_chunk(ch + 3, v1);
       }
     }
+    if (warp >= 4) goto teardown;             // warps 0-3 own the TMEM lanes
 
     // ===== epilogue: TMEM -> registers (thread = block-row) -> shared tile ->
     // row-contiguous global stores (a block-row is L consecutive outputs)
@@ -293,9 +311,10 @@ resample_gemm_kernel(const GemmResampleArgs a) {
       }
     }
   }
+teardown:
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4)
+  if (warp == kMmaWarp)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
                  "r"(a.tmem_cols) : "memory");
 }
