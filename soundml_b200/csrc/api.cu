@@ -104,6 +104,73 @@ struct StreamOwner {
   }
 };
 
+// Host-memory calls stage the batch through the device in slices on three
+// streams (H2D, compute, D2H) with two buffer slots, so the PCIe transfers of
+// neighbouring slices overlap each other and the kernels (full-duplex link).
+// With pageable host memory the copies degrade to synchronous staging; pinned
+// memory (smb_host_alloc_pinned) gets the full overlap.
+struct HostPipe {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr},
+              ev_out[2] = {nullptr, nullptr};
+  DeviceBuffer in[2], out[2];
+  bool ready = false;
+  void ensure() {
+    if (ready) return;
+    CK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_run[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+    }
+    ready = true;
+  }
+  void release() {
+    if (!ready) return;
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(ev_in[i]);
+      cudaEventDestroy(ev_run[i]);
+      cudaEventDestroy(ev_out[i]);
+      in[i].release();
+      out[i].release();
+    }
+    cudaStreamDestroy(h2d);
+    cudaStreamDestroy(d2h);
+    ready = false;
+  }
+  // run(din, dout, items) enqueues the kernels for `items` batch items on `compute`.
+  template <typename Run>
+  void execute(cudaStream_t compute, const void* x, void* out_host, int64_t batch,
+               size_t in_item, size_t out_item, Run&& run) {
+    ensure();
+    const size_t slice_bytes = (size_t)64 << 20;
+    int64_t per = (int64_t)(slice_bytes / std::max<size_t>(1, in_item + out_item));
+    per = std::max<int64_t>(1, std::min<int64_t>(per, batch));
+    const int64_t slices = (batch + per - 1) / per;
+    for (int64_t i = 0; i < slices; ++i) {
+      const int slot = (int)(i & 1);
+      const int64_t b0 = i * per, nb = std::min<int64_t>(per, batch - b0);
+      void* din = in[slot].ensure((size_t)per * in_item);
+      void* dout = out[slot].ensure((size_t)per * out_item);
+      if (i >= 2) CK(cudaStreamWaitEvent(h2d, ev_run[slot], 0));      // input slot consumed
+      CK(cudaMemcpyAsync(din, (const char*)x + (size_t)b0 * in_item, (size_t)nb * in_item,
+                         cudaMemcpyHostToDevice, h2d));
+      CK(cudaEventRecord(ev_in[slot], h2d));
+      CK(cudaStreamWaitEvent(compute, ev_in[slot], 0));
+      if (i >= 2) CK(cudaStreamWaitEvent(compute, ev_out[slot], 0));  // output slot drained
+      run(din, dout, nb);
+      CK(cudaEventRecord(ev_run[slot], compute));
+      CK(cudaStreamWaitEvent(d2h, ev_run[slot], 0));
+      CK(cudaMemcpyAsync((char*)out_host + (size_t)b0 * out_item, dout, (size_t)nb * out_item,
+                         cudaMemcpyDeviceToHost, d2h));
+      CK(cudaEventRecord(ev_out[slot], d2h));
+    }
+    CK(cudaStreamSynchronize(d2h));
+    CK(cudaStreamSynchronize(compute));
+  }
+};
+
 size_t dtype_size(int dtype) {
   if (dtype == SMB_F32) return 4;
   if (dtype == SMB_F64) return 8;
@@ -127,7 +194,8 @@ struct smb_stft_plan {
   float* d_window32 = nullptr;       // fast path tables (fft 2048 only)
   float2* d_tw_pass = nullptr;
   float2* d_tw_post = nullptr;
-  DeviceBuffer in, out, tmp;
+  HostPipe pipe;
+  DeviceBuffer tmp;
 
   void ensure_device() {
     if (device_ready) return;
@@ -181,8 +249,7 @@ struct smb_stft_plan {
     cudaFree(d_window32);
     cudaFree(d_tw_pass);
     cudaFree(d_tw_post);
-    in.release();
-    out.release();
+    pipe.release();
     tmp.release();
     stream.destroy();
   }
@@ -654,13 +721,10 @@ void spectrum_call(const char* op, smb_stft_plan* p, const void* x, int64_t batc
     return;
   }
   if (mem != SMB_MEM_HOST) throw smb::invalid_argument("soundml_b200: unknown memory kind");
-  const size_t in_bytes = (size_t)batch * (size_t)n * esz;
-  void* din = p->in.ensure(in_bytes);
-  void* dout = p->out.ensure(out_elems * esz);
-  CK(cudaMemcpyAsync(din, x, in_bytes, cudaMemcpyHostToDevice, st));
-  run_spectrum(p, din, batch, g, dtype, kind, power, dout);
-  CK(cudaMemcpyAsync(out, dout, out_elems * esz, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  p->pipe.execute(st, x, out, batch, (size_t)n * esz, out_elems / (size_t)batch * esz,
+                  [&](const void* din, void* dout, int64_t nb) {
+                    run_spectrum(p, din, nb, g, dtype, kind, power, dout);
+                  });
 }
 
 void run_mel_apply(smb_mel_plan* m, const void* ds, int64_t batch, int64_t frames, int dtype,
@@ -784,46 +848,41 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
     stft->ensure_device();
     mel->ensure_device();
     cudaStream_t st = stft->stream.use;
-    const size_t in_bytes = (size_t)batch * (size_t)n * esz;
-    const size_t out_bytes = (size_t)batch * mel->n_mels * g.frames * esz;
-    const void* din = x;
-    void* dout = out;
-    if (mem == SMB_MEM_HOST) {
-      void* stage = stft->in.ensure(in_bytes);
-      dout = stft->out.ensure(out_bytes);
-      CK(cudaMemcpyAsync(stage, x, in_bytes, cudaMemcpyHostToDevice, st));
-      din = stage;
-    } else if (mem != SMB_MEM_DEVICE) {
-      throw smb::invalid_argument("soundml_b200: unknown memory kind");
-    }
-    if (want_fast(stft, dtype, g, smb::kFastMel, mel)) {
-      smb::Stft2048Args a{};
-      a.x = (const float*)din;
-      a.out = (float*)dout;
-      a.batch = batch;
-      a.g = g;
-      a.window = stft->d_window32;
-      a.tw_pass = stft->d_tw_pass;
-      a.tw_post = stft->d_tw_post;
-      a.n_mels = (int)mel->n_mels;
-      a.nnz = (int)mel->vals.size();
-      a.vals = mel->d_vals;
-      a.bands = mel->d_bands;
-      a.mel_rounds = mel->mel_rounds;
-      a.mel_order = mel->d_mel_order;
-      a.power = (float)power;
-      CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
+    const bool fast = want_fast(stft, dtype, g, smb::kFastMel, mel);
+    auto run = [&](const void* din, void* dout, int64_t nb) {
+      if (fast) {
+        smb::Stft2048Args a{};
+        a.x = (const float*)din;
+        a.out = (float*)dout;
+        a.batch = nb;
+        a.g = g;
+        a.window = stft->d_window32;
+        a.tw_pass = stft->d_tw_pass;
+        a.tw_post = stft->d_tw_post;
+        a.n_mels = (int)mel->n_mels;
+        a.nnz = (int)mel->vals.size();
+        a.vals = mel->d_vals;
+        a.bands = mel->d_bands;
+        a.mel_rounds = mel->mel_rounds;
+        a.mel_order = mel->d_mel_order;
+        a.power = (float)power;
+        CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
+      } else {
+        // two kernels through a plan-owned power spectrogram
+        const size_t spec_bytes = (size_t)nb * stft->geom.bins() * g.frames * esz;
+        void* spec = stft->tmp.ensure(spec_bytes);
+        CK(smb::launch_stft_generic(din, dtype, nb, g, stft->d_window64, stft->d_twiddle64,
+                                    smb::kModePower, power, spec, st));
+        run_mel_apply(mel, spec, nb, g.frames, dtype, dout, st);
+      }
+    };
+    if (mem == SMB_MEM_DEVICE) {
+      run(x, out, batch);
+    } else if (mem == SMB_MEM_HOST) {
+      stft->pipe.execute(st, x, out, batch, (size_t)n * esz,
+                         (size_t)mel->n_mels * g.frames * esz, run);
     } else {
-      // two kernels through a plan-owned power spectrogram
-      const size_t spec_bytes = (size_t)batch * stft->geom.bins() * g.frames * esz;
-      void* spec = stft->tmp.ensure(spec_bytes);
-      CK(smb::launch_stft_generic(din, dtype, batch, g, stft->d_window64, stft->d_twiddle64,
-                                  smb::kModePower, power, spec, st));
-      run_mel_apply(mel, spec, batch, g.frames, dtype, dout, st);
-    }
-    if (mem == SMB_MEM_HOST) {
-      CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
     }
   });
 }
