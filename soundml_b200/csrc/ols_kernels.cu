@@ -26,20 +26,57 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
-// Forward complex FFT of `n` points (power of two), radix-2 Stockham autosort.
-// `tw` holds exp(-2 pi i j / tn) for j < tn/2, tn a multiple of n.  Returns the
-// buffer that holds the natural-order result.
+// exp(-2 pi i idx / tn) from the half-circle table (idx < tn): W^(k + tn/2) = -W^k.
+__device__ __forceinline__ float2 twiddle(const float2* tw, int idx, int tn) {
+  const int half = tn >> 1;
+  if (idx < half) return tw[idx];
+  const float2 w = tw[idx - half];
+  return make_float2(-w.x, -w.y);
+}
+
+// Forward complex FFT of `n` points (power of two), Stockham autosort: radix-4
+// passes, one radix-2 pass when log2 n is odd.  `tw` holds exp(-2 pi i j / tn)
+// for j < tn/2, tn a multiple of n.  Returns the buffer with the natural-order
+// result.
 __device__ float2* stockham_forward(float2* x, float2* y, int n, const float2* tw, int tn) {
-  for (int ncur = n, s = 1; ncur > 1; ncur >>= 1, s <<= 1) {
-    const int m = ncur >> 1;
+  int ncur = n, s = 1;
+  for (; ncur >= 4; ncur >>= 2, s <<= 2) {
+    const int m = ncur >> 2;
     const int step = tn / ncur;
-    for (int idx = threadIdx.x; idx < (n >> 1); idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < (n >> 2); idx += blockDim.x) {
       const int p = idx / s, q = idx - p * s;
       const float2 a = x[q + s * p];
       const float2 b = x[q + s * (p + m)];
-      const float2 w = tw[p * step];
-      y[q + s * (2 * p)] = make_float2(a.x + b.x, a.y + b.y);
-      y[q + s * (2 * p + 1)] = cmul(make_float2(a.x - b.x, a.y - b.y), w);
+      const float2 c = x[q + s * (p + 2 * m)];
+      const float2 d = x[q + s * (p + 3 * m)];
+      const float2 apc = make_float2(a.x + c.x, a.y + c.y), amc = make_float2(a.x - c.x, a.y - c.y);
+      const float2 bpd = make_float2(b.x + d.x, b.y + d.y);
+      const float2 jbmd = make_float2(-(b.y - d.y), b.x - d.x);          // i (b - d)
+      float2* o = y + q + s * (4 * p);
+      o[0] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
+      const float2 t1 = make_float2(amc.x - jbmd.x, amc.y - jbmd.y);
+      const float2 t2 = make_float2(apc.x - bpd.x, apc.y - bpd.y);
+      const float2 t3 = make_float2(amc.x + jbmd.x, amc.y + jbmd.y);
+      if (p == 0) {
+        o[s] = t1;
+        o[2 * s] = t2;
+        o[3 * s] = t3;
+      } else {
+        o[s] = cmul(t1, tw[p * step]);
+        o[2 * s] = cmul(t2, twiddle(tw, 2 * p * step, tn));
+        o[3 * s] = cmul(t3, twiddle(tw, 3 * p * step, tn));
+      }
+    }
+    __syncthreads();
+    float2* t = x;
+    x = y;
+    y = t;
+  }
+  if (ncur == 2) {
+    for (int q = threadIdx.x; q < s; q += blockDim.x) {
+      const float2 a = x[q], b = x[q + s];
+      y[q] = make_float2(a.x + b.x, a.y + b.y);
+      y[q + s] = make_float2(a.x - b.x, a.y - b.y);
     }
     __syncthreads();
     float2* t = x;
@@ -55,11 +92,9 @@ ols_kernel(const OlsArgs a) {
   const int half_n = a.N >> 1, half_w = a.W >> 1;
   const int cap = half_n > half_w ? half_n : half_w;
   const int tn = a.N > a.W ? a.N : a.W;
-  float2* bufA = sm2;
-  float2* bufB = bufA + cap;
-  float2* Xs = bufB + cap;              // N/2 + 1 bins
-  float2* Ys = Xs + half_n + 1;         // W/2 + 1 bins
-  float2* tw = Ys + half_w + 1;         // tn/2 twiddles
+  float2* bufA = sm2;                   // two ping-pong buffers of cap + 1 complex values
+  float2* bufB = bufA + cap + 1;
+  float2* tw = bufB + cap + 1;          // tn/2 twiddles
 
   const long long b = blockIdx.x;
   const long long c = blockIdx.y;
@@ -76,6 +111,8 @@ ols_kernel(const OlsArgs a) {
   }
   __syncthreads();
   float2* z = stockham_forward(bufA, bufB, half_n, tw, tn);   // z = FFT of x[2n] + i x[2n+1]
+  float2* Xs = z == bufA ? bufB : bufA;  // N/2 + 1 bins, in the buffer z does not occupy
+  float2* Ys = z;                         // W/2 + 1 bins, over z once X is complete
 
   // half spectrum X[0 .. N/2] of the real block
   const int sN = tn / a.N;
@@ -128,10 +165,10 @@ ols_kernel(const OlsArgs a) {
     const float2 w = cconj(tw[k * sW]);                        // W_W^-k, k < W/2
     const float2 o = cmul(d, w);
     const float2 zi = make_float2(e.x - o.y, e.y + o.x);       // e + i o
-    bufA[k] = cconj(zi);
+    Xs[k] = cconj(zi);                                         // X is dead: reuse its buffer
   }
   __syncthreads();
-  float2* r = stockham_forward(bufA, bufB, half_w, tw, tn);
+  float2* r = stockham_forward(Xs, Ys, half_w, tw, tn);
 
   // block b extends the output run to hi(b) (resample.ml:1309-1319)
   long long hi, lo;
@@ -159,7 +196,7 @@ ols_kernel(const OlsArgs a) {
 size_t ols_smem_bytes(int N, int W) {
   const int cap = (N > W ? N : W) / 2;
   const int tn = N > W ? N : W;
-  return (size_t)(2 * cap + (N / 2 + 1) + (W / 2 + 1) + tn / 2) * sizeof(float2);
+  return (size_t)(2 * (cap + 1) + tn / 2) * sizeof(float2);
 }
 
 cudaError_t launch_ols(const OlsArgs& a, long long batch, cudaStream_t st) {
