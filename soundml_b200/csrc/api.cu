@@ -263,16 +263,14 @@ struct smb_mel_plan {
   std::vector<int> band_lo, band_hi;
   // band storage for the fused kernel: filter m keeps bins [lo, lo+len)
   std::vector<float> vals;
-  std::vector<smb::MelBand> bands;
-  std::vector<short> mel_order;      // [8][mel_rounds][4]
+  std::vector<smb::MelLane> mel_lanes;   // [8 warps][mel_rounds][4 lane groups]
   int mel_rounds = 0;
   bool device_ready = false;
   StreamOwner stream;
   double* d_weights = nullptr;
   int *d_band_lo = nullptr, *d_band_hi = nullptr;
   float* d_vals = nullptr;
-  smb::MelBand* d_bands = nullptr;
-  short* d_mel_order = nullptr;
+  smb::MelLane* d_mel_lanes = nullptr;
   DeviceBuffer in, out;
 
   void finish_host() {
@@ -289,45 +287,65 @@ struct smb_mel_plan {
       if (hi == 0) lo = 0;
       band_lo[(size_t)m] = lo;
       band_hi[(size_t)m] = hi;
-      if (small) {
-        // stored band: widened to whole float4s of the 16-byte aligned power row,
-        // an even number of them so the product loop unrolls by two cleanly
-        const int slo = lo & ~3;
-        int shi = (hi + 3) & ~3;
-        if (((shi - slo) >> 2) & 1) shi += 4;
-        bands.push_back(smb::MelBand{(int)vals.size(), (short)slo, (short)(shi - slo)});
-        for (int k = slo; k < shi; ++k)
-          vals.push_back(k < bins ? (float)weights[(size_t)(m * bins + k)] : 0.0f);
-      }
     }
-    if (!small) return;
-    // Schedule for the fused kernel: filters sorted by stored length are cut into
-    // quads (four lanes-groups of a warp run them in lockstep), quads go to the
-    // 8 warps longest-first onto the lightest warp.
+    if (!small || bins + 3 > 32767) return;
+    // Schedule for the fused kernel.  Filters sorted by band length are cut into
+    // quads; the four bands of a quad are stored zero-padded to one common length
+    // (a whole number of 8-float steps, starting on a float4 of the 16-byte
+    // aligned power row), so the four lane groups of a warp run them in lock
+    // step.  Quads go to the 8 warps longest-first onto the lightest warp.
+    const int row_floats = (int)((bins + 3) / 4 * 4);        // the kernel zeroes the row tail
     std::vector<int> order((size_t)n_mels);
     for (int64_t m = 0; m < n_mels; ++m) order[(size_t)m] = (int)m;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      return bands[(size_t)a].len > bands[(size_t)b].len;
-    });
+    auto span = [&](int m) { return band_hi[(size_t)m] - (band_lo[(size_t)m] & ~3); };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return span(a) > span(b); });
     const int warps = 8;
     const int quads = (int)((n_mels + 3) / 4);
+    struct Quad { int n8; smb::MelLane lane[4]; };
+    std::vector<Quad> built((size_t)quads);
+    bool fits = n_mels <= 255;
+    for (int q = 0; q < quads && fits; ++q) {
+      int longest = 0;
+      for (int j = 0; j < 4; ++j)
+        if ((size_t)(q * 4 + j) < order.size()) longest = std::max(longest, span(order[(size_t)(q * 4 + j)]));
+      const int n8 = std::max(1, (longest + 7) / 8);
+      if (n8 * 8 > row_floats || n8 > 255) { fits = false; break; }
+      built[(size_t)q].n8 = n8;
+      for (int j = 0; j < 4; ++j) {
+        smb::MelLane& ln = built[(size_t)q].lane[j];
+        ln.n8 = (unsigned char)n8;
+        ln.off = (int)vals.size();
+        const bool real = (size_t)(q * 4 + j) < order.size();
+        const int m = real ? order[(size_t)(q * 4 + j)] : -1;
+        // stored band [slo, slo + 8 n8): inside the row, covering the filter's band
+        int slo = real ? (band_lo[(size_t)m] & ~3) : 0;
+        slo = std::min(slo, row_floats - n8 * 8);
+        ln.lo = (short)slo;
+        ln.out = (unsigned char)(real ? m : n_mels);
+        for (int k = slo; k < slo + n8 * 8; ++k)
+          vals.push_back(real && k < bins ? (float)weights[(size_t)((int64_t)m * bins + k)] : 0.0f);
+      }
+    }
+    if (!fits) { vals.clear(); return; }
     std::vector<std::vector<int>> lists((size_t)warps);
     std::vector<long long> load((size_t)warps, 0);
     for (int q = 0; q < quads; ++q) {
       const size_t w = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
       lists[w].push_back(q);
-      load[w] += bands[(size_t)order[(size_t)q * 4]].len + 8;
+      load[w] += built[(size_t)q].n8 + 2;
     }
     mel_rounds = 0;
     for (const auto& l : lists) mel_rounds = std::max(mel_rounds, (int)l.size());
-    mel_order.assign((size_t)(warps * mel_rounds * 4), (short)-1);
+    // idle rounds: one step over zero weights into the scratch row
+    const int zero_off = (int)vals.size();
+    vals.insert(vals.end(), 8, 0.0f);
+    smb::MelLane idle{zero_off, 0, (unsigned char)n_mels, 1};
+    mel_lanes.assign((size_t)(warps * mel_rounds * 4), idle);
     for (int w = 0; w < warps; ++w)
       for (size_t r = 0; r < lists[(size_t)w].size(); ++r)
-        for (int j = 0; j < 4; ++j) {
-          const size_t idx = (size_t)lists[(size_t)w][r] * 4 + (size_t)j;
-          if (idx < order.size())
-            mel_order[((size_t)w * mel_rounds + r) * 4 + (size_t)j] = (short)order[idx];
-        }
+        for (int j = 0; j < 4; ++j)
+          mel_lanes[((size_t)w * mel_rounds + r) * 4 + (size_t)j] =
+              built[(size_t)lists[(size_t)w][r]].lane[j];
   }
   void ensure_device() {
     if (device_ready) return;
@@ -337,8 +355,7 @@ struct smb_mel_plan {
     d_band_lo = upload(band_lo);
     d_band_hi = upload(band_hi);
     d_vals = upload(vals);
-    d_bands = upload(bands);
-    d_mel_order = upload(mel_order);
+    d_mel_lanes = upload(mel_lanes);
     device_ready = true;
   }
   ~smb_mel_plan() {
@@ -347,8 +364,7 @@ struct smb_mel_plan {
     cudaFree(d_band_lo);
     cudaFree(d_band_hi);
     cudaFree(d_vals);
-    cudaFree(d_bands);
-    cudaFree(d_mel_order);
+    cudaFree(d_mel_lanes);
     in.release();
     out.release();
     stream.destroy();
@@ -673,7 +689,7 @@ bool want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int o
                const smb_mel_plan* mel) {
   if (p->path == SMB_PATH_GENERIC) return false;
   const bool ok = dtype == SMB_F32 && g.fft == 2048 &&
-                  (!mel || (mel->bins == 1025 && !mel->bands.empty())) &&
+                  (!mel || (mel->bins == 1025 && !mel->mel_lanes.empty())) &&
                   smb::stft2048_supports(g, out_kind, mel ? (int)mel->n_mels : 0,
                                          mel ? (int)mel->vals.size() : 0,
                                          mel ? mel->mel_rounds : 0);
@@ -862,9 +878,8 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
         a.n_mels = (int)mel->n_mels;
         a.nnz = (int)mel->vals.size();
         a.vals = mel->d_vals;
-        a.bands = mel->d_bands;
         a.mel_rounds = mel->mel_rounds;
-        a.mel_order = mel->d_mel_order;
+        a.mel_lanes = mel->d_mel_lanes;
         a.power = (float)power;
         CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
       } else {

@@ -34,10 +34,11 @@ cudaError_t launch_mel_apply(const void* s, int dtype, long long batch, int bins
                              cudaStream_t st);
 
 // ---- fast path: fft 2048, float32, fused frame+window+rFFT+|X|^p(+mel) -------
-struct MelBand {           // one filter of the band-stored filterbank
-  int off;                 // first weight in vals (multiple of 4)
+struct MelLane {           // what one lane group (8 frames) of a warp does in a mel round
+  int off;                 // first weight of the stored band in vals (multiple of 4)
   short lo;                // first bin of the stored band (multiple of 4)
-  short len;               // stored bins (multiple of 4; padding weights are zero)
+  unsigned char out;       // output filter; n_mels = scratch row (padding entry)
+  unsigned char n8;        // 8-float steps, the same for the four lane groups of a round
 };
 enum FastOut { kFastComplex = 0, kFastPower = 1, kFastMel = 2 };
 struct Stft2048Args {
@@ -50,10 +51,9 @@ struct Stft2048Args {
   const float2* tw_post;   // [16][32]  W_2048^(l + 32 j), index j*32 + l
   // band-stored mel filterbank (kFastMel only)
   int n_mels, nnz;
-  const float* vals;           // [nnz] weights, filter by filter
-  const MelBand* bands;        // [n_mels]
-  int mel_rounds;              // filter quads each warp walks
-  const short* mel_order;      // [8 warps][mel_rounds][4] filter ids, -1 = none
+  const float* vals;           // [nnz] zero-padded band weights
+  int mel_rounds;              // rounds each warp walks
+  const MelLane* mel_lanes;    // [8 warps][mel_rounds][4 lane groups]
   float power;
 };
 // True when the fused kernel can take this geometry (hop small enough for the

@@ -165,16 +165,16 @@ struct Params {
 // aligned, else 8 or 4); border positions are resolved by the reference's
 // boundary rule (stft.ml:300-338) and stored directly.  Completion is awaited
 // by the caller (cp.async.wait_all + group barrier).
-__device__ __forceinline__ void stage_tile(const Params& p, long long tile, float* sSamples,
-                                           int gtid) {
+__device__ __forceinline__ void stage_tile(const Params& p, int tile, float* sSamples, int gtid) {
   const FrameGeom& g = p.a.g;
-  const long long b = tile / p.tiles_per_signal;
-  const long long p0 = (tile % p.tiles_per_signal) * kTile;
+  const int tps = (int)p.tiles_per_signal;
+  const int b = tile / tps;
+  const long long p0 = (long long)(tile - b * tps) * kTile;
   const int nf = (int)min((long long)kTile, g.frames - p0);
   const int span = (nf - 1) * g.hop + kFft;
   const long long q0 = p0 * g.hop;
   const long long s0 = q0 - g.left;
-  const float* xs = p.a.x + b * g.n;
+  const float* xs = p.a.x + (long long)b * g.n;
   // [lo, hi): positions of the span that are real samples
   const int lo = (int)max(0LL, min((long long)span, -s0));
   const int hi = (int)max((long long)lo, min((long long)span, g.n - s0));
@@ -222,14 +222,13 @@ stft2048_kernel(const Params p) {
   float2* sTwPost = sTwPass + 1024;                             // [8][32][2]   W_2048^(l + 32 k2), k2 = 2 pair + {0,1}
   float* sMelVals = reinterpret_cast<float*>(sTwPost + 512);    // band weights, filter by filter
   const int nnz_pad = (p.a.nnz + 3) & ~3;
-  MelBand* sBands = reinterpret_cast<MelBand*>(sMelVals + nnz_pad);      // [n_mels]
-  short* sMelOrder = reinterpret_cast<short*>(sBands + p.a.n_mels);     // [8 warps][rounds][4]
+  MelLane* sMelLanes = reinterpret_cast<MelLane*>(sMelVals + nnz_pad);   // [8 warps][rounds][4]
   // offsets stay integers so every pointer keeps its shared-memory provenance
   // (generic LD/ST would go through the slower generic path)
   const int tables_bytes = (kFft + 2 * 1024 + 2 * 512 + nnz_pad) * 4 +
-                           p.a.n_mels * (int)sizeof(MelBand) + kTile * p.a.mel_rounds * 4 * 2;
+                           kTile * p.a.mel_rounds * 4 * (int)sizeof(MelLane);
   float* groups_base = smem + (((tables_bytes + 15) & ~15) >> 2);
-  const int group_floats = p.span_cap + kTile * kRowStride + kMaxMel * kTile;
+  const int group_floats = p.span_cap + kTile * kRowStride + (kMaxMel + 1) * kTile;
 
   const int tid = threadIdx.x;
   const int group = tid / kGroupThreads;
@@ -255,21 +254,22 @@ stft2048_kernel(const Params p) {
   }
   if (OUT == kFastMel) {
     for (int i = tid; i < p.a.nnz; i += blockDim.x) sMelVals[i] = p.a.vals[i];
-    for (int i = tid; i < p.a.n_mels; i += blockDim.x) sBands[i] = p.a.bands[i];
-    for (int i = tid; i < kTile * p.a.mel_rounds * 4; i += blockDim.x) sMelOrder[i] = p.a.mel_order[i];
+    for (int i = tid; i < kTile * p.a.mel_rounds * 4; i += blockDim.x) sMelLanes[i] = p.a.mel_lanes[i];
   }
   __syncthreads();
 
   const FrameGeom g = p.a.g;
-  const long long slot = (long long)blockIdx.x * kGroups + group;
-  const long long stride = (long long)gridDim.x * kGroups;
+  // tile indices fit 32 bits (checked by the launcher): cheap decode
+  const int slot = blockIdx.x * kGroups + group;
+  const int stride = gridDim.x * kGroups;
+  const int total_tiles = (int)p.total_tiles, tiles_per_signal = (int)p.tiles_per_signal;
   float* row = sRows + warp * kRowStride;
   float2* ex = reinterpret_cast<float2*>(row);
 
-  if (slot < p.total_tiles) stage_tile(p, slot, sSamples, gtid);
-  for (long long tile = slot; tile < p.total_tiles; tile += stride) {
-    const long long b = tile / p.tiles_per_signal;
-    const long long p0 = (tile % p.tiles_per_signal) * kTile;
+  if (slot < total_tiles) stage_tile(p, slot, sSamples, gtid);
+  for (int tile = slot; tile < total_tiles; tile += stride) {
+    const int b = tile / tiles_per_signal;
+    const long long p0 = (long long)(tile - b * tiles_per_signal) * kTile;
     const int nf = (int)min((long long)kTile, g.frames - p0);
 
     // ---- the tile's samples were requested one iteration ago (or just above
@@ -385,7 +385,7 @@ stft2048_kernel(const Params p) {
 
     // ---- the sample buffer is free: start fetching the next tile's samples
     // under the mel / write-out phases.
-    if (tile + stride < p.total_tiles) stage_tile(p, tile + stride, sSamples, gtid);
+    if (tile + stride < total_tiles) stage_tile(p, tile + stride, sSamples, gtid);
 
     if (OUT == kFastMel) {
       // ---- mel projection over the tile's power rows.  A warp takes four
@@ -395,23 +395,26 @@ stft2048_kernel(const Params p) {
       // read one conflict-free 128-byte wavefront per float4 and share the weight.
       const int f = lane & (kTile - 1), j = lane >> 3;
       const float4* prow4 = reinterpret_cast<const float4*>(sRows + f * kRowStride);
+      const MelLane* mine = sMelLanes + warp * p.a.mel_rounds * 4 + j;
       for (int r = 0; r < p.a.mel_rounds; ++r) {
-        const int m = sMelOrder[(warp * p.a.mel_rounds + r) * 4 + j];
-        if (m < 0) continue;
-        const MelBand band = sBands[m];
-        const float4* w4 = reinterpret_cast<const float4*>(sMelVals + band.off);
-        const float4* v4 = prow4 + (band.lo >> 2);
+        const MelLane q = mine[r * 4];
+        const float4* w4 = reinterpret_cast<const float4*>(sMelVals + q.off);
+        const float4* v4 = prow4 + (q.lo >> 2);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        const int n4 = band.len >> 2;
-#pragma unroll 2
-        for (int i = 0; i < n4; ++i) {
-          const float4 w = w4[i], v = v4[i];
-          a0 = fmaf(w.x, v.x, a0);
-          a1 = fmaf(w.y, v.y, a1);
-          a2 = fmaf(w.z, v.z, a2);
-          a3 = fmaf(w.w, v.w, a3);
+        // the trip count is the same for the whole warp: no divergence
+        for (int i = 0; i < q.n8; ++i) {
+          const float4 w0 = w4[2 * i], v0 = v4[2 * i];
+          const float4 w1 = w4[2 * i + 1], v1 = v4[2 * i + 1];
+          a0 = fmaf(w0.x, v0.x, a0);
+          a1 = fmaf(w0.y, v0.y, a1);
+          a2 = fmaf(w0.z, v0.z, a2);
+          a3 = fmaf(w0.w, v0.w, a3);
+          a0 = fmaf(w1.x, v1.x, a0);
+          a1 = fmaf(w1.y, v1.y, a1);
+          a2 = fmaf(w1.z, v1.z, a2);
+          a3 = fmaf(w1.w, v1.w, a3);
         }
-        sMelOut[m * kTile + f] = (a0 + a1) + (a2 + a3);
+        sMelOut[q.out * kTile + f] = (a0 + a1) + (a2 + a3);
       }
       group_sync(group);
     }
@@ -422,19 +425,21 @@ stft2048_kernel(const Params p) {
       const int f = gtid & (kTile - 1), r0 = gtid >> 3;
       if (f < nf) {
         if (OUT == kFastMel) {
-          float* ob = p.a.out + (b * p.a.n_mels) * g.frames + p0 + f;
-          for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile)
-            ob[(long long)m * g.frames] = sMelOut[m * kTile + f];
+          float* ob = p.a.out + ((long long)b * p.a.n_mels + r0) * g.frames + p0 + f;
+          const long long step = (long long)(kGroupThreads / kTile) * g.frames;
+          for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step)
+            *ob = sMelOut[m * kTile + f];
         } else if (OUT == kFastPower) {
-          float* ob = p.a.out + (b * kBins) * g.frames + p0 + f;
+          float* ob = p.a.out + ((long long)b * kBins + r0) * g.frames + p0 + f;
+          const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float* src = sRows + f * kRowStride;
-          for (int k = r0; k < kBins; k += kGroupThreads / kTile)
-            ob[(long long)k * g.frames] = src[k];
+          for (int k = r0; k < kBins; k += kGroupThreads / kTile, ob += step) *ob = src[k];
         } else {
-          float2* ob = reinterpret_cast<float2*>(p.a.out) + (b * kBins) * g.frames + p0 + f;
+          float2* ob = reinterpret_cast<float2*>(p.a.out) + ((long long)b * kBins + r0) * g.frames +
+                       p0 + f;
+          const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float2* src = reinterpret_cast<const float2*>(sRows + f * kRowStride);
-          for (int k = r0; k < kBins; k += kGroupThreads / kTile)
-            ob[(long long)k * g.frames] = src[k];
+          for (int k = r0; k < kBins; k += kGroupThreads / kTile, ob += step) *ob = src[k];
         }
       }
     }
@@ -444,13 +449,13 @@ stft2048_kernel(const Params p) {
 
 }  // namespace
 
-static size_t smem_layout(int nnz, int n_mels, int mel_rounds, int span_cap) {
+static size_t smem_layout(int nnz, int mel_rounds, int span_cap) {
   const int nnz_pad = (nnz + 3) & ~3;
   size_t bytes = (size_t)(kFft + 2 * 1024 + 2 * 512) * 4;        // window, tw_pass, tw_post
-  bytes += (size_t)nnz_pad * 4 + (size_t)n_mels * sizeof(MelBand); // band weights, descriptors
-  bytes += (size_t)kTile * mel_rounds * 4 * 2;                     // warp -> filter schedule
+  bytes += (size_t)nnz_pad * 4;                                    // band weights
+  bytes += (size_t)kTile * mel_rounds * 4 * sizeof(MelLane);      // warp schedule
   bytes = (bytes + 15) & ~(size_t)15;
-  bytes += (size_t)kGroups * (span_cap + kTile * kRowStride + kMaxMel * kTile) * 4;
+  bytes += (size_t)kGroups * (span_cap + kTile * kRowStride + (kMaxMel + 1) * kTile) * 4;
   return bytes;
 }
 
@@ -464,19 +469,30 @@ bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, in
   if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;
   if (out_kind == kFastMel && (n_mels < 1 || n_mels > kMaxMel || nnz > 65536)) return false;
   const bool mel = out_kind == kFastMel;
-  return smem_layout(mel ? nnz : 0, mel ? n_mels : 0, mel ? mel_rounds : 0, span_needed(g)) <=
-         kSmemLimit;
+  return smem_layout(mel ? nnz : 0, mel ? mel_rounds : 0, span_needed(g)) <= kSmemLimit;
 }
 
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st) {
   if (a.batch == 0 || a.g.frames == 0) return cudaSuccess;
+  if ((a.g.frames + kTile - 1) / kTile * a.batch >= (1LL << 31)) {
+    // tile indices are 32-bit inside the kernel: split the batch
+    const long long half = a.batch / 2;
+    Stft2048Args lo = a, hi = a;
+    lo.batch = half;
+    hi.batch = a.batch - half;
+    hi.x = a.x + half * a.g.n;
+    const long long rows = out_kind == kFastMel ? a.n_mels : kBins;
+    hi.out = a.out + half * rows * a.g.frames * (out_kind == kFastComplex ? 2 : 1);
+    cudaError_t e1 = launch_stft2048(lo, out_kind, sm_count, st);
+    return e1 != cudaSuccess ? e1 : launch_stft2048(hi, out_kind, sm_count, st);
+  }
   Params p;
   p.a = a;
   if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; }
   p.span_cap = span_needed(a.g);
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
   p.total_tiles = p.tiles_per_signal * a.batch;
-  const size_t smem = smem_layout(p.a.nnz, p.a.n_mels, p.a.mel_rounds, p.span_cap);
+  const size_t smem = smem_layout(p.a.nnz, p.a.mel_rounds, p.span_cap);
   if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
   long long want = (p.total_tiles + kGroups - 1) / kGroups;
   const int grid = (int)(want < sm_count ? want : sm_count);
