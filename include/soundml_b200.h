@@ -131,6 +131,11 @@ int smb_stft_source_indices(const smb_stft_plan* plan, int64_t n, int64_t* out,
  * (interleaved re, im; complex64 for SMB_F32, complex128 for SMB_F64). */
 int smb_stft_transform(smb_stft_plan* plan, const void* x, int64_t batch, int64_t n,
                        int dtype, void* out, int mem);
+/* Stft.transform_range ~p0 ~p1 (stft.ml:652-666): frames [p0, p1) of the full
+ * transform without evaluating the others; out [batch, bins, p1 - p0] complex.
+ * Adjacent ranges reassemble the full transform exactly. */
+int smb_stft_transform_range(smb_stft_plan* plan, const void* x, int64_t batch, int64_t n,
+                             int dtype, int64_t p0, int64_t p1, void* out, int mem);
 /* Stft.power_spectrum ?power: out [batch, bins, frames] real. */
 int smb_stft_power_spectrum(smb_stft_plan* plan, const void* x, int64_t batch,
                             int64_t n, int dtype, double power, void* out, int mem);

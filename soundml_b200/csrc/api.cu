@@ -417,6 +417,7 @@ struct GemmDevice {
   bool ok = false;
   int n_pad = 0, chunks = 0, tmem_cols = 0;
   float* d_images = nullptr;
+  int4* d_meta = nullptr;
   void build(const smb::ResampleStage& s) {
     const int64_t l = s.l, m = s.m, k = s.k, taps = 2 * k + 1;
     n_pad = (int)((l + 15) / 16 * 16);
@@ -425,7 +426,32 @@ struct GemmDevice {
     chunks = (int)((p_len + 31) / 32);
     tmem_cols = 32;
     while (tmem_cols < 3 * n_pad) tmem_cols *= 2;
-    std::vector<float> img((size_t)chunks * 2 * n_pad * 32, 0.0f);
+    // G is banded: chunk ch (rows 32 ch .. 32 ch + 31 of G) only has nonzeros in a
+    // run of columns.  Store and multiply just that run, widened to multiples
+    // of 16 columns; chunks 0 and 1 keep the full width because their first
+    // products zero-initialise the accumulators.
+    std::vector<int> cmin((size_t)chunks, n_pad), cmax((size_t)chunks, -1);
+    for (int64_t r = 0; r < l; ++r) {
+      const int64_t d = (r * m) / l;
+      for (int64_t ch = d / 32; ch <= (d + taps - 1) / 32; ++ch) {
+        cmin[(size_t)ch] = std::min(cmin[(size_t)ch], (int)r);
+        cmax[(size_t)ch] = std::max(cmax[(size_t)ch], (int)r);
+      }
+    }
+    std::vector<int4> meta((size_t)chunks);
+    size_t total_floats = 0;
+    for (int ch = 0; ch < chunks; ++ch) {
+      int col0 = 0, ncols = n_pad;
+      if (ch >= 2 && cmax[(size_t)ch] >= 0) {
+        col0 = cmin[(size_t)ch] / 16 * 16;
+        ncols = (cmax[(size_t)ch] + 1 - col0 + 15) / 16 * 16;
+      } else if (ch >= 2) {
+        ncols = 16;                                          // empty chunk: a zero slice
+      }
+      meta[(size_t)ch] = make_int4((int)(total_floats * 4), col0, ncols, 0);
+      total_floats += (size_t)2 * ncols * 32;
+    }
+    std::vector<float> img(total_floats, 0.0f);
     for (int64_t r = 0; r < l; ++r) {
       const int64_t d = (r * m) / l, ph = (r * m) % l;
       for (int64_t t = 0; t < taps; ++t) {
@@ -439,17 +465,23 @@ struct GemmDevice {
         std::memcpy(&hi, &bits, 4);
         const float lo = (float)(g - (double)hi);
         const int64_t ch = j / 32, kk = j % 32;
-        const size_t cell = (size_t)(r * 32 + ((((kk >> 2) ^ (r & 7)) << 2) | (kk & 3)));
-        img[((size_t)ch * 2 + 0) * n_pad * 32 + cell] = hi;
-        img[((size_t)ch * 2 + 1) * n_pad * 32 + cell] = lo;
+        const int4 mt = meta[(size_t)ch];
+        const int64_t rr = r - mt.y;                           // row inside the stored slice
+        const size_t cell = (size_t)(rr * 32 + ((((kk >> 2) ^ (rr & 7)) << 2) | (kk & 3)));
+        const size_t base = (size_t)mt.x / 4;
+        img[base + cell] = hi;
+        img[base + (size_t)mt.z * 32 + cell] = lo;
       }
     }
+    d_meta = upload(meta);
     d_images = upload(img);
     ok = true;
   }
   void release() {
     cudaFree(d_images);
+    cudaFree(d_meta);
     d_images = nullptr;
+    d_meta = nullptr;
   }
 };
 
@@ -496,6 +528,7 @@ struct smb_resample_plan {
       a.chunks = gemm[i].chunks;
       a.tmem_cols = gemm[i].tmem_cols;
       a.b_images = gemm[i].d_images;
+      a.chunk_meta = gemm[i].d_meta;
       CK(smb::launch_resample_gemm(a, batch, st));
     } else
       CK(smb::launch_polyphase_direct(x, batch, n, d_bank[i], (int)s.l, (int)s.m, (int)s.k,
@@ -723,10 +756,23 @@ void run_spectrum(smb_stft_plan* p, const void* dx, int64_t batch, const smb::Fr
 }
 
 void spectrum_call(const char* op, smb_stft_plan* p, const void* x, int64_t batch, int64_t n,
-                   int dtype, SpecKind kind, double power, void* out, int mem) {
+                   int dtype, SpecKind kind, double power, void* out, int mem,
+                   int64_t p0 = 0, int64_t p1 = -1) {
   check_signal(op, batch, n);
   const size_t esz = dtype_size(dtype);
-  const smb::FrameGeom g = p->frame_geom(n);
+  smb::FrameGeom g = p->frame_geom(n);
+  if (p1 >= 0) {
+    // transform_range (stft.ml:652-666): frames [p0, p1) of the full transform.
+    // Frame p0 + p' starts at padded position (p0 + p') hop, so shifting the
+    // left width by p0 hop makes the kernels' frame 0 the range's first frame.
+    if (p0 < 0 || p0 > p1 || p1 > g.frames)
+      throw smb::invalid_argument(smb::format(
+          "transform_range: cannot take frames [%lld, %lld) of a %lld-frame transform (the "
+          "range must satisfy 0 <= p0 <= p1 <= frames)",
+          (long long)p0, (long long)p1, (long long)g.frames));
+    g.left = (int)(g.left - p0 * g.hop);
+    g.frames = p1 - p0;
+  }
   const size_t out_elems =
       (size_t)batch * (size_t)p->geom.bins() * (size_t)g.frames * (kind == kSpecComplex ? 2 : 1);
   if (batch == 0 || g.frames == 0) return;       // frameless spectrum: nothing to write
@@ -757,6 +803,14 @@ int smb_stft_transform(smb_stft_plan* plan, const void* x, int64_t batch, int64_
                        int dtype, void* out, int mem) {
   return guarded([&] {
     spectrum_call("transform", plan, x, batch, n, dtype, kSpecComplex, 1.0, out, mem);
+  });
+}
+
+int smb_stft_transform_range(smb_stft_plan* plan, const void* x, int64_t batch, int64_t n,
+                             int dtype, int64_t p0, int64_t p1, void* out, int mem) {
+  return guarded([&] {
+    spectrum_call("transform_range", plan, x, batch, n, dtype, kSpecComplex, 1.0, out, mem, p0,
+                  p1 < 0 ? 0 : p1);
   });
 }
 

@@ -89,7 +89,8 @@ struct GemmResampleArgs {
   int n_pad;               // l rounded up to a multiple of 16 (UMMA N)
   int chunks;              // ceil(P / 32) K-chunks
   int tmem_cols;           // power of two >= 3 * n_pad
-  const float* b_images;   // [chunks][hi, lo][n_pad][32] pre-swizzled K-major tiles of G
+  const float* b_images;   // per chunk: [hi, lo][ncols][32] pre-swizzled K-major tiles of G
+  const int4* chunk_meta;  // per chunk: {byte offset into b_images, first column, columns, 0}
 };
 size_t resample_gemm_smem_bytes(int n_pad);
 cudaError_t launch_resample_gemm(const GemmResampleArgs& a, long long batch, cudaStream_t st);

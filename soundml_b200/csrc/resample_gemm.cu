@@ -167,16 +167,19 @@ resample_gemm_kernel(const GemmResampleArgs a) {
   if (warp == kMmaWarp) {
     // ===== B loader + MMA issuer (one elected lane) =====
     if (lane == 0) {
-      // instruction descriptor: D f32, A/B tf32, both K-major, N = n_pad, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
-                             ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+      // instruction descriptor: D f32, A/B tf32, both K-major, M = 128; N per chunk
+      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24);
       uint32_t used_main0 = 0, used_main1 = 0, used_corr = 0;
       const uint8_t* images = reinterpret_cast<const uint8_t*>(a.b_images);
+      // G is banded: chunk ch only touches columns [col0, col0 + ncols) of the
+      // accumulators, and only that slice of the image exists (chunk_meta).
       auto load_b = [&](int ch) {
         const int s = ch % kStages;
-        mbar_expect_tx(bar_b + 8 * s, 2 * b_bytes);
-        bulk_g2s(smem_u32(smem + s * stage_bytes + 2 * kABytes), images + (size_t)ch * 2 * b_bytes,
-                 2 * b_bytes, bar_b + 8 * s);
+        const int4 meta = __ldg(a.chunk_meta + ch);
+        const uint32_t bytes = 2u * (uint32_t)meta.z * 128u;
+        mbar_expect_tx(bar_b + 8 * s, bytes);
+        bulk_g2s(smem_u32(smem + s * stage_bytes + 2 * kABytes), images + meta.x, bytes,
+                 bar_b + 8 * s);
       };
       for (int ch = 0; ch < kStages && ch < a.chunks; ++ch) load_b(ch);
       for (int ch = 0; ch < a.chunks; ++ch) {
@@ -185,18 +188,21 @@ resample_gemm_kernel(const GemmResampleArgs a) {
         mbar_wait(bar_a + 8 * s, parity);
         mbar_wait(bar_b + 8 * s, parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int4 meta = __ldg(a.chunk_meta + ch);
+        const uint32_t idesc = idesc0 | ((uint32_t)(meta.z >> 3) << 17);
         const uint32_t a_hi = smem_u32(smem + s * stage_bytes), a_lo = a_hi + kABytes;
-        const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + b_bytes;
-        const uint32_t acc = (ch & 1) ? acc_main1 : acc_main0;
+        const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + (uint32_t)meta.z * 128u;
+        const uint32_t acc = ((ch & 1) ? acc_main1 : acc_main0) + (uint32_t)meta.y;
+        const uint32_t acc_c = acc_corr + (uint32_t)meta.y;
         uint32_t& used = (ch & 1) ? used_main1 : used_main0;
 #pragma unroll
         for (int ks = 0; ks < kChunk / 8; ++ks) {
           const uint32_t off = ks * 32;                             // 8 tf32 = 32 bytes along K
           umma_tf32(acc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, used);
           used = 1;
-          umma_tf32(acc_corr, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, used_corr);
+          umma_tf32(acc_c, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, used_corr);
           used_corr = 1;
-          umma_tf32(acc_corr, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+          umma_tf32(acc_c, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
         }
         umma_commit(bar_empty + 8 * s);
         if (ch == a.chunks - 1) umma_commit(bar_done);

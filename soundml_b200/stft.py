@@ -124,6 +124,31 @@ def transform(c, x, out=None):
     return _run("transform", c, x, True, 1.0, out)
 
 
+def transform_range(c, x, p0, p1):
+    """``Stft.transform_range cdtype c ~p0 ~p1 x`` (stft.ml:652-666): frames
+    ``[p0, p1)`` of ``transform c x`` without evaluating the others."""
+    _check_rank("transform_range", x)
+    x = _lib.contiguous(x)
+    n = int(x.shape[-1])
+    lead = tuple(int(d) for d in x.shape[:-1])
+    batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    total = frames(c, n)
+    if p0 < 0 or p0 > p1 or p1 > total:
+        raise ValueError(
+            f"transform_range: cannot take frames [{p0}, {p1}) of a {total}-frame transform "
+            "(the range must satisfy 0 <= p0 <= p1 <= frames)")
+    out = _lib.empty_like_kind(x, lead + (c.bins, p1 - p0), True)
+    if batch == 0 or p1 == p0:
+        return out
+    ptr, mem, dtype = _lib.describe(x)
+    stream = _lib.current_stream(x)
+    if stream is not None:
+        _lib.check(_lib.lib.smb_stft_plan_set_stream(c._h, stream))
+    _lib.check(_lib.lib.smb_stft_transform_range(c._h, ptr, batch, n, dtype, int(p0), int(p1),
+                                                 _lib.out_pointer(out), mem))
+    return out
+
+
 def power_spectrum(c, x, power=2.0, out=None):
     """``Stft.power_spectrum ?power c x`` (stft.ml:687-691)."""
     return _run("power_spectrum", c, x, False, power, out)

@@ -287,3 +287,20 @@ def test_parseval_at_scale(sb):
     lhs = (p.double() * weights[None, :, None]).sum(1)        # [96, 431]
     rel = ((lhs - energy).abs() / energy).max().item()
     assert rel <= 2e-6, rel
+
+
+@pytest.mark.parametrize("fft,hop,path", [(2048, 512, "fast"), (2048, 300, "fast"), (64, 16, "generic")])
+def test_transform_range_tiles_the_full_transform(sb, fft, hop, path):
+    """stft_grid.ml:32-73: adjacent ranges reassemble the transform exactly."""
+    x = np.stack([_signal(20000, 21), _signal(20000, 22)])
+    c = sb.Stft.Config.create(fft_size=fft, hop=hop).set_path(path)
+    full = sb.Stft.transform(c, x)
+    total = sb.Stft.frames(c, 20000)
+    cuts = [0, 1, 7, 8, 9, total // 2, total - 1, total]
+    parts = [sb.Stft.transform_range(c, x, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts, axis=-1), full)
+    assert sb.Stft.transform_range(c, x, 5, 5).shape == (2, fft // 2 + 1, 0)
+    with pytest.raises(ValueError, match=r"transform_range: cannot take frames \[3, 2\)"):
+        sb.Stft.transform_range(c, x, 3, 2)
+    with pytest.raises(ValueError, match=r"the range must satisfy 0 <= p0 <= p1 <= frames"):
+        sb.Stft.transform_range(c, x, 0, total + 1)
