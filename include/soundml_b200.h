@@ -203,6 +203,11 @@ int64_t smb_resample_output_frames(const smb_resample_plan* plan, int64_t n);
 int smb_resample_apply(smb_resample_plan* plan, const float* x, int64_t batch,
                        int64_t n, float* out, int mem);
 
+/* Same for float64 audio (the reference carries both, resample.ml:72-84); runs
+ * the direct polyphase kernel in double. */
+int smb_resample_apply_f64(smb_resample_plan* plan, const double* x, int64_t batch,
+                           int64_t n, double* out, int mem);
+
 /* ---- FIR ------------------------------------------------------------------ */
 /* y[c,i] = sum_t h[t] * x[c, i + (taps-1)/2 - t], zeros outside, taps odd.
  * method: SMB_EXEC_DIRECT or SMB_EXEC_OLS (overlap-save on the rFFT kernels). */

@@ -101,6 +101,7 @@ SIGNATURES = {
     "smb_resample_stage_prototype": (_int, [_vp, _int, _pd, _pi64]),
     "smb_resample_output_frames": (_i64, [_vp, _i64]),
     "smb_resample_apply": (_int, [_vp, _vp, _i64, _i64, _vp, _int]),
+    "smb_resample_apply_f64": (_int, [_vp, _vp, _i64, _i64, _vp, _int]),
     "smb_fir_plan_create": (_int, [_pvp, _pd, _i64]),
     "smb_fir_plan_destroy": (_int, [_vp]),
     "smb_fir_plan_set_stream": (_int, [_vp, _vp]),

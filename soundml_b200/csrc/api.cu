@@ -490,6 +490,7 @@ struct smb_resample_plan {
   bool device_ready = false;
   StreamOwner stream;
   std::vector<float*> d_bank;        // per stage, [l][2k+1] float32
+  std::vector<double*> d_bank64;     // the same banks uncast, for float64 audio
   std::vector<OlsDevice> ols;        // per stage; plan.ok only for OLS-tagged power-of-two stages
   std::vector<GemmDevice> gemm;      // per stage; ok only for GEMM-tagged stages with L <= 160
   int executor = SMB_EXEC_PLANNED;   // SMB_EXEC_DIRECT forces the dot-product kernel everywhere
@@ -502,6 +503,7 @@ struct smb_resample_plan {
       std::vector<float> b(s.bank.size());
       for (size_t i = 0; i < b.size(); ++i) b[i] = (float)s.bank[i];   // cast at prepare
       d_bank.push_back(upload(b));
+      d_bank64.push_back(upload(s.bank));
       ols.emplace_back();
       ols.back().upload_from(smb::ols_plan_for_stage(s));
       gemm.emplace_back();
@@ -537,6 +539,7 @@ struct smb_resample_plan {
   ~smb_resample_plan() {
     if (!device_ready) return;
     for (float* p : d_bank) cudaFree(p);
+    for (double* p : d_bank64) cudaFree(p);
     for (OlsDevice& o : ols) o.release();
     for (GemmDevice& g : gemm) g.release();
     in.release();
@@ -1068,6 +1071,51 @@ int smb_resample_apply(smb_resample_plan* plan, const float* x, int64_t batch, i
       float* mid = (float*)plan->mid.ensure((size_t)batch * n1 * 4);
       plan->run_stage(0, din, batch, n, n1, mid, st);
       plan->run_stage(1, mid, batch, n1, total, dout, st);
+    }
+    if (mem == SMB_MEM_HOST) {
+      CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  });
+}
+
+// float64 audio: the reference's executor carries both dtypes (resample.ml:72-84);
+// here double always takes the direct kernel, in double.
+int smb_resample_apply_f64(smb_resample_plan* plan, const double* x, int64_t batch, int64_t n,
+                           double* out, int mem) {
+  return guarded([&] {
+    if (batch < 0) throw smb::invalid_argument("apply: negative batch");
+    const smb::ResamplePlan& rp = plan->plan;
+    const int64_t total = rp.output_frames(n);
+    if (batch == 0 || n == 0 || total == 0) return;
+    plan->ensure_device();
+    cudaStream_t st = plan->stream.use;
+    const size_t in_bytes = (size_t)batch * n * 8, out_bytes = (size_t)batch * total * 8;
+    const double* din = x;
+    double* dout = out;
+    if (mem == SMB_MEM_HOST) {
+      double* stage = (double*)plan->in.ensure(in_bytes);
+      dout = (double*)plan->out.ensure(out_bytes);
+      CK(cudaMemcpyAsync(stage, x, in_bytes, cudaMemcpyHostToDevice, st));
+      din = stage;
+    } else if (mem != SMB_MEM_DEVICE) {
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    }
+    auto stage_run = [&](size_t i, const double* src, int64_t len, int64_t n_out, double* dst) {
+      const smb::ResampleStage& s = rp.stages[i];
+      CK(smb::launch_polyphase_direct_f64(src, batch, len, plan->d_bank64[i], (int)s.l, (int)s.m,
+                                          (int)s.k, n_out, dst, st));
+    };
+    if (rp.identity()) {
+      CK(cudaMemcpyAsync(dout, din, in_bytes, cudaMemcpyDeviceToDevice, st));
+    } else if (rp.stages.size() == 1) {
+      stage_run(0, din, n, total, dout);
+    } else {
+      const smb::ResampleStage& s1 = rp.stages[0];
+      const int64_t n1 = (n * s1.l + s1.m - 1) / s1.m;
+      double* mid = (double*)plan->mid.ensure((size_t)batch * n1 * 8);
+      stage_run(0, din, n, n1, mid);
+      stage_run(1, mid, n1, total, dout);
     }
     if (mem == SMB_MEM_HOST) {
       CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));

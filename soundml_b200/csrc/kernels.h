@@ -67,6 +67,11 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
 cudaError_t launch_polyphase_direct(const float* x, long long batch, long long n,
                                     const float* bank, int l, int m, int k,
                                     long long n_out, float* out, cudaStream_t st);
+// float64 audio: the same kernel in double (the reference's executor carries
+// float32 and float64, resample.ml:72-84).
+cudaError_t launch_polyphase_direct_f64(const double* x, long long batch, long long n,
+                                        const double* bank, int l, int m, int k,
+                                        long long n_out, double* out, cudaStream_t st);
 
 // Overlap-save stage (FIR, xL, /M) on half-length complex FFTs.
 struct OlsArgs {

@@ -87,20 +87,20 @@ class Config:
         return out
 
 
-def _check(op, x):
+def _check(op, x, allow_f64=False):
     if x.ndim < 1:
         raise ValueError(f"{op}: cannot resample a rank-zero tensor (the time axis must exist)")
     ptr, mem, dtype = _lib.describe(x)
-    if dtype != _lib.F32:
-        raise ValueError(f"{op}: this build's resampler carries float32 audio only")
-    return ptr, mem
+    if dtype != _lib.F32 and not allow_f64:
+        raise ValueError(f"{op}: this kernel carries float32 audio only")
+    return ptr, mem, dtype
 
 
 def apply(c, x, out=None):
     """``Resample.apply c x`` (resample.ml:1913-1936): ``[..., n]`` ->
     ``[..., ceil(n*L/M)]``."""
     x = _lib.contiguous(x)
-    ptr, mem = _check("apply", x)
+    ptr, mem, dtype = _check("apply", x, allow_f64=True)
     n = int(x.shape[-1])
     lead = tuple(int(d) for d in x.shape[:-1])
     batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
@@ -111,7 +111,8 @@ def apply(c, x, out=None):
     stream = _lib.current_stream(x)
     if stream is not None:
         _lib.check(_lib.lib.smb_resample_plan_set_stream(c._h, stream))
-    _lib.check(_lib.lib.smb_resample_apply(c._h, ptr, batch, n, _lib.out_pointer(out), mem))
+    fn = _lib.lib.smb_resample_apply if dtype == _lib.F32 else _lib.lib.smb_resample_apply_f64
+    _lib.check(fn(c._h, ptr, batch, n, _lib.out_pointer(out), mem))
     return out
 
 
@@ -143,7 +144,7 @@ class Fir:
 
     def apply(self, x, method="direct", out=None):
         x = _lib.contiguous(x)
-        ptr, mem = _check("fir", x)
+        ptr, mem, _ = _check("fir", x)
         n = int(x.shape[-1])
         lead = tuple(int(d) for d in x.shape[:-1])
         batch = int(np.prod(lead, dtype=np.int64)) if lead else 1

@@ -85,8 +85,20 @@ def test_identity_and_flat_api(sb):
     assert np.array_equal(sb.Resample.apply(cfg, x), x)
     y = sb.resample(x, sample_rate=44100, target=22050)
     assert y.shape == (2, 389)
+    assert np.array_equal(sb.Resample.apply(cfg, x.astype(np.float64)), x.astype(np.float64))
     with pytest.raises(ValueError, match="float32 audio only"):
-        sb.Resample.apply(cfg, x.astype(np.float64))
+        sb.Fir(np.ones(3)).apply(x.astype(np.float64))
+
+
+@pytest.mark.parametrize("sr,target", [(44100, 48000), (44100, 16000), (48000, 8000), (22050, 44100)])
+def test_float64_audio_matches_oracle_tightly(sb, sr, target):
+    """The reference resamples float32 and float64 (resample.ml:72-84)."""
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
+    x = np.random.default_rng(sr).uniform(-1, 1, (2, 4000))
+    got = sb.Resample.apply(cfg, x)
+    want = R.apply_plan(x, oracle_stages(cfg), cfg.l, cfg.m)
+    assert got.dtype == np.float64 and got.shape == want.shape
+    assert np.abs(got - want).max() / np.abs(want).max() <= 1e-13
 
 
 def test_device_tensors(sb):
