@@ -164,6 +164,21 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x,
                         int64_t batch, int64_t n, int dtype, double power, void* out,
                         int mem);
 
+/* ---- dB conversion and MFCC ------------------------- */
+/* Convert.power_to_db / amplitude_to_db ?reference ?amin ?top_db (convert.ml:20-56):
+ * elementwise over `count` values in the input's dtype; top_db = NaN means "no
+ * clamp", otherwise the clamp sits top_db below the maximum of the whole tensor.
+ * Runs on `cuda_stream` (NULL = default stream) and returns when done. */
+int smb_power_to_db(const void* x, int64_t count, int dtype, double reference, double amin,
+                    double top_db, void* out, int mem, void* cuda_stream);
+int smb_amplitude_to_db(const void* x, int64_t count, int dtype, double reference, double amin,
+                        double top_db, void* out, int mem, void* cuda_stream);
+/* Soundml.mfcc stft mel ?n_mfcc ?lifter x (soundml.ml:50-95): x [batch, n] ->
+ * out [batch, n_mfcc, frames]; lifter = NaN or 0 means none.  Log-mel with the
+ * 80 dB clamp below the whole-tensor maximum, orthonormal DCT-II, in double. */
+int smb_mfcc(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batch, int64_t n,
+             int dtype, int64_t n_mfcc, double lifter, void* out, int mem);
+
 /* ---- resampler ------------------------------------------------------------ */
 /* Resample.Config.create ?quality ~sample_rate ~target; attenuation/passband
  * are read only for SMB_QUALITY_CUSTOM. */

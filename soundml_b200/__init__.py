@@ -7,17 +7,21 @@ for sm_100a behind the C ABI in ``include/soundml_b200.h``).
 """
 import numpy as np
 
-from . import _lib, mel, stft, window
+import math
+
+from . import _lib, convert, mel, stft, window
 from . import resample as _resample_mod
 from ._lib import SoundmlError
 
 Stft = stft
 Mel = mel
 Window = window
+Convert = convert
 Resample = _resample_mod
 Fir = _resample_mod.Fir
 
-__all__ = ["Stft", "Mel", "Window", "Resample", "Fir", "mel_spectrogram", "resample",
+__all__ = ["Stft", "Mel", "Window", "Convert", "Resample", "Fir", "mel_spectrogram", "mfcc",
+           "resample",
            "kernel_launch_count", "SoundmlError"]
 
 
@@ -47,6 +51,31 @@ def mel_spectrogram(stft_config, mel_config, x, power=2.0, out=None):
         _lib.check(_lib.lib.smb_stft_plan_set_stream(stft_config._h, stream))
     _lib.check(_lib.lib.smb_mel_spectrogram(stft_config._h, mel_config._h, ptr, batch, n, dtype,
                                             float(power), _lib.out_pointer(out), mem))
+    return out
+
+
+def mfcc(stft_config, mel_config, x, n_mfcc=20, lifter=None):
+    """``Soundml.mfcc stft mel ?n_mfcc ?lifter x`` (soundml.ml:50-95):
+    ``[..., n]`` -> ``[..., n_mfcc, frames]``."""
+    if x.ndim < 1:
+        raise ValueError("power_spectrum: cannot analyse a rank-zero tensor "
+                         "(the time axis must exist)")
+    x = _lib.contiguous(x)
+    ptr, mem, dtype = _lib.describe(x)
+    n = int(x.shape[-1])
+    lead = tuple(int(d) for d in x.shape[:-1])
+    batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    lift = math.nan if lifter is None else float(lifter)
+    count = stft.frames(stft_config, n)
+    empty = batch == 0 or count == 0
+    out = _lib.empty_like_kind(x, lead + (int(n_mfcc), count))
+    stream = _lib.current_stream(x)
+    if stream is not None:
+        _lib.check(_lib.lib.smb_stft_plan_set_stream(stft_config._h, stream))
+    # argument checks run in the library even when there is nothing to compute
+    _lib.check(_lib.lib.smb_mfcc(stft_config._h, mel_config._h, None if empty else ptr,
+                                 0 if empty else batch, n, dtype, int(n_mfcc), lift,
+                                 None if empty else _lib.out_pointer(out), mem))
     return out
 
 

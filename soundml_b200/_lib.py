@@ -86,6 +86,9 @@ SIGNATURES = {
     "smb_mel_filterbank": (_int, [_vp, _pd]),
     "smb_mel_apply": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _int]),
     "smb_mel_spectrogram": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _dbl, _vp, _int]),
+    "smb_power_to_db": (_int, [_vp, _i64, _int, _dbl, _dbl, _dbl, _vp, _int, _vp]),
+    "smb_amplitude_to_db": (_int, [_vp, _i64, _int, _dbl, _dbl, _dbl, _vp, _int, _vp]),
+    "smb_mfcc": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _i64, _dbl, _vp, _int]),
     "smb_resample_plan_create": (_int, [_pvp, _i64, _i64, _int, _dbl, _dbl]),
     "smb_resample_plan_destroy": (_int, [_vp]),
     "smb_resample_plan_set_stream": (_int, [_vp, _vp]),

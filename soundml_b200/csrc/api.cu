@@ -195,7 +195,8 @@ struct smb_stft_plan {
   float2* d_tw_pass = nullptr;
   float2* d_tw_post = nullptr;
   HostPipe pipe;
-  DeviceBuffer tmp;
+  DeviceBuffer tmp;        // power spectrogram of the generic mel path
+  DeviceBuffer cepstral;   // mel spectrogram (+ host-call output) of the MFCC path
 
   void ensure_device() {
     if (device_ready) return;
@@ -251,6 +252,7 @@ struct smb_stft_plan {
     cudaFree(d_tw_post);
     pipe.release();
     tmp.release();
+    cepstral.release();
     stream.destroy();
   }
 };
@@ -272,6 +274,30 @@ struct smb_mel_plan {
   float* d_vals = nullptr;
   smb::MelLane* d_mel_lanes = nullptr;
   DeviceBuffer in, out;
+  // MFCC epilogue: DCT table of the last (n_mfcc, lifter) asked for, max scratch
+  double* d_dct = nullptr;
+  unsigned long long* d_max = nullptr;
+  int64_t dct_n_mfcc = -1;
+  double dct_lifter = -1.0;
+  const double* dct_table(int64_t n_mfcc, double lifter) {
+    if (d_dct && dct_n_mfcc == n_mfcc && dct_lifter == lifter) return d_dct;
+    // raw DCT-II rows 2 cos(pi k (2m+1) / 2N), orthonormal scales and lifter folded
+    // in (soundml.ml:26-43, 84-93), all in double
+    std::vector<double> t((size_t)(n_mfcc * n_mels));
+    const double pi = 3.14159265358979323846;
+    for (int64_t k = 0; k < n_mfcc; ++k) {
+      double w = k == 0 ? 1.0 / std::sqrt(4.0 * double(n_mels)) : 1.0 / std::sqrt(2.0 * double(n_mels));
+      if (lifter > 0.0) w *= 1.0 + lifter / 2.0 * std::sin(pi * double(k + 1) / lifter);
+      for (int64_t m = 0; m < n_mels; ++m)
+        t[(size_t)(k * n_mels + m)] =
+            2.0 * std::cos(pi * double(k) * double(2 * m + 1) / (2.0 * double(n_mels))) * w;
+    }
+    cudaFree(d_dct);
+    d_dct = upload(t);
+    dct_n_mfcc = n_mfcc;
+    dct_lifter = lifter;
+    return d_dct;
+  }
 
   void finish_host() {
     band_lo.assign((size_t)n_mels, 0);
@@ -356,6 +382,7 @@ struct smb_mel_plan {
     d_band_hi = upload(band_hi);
     d_vals = upload(vals);
     d_mel_lanes = upload(mel_lanes);
+    CK(cudaMalloc(&d_max, sizeof(unsigned long long)));
     device_ready = true;
   }
   ~smb_mel_plan() {
@@ -365,6 +392,8 @@ struct smb_mel_plan {
     cudaFree(d_band_hi);
     cudaFree(d_vals);
     cudaFree(d_mel_lanes);
+    cudaFree(d_dct);
+    cudaFree(d_max);
     in.release();
     out.release();
     stream.destroy();
@@ -955,6 +984,134 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
                          (size_t)mel->n_mels * g.frames * esz, run);
     } else {
       throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    }
+  });
+}
+
+// ---- dB conversion and MFCC ------------------------------------------------------
+
+}  // extern "C"
+
+namespace {
+
+const double kDecade = 10.0 / std::log(10.0);     // convert.ml:27
+
+void to_db_call(const char* fn, double gain, int magnitude, const void* x, int64_t count,
+                int dtype, double reference, double amin, double top_db, void* out, int mem,
+                void* stream) {
+  // convert.ml:8-22: checks in the reference's order and wording
+  if (!(std::isfinite(reference) && reference > 0.0))
+    throw smb::invalid_argument(smb::format("Soundml.Convert.%s: reference must be finite and positive", fn));
+  if (!(std::isfinite(amin) && amin > 0.0))
+    throw smb::invalid_argument(smb::format("Soundml.Convert.%s: amin must be finite and positive", fn));
+  const bool clamp = !std::isnan(top_db);
+  if (clamp && !(std::isfinite(top_db) && top_db >= 0.0))
+    throw smb::invalid_argument(smb::format("Soundml.Convert.%s: top_db must be finite and non-negative", fn));
+  if (count < 0) throw smb::invalid_argument("to_db: negative extent");
+  const size_t esz = dtype_size(dtype);
+  if (count == 0) return;
+  require_device();
+  cudaStream_t st = (cudaStream_t)stream;
+  const double scale = gain / 10.0 * kDecade;
+  const double offset = scale * std::log(std::max(amin, reference));
+  unsigned long long* slot = nullptr;
+  CK(cudaMalloc(&slot, sizeof(unsigned long long)));
+  void *din = nullptr, *dout = nullptr;
+  try {
+    const void* src = x;
+    void* dst = out;
+    if (mem == SMB_MEM_HOST) {
+      CK(cudaMalloc(&din, (size_t)count * esz));
+      CK(cudaMalloc(&dout, (size_t)count * esz));
+      CK(cudaMemcpyAsync(din, x, (size_t)count * esz, cudaMemcpyHostToDevice, st));
+      src = din;
+      dst = dout;
+    } else if (mem != SMB_MEM_DEVICE) {
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    }
+    CK(smb::launch_to_db(src, count, dtype, magnitude, amin, scale, offset, clamp,
+                         clamp ? top_db : 0.0, slot, dst, st));
+    if (mem == SMB_MEM_HOST)
+      CK(cudaMemcpyAsync(out, dout, (size_t)count * esz, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  } catch (...) {
+    cudaFree(slot);
+    cudaFree(din);
+    cudaFree(dout);
+    throw;
+  }
+  cudaFree(slot);
+  cudaFree(din);
+  cudaFree(dout);
+}
+
+}  // namespace
+
+extern "C" {
+
+int smb_power_to_db(const void* x, int64_t count, int dtype, double reference, double amin,
+                    double top_db, void* out, int mem, void* cuda_stream) {
+  return guarded([&] {
+    to_db_call("power_to_db", 10.0, 0, x, count, dtype, reference, amin, top_db, out, mem, cuda_stream);
+  });
+}
+int smb_amplitude_to_db(const void* x, int64_t count, int dtype, double reference, double amin,
+                        double top_db, void* out, int mem, void* cuda_stream) {
+  return guarded([&] {
+    to_db_call("amplitude_to_db", 20.0, 1, x, count, dtype, reference, amin, top_db, out, mem,
+               cuda_stream);
+  });
+}
+
+int smb_mfcc(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batch, int64_t n,
+             int dtype, int64_t n_mfcc, double lifter, void* out, int mem) {
+  return guarded([&] {
+    // soundml.ml:50-70
+    if (stft->geom.fft != mel->fft)
+      throw smb::invalid_argument(smb::format(
+          "mfcc: cannot project a %lld-point STFT through a filterbank built for an FFT of size "
+          "%lld (the two configurations must agree on fft_size)",
+          (long long)stft->geom.fft, (long long)mel->fft));
+    if (n_mfcc < 1 || n_mfcc > mel->n_mels)
+      throw smb::invalid_argument(smb::format(
+          "mfcc: cannot keep %lld cepstral coefficients of %lld mel bands (n_mfcc must lie in "
+          "[1, n_mels])", (long long)n_mfcc, (long long)mel->n_mels));
+    const bool has_lifter = !std::isnan(lifter);
+    if (has_lifter && !(std::isfinite(lifter) && lifter >= 0.0))
+      throw smb::invalid_argument(smb::format(
+          "mfcc: cannot lifter with a coefficient of %g (lifter must be finite and non-negative)",
+          lifter));
+    check_signal("power_spectrum", batch, n);
+    const size_t esz = dtype_size(dtype);
+    const smb::FrameGeom g = stft->frame_geom(n);
+    if (batch == 0 || g.frames == 0) return;
+    stft->ensure_device();
+    mel->ensure_device();
+    cudaStream_t st = stft->stream.use;
+    // log-mel needs the whole-tensor maximum, so the mel spectrogram is
+    // materialised (plan-owned), then reduced, then transformed
+    const size_t mel_bytes = (size_t)batch * mel->n_mels * g.frames * esz;
+    const size_t out_bytes = (size_t)batch * n_mfcc * g.frames * esz;
+    void* dmel = stft->cepstral.ensure(mel_bytes + out_bytes);
+    void* dout = mem == SMB_MEM_HOST ? (void*)((char*)dmel + mel_bytes) : out;
+    const int inner_mem = mem == SMB_MEM_HOST ? SMB_MEM_HOST : SMB_MEM_DEVICE;
+    const void* din = x;
+    if (inner_mem == SMB_MEM_HOST) {
+      void* stage = stft->pipe.in[0].ensure((size_t)batch * n * esz);
+      CK(cudaMemcpyAsync(stage, x, (size_t)batch * n * esz, cudaMemcpyHostToDevice, st));
+      din = stage;
+    } else if (mem != SMB_MEM_DEVICE) {
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    }
+    if (smb_mel_spectrogram(stft, mel, din, batch, n, dtype, 2.0, dmel, SMB_MEM_DEVICE) != SMB_OK)
+      throw cuda_failure(t_error);
+    const double scale = kDecade, offset = scale * std::log(1.0);   // reference 1, amin 1e-10
+    CK(smb::launch_mfcc(dmel, dtype, batch, (int)mel->n_mels, g.frames, (int)n_mfcc,
+                        mel->dct_table(n_mfcc, has_lifter ? lifter : 0.0), mel->d_max, 1e-10,
+                        scale, offset, 80.0, dout, st));
+    if (mem == SMB_MEM_HOST) {
+      CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
     }
   });
 }

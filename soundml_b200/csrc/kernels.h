@@ -73,6 +73,14 @@ cudaError_t launch_polyphase_direct_f64(const double* x, long long batch, long l
                                         const double* bank, int l, int m, int k,
                                         long long n_out, double* out, cudaStream_t st);
 
+// Decibel conversion (convert.ml:20-56) and the MFCC epilogue (soundml.ml:50-95).
+cudaError_t launch_to_db(const void* x, long long count, int dtype, int magnitude, double amin,
+                         double scale, double offset, bool clamp, double range,
+                         unsigned long long* max_slot, void* out, cudaStream_t st);
+cudaError_t launch_mfcc(const void* mel, int dtype, long long batch, int n_mels, long long frames,
+                        int n_mfcc, const double* dct, unsigned long long* max_slot, double amin,
+                        double scale, double offset, double range, void* out, cudaStream_t st);
+
 // Overlap-save stage (FIR, xL, /M) on half-length complex FFTs.
 struct OlsArgs {
   const float* x;        // [batch, n]

@@ -10,7 +10,8 @@ Reads the librosa-0.11 / SoXR golden JSON files of the reference test suites
 
     soundml/test/window/vectors/*.json
     soundml/test/stft/vectors/*.json
-    soundml/test/mel/vectors/{filterbank,mel_spectrogram}.json
+    soundml/test/mel/vectors/{filterbank,mel_spectrogram,mfcc}.json
+    soundml/test/db/vectors/*.json
     soundml/test/resample/vectors/soxr_reference.json
 
 and writes ``tests/golden/reference_vectors.npz``: one float64 array per case
@@ -32,7 +33,9 @@ SUITES = {
     "window": sorted(glob.glob(f"{REF}/window/vectors/*.json")),
     "stft": sorted(glob.glob(f"{REF}/stft/vectors/*.json")),
     "mel": [f"{REF}/mel/vectors/filterbank.json",
-            f"{REF}/mel/vectors/mel_spectrogram.json"],
+            f"{REF}/mel/vectors/mel_spectrogram.json",
+            f"{REF}/mel/vectors/mfcc.json"],
+    "db": sorted(glob.glob(f"{REF}/db/vectors/*.json")),
     "resample": [f"{REF}/resample/vectors/soxr_reference.json"],
 }
 
@@ -45,7 +48,10 @@ def main():
             doc = json.load(open(path))
             for case in doc["cases"]:
                 key = f"{suite}/{stem}/{case['name']}"
-                entry = {"params": case["params"]}
+                params = dict(case["params"])
+                if "input" in params:          # db suite: the input rides in the params
+                    arrays[key + "#input"] = np.asarray(params.pop("input"), dtype=np.float64)
+                entry = {"params": params}
                 if "values" in case:
                     arrays[key] = np.asarray(case["values"], dtype=np.float64)
                     entry["shape"] = case["shape"]

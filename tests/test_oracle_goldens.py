@@ -107,3 +107,38 @@ def test_reflect_index_matches_numpy_pad():
             if want is not None:
                 assert np.array_equal(padded, want)
         assert padded.shape[-1] == n + 16
+
+
+def test_db_goldens(goldens):
+    """convert.ml to_db against the reference's librosa vectors
+    (soundml/test/db/test_golden.ml:52-57: f32 1e-4/1e-4, f64 1e-10/1e-10)."""
+    from oracle import convert_oracle
+    n = 0
+    for key, stem, name, e in goldens.cases("db"):
+        p = e["params"]
+        x = goldens.arrays[key + "#input"].reshape(e["shape"]).astype(p["dtype"])
+        fn = convert_oracle.power_to_db if p["function"] == "power_to_db" else convert_oracle.amplitude_to_db
+        got = fn(x, p["reference"], p["amin"], p["top_db"])
+        tol = 1e-10 if p["dtype"] == "float64" else 1e-4
+        assert_close(got, goldens.values(key), tol, tol, key)
+        n += 1
+    assert n == 18
+
+
+def test_mfcc_goldens(goldens):
+    """soundml.ml mfcc (mel_goldens.ml:134-157: f64 rtol 1e-9 / atol 1e-9, f32 1e-4 / 1e-4)."""
+    from oracle import convert_oracle
+    n = 0
+    for key, stem, name, e in goldens.cases("mel", "mfcc"):
+        p = e["params"]
+        sc = stft_oracle.StftConfig(p["fft_size"], p["hop"], alignment=p["alignment"])
+        mc = mel_oracle.MelConfig(p["n_mels"], p["sample_rate"], p["fft_size"], p["f_min"],
+                                  p["f_max"], p["scale"], p["norm"])
+        x = lcg_signal(p["length"], MEL_SEED, p["envelope"])
+        if p["dtype"] == "float32":
+            x = x.astype(np.float32)
+        got = convert_oracle.mfcc(sc, mc, x, p["n_mfcc"], p["lifter"] if p["lifter"] > 0 else None)
+        tol = (1e-9, 1e-9) if p["dtype"] == "float64" else (1e-4, 1e-4)
+        assert_close(got, goldens.values(key), tol[0], tol[1], key)
+        n += 1
+    assert n == 9
