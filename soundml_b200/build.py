@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libsoundml_b200.so")
 CUDA_SOURCES = ["api.cu", "kernels_generic.cu", "stft2048.cu", "resample_kernels.cu",
                 "ols_kernels.cu", "resample_gemm.cu", "db_kernels.cu"]
 HOST_SOURCES = ["host_design.cpp"]
-HEADERS = ["host_design.h", "kernels.h", os.path.join("..", "..", "include", "soundml_b200.h")]
+HEADERS = ["host_design.h", "kernels.h", "fft32.cuh", os.path.join("..", "..", "include", "soundml_b200.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

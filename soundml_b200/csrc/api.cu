@@ -265,7 +265,7 @@ struct smb_mel_plan {
   std::vector<int> band_lo, band_hi;
   // band storage for the fused kernel: filter m keeps bins [lo, lo+len)
   std::vector<float> vals;
-  std::vector<smb::MelLane> mel_lanes;   // [8 warps][mel_rounds][4 lane groups]
+  std::vector<smb::MelLane> mel_lanes;   // [kFastTile warps][mel_rounds][kFastRoundFilters]
   int mel_rounds = 0;
   bool device_ready = false;
   StreamOwner stream;
@@ -316,46 +316,69 @@ struct smb_mel_plan {
     }
     if (!small || bins + 3 > 32767) return;
     // Schedule for the fused kernel.  Filters sorted by band length are cut into
-    // quads; the four bands of a quad are stored zero-padded to one common length
-    // (a whole number of 8-float steps, starting on a float4 of the 16-byte
-    // aligned power row), so the four lane groups of a warp run them in lock
-    // step.  Quads go to the 8 warps longest-first onto the lightest warp.
+    // rounds of kFastRoundFilters (two sets A and B); a warp lane is (filter j,
+    // frame f) and walks its A and B filter together.  The bands of a round are
+    // stored zero-padded to one common length (a whole number of 8-float steps,
+    // starting on a float4 of the 16-byte aligned power row) and interleaved
+    // [step][set][half][j] x float4, so every weight load of a warp is one
+    // contiguous run.  With 4-frame tiles two neighbouring filters (j even, j
+    // odd) share a quarter-warp: their band starts are then kept an odd number of
+    // float4s apart, which with the kernel's row stride (8 mod 32) keeps the
+    // power-row loads conflict-free.  Rounds go to the group's warps
+    // longest-first onto the lightest warp.
     const int row_floats = (int)((bins + 3) / 4 * 4);        // the kernel zeroes the row tail
     std::vector<int> order((size_t)n_mels);
     for (int64_t m = 0; m < n_mels; ++m) order[(size_t)m] = (int)m;
     auto span = [&](int m) { return band_hi[(size_t)m] - (band_lo[(size_t)m] & ~3); };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return span(a) > span(b); });
-    const int warps = 8;
-    const int quads = (int)((n_mels + 3) / 4);
-    struct Quad { int n8; smb::MelLane lane[4]; };
-    std::vector<Quad> built((size_t)quads);
+    const int warps = smb::kFastTile, lf = smb::kFastLaneFilters, per_round = smb::kFastRoundFilters;
+    const int rounds_total = (int)((n_mels + per_round - 1) / per_round);
+    struct Round { int n8; smb::MelLane lane[smb::kFastRoundFilters]; };
+    std::vector<Round> built((size_t)rounds_total);
     bool fits = n_mels <= 255;
-    for (int q = 0; q < quads && fits; ++q) {
-      int longest = 0;
-      for (int j = 0; j < 4; ++j)
-        if ((size_t)(q * 4 + j) < order.size()) longest = std::max(longest, span(order[(size_t)(q * 4 + j)]));
-      const int n8 = std::max(1, (longest + 7) / 8);
+    for (int q = 0; q < rounds_total && fits; ++q) {
+      int member[smb::kFastRoundFilters], slo[smb::kFastRoundFilters];
+      for (int t = 0; t < per_round; ++t) {
+        const size_t at = (size_t)(q * per_round + t);
+        member[t] = at < order.size() ? order[at] : -1;
+        slo[t] = member[t] >= 0 ? (band_lo[(size_t)member[t]] & ~3) : 0;
+      }
+      for (int t = 0; t < per_round && smb::kFastTile == 4; t += 2) {
+        if (member[t] < 0 || member[t + 1] < 0) continue;
+        if ((((slo[t] ^ slo[t + 1]) >> 2) & 1) == 0) {
+          if (slo[t + 1] >= 4) slo[t + 1] -= 4;
+          else if (slo[t] >= 4) slo[t] -= 4;
+        }
+      }
+      int n8 = 1;
+      for (int t = 0; t < per_round; ++t)
+        if (member[t] >= 0) n8 = std::max(n8, (band_hi[(size_t)member[t]] - slo[t] + 7) / 8);
       if (n8 * 8 > row_floats || n8 > 255) { fits = false; break; }
       built[(size_t)q].n8 = n8;
-      for (int j = 0; j < 4; ++j) {
-        smb::MelLane& ln = built[(size_t)q].lane[j];
+      const size_t base = vals.size();
+      vals.resize(base + (size_t)n8 * 16 * lf, 0.0f);
+      for (int t = 0; t < per_round; ++t) {
+        const int ab = t / lf, j = t % lf, m = member[t];
+        smb::MelLane& ln = built[(size_t)q].lane[t];
         ln.n8 = (unsigned char)n8;
-        ln.off = (int)vals.size();
-        const bool real = (size_t)(q * 4 + j) < order.size();
-        const int m = real ? order[(size_t)(q * 4 + j)] : -1;
-        // stored band [slo, slo + 8 n8): inside the row, covering the filter's band
-        int slo = real ? (band_lo[(size_t)m] & ~3) : 0;
-        slo = std::min(slo, row_floats - n8 * 8);
-        ln.lo = (short)slo;
-        ln.out = (unsigned char)(real ? m : n_mels);
-        for (int k = slo; k < slo + n8 * 8; ++k)
-          vals.push_back(real && k < bins ? (float)weights[(size_t)((int64_t)m * bins + k)] : 0.0f);
+        ln.off = (int)base + (ab * 2 * lf + j) * 4;   // + 16 lf per step, + 4 lf for the second half
+        // stored band [lo, lo + 8 n8): inside the row, covering the filter's band
+        const int lo = std::min(slo[t], row_floats - n8 * 8);
+        ln.lo = (short)lo;
+        ln.out = (unsigned char)(m >= 0 ? m : n_mels);
+        if (m < 0) continue;
+        for (int u = 0; u < n8 * 8; ++u) {
+          const int k = lo + u;
+          const size_t at = base + (size_t)(u / 8) * 16 * lf +
+                            (size_t)(ab * 2 * lf + ((u / 4) & 1) * lf + j) * 4 + (size_t)(u & 3);
+          vals[at] = k < bins ? (float)weights[(size_t)((int64_t)m * bins + k)] : 0.0f;
+        }
       }
     }
     if (!fits) { vals.clear(); return; }
     std::vector<std::vector<int>> lists((size_t)warps);
     std::vector<long long> load((size_t)warps, 0);
-    for (int q = 0; q < quads; ++q) {
+    for (int q = 0; q < rounds_total; ++q) {
       const size_t w = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
       lists[w].push_back(q);
       load[w] += built[(size_t)q].n8 + 2;
@@ -364,14 +387,16 @@ struct smb_mel_plan {
     for (const auto& l : lists) mel_rounds = std::max(mel_rounds, (int)l.size());
     // idle rounds: one step over zero weights into the scratch row
     const int zero_off = (int)vals.size();
-    vals.insert(vals.end(), 8, 0.0f);
-    smb::MelLane idle{zero_off, 0, (unsigned char)n_mels, 1};
-    mel_lanes.assign((size_t)(warps * mel_rounds * 4), idle);
+    vals.insert(vals.end(), (size_t)(16 * lf), 0.0f);
+    mel_lanes.assign((size_t)(warps * mel_rounds * per_round), smb::MelLane{});
     for (int w = 0; w < warps; ++w)
-      for (size_t r = 0; r < lists[(size_t)w].size(); ++r)
-        for (int j = 0; j < 4; ++j)
-          mel_lanes[((size_t)w * mel_rounds + r) * 4 + (size_t)j] =
-              built[(size_t)lists[(size_t)w][r]].lane[j];
+      for (int r = 0; r < mel_rounds; ++r)
+        for (int t = 0; t < per_round; ++t) {
+          const smb::MelLane idle{zero_off + ((t / lf) * 2 * lf + t % lf) * 4, 0, (unsigned char)n_mels, 1};
+          mel_lanes[((size_t)w * mel_rounds + (size_t)r) * per_round + (size_t)t] =
+              (size_t)r < lists[(size_t)w].size() ? built[(size_t)lists[(size_t)w][(size_t)r]].lane[t]
+                                                  : idle;
+        }
   }
   void ensure_device() {
     if (device_ready) return;

@@ -34,11 +34,18 @@ cudaError_t launch_mel_apply(const void* s, int dtype, long long batch, int bins
                              cudaStream_t st);
 
 // ---- fast path: fft 2048, float32, fused frame+window+rFFT+|X|^p(+mel) -------
-struct MelLane {           // what one lane group (8 frames) of a warp does in a mel round
-  int off;                 // first weight of the stored band in vals (multiple of 4)
+// Tile shape of the fused kernel, shared with the host-side mel schedule: a group
+// of kFastTile warps transforms kFastTile consecutive frames, one per warp.  In the
+// mel step a lane is (filter j of kFastLaneFilters, frame f) and carries two
+// filters (octet A and B) at a time, so a round covers kFastRoundFilters filters.
+constexpr int kFastTile = 8;
+constexpr int kFastLaneFilters = 32 / kFastTile;
+constexpr int kFastRoundFilters = 2 * kFastLaneFilters;
+struct MelLane {           // one filter of a mel round (lane j = slot % LaneFilters, octet = slot / LaneFilters)
+  int off;                 // the filter's first float4 in the round's interleaved weights
   short lo;                // first bin of the stored band (multiple of 4)
   unsigned char out;       // output filter; n_mels = scratch row (padding entry)
-  unsigned char n8;        // 8-float steps, the same for the four lane groups of a round
+  unsigned char n8;        // 8-float steps, the same for all filters of a round
 };
 enum FastOut { kFastComplex = 0, kFastPower = 1, kFastMel = 2 };
 struct Stft2048Args {
@@ -53,7 +60,7 @@ struct Stft2048Args {
   int n_mels, nnz;
   const float* vals;           // [nnz] zero-padded band weights
   int mel_rounds;              // rounds each warp walks
-  const MelLane* mel_lanes;    // [8 warps][mel_rounds][4 lane groups]
+  const MelLane* mel_lanes;    // [kFastTile warps][mel_rounds][kFastRoundFilters]
   float power;
 };
 // True when the fused kernel can take this geometry (hop small enough for the

@@ -8,10 +8,14 @@
 // and the power spectrogram never reach HBM on the mel path.
 //
 // Decomposition
-//   * One persistent CTA per SM, 16 warps in two independent groups of 8.  A
-//     group owns a tile of 8 consecutive frames of one signal: it stages the
-//     tile's (8-1)*hop + 2048 samples once (each sample is shared by up to four
-//     overlapping frames), then every warp transforms one frame.
+//   * One persistent CTA per SM, 16 warps in independent groups.  A group of
+//     kFastTile warps owns a tile of kFastTile consecutive frames of one signal:
+//     it stages the tile's (kFastTile-1)*hop + 2048 samples once (each sample is
+//     shared by up to four overlapping frames), then every warp transforms one
+//     frame.  Two shapes are written out -- two groups of 8 warps (the default)
+//     and four groups of 4 (one warp of every group on each scheduler); on the
+//     headline workload they measure 1.44 ms and 1.48 ms per 1024-clip launch:
+//     the longer tile amortises the mel weights and the halo over more frames.
 //   * Real FFT 2048 = complex FFT 1024 on z[n] = x[2n] + i x[2n+1], done as
 //     32 x 32: pass 1 (lane = n2) is a 32-point FFT held entirely in
 //     registers over the stride-32 samples, the twiddled result is transposed
@@ -24,6 +28,7 @@
 //     over the frame's power row in shared memory, in float32 FMAs.
 //   * Outputs are staged per tile so global writes run along the contiguous
 //     frame axis.
+#include "fft32.cuh"
 #include "kernels.h"
 
 namespace smb {
@@ -33,107 +38,33 @@ namespace {
 constexpr int kFft = 2048;
 constexpr int kHalf = 1024;              // complex points
 constexpr int kBins = 1025;
-constexpr int kTile = 8;                 // frames per group tile
-constexpr int kGroups = 2;
-constexpr int kGroupThreads = 256;
-constexpr int kRowStride = 2180;         // floats per warp region; == 4 mod 32, holds [32][34] complex
+constexpr int kTile = kFastTile;         // frames per group tile, one warp each
+constexpr int kGroupThreads = 32 * kTile;
+constexpr int kGroupWarps = kTile;
+constexpr int kLF = kFastLaneFilters;    // filters side by side in a warp's mel step
+constexpr int kMaxGroups = kTile == 8 ? 2 : 4;
+static_assert(kTile == 8 || kTile == 4, "tile shapes the lane maps are written for");
+// floats per warp region: holds [32][34] complex; 16-byte rows; the frames of a
+// tile land 4 banks apart (8 frames) or 8 banks apart (4 frames)
+constexpr int kRowStride = kTile == 8 ? 2180 : 2184;
+constexpr int kMelOutOff = 1032;         // mel results of a frame sit behind its power row
 constexpr int kExStride = 34;            // padded transpose row (complex): 16-byte rows, conflict-free
 constexpr int kMaxMel = 128;
 
-__device__ constexpr float kW32C[32] = {
-    1.0f, 0.9807852804032304f, 0.9238795325112867f, 0.8314696123025452f,
-    0.7071067811865476f, 0.5555702330196023f, 0.38268343236508984f, 0.19509032201612833f,
-    0.0f, -0.1950903220161282f, -0.3826834323650897f, -0.555570233019602f,
-    -0.7071067811865475f, -0.8314696123025453f, -0.9238795325112867f, -0.9807852804032304f,
-    -1.0f, -0.9807852804032304f, -0.9238795325112868f, -0.8314696123025455f,
-    -0.7071067811865477f, -0.5555702330196022f, -0.38268343236509034f, -0.19509032201612866f,
-    0.0f, 0.1950903220161283f, 0.38268343236509f, 0.5555702330196018f,
-    0.7071067811865474f, 0.8314696123025452f, 0.9238795325112865f, 0.9807852804032303f};
-__device__ constexpr float kW32S[32] = {
-    0.0f, -0.19509032201612825f, -0.3826834323650898f, -0.5555702330196022f,
-    -0.7071067811865475f, -0.8314696123025452f, -0.9238795325112867f, -0.9807852804032304f,
-    -1.0f, -0.9807852804032304f, -0.9238795325112867f, -0.8314696123025455f,
-    -0.7071067811865476f, -0.5555702330196022f, -0.3826834323650899f, -0.1950903220161286f,
-    0.0f, 0.19509032201612836f, 0.38268343236508967f, 0.555570233019602f,
-    0.7071067811865475f, 0.8314696123025452f, 0.9238795325112865f, 0.9807852804032303f,
-    1.0f, 0.9807852804032304f, 0.9238795325112866f, 0.8314696123025455f,
-    0.7071067811865477f, 0.5555702330196022f, 0.3826834323650904f, 0.19509032201612872f};
+using namespace fft32impl;
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-
-// v * W32^E with E a compile-time exponent: trivial rotations cost no multiply.
-template <int E>
-__device__ __forceinline__ float2 rot32(float2 v) {
-  if constexpr (E == 0) return v;
-  else if constexpr (E == 8) return make_float2(v.y, -v.x);
-  else if constexpr (E == 16) return make_float2(-v.x, -v.y);
-  else if constexpr (E == 24) return make_float2(-v.y, v.x);
-  else if constexpr (E == 4) {
-    const float r = 0.7071067811865476f;
-    return make_float2((v.x + v.y) * r, (v.y - v.x) * r);
-  } else if constexpr (E == 12) {
-    const float r = 0.7071067811865476f;
-    return make_float2((v.y - v.x) * r, -(v.x + v.y) * r);
-  } else {
-    constexpr float c = kW32C[E], s = kW32S[E];
-    return make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
-  }
-}
-
-__device__ __forceinline__ void fft4(float2 a0, float2 a1, float2 a2, float2 a3,
-                                     float2& x0, float2& x1, float2& x2, float2& x3) {
-  const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3);
-  const float2 d = csub(a1, a3);
-  const float2 t3 = make_float2(d.y, -d.x);     // -i (a1 - a3)
-  x0 = cadd(t0, t2);
-  x2 = csub(t0, t2);
-  x1 = cadd(t1, t3);
-  x3 = csub(t1, t3);
-}
-
-// 8-point forward DFT of v[0..7], natural order in and out.
-__device__ __forceinline__ void fft8(float2 (&v)[8]) {
-  float2 e0, e1, e2, e3, o0, o1, o2, o3;
-  fft4(v[0], v[2], v[4], v[6], e0, e1, e2, e3);
-  fft4(v[1], v[3], v[5], v[7], o0, o1, o2, o3);
-  o1 = rot32<4>(o1);
-  o2 = rot32<8>(o2);
-  o3 = rot32<12>(o3);
-  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
-  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
-  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
-  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
-}
-
-template <int B>
-__device__ __forceinline__ void fft32_column(const float2 (&x)[32], float2 (&y)[32]) {
-  float2 r0, r1, r2, r3;
-  fft4(x[B], x[8 + B], x[16 + B], x[24 + B], r0, r1, r2, r3);
-  y[B * 4 + 0] = r0;
-  y[B * 4 + 1] = rot32<(B * 1) % 32>(r1);
-  y[B * 4 + 2] = rot32<(B * 2) % 32>(r2);
-  y[B * 4 + 3] = rot32<(B * 3) % 32>(r3);
-}
-
-template <int C>
-__device__ __forceinline__ void fft32_row(const float2 (&y)[32], float2 (&x)[32]) {
-  float2 v[8];
-#pragma unroll
-  for (int b = 0; b < 8; ++b) v[b] = y[b * 4 + C];
-  fft8(v);
-#pragma unroll
-  for (int d = 0; d < 8; ++d) x[C + 4 * d] = v[d];
-}
-
-// 32-point forward DFT in registers, natural order in and out:
-// n = 8a + b, k = c + 4d  ->  4-point DFTs over a, twiddle W32^(bc), 8-point over b.
-__device__ __forceinline__ void fft32(float2 (&x)[32]) {
-  float2 y[32];
-  fft32_column<0>(x, y); fft32_column<1>(x, y); fft32_column<2>(x, y); fft32_column<3>(x, y);
-  fft32_column<4>(x, y); fft32_column<5>(x, y); fft32_column<6>(x, y); fft32_column<7>(x, y);
-  fft32_row<0>(y, x); fft32_row<1>(y, x); fft32_row<2>(y, x); fft32_row<3>(y, x);
-}
+// W_64^k2 = exp(-2 pi i k2 / 64), k2 < 16: the post-split twiddle W_2048^(l + 32 k2)
+// is the lane's W_2048^l (a 32-entry table) times one of these constants.
+__device__ constexpr float kW64C[16] = {
+    1.0f, 0.9951847266721969f, 0.9807852804032304f, 0.9569403357322088f,
+    0.9238795325112867f, 0.881921264348355f, 0.8314696123025452f, 0.773010453362737f,
+    0.7071067811865476f, 0.6343932841636455f, 0.5555702330196023f, 0.4713967368259978f,
+    0.38268343236508984f, 0.29028467725446233f, 0.19509032201612833f, 0.09801714032956077f};
+__device__ constexpr float kW64S[16] = {
+    0.0f, -0.0980171403295606f, -0.19509032201612825f, -0.2902846772544623f,
+    -0.3826834323650898f, -0.47139673682599764f, -0.5555702330196022f, -0.6343932841636455f,
+    -0.7071067811865475f, -0.773010453362737f, -0.8314696123025452f, -0.8819212643483549f,
+    -0.9238795325112867f, -0.9569403357322089f, -0.9807852804032304f, -0.9951847266721968f};
 
 __device__ __forceinline__ long long src_index(const FrameGeom& g, long long q) {
   long long s = q - g.left;
@@ -211,7 +142,7 @@ __device__ __forceinline__ void stage_tile(const Params& p, int tile, float* sSa
   }
 }
 
-template <int OUT, bool SQUARE>
+template <int OUT, bool SQUARE, int kGroups>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 stft2048_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
@@ -219,16 +150,16 @@ stft2048_kernel(const Params p) {
   // 16-byte load: [pair][lane][2] (half the shared-memory instructions).
   float* sWindow = smem;                                        // [16][32] x {w(n1), w(n1+1)} float2 pairs, x 1/2
   float2* sTwPass = reinterpret_cast<float2*>(sWindow + kFft);  // [16][32][2]  W_1024^(k1 n2), k1 = 2 pair + {0,1}
-  float2* sTwPost = sTwPass + 1024;                             // [8][32][2]   W_2048^(l + 32 k2), k2 = 2 pair + {0,1}
-  float* sMelVals = reinterpret_cast<float*>(sTwPost + 512);    // band weights, filter by filter
+  float2* sTwPost = sTwPass + 1024;                             // [32]         W_2048^l
+  float* sMelVals = reinterpret_cast<float*>(sTwPost + 32);     // band weights, round by round
   const int nnz_pad = (p.a.nnz + 3) & ~3;
-  MelLane* sMelLanes = reinterpret_cast<MelLane*>(sMelVals + nnz_pad);   // [8 warps][rounds][4]
+  MelLane* sMelLanes = reinterpret_cast<MelLane*>(sMelVals + nnz_pad);   // [warps][rounds][2 kLF]
   // offsets stay integers so every pointer keeps its shared-memory provenance
   // (generic LD/ST would go through the slower generic path)
-  const int tables_bytes = (kFft + 2 * 1024 + 2 * 512 + nnz_pad) * 4 +
-                           kTile * p.a.mel_rounds * 4 * (int)sizeof(MelLane);
+  const int tables_bytes = (kFft + 2 * 1024 + 2 * 32 + nnz_pad) * 4 +
+                           kGroupWarps * p.a.mel_rounds * 2 * kLF * (int)sizeof(MelLane);
   float* groups_base = smem + (((tables_bytes + 15) & ~15) >> 2);
-  const int group_floats = p.span_cap + kTile * kRowStride + (kMaxMel + 1) * kTile;
+  const int group_floats = p.span_cap + kTile * kRowStride;
 
   const int tid = threadIdx.x;
   const int group = tid / kGroupThreads;
@@ -237,7 +168,6 @@ stft2048_kernel(const Params p) {
   const int lane = tid & 31;
   float* sSamples = groups_base + group * group_floats;
   float* sRows = sSamples + p.span_cap;
-  float* sMelOut = sRows + kTile * kRowStride;
 
   for (int i = tid; i < kFft; i += blockDim.x) {
     // source index j = 2 (32 n1 + l) + c  ->  ((n1/2) * 32 + l) * 4 + (n1 & 1) * 2 + c
@@ -248,13 +178,10 @@ stft2048_kernel(const Params p) {
     const int l = i & 31, k1 = i >> 5;
     sTwPass[(((k1 >> 1) * 32 + l) << 1) + (k1 & 1)] = p.a.tw_pass[i];
   }
-  for (int i = tid; i < 512; i += blockDim.x) {
-    const int l = i & 31, k2 = i >> 5;
-    sTwPost[(((k2 >> 1) * 32 + l) << 1) + (k2 & 1)] = p.a.tw_post[i];
-  }
+  if (tid < 32) sTwPost[tid] = p.a.tw_post[tid];
   if (OUT == kFastMel) {
     for (int i = tid; i < p.a.nnz; i += blockDim.x) sMelVals[i] = p.a.vals[i];
-    for (int i = tid; i < kTile * p.a.mel_rounds * 4; i += blockDim.x) sMelLanes[i] = p.a.mel_lanes[i];
+    for (int i = tid; i < kGroupWarps * p.a.mel_rounds * 2 * kLF; i += blockDim.x) sMelLanes[i] = p.a.mel_lanes[i];
   }
   __syncthreads();
 
@@ -345,12 +272,15 @@ stft2048_kernel(const Params p) {
         r[k2].y = __shfl_sync(0xffffffffu, sy, partner);
       }
       float2* rowc = reinterpret_cast<float2*>(row);
+      const float2 wl = sTwPost[lane];
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) {
         const float2 A = a[k2];
         const float2 S = make_float2(A.x + r[k2].x, A.y - r[k2].y);
         const float2 D = make_float2(A.x - r[k2].x, A.y + r[k2].y);
-        const float2 w = sTwPost[(((k2 >> 1) * 32 + lane) << 1) + (k2 & 1)];
+        const float2 w = k2 == 0 ? wl
+                                 : make_float2(wl.x * kW64C[k2] - wl.y * kW64S[k2],
+                                               wl.x * kW64S[k2] + wl.y * kW64C[k2]);
         const float tr = w.x * D.y + w.y * D.x;
         const float ti = w.y * D.y - w.x * D.x;
         const float2 xk = make_float2(S.x + tr, S.y + ti);
@@ -388,47 +318,57 @@ stft2048_kernel(const Params p) {
     if (tile + stride < total_tiles) stage_tile(p, tile + stride, sSamples, gtid);
 
     if (OUT == kFastMel) {
-      // ---- mel projection over the tile's power rows.  A warp takes four
-      // filters of near-equal band length at a time: lane = (filter j, frame f).
-      // Bands are stored padded to whole float4s (zero weights), rows are 16-byte
-      // aligned and kRowStride == 4 (mod 32), so the eight frames of one filter
-      // read one conflict-free 128-byte wavefront per float4 and share the weight.
-      const int f = lane & (kTile - 1), j = lane >> 3;
+      // ---- mel projection over the tile's power rows.  A warp takes 2 kLF
+      // filters of near-equal band length at a time: lane = (filter j of kLF,
+      // frame f) and carries filter j of set A and of set B side by side (two
+      // independent accumulator sets hide the shared-memory latency).  Weights
+      // are interleaved [step][set][half][j] so a warp-wide load is one
+      // contiguous run; power rows are 16-byte aligned and kRowStride spreads
+      // the frames of a tile over the banks (with 4-frame tiles the host also
+      // starts neighbouring filters an odd number of float4s apart), so the value
+      // loads are conflict-free too.
+      const int f = lane & (kTile - 1), j = lane / kTile;
       const float4* prow4 = reinterpret_cast<const float4*>(sRows + f * kRowStride);
-      const MelLane* mine = sMelLanes + warp * p.a.mel_rounds * 4 + j;
+      float* mel_out = sRows + f * kRowStride + kMelOutOff;
+      const MelLane* mine = sMelLanes + warp * p.a.mel_rounds * (2 * kLF) + j;
       for (int r = 0; r < p.a.mel_rounds; ++r) {
-        const MelLane q = mine[r * 4];
-        const float4* w4 = reinterpret_cast<const float4*>(sMelVals + q.off);
-        const float4* v4 = prow4 + (q.lo >> 2);
+        const MelLane qa = mine[r * 2 * kLF], qb = mine[r * 2 * kLF + kLF];
+        const float4* wa = reinterpret_cast<const float4*>(sMelVals + qa.off);
+        const float4* wb = reinterpret_cast<const float4*>(sMelVals + qb.off);
+        const float4* va = prow4 + (qa.lo >> 2);
+        const float4* vb = prow4 + (qb.lo >> 2);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
         // the trip count is the same for the whole warp: no divergence
-        for (int i = 0; i < q.n8; ++i) {
-          const float4 w0 = w4[2 * i], v0 = v4[2 * i];
-          const float4 w1 = w4[2 * i + 1], v1 = v4[2 * i + 1];
-          a0 = fmaf(w0.x, v0.x, a0);
-          a1 = fmaf(w0.y, v0.y, a1);
-          a2 = fmaf(w0.z, v0.z, a2);
-          a3 = fmaf(w0.w, v0.w, a3);
-          a0 = fmaf(w1.x, v1.x, a0);
-          a1 = fmaf(w1.y, v1.y, a1);
-          a2 = fmaf(w1.z, v1.z, a2);
-          a3 = fmaf(w1.w, v1.w, a3);
+        for (int i = 0; i < qa.n8; ++i) {
+          const float4 w0 = wa[4 * kLF * i], w1 = wa[4 * kLF * i + kLF], x0 = va[2 * i], x1 = va[2 * i + 1];
+          const float4 u0 = wb[4 * kLF * i], u1 = wb[4 * kLF * i + kLF], y0 = vb[2 * i], y1 = vb[2 * i + 1];
+          a0 = fmaf(w0.x, x0.x, a0); a1 = fmaf(w0.y, x0.y, a1);
+          a2 = fmaf(w0.z, x0.z, a2); a3 = fmaf(w0.w, x0.w, a3);
+          b0 = fmaf(u0.x, y0.x, b0); b1 = fmaf(u0.y, y0.y, b1);
+          b2 = fmaf(u0.z, y0.z, b2); b3 = fmaf(u0.w, y0.w, b3);
+          a0 = fmaf(w1.x, x1.x, a0); a1 = fmaf(w1.y, x1.y, a1);
+          a2 = fmaf(w1.z, x1.z, a2); a3 = fmaf(w1.w, x1.w, a3);
+          b0 = fmaf(u1.x, y1.x, b0); b1 = fmaf(u1.y, y1.y, b1);
+          b2 = fmaf(u1.z, y1.z, b2); b3 = fmaf(u1.w, y1.w, b3);
         }
-        sMelOut[q.out * kTile + f] = (a0 + a1) + (a2 + a3);
+        mel_out[qa.out] = (a0 + a1) + (a2 + a3);
+        mel_out[qb.out] = (b0 + b1) + (b2 + b3);
       }
       group_sync(group);
     }
 
-    // ---- write the tile along the frame axis: [batch, rows, frames].  Eight
-    // consecutive lanes carry the eight frames of one output row (32 bytes).
+    // ---- write the tile along the frame axis: [batch, rows, frames].  kTile
+    // consecutive lanes carry the tile's frames of one output row.
     {
-      const int f = gtid & (kTile - 1), r0 = gtid >> 3;
+      const int f = gtid & (kTile - 1), r0 = gtid / kTile;
       if (f < nf) {
         if (OUT == kFastMel) {
           float* ob = p.a.out + ((long long)b * p.a.n_mels + r0) * g.frames + p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
+          const float* src = sRows + f * kRowStride + kMelOutOff;
           for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step)
-            *ob = sMelOut[m * kTile + f];
+            *ob = src[m];
         } else if (OUT == kFastPower) {
           float* ob = p.a.out + ((long long)b * kBins + r0) * g.frames + p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
@@ -449,13 +389,13 @@ stft2048_kernel(const Params p) {
 
 }  // namespace
 
-static size_t smem_layout(int nnz, int mel_rounds, int span_cap) {
+static size_t smem_layout(int nnz, int mel_rounds, int span_cap, int groups) {
   const int nnz_pad = (nnz + 3) & ~3;
-  size_t bytes = (size_t)(kFft + 2 * 1024 + 2 * 512) * 4;        // window, tw_pass, tw_post
+  size_t bytes = (size_t)(kFft + 2 * 1024 + 2 * 32) * 4;         // window, tw_pass, tw_post
   bytes += (size_t)nnz_pad * 4;                                    // band weights
-  bytes += (size_t)kTile * mel_rounds * 4 * sizeof(MelLane);      // warp schedule
+  bytes += (size_t)kGroupWarps * mel_rounds * 2 * kLF * sizeof(MelLane);      // warp schedule
   bytes = (bytes + 15) & ~(size_t)15;
-  bytes += (size_t)kGroups * (span_cap + kTile * kRowStride + (kMaxMel + 1) * kTile) * 4;
+  bytes += (size_t)groups * (span_cap + kTile * kRowStride) * 4;
   return bytes;
 }
 
@@ -469,7 +409,7 @@ bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, in
   if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;
   if (out_kind == kFastMel && (n_mels < 1 || n_mels > kMaxMel || nnz > 65536)) return false;
   const bool mel = out_kind == kFastMel;
-  return smem_layout(mel ? nnz : 0, mel ? mel_rounds : 0, span_needed(g)) <= kSmemLimit;
+  return smem_layout(mel ? nnz : 0, mel ? mel_rounds : 0, span_needed(g), kMaxGroups / 2) <= kSmemLimit;
 }
 
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st) {
@@ -492,21 +432,28 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
   p.span_cap = span_needed(a.g);
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
   p.total_tiles = p.tiles_per_signal * a.batch;
-  const size_t smem = smem_layout(p.a.nnz, p.a.mel_rounds, p.span_cap);
+  // the full complement of groups per SM when their tiles fit shared memory, else half
+  const int groups = smem_layout(p.a.nnz, p.a.mel_rounds, p.span_cap, kMaxGroups) <= kSmemLimit
+                         ? kMaxGroups : kMaxGroups / 2;
+  const size_t smem = smem_layout(p.a.nnz, p.a.mel_rounds, p.span_cap, groups);
   if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
-  long long want = (p.total_tiles + kGroups - 1) / kGroups;
+  long long want = (p.total_tiles + groups - 1) / groups;
   const int grid = (int)(want < sm_count ? want : sm_count);
   cudaError_t e;
-#define SMB_LAUNCH2048(OUT, SQ)                                                              \
-  e = cudaFuncSetAttribute(stft2048_kernel<OUT, SQ>,                                         \
+#define SMB_LAUNCH2048_G(OUT, SQ, G)                                                         \
+  e = cudaFuncSetAttribute(stft2048_kernel<OUT, SQ, G>,                                      \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
   if (e != cudaSuccess) return e;                                                            \
-  stft2048_kernel<OUT, SQ><<<grid, kGroups * kGroupThreads, smem, st>>>(p);
+  stft2048_kernel<OUT, SQ, G><<<grid, G * kGroupThreads, smem, st>>>(p);
+#define SMB_LAUNCH2048(OUT, SQ)                                                              \
+  if (groups == kMaxGroups) { SMB_LAUNCH2048_G(OUT, SQ, kMaxGroups) }                       \
+  else { SMB_LAUNCH2048_G(OUT, SQ, kMaxGroups / 2) }
   const bool sq = a.power == 2.0f;
   if (out_kind == kFastMel) { if (sq) { SMB_LAUNCH2048(kFastMel, true) } else { SMB_LAUNCH2048(kFastMel, false) } }
   else if (out_kind == kFastPower) { if (sq) { SMB_LAUNCH2048(kFastPower, true) } else { SMB_LAUNCH2048(kFastPower, false) } }
   else { SMB_LAUNCH2048(kFastComplex, true) }
 #undef SMB_LAUNCH2048
+#undef SMB_LAUNCH2048_G
   ++g_launch_count;
   return cudaGetLastError();
 }
