@@ -430,9 +430,29 @@ struct OlsDevice {
   smb::OlsPlan plan;
   float2* d_h = nullptr;
   float2* d_tw = nullptr;
+  float2 *d_tw_pass = nullptr, *d_tw_base = nullptr;   // tables of the N = 2048 kernel
+  int sm_count = 0;
+  bool fast = true;                                     // the N = 2048 kernel may be used
   void upload_from(const smb::OlsPlan& p) {
     plan = p;
     if (!p.ok) return;
+    if (p.n == 2048 && p.l == 1) {
+      std::vector<float2> pass(1024), base(32);
+      for (int k1 = 0; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+          const double a = kTwoPi * double(k1 * n2) / 1024.0;
+          pass[(size_t)(k1 * 32 + n2)] = make_float2((float)std::cos(a), (float)-std::sin(a));
+        }
+      for (int l = 0; l < 32; ++l) {
+        const double a = kTwoPi * double(l) / 2048.0;
+        base[(size_t)l] = make_float2((float)std::cos(a), (float)-std::sin(a));
+      }
+      d_tw_pass = upload(pass);
+      d_tw_base = upload(base);
+      int device = 0;
+      CK(cudaGetDevice(&device));
+      CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    }
     std::vector<float2> h(p.spectrum_re.size());
     for (size_t i = 0; i < h.size(); ++i)
       h[i] = make_float2((float)p.spectrum_re[i], (float)p.spectrum_im[i]);
@@ -448,7 +468,9 @@ struct OlsDevice {
   void release() {
     cudaFree(d_h);
     cudaFree(d_tw);
-    d_h = d_tw = nullptr;
+    cudaFree(d_tw_pass);
+    cudaFree(d_tw_base);
+    d_h = d_tw = d_tw_pass = d_tw_base = nullptr;
   }
   void run(const float* x, int64_t batch, int64_t n, int64_t n_out, float* out,
            cudaStream_t st) const {
@@ -462,7 +484,10 @@ struct OlsDevice {
     a.N = (int)plan.n; a.B = (int)plan.b; a.delta = (int)plan.delta; a.W = (int)plan.w;
     a.H = d_h;
     a.tw = d_tw;
-    CK(smb::launch_ols(a, batch, st));
+    if (fast && d_tw_pass && smb::ols2048_supports(a))
+      CK(smb::launch_ols2048(a, d_tw_pass, d_tw_base, batch, sm_count, st));
+    else
+      CK(smb::launch_ols(a, batch, st));
   }
 };
 

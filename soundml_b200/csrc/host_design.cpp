@@ -711,6 +711,14 @@ OlsPlan ols_plan_for_stage(const ResampleStage& s) {
 OlsPlan ols_plan_for_fir(const std::vector<double>& h) {
   OlsPlan p;
   p.k = ((int64_t)h.size() - 1) / 2;
+  if (p.k <= 512) {
+    // N = 2048 runs on the warp-per-block register-FFT kernel; the one-sample
+    // shift delta makes every block's first output even, so stores pair up.
+    p.n = 2048;
+    p.b = 2048 - 2 * p.k;
+    p.delta = p.k & 1;
+    return finish_ols(p, h);
+  }
   int64_t n = 64;
   while (n < 10 * p.k) n *= 2;                               // resample.ml:279-286
   if (n > 16384) n = 16384;

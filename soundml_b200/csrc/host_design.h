@@ -99,7 +99,8 @@ struct OlsPlan {
 // GPU-executable OLS plan for a stage, or ok = false when the transform lengths
 // are not powers of two / too long for one CTA (the direct kernel runs instead).
 OlsPlan ols_plan_for_stage(const ResampleStage& s);
-// FIR as an L = M = 1 stage: N = smallest power of two >= max(64, 10 K).
+// FIR as an L = M = 1 stage: N = 2048 up to 1025 taps, else the smallest power of
+// two >= 10 K.
 OlsPlan ols_plan_for_fir(const std::vector<double>& h);
 
 ResamplePlan resample_plan(int64_t sample_rate, int64_t target, int quality,

@@ -99,6 +99,10 @@ struct OlsArgs {
 };
 size_t ols_smem_bytes(int N, int W);
 cudaError_t launch_ols(const OlsArgs& a, long long batch, cudaStream_t st);
+// Warp-per-block register-FFT variant for N = 2048, L = 1 (ols2048.cu).
+bool ols2048_supports(const OlsArgs& a);
+cudaError_t launch_ols2048(const OlsArgs& a, const float2* tw_pass, const float2* tw_base,
+                           long long batch, int sm_count, cudaStream_t st);
 
 // Phase-rich polyphase stage as a banded tf32x3 product on tcgen05 (resample_gemm.cu).
 struct GemmResampleArgs {
