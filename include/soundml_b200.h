@@ -140,6 +140,21 @@ int smb_stft_transform_range(smb_stft_plan* plan, const void* x, int64_t batch, 
 int smb_stft_power_spectrum(smb_stft_plan* plan, const void* x, int64_t batch,
                             int64_t n, int dtype, double power, void* out, int mem);
 
+/* Least-squares synthesis, Stft.invert dtype c ?length z (stft.ml:693-939).
+ * smb_stft_nola: 1 when the overlap-added squared window stays above 1e-10 of
+ * its maximum (stft.ml:731-742), else 0.  smb_stft_output_length: the length
+ * synthesis returns for `frames` frames when none is named (stft.ml:790-794),
+ * -1 on error.  smb_stft_invert: z [batch, bins, frames] complex (in_dtype
+ * SMB_F32 = complex64, SMB_F64 = complex128) -> out [batch, length] real
+ * (out_dtype); has_length = 0 takes the natural length.  Interior in double,
+ * one rounding into out_dtype.  Fails with the reference's messages for a
+ * non-invertible configuration or a negative length. */
+int smb_stft_nola(const smb_stft_plan* plan);
+int64_t smb_stft_output_length(const smb_stft_plan* plan, int64_t frames);
+int smb_stft_invert(smb_stft_plan* plan, const void* z, int64_t batch, int64_t frames,
+                    int in_dtype, int has_length, int64_t length, int out_dtype, void* out,
+                    int mem);
+
 /* ---- mel ----------------------------------------------------------------- */
 /* Mel.Config.create; f_max = NaN means "Nyquist" (the OCaml default). */
 int smb_mel_plan_create(smb_mel_plan** plan, int64_t n_mels, int64_t sample_rate,

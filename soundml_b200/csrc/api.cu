@@ -191,6 +191,7 @@ struct smb_stft_plan {
   StreamOwner stream;
   double* d_window64 = nullptr;
   double2* d_twiddle64 = nullptr;
+  double* d_folded = nullptr;        // synthesis: folded squared window, one entry per residue
   float* d_window32 = nullptr;       // fast path tables (fft 2048 only)
   float2* d_tw_pass = nullptr;
   float2* d_tw_post = nullptr;
@@ -232,6 +233,27 @@ struct smb_stft_plan {
     }
     device_ready = true;
   }
+  // stft.ml:712-721: position m receives w[j]^2 for the j congruent to m modulo the hop
+  std::vector<double> folded_square_window() const {
+    std::vector<double> folded((size_t)geom.hop, 0.0);
+    for (int64_t j = 0; j < geom.fft; ++j)
+      folded[(size_t)(j % geom.hop)] += window[(size_t)j] * window[(size_t)j];
+    return folded;
+  }
+  bool nola() const {                                    // stft.ml:731-742
+    if (geom.hop > geom.fft) return false;
+    const std::vector<double> folded = folded_square_window();
+    double lo = HUGE_VAL, hi = 0.0;
+    for (double v : folded) {
+      if (v < lo) lo = v;
+      if (v > hi) hi = v;
+    }
+    return lo > 1e-10 * hi;
+  }
+  int64_t output_length(int64_t frames) const {          // stft.ml:790-794
+    if (frames == 0) return 0;
+    return (frames - 1) * geom.hop + geom.fft - geom.left_width() - geom.right_width();
+  }
   smb::FrameGeom frame_geom(int64_t n) const {
     smb::FrameGeom g;
     g.n = n;
@@ -247,6 +269,7 @@ struct smb_stft_plan {
     if (!device_ready) return;
     cudaFree(d_window64);
     cudaFree(d_twiddle64);
+    cudaFree(d_folded);
     cudaFree(d_window32);
     cudaFree(d_tw_pass);
     cudaFree(d_tw_post);
@@ -900,6 +923,82 @@ int smb_stft_power_spectrum(smb_stft_plan* plan, const void* x, int64_t batch, i
                             int dtype, double power, void* out, int mem) {
   return guarded([&] {
     spectrum_call("power_spectrum", plan, x, batch, n, dtype, kSpecPower, power, out, mem);
+  });
+}
+
+int smb_stft_nola(const smb_stft_plan* plan) { return plan->nola() ? 1 : 0; }
+
+int64_t smb_stft_output_length(const smb_stft_plan* plan, int64_t frames) {
+  int64_t r = -1;
+  guarded([&] {
+    if (frames < 0)
+      throw smb::invalid_argument(smb::format(
+          "output_length: cannot size the synthesis of %lld frames (frames must be non-negative)",
+          (long long)frames));
+    r = plan->output_length(frames);
+  });
+  return r;
+}
+
+int smb_stft_invert(smb_stft_plan* plan, const void* z, int64_t batch, int64_t frames,
+                    int in_dtype, int has_length, int64_t length, int out_dtype, void* out,
+                    int mem) {
+  return guarded([&] {
+    smb_stft_plan* p = plan;
+    if (batch < 0 || frames < 0)
+      throw smb::invalid_argument("invert: batch and frame counts must be non-negative");
+    if (has_length && length < 0)                       // stft.ml:776-785
+      throw smb::invalid_argument(smb::format(
+          "invert: cannot synthesise a signal of length %lld (length must be non-negative)",
+          (long long)length));
+    if (!p->nola())                                     // stft.ml:744-753
+      throw smb::invalid_argument(smb::format(
+          "invert: cannot invert a %lld-point window advanced by %lld samples inside a "
+          "%lld-point frame (the overlap-added squared window must stay above 1e-10 of its "
+          "largest value at every position)",
+          (long long)p->geom.win_length, (long long)p->geom.hop, (long long)p->geom.fft));
+    const size_t isz = 2 * dtype_size(in_dtype), osz = dtype_size(out_dtype);
+    const int64_t left = p->geom.left_width(), hop = p->geom.hop;
+    const int64_t out_len = has_length ? length : p->output_length(frames);
+    // only the frames the output can reach are inverted (stft.ml:907-915)
+    int64_t count = frames;
+    if (has_length) count = std::min(frames, (length + left + hop - 1) / hop);
+    if (batch == 0 || out_len == 0) return;
+    p->ensure_device();
+    cudaStream_t st = p->stream.use;
+    if (!p->d_folded) p->d_folded = upload(p->folded_square_window());
+    auto run = [&](const void* dz, void* dout, int64_t nb) {
+      if (count == 0) {                                 // nothing reaches the output: zeros
+        CK(cudaMemsetAsync(dout, 0, (size_t)nb * (size_t)out_len * osz, st));
+        return;
+      }
+      smb::IstftArgs a{};
+      a.z = dz;
+      a.out = dout;
+      a.frames = frames;
+      a.count = count;
+      a.out_len = out_len;
+      a.fft = (int)p->geom.fft;
+      a.hop = (int)hop;
+      a.left = (int)left;
+      a.window = p->d_window64;
+      a.twiddle = p->d_twiddle64;
+      a.folded = p->d_folded;
+      a.in_f64 = in_dtype == SMB_F64;
+      a.out_f64 = out_dtype == SMB_F64;
+      CK(smb::launch_istft(a, nb, st));
+    };
+    if (mem == SMB_MEM_DEVICE) {
+      run(z, out, batch);
+      return;
+    }
+    if (mem != SMB_MEM_HOST) throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    if (frames == 0) {
+      std::memset(out, 0, (size_t)batch * (size_t)out_len * osz);
+      return;
+    }
+    p->pipe.execute(st, z, out, batch, (size_t)p->geom.bins() * (size_t)frames * isz,
+                    (size_t)out_len * osz, run);
   });
 }
 

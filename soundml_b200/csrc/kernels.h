@@ -33,6 +33,21 @@ cudaError_t launch_mel_apply(const void* s, int dtype, long long batch, int bins
                              const int* band_lo, const int* band_hi, void* out,
                              cudaStream_t st);
 
+// ---- synthesis (istft_kernels.cu) ----------------------------------------------
+struct IstftArgs {
+  const void* z;            // [batch, bins, frames] complex (float2 or double2)
+  void* out;                // [batch, out_len] real
+  long long frames;         // frame axis of z
+  long long count;          // frames that reach the output (<= frames)
+  long long out_len;
+  int fft, hop, left;
+  const double* window;     // [fft] analysis window
+  const double2* twiddle;   // exp(-2 pi i j / fft), j < fft
+  const double* folded;     // [hop] overlap-added squared window per residue class
+  int in_f64, out_f64;
+};
+cudaError_t launch_istft(const IstftArgs& a, long long batch, cudaStream_t st);
+
 // ---- fast path: fft 2048, float32, fused frame+window+rFFT+|X|^p(+mel) -------
 // Tile shape of the fused kernel, shared with the host-side mel schedule: a group
 // of kFastTile warps transforms kFastTile consecutive frames, one per warp.  In the

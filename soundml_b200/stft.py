@@ -154,6 +154,82 @@ def power_spectrum(c, x, power=2.0, out=None):
     return _run("power_spectrum", c, x, False, power, out)
 
 
+def nola(c):
+    """``Stft.nola c`` (stft.ml:731-742): the overlap-added squared window clears
+    1e-10 of its maximum at every position, so synthesis is defined."""
+    return bool(_lib.lib.smb_stft_nola(c._h))
+
+
+def output_length(c, frames):
+    """``Stft.output_length c ~frames`` (stft.ml:790-794)."""
+    r = _lib.lib.smb_stft_output_length(c._h, int(frames))
+    if r < 0:
+        raise ValueError(_lib.last_error())
+    return int(r)
+
+
+def invert(c, z, length=None, dtype=None):
+    """``Stft.invert dtype c ?length z`` (stft.ml:693-939): least-squares
+    synthesis of ``[..., bins, frames]`` complex frames into ``[..., length]``
+    real samples (``output_length`` when no length is named).  The interior is
+    double; ``dtype`` (default: the component width of ``z``) is the one
+    rounding at the end."""
+    if z.ndim < 2:
+        raise ValueError(
+            f"invert: cannot invert a rank-{z.ndim} tensor (the bin and frame axes must exist)")
+    bins, count = int(z.shape[-2]), int(z.shape[-1])
+    if bins != c.bins:
+        raise ValueError(
+            f"invert: cannot invert {bins} frequency bins of a {c.fft_size}-point transform "
+            f"(the bin axis must hold fft_size / 2 + 1 = {c.bins} values)")
+    z = _lib.contiguous(z)
+    lead = tuple(int(d) for d in z.shape[:-2])
+    batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    if _lib.is_torch(z):
+        import torch
+        if not z.is_cuda:
+            raise ValueError("torch tensors must live on a CUDA device; pass numpy for host data")
+        codes = {torch.complex64: _lib.F32, torch.complex128: _lib.F64}
+        outs = {_lib.F32: torch.float32, _lib.F64: torch.float64}
+        names = {torch.float32: _lib.F32, torch.float64: _lib.F64, None: None}
+    else:
+        codes = {np.dtype(np.complex64): _lib.F32, np.dtype(np.complex128): _lib.F64}
+        outs = {_lib.F32: np.float32, _lib.F64: np.float64}
+        names = {None: None}
+        if dtype is not None:
+            names[dtype] = {np.dtype(np.float32): _lib.F32,
+                            np.dtype(np.float64): _lib.F64}.get(np.dtype(dtype))
+    in_code = codes.get(z.dtype)
+    if in_code is None:
+        raise ValueError(f"unsupported dtype {z.dtype} (complex64 and complex128 are carried)")
+    out_code = in_code if dtype is None else names.get(dtype)
+    if out_code is None:
+        raise ValueError(f"unsupported dtype {dtype} (float32 and float64 are carried)")
+    if length is not None and length < 0:
+        raise ValueError(
+            f"invert: cannot synthesise a signal of length {length} (length must be non-negative)")
+    if not nola(c):
+        _lib.check(_lib.lib.smb_stft_invert(c._h, None, 0, 0, in_code, 0, 0, out_code, None,
+                                            _lib.MEM_HOST))
+    out_len = output_length(c, count) if length is None else int(length)
+    if _lib.is_torch(z):
+        import torch
+        out = torch.zeros(lead + (out_len,), dtype=outs[out_code], device=z.device)
+        mem, zp, op = _lib.MEM_DEVICE, z.data_ptr(), out.data_ptr()
+    else:
+        out = np.zeros(lead + (out_len,), dtype=outs[out_code])
+        mem, zp, op = _lib.MEM_HOST, z.ctypes.data, out.ctypes.data
+    if batch == 0 or out_len == 0 or count == 0:
+        return out
+    stream = _lib.current_stream(z)
+    if stream is not None:
+        _lib.check(_lib.lib.smb_stft_plan_set_stream(c._h, stream))
+    _lib.check(_lib.lib.smb_stft_invert(c._h, zp, batch, count, in_code,
+                                        0 if length is None else 1,
+                                        0 if length is None else int(length), out_code, op, mem))
+    return out
+
+
 def times(c, sample_rate, n, dtype=np.float64):
     """``Stft.times`` (stft.ml:245-254)."""
     if sample_rate < 1:

@@ -12,6 +12,7 @@ Reads the librosa-0.11 / SoXR golden JSON files of the reference test suites
     soundml/test/stft/vectors/*.json
     soundml/test/mel/vectors/{filterbank,mel_spectrogram,mfcc}.json
     soundml/test/db/vectors/*.json
+    soundml/test/istft/vectors/{inverse_*,lengths}.json
     soundml/test/resample/vectors/soxr_reference.json
 
 and writes ``tests/golden/reference_vectors.npz``: one float64 array per case
@@ -36,6 +37,8 @@ SUITES = {
             f"{REF}/mel/vectors/mel_spectrogram.json",
             f"{REF}/mel/vectors/mfcc.json"],
     "db": sorted(glob.glob(f"{REF}/db/vectors/*.json")),
+    "istft": sorted(glob.glob(f"{REF}/istft/vectors/inverse_*.json")) +
+             [f"{REF}/istft/vectors/lengths.json"],
     "resample": [f"{REF}/resample/vectors/soxr_reference.json"],
 }
 

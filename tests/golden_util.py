@@ -27,6 +27,23 @@ def lcg_signal(n, seed, envelope=False):
     return out
 
 
+ISTFT_SEED_RE, ISTFT_SEED_IM = 20250803, 20250804   # soundml/test/istft/istft_goldens.ml:38-47
+
+
+def istft_spectrum(fft_size, frames, dtype):
+    """The synthetic (inconsistent) spectrum of the reference's synthesis goldens:
+    two LCG streams, one per complex component, DC / Nyquist made real
+    (istft_goldens.ml:30-47); float32 cases quantise both components."""
+    bins = fft_size // 2 + 1
+    re = lcg_signal(bins * frames, ISTFT_SEED_RE).reshape(bins, frames)
+    im = lcg_signal(bins * frames, ISTFT_SEED_IM).reshape(bins, frames)
+    im[0, :] = 0.0
+    if fft_size % 2 == 0:
+        im[bins - 1, :] = 0.0
+    z = re + 1j * im
+    return z.astype(np.complex64 if dtype == "float32" else np.complex128)
+
+
 class Goldens:
     def __init__(self):
         z = np.load(os.path.join(HERE, "golden", "reference_vectors.npz"))

@@ -4,8 +4,9 @@ import numpy as np
 import pytest
 
 from golden_util import (F32_ATOL, F32_RTOL, F64_ATOL, F64_RTOL, MEL_SEED, STFT_SEED,
-                         WINDOW_ATOL, WINDOW_RTOL, assert_close, lcg_signal, window_spec)
-from oracle import mel_oracle, stft_oracle, window_oracle
+                         WINDOW_ATOL, WINDOW_RTOL, assert_close, istft_spectrum, lcg_signal,
+                         window_spec)
+from oracle import istft_oracle, mel_oracle, stft_oracle, window_oracle
 
 
 def _param(spec):
@@ -142,3 +143,42 @@ def test_mfcc_goldens(goldens):
         assert_close(got, goldens.values(key), tol[0], tol[1], key)
         n += 1
     assert n == 9
+
+
+def test_istft_goldens(goldens):
+    """Stft.invert against librosa's least-squares synthesis
+    (soundml/test/istft/istft_goldens.ml:62-88), incl. explicit lengths."""
+    n = 0
+    for key, stem, name, e in goldens.cases("istft"):
+        p = e["params"]
+        c = stft_oracle.StftConfig(p["fft_size"], hop=p["hop"], win_length=p["win_length"],
+                                   alignment=p["alignment"], pad="constant", pad_value=0.0)
+        z = istft_spectrum(p["fft_size"], p["frames"], p["dtype"])
+        f32 = p["dtype"] == "float32"
+        got = istft_oracle.invert(c, z, length=p.get("length"),
+                                  dtype=np.float32 if f32 else np.float64)
+        assert_close(got, goldens.values(key), F32_RTOL if f32 else F64_RTOL,
+                     F32_ATOL if f32 else F64_ATOL, key)
+        n += 1
+    assert n == 88
+
+
+def test_istft_round_trip_and_errors():
+    """invert(transform(x)) == x wherever the envelope is conditioned
+    (istft_law.ml), and the reference's precondition messages."""
+    x = lcg_signal(3000, STFT_SEED)
+    for alignment in ("centered", "left"):
+        c = stft_oracle.StftConfig(256, hop=64, alignment=alignment)
+        z = stft_oracle.transform(c, x)
+        y = istft_oracle.invert(c, z, length=len(x))
+        lo, hi = (0, len(x)) if alignment == "centered" else (256, len(x) - 256)
+        np.testing.assert_allclose(y[lo:hi], x[lo:hi], rtol=0, atol=1e-12)
+    with pytest.raises(ValueError, match="overlap-added squared"):
+        istft_oracle.invert(stft_oracle.StftConfig(64, hop=65), np.zeros((33, 2), complex))
+    with pytest.raises(ValueError, match="frequency bins"):
+        istft_oracle.invert(stft_oracle.StftConfig(64, hop=16), np.zeros((32, 2), complex))
+    with pytest.raises(ValueError, match="length must be non-negative"):
+        istft_oracle.invert(stft_oracle.StftConfig(64, hop=16), np.zeros((33, 2), complex), length=-1)
+    c = stft_oracle.StftConfig(64, hop=16)
+    assert istft_oracle.output_length(c, 0) == 0 and istft_oracle.output_length(c, 9) == 128
+    assert istft_oracle.invert(c, np.zeros((33, 0), complex)).shape == (0,)
