@@ -104,6 +104,23 @@ def main():
         report("resample_stft_mel", f"{clips} clips x 10 s @44.1 kHz -> 22.05 kHz -> mel 128",
                ms, clips * (n * 4 + 128 * frames * 4), clips * 10.0, per)
 
+    # ---- analysis + least-squares synthesis round trip, 1024 x 10 s clips
+    if not args.only or "istft" in args.only:
+        clips = max(1, int(1024 * args.scale))
+        n = 220500
+        from soundml_b200 import synth
+        x = synth.clips_torch(clips, n, device=dev)
+        sc = sb.Stft.Config.create(fft_size=2048, hop=512)
+        z = sb.Stft.transform(sc, x)
+        c0 = sb.kernel_launch_count()
+        ms = timed(lambda: sb.Stft.invert(sc, z, length=n), max(1, args.steps // 2), 1)
+        per = (sb.kernel_launch_count() - c0) // (max(1, args.steps // 2) + 1)
+        y = sb.Stft.invert(sc, z, length=n)
+        err = ((y - x).abs().max() / x.abs().max()).item()
+        report("istft", f"{clips} clips x 10 s @22.05 kHz, fft 2048 hop 512, complex64 -> f32",
+               ms, z.numel() * 8 + clips * n * 4, clips * 10.0, per,
+               {"round_trip_peak_rel_err": err})
+
 
 if __name__ == "__main__":
     main()

@@ -192,6 +192,7 @@ struct smb_stft_plan {
   double* d_window64 = nullptr;
   double2* d_twiddle64 = nullptr;
   double* d_folded = nullptr;        // synthesis: folded squared window, one entry per residue
+  float* d_window_inv = nullptr;     // synthesis fast path: window / 2048
   float* d_window32 = nullptr;       // fast path tables (fft 2048 only)
   float2* d_tw_pass = nullptr;
   float2* d_tw_post = nullptr;
@@ -270,6 +271,7 @@ struct smb_stft_plan {
     cudaFree(d_window64);
     cudaFree(d_twiddle64);
     cudaFree(d_folded);
+    cudaFree(d_window_inv);
     cudaFree(d_window32);
     cudaFree(d_tw_pass);
     cudaFree(d_tw_post);
@@ -986,6 +988,20 @@ int smb_stft_invert(smb_stft_plan* plan, const void* z, int64_t batch, int64_t f
       a.folded = p->d_folded;
       a.in_f64 = in_dtype == SMB_F64;
       a.out_f64 = out_dtype == SMB_F64;
+      const bool fast = p->path != SMB_PATH_GENERIC && smb::istft2048_supports(a);
+      if (!fast && p->path == SMB_PATH_FAST)
+        throw smb::invalid_argument(
+            "soundml_b200: the fft-2048 synthesis kernel does not cover this geometry");
+      if (fast) {
+        if (!p->d_window_inv) {
+          std::vector<float> w((size_t)p->geom.fft);
+          for (size_t j = 0; j < w.size(); ++j) w[j] = (float)(p->window[j] / 2048.0);
+          p->d_window_inv = upload(w);
+        }
+        CK(smb::launch_istft2048(a, p->d_window_inv, p->d_tw_pass, p->d_tw_post, nb, p->sm_count,
+                                 st));
+        return;
+      }
       CK(smb::launch_istft(a, nb, st));
     };
     if (mem == SMB_MEM_DEVICE) {

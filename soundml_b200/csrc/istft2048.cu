@@ -1,0 +1,276 @@
+// Least-squares STFT synthesis for fft_size = 2048, complex64 -> float32 (sm_100a).
+//
+// Same synthesis equation and envelope as istft_kernels.cu (Stft.invert,
+// stft.ml:693-939), with the inverse transforms on the register FFT of the fused
+// analysis kernel.  A CTA of 16 warps owns a run of R hops of output; with C =
+// ceil(2048 / hop) frames overlapping one position, R = 16 - (C - 1) when runs
+// start on a frame boundary (left width a multiple of the hop) and 16 - C
+// otherwise, so at most 16 frames reach a run.  They are
+//   * fetched together, [bins][16 frames] along the contiguous frame axis, into a
+//     padded shared-memory tile (the spectrum is stored frames-last, so a single
+//     frame is a stride-`frames` column: the tile is what keeps the reads
+//     coalesced),
+//   * inverted one per warp: Zinv[k] = (Y[k] + conj Y[1024-k]) + i W^-k (Y[k] -
+//     conj Y[1024-k]) for the bin pair each lane holds, the 1024-k halves moved
+//     into place by warp shuffle, then the 32 x 32 forward FFT of conj(Zinv)
+//     (the tile's memory is reused for the transposes),
+//   * windowed (1/2048 folded into the window) and added into the run's
+//     accumulator in C phases -- frames of one residue class modulo C never
+//     overlap, so each phase is collision-free and the summation order is fixed
+//     (deterministic output),
+//   * divided by the envelope and written once.
+// 3 of every 16 transforms (hop 512) are recomputed by the neighbouring run.
+#include <cstdint>
+
+#include "fft32.cuh"
+#include "kernels.h"
+
+namespace smb {
+
+namespace {
+
+using namespace fft32impl;
+
+constexpr int kN = 2048;
+constexpr int kHalf = 1024;
+constexpr int kBins = 1025;
+constexpr int kWarps = 16;
+constexpr int kTileStride = 17;                     // float2 per bin row: 16 frames + 1 pad
+constexpr int kExStride = 34;
+constexpr int kExFloats = 32 * kExStride * 2;
+// shared by the spectrum tile [1025][17] complex and, after it, the 16 transposes
+constexpr int kWorkFloats = ((kBins * kTileStride * 2 + 3) / 4) * 4;
+static_assert(kWorkFloats >= kWarps * kExFloats, "transposes fit the tile space");
+
+__device__ constexpr float kW64C[16] = {
+    1.0f, 0.9951847266721969f, 0.9807852804032304f, 0.9569403357322088f,
+    0.9238795325112867f, 0.881921264348355f, 0.8314696123025452f, 0.773010453362737f,
+    0.7071067811865476f, 0.6343932841636455f, 0.5555702330196023f, 0.4713967368259978f,
+    0.38268343236508984f, 0.29028467725446233f, 0.19509032201612833f, 0.09801714032956077f};
+__device__ constexpr float kW64S[16] = {
+    0.0f, -0.0980171403295606f, -0.19509032201612825f, -0.2902846772544623f,
+    -0.3826834323650898f, -0.47139673682599764f, -0.5555702330196022f, -0.6343932841636455f,
+    -0.7071067811865475f, -0.773010453362737f, -0.8314696123025452f, -0.8819212643483549f,
+    -0.9238795325112867f, -0.9569403357322089f, -0.9807852804032304f, -0.9951847266721968f};
+
+__device__ __forceinline__ long long ceil_div_ll(long long a, long long b) {   // b > 0
+  return a >= 0 ? (a + b - 1) / b : -((-a) / b);
+}
+
+// Forward complex FFT of 1024 points spread over a warp (see ols2048.cu).
+__device__ __forceinline__ void fft1024(float2 (&a)[32], float2* ex, const float4* tw4, int lane) {
+  fft32(a);
+#pragma unroll
+  for (int k1 = 0; k1 < 32; k1 += 2) {
+    const float4 t = tw4[(k1 >> 1) * 32 + lane];
+    ex[k1 * kExStride + lane] =
+        k1 == 0 ? a[0] : make_float2(a[k1].x * t.x - a[k1].y * t.y, a[k1].x * t.y + a[k1].y * t.x);
+    ex[(k1 + 1) * kExStride + lane] = make_float2(a[k1 + 1].x * t.z - a[k1 + 1].y * t.w,
+                                                  a[k1 + 1].x * t.w + a[k1 + 1].y * t.z);
+  }
+  __syncwarp();
+  const float4* e4 = reinterpret_cast<const float4*>(ex + lane * kExStride);
+#pragma unroll
+  for (int n2 = 0; n2 < 32; n2 += 2) {
+    const float4 v = e4[n2 >> 1];
+    a[n2] = make_float2(v.x, v.y);
+    a[n2 + 1] = make_float2(v.z, v.w);
+  }
+  __syncwarp();
+  fft32(a);
+}
+
+struct Istft2048Params {
+  IstftArgs a;
+  const float* window;       // [2048] analysis window / 2048
+  const float2* tw_pass;     // [32][32]  W_1024^(k1 n2)
+  const float2* tw_base;     // [32]      W_2048^l
+  int classes;               // C = ceil(2048 / hop)
+  int run_hops;              // R
+  long long runs_per_signal, total_runs;
+};
+
+__global__ void __launch_bounds__(kWarps * 32, 1)
+istft2048_kernel(const Istft2048Params p) {
+  extern __shared__ __align__(16) float smem[];
+  float2* sTwPass = reinterpret_cast<float2*>(smem);                  // [16][32][2]
+  float2* sTwBase = sTwPass + 1024;                                   // [32]
+  float* sWindow = reinterpret_cast<float*>(sTwBase + 32);            // [2048]
+  float* sWork = sWindow + kN;                 // spectrum tile [1025][17] float2, then 16 transposes
+  float* sAcc = sWork + kWorkFloats;           // [run_hops * hop]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const IstftArgs& a = p.a;
+  for (int i = tid; i < 1024; i += blockDim.x) {
+    const int l = i & 31, k1 = i >> 5;
+    sTwPass[(((k1 >> 1) * 32 + l) << 1) + (k1 & 1)] = p.tw_pass[i];
+  }
+  if (tid < 32) sTwBase[tid] = p.tw_base[tid];
+  for (int i = tid; i < kN; i += blockDim.x) sWindow[i] = p.window[i];
+  __syncthreads();
+
+  float2* tile = reinterpret_cast<float2*>(sWork);
+  float2* ex = reinterpret_cast<float2*>(sWork + warp * kExFloats);
+  const float4* tw4 = reinterpret_cast<const float4*>(sTwPass);
+  const float2 wl = sTwBase[lane];
+  const int partner = (32 - lane) & 31;
+  const int hop = a.hop;
+  const int run_len = p.run_hops * hop;
+  const long long span = (a.count - 1) * (long long)hop + kN;
+  const unsigned tile_base = (unsigned)__cvta_generic_to_shared(tile);
+
+  for (long long run = blockIdx.x; run < p.total_runs; run += gridDim.x) {
+    const long long b = run / p.runs_per_signal;
+    const long long m0 = (run - b * p.runs_per_signal) * run_len;
+    const long long m1 = min(m0 + run_len, a.out_len);
+    const long long q0 = m0 + a.left;
+    const long long q1 = min(m1 + a.left, span);                      // positions [q0, q1) receive taps
+    const float2* z = reinterpret_cast<const float2*>(a.z) + b * kBins * a.frames;
+    float* out = reinterpret_cast<float*>(a.out) + b * a.out_len;
+    long long p_lo = 0, p_hi = -1;
+    if (q1 > q0) {
+      p_hi = min(a.count - 1, (q1 - 1) / hop);
+      p_lo = max(0LL, ceil_div_ll(q0 - kN + 1, hop));
+    }
+    const int nf = (int)(p_hi - p_lo + 1);                             // <= 16 by construction
+
+    for (int i = tid; i < run_len; i += blockDim.x) sAcc[i] = 0.0f;
+    // ---- spectrum tile: bins x nf frames, frames contiguous in global memory
+    for (int i = tid; i < kBins * 16; i += blockDim.x) {
+      const int k = i >> 4, t = i & 15;
+      if (t < nf)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_base + 8u * (k * kTileStride + t)),
+                     "l"(z + (long long)k * a.frames + p_lo + t) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    float2 v[32];
+    const bool active = warp < nf;
+    float2 r[16];
+    float2 mid = make_float2(0.f, 0.f);
+    if (active) {
+      // lane l, register k2 < 16 holds the bin pair k = l + 32 k2 and 1024 - k
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const int k = lane + 32 * k2;
+        v[k2] = tile[k * kTileStride + warp];
+        r[k2] = tile[(kHalf - k) * kTileStride + warp];
+      }
+      mid = tile[512 * kTileStride + warp];
+      if (lane == 0) { v[0].y = 0.0f; r[0].y = 0.0f; }                // DC and Nyquist are real
+    }
+    __syncthreads();                                                   // the tile becomes transpose space
+    if (active) {
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const float2 yk = v[k2], yn = r[k2];
+        const float2 w = k2 == 0 ? wl
+                                 : make_float2(wl.x * kW64C[k2] - wl.y * kW64S[k2],
+                                               wl.x * kW64S[k2] + wl.y * kW64C[k2]);   // W_2048^k
+        const float2 E = make_float2(yk.x + yn.x, yk.y - yn.y);       // Y[k] + conj Y[nk]
+        const float2 O = make_float2(yk.x - yn.x, yk.y + yn.y);       // Y[k] - conj Y[nk]
+        const float2 co = make_float2(w.x * O.x + w.y * O.y, w.x * O.y - w.y * O.x);    // conj(w) O
+        const float2 wo = make_float2(co.x, -co.y);                                      // w conj(O)
+        const float2 zk = make_float2(E.x - co.y, E.y + co.x);        // Zinv[k]
+        const float2 zn = make_float2(E.x - wo.y, -E.y + wo.x);       // Zinv[1024-k]
+        v[k2] = make_float2(zk.x, -zk.y);
+        r[k2] = make_float2(zn.x, -zn.y);
+      }
+      mid = make_float2(2.0f * mid.x, 2.0f * mid.y);                  // conj(Zinv[512]) = 2 Y[512]
+#pragma unroll
+      for (int R = 16; R < 32; ++R) {
+        const float2 own = r[31 - R];
+        const float2 alt = R == 16 ? mid : r[(32 - R) & 15];
+        const float sx = lane == 0 ? alt.x : own.x;
+        const float sy = lane == 0 ? alt.y : own.y;
+        v[R].x = __shfl_sync(0xffffffffu, sx, partner);
+        v[R].y = __shfl_sync(0xffffffffu, sy, partner);
+      }
+      fft1024(v, ex, tw4, lane);
+      // v[q] = conj(z[n]), n = lane + 32 q:  y[2n] = v.x, y[2n+1] = -v.y; window now
+      const float2* w2 = reinterpret_cast<const float2*>(sWindow);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float2 w = w2[lane + 32 * q];
+        v[q] = make_float2(v[q].x * w.x, -v[q].y * w.y);
+      }
+    }
+    // ---- overlap-add in C collision-free phases
+    const long long frame = p_lo + warp;
+    const long long off = frame * hop - q0;                            // run position of the frame's tap 0
+    for (int c = p.classes - 1; c >= 0; --c) {
+      if (active && (int)(frame % p.classes) == c) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const long long i0 = off + 2 * (lane + 32 * q);
+          if (i0 >= 0 && i0 < q1 - q0) sAcc[i0] += v[q].x;
+          if (i0 + 1 >= 0 && i0 + 1 < q1 - q0) sAcc[i0 + 1] += v[q].y;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- envelope division, trim, zero extension (stft.ml:846-894)
+    const long long head = min(span, (long long)(kN - hop));
+    const long long stop = max(head, min(span, a.count * (long long)hop));
+    for (long long m = m0 + tid; m < m1; m += blockDim.x) {
+      const long long q = m + a.left;
+      float val = 0.0f;
+      if (q < span) {
+        double e;
+        if (q >= head && q < stop) {
+          e = a.folded[q % hop];
+        } else {
+          const long long first = max(0LL, ceil_div_ll(q - kN + 1, hop));
+          const long long last = min(a.count - 1, q / hop);
+          e = 0.0;
+          for (long long pp = first; pp <= last; ++pp) {
+            const double w = a.window[q - pp * hop];
+            e += w * w;
+          }
+        }
+        if (e == 0.0) e = 1.0;
+        val = (float)((double)sAcc[m - m0] / e);
+      }
+      out[m] = val;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+bool istft2048_supports(const IstftArgs& a) {
+  if (a.fft != kN || a.in_f64 || a.out_f64 || a.hop < 1 || a.hop > kN) return false;
+  const int classes = (kN + a.hop - 1) / a.hop;
+  const int run_hops = 16 - classes + (a.left % a.hop == 0 ? 1 : 0);
+  if (run_hops < 1) return false;
+  // accumulator must fit beside the tile / transpose space
+  return (size_t)run_hops * a.hop * 4 <= 64 * 1024;
+}
+
+cudaError_t launch_istft2048(const IstftArgs& a, const float* window_scaled, const float2* tw_pass,
+                             const float2* tw_base, long long batch, int sm_count,
+                             cudaStream_t st) {
+  if (batch == 0 || a.out_len == 0) return cudaSuccess;
+  Istft2048Params p;
+  p.a = a;
+  p.window = window_scaled;
+  p.tw_pass = tw_pass;
+  p.tw_base = tw_base;
+  p.classes = (kN + a.hop - 1) / a.hop;
+  p.run_hops = 16 - p.classes + (a.left % a.hop == 0 ? 1 : 0);
+  const long long run_len = (long long)p.run_hops * a.hop;
+  p.runs_per_signal = (a.out_len + run_len - 1) / run_len;
+  p.total_runs = p.runs_per_signal * batch;
+  const size_t smem = (size_t)(1024 + 32) * sizeof(float2) + (size_t)kN * 4 +
+                      (size_t)kWorkFloats * 4 + (size_t)run_len * 4;
+  cudaError_t e = cudaFuncSetAttribute(istft2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = (int)(p.total_runs < sm_count ? p.total_runs : sm_count);
+  istft2048_kernel<<<grid, kWarps * 32, smem, st>>>(p);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+}  // namespace smb

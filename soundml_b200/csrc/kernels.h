@@ -47,6 +47,11 @@ struct IstftArgs {
   int in_f64, out_f64;
 };
 cudaError_t launch_istft(const IstftArgs& a, long long batch, cudaStream_t st);
+// fft 2048, complex64 -> float32 on the register FFT (istft2048.cu)
+bool istft2048_supports(const IstftArgs& a);
+cudaError_t launch_istft2048(const IstftArgs& a, const float* window_scaled, const float2* tw_pass,
+                             const float2* tw_base, long long batch, int sm_count,
+                             cudaStream_t st);
 
 // ---- fast path: fft 2048, float32, fused frame+window+rFFT+|X|^p(+mel) -------
 // Tile shape of the fused kernel, shared with the host-side mel schedule: a group

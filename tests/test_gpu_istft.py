@@ -9,6 +9,8 @@ from oracle import istft_oracle, stft_oracle
 
 pytestmark = pytest.mark.gpu
 
+FAST_TOL = 2e-6      # float32 synthesis kernel, max |got - want| / max |want| per call
+
 
 @pytest.fixture(scope="module")
 def sb(lib):
@@ -39,6 +41,8 @@ def test_istft_goldens_on_gpu(sb, goldens):
     (256, 64, None, "centered"), (256, 64, None, "left"), (256, 64, None, "right"),
     (100, 30, 80, "centered"), (2048, 512, None, "centered"), (2048, 500, 1200, "left"),
     (31, 5, None, "centered"), (64, 1, None, "centered"), (512, 512, None, "centered"),
+    (2048, 512, None, "right"), (2048, 1024, None, "centered"), (2048, 150, None, "centered"),
+    (2048, 300, 2000, "left"),
 ])
 def test_invert_matches_oracle(sb, fft, hop, win, alignment):
     window = "rectangular" if hop == fft else "hann"
@@ -47,7 +51,7 @@ def test_invert_matches_oracle(sb, fft, hop, win, alignment):
     oc = stft_oracle.StftConfig(fft, hop=hop, win_length=win, alignment=alignment, window=window)
     rng = np.random.default_rng(fft + hop)
     bins = fft // 2 + 1
-    for frames in (1, 2, 7, 40):
+    for frames in (1, 2, 7, 40) + ((3000 // hop + 20,) if fft == 2048 else ()):
         z = rng.standard_normal((2, 3, bins, frames)) + 1j * rng.standard_normal((2, 3, bins, frames))
         for length in (None, 0, 1, hop * frames // 2 + 3, istft_oracle.output_length(oc, frames) + 50):
             want = istft_oracle.invert(oc, z, length=length)
@@ -57,12 +61,35 @@ def test_invert_matches_oracle(sb, fft, hop, win, alignment):
                 scale = max(np.abs(want).max(), 1e-300)
                 assert np.abs(got - want).max() / scale <= 1e-12, (frames, length)
         z32 = z.astype(np.complex64)
-        got32 = sb.Stft.invert(c, z32)
         want32 = istft_oracle.invert(oc, z32, dtype=np.float32)
+        c.set_path("generic")                    # double interior: the reference's f32 gate
+        got32 = sb.Stft.invert(c, z32)
         assert got32.dtype == np.float32
         assert_close(got32, want32, F32_RTOL, F32_ATOL, "f32")
+        c.set_path("auto")                       # fft 2048: float32 register-FFT kernel
+        auto32 = sb.Stft.invert(c, z32)
+        if want32.size:
+            assert np.abs(auto32 - want32).max() / np.abs(want32).max() <= FAST_TOL, (frames,)
         mixed = sb.Stft.invert(c, z32, dtype=np.float64)
         assert mixed.dtype == np.float64
+
+
+def test_fast_and_generic_kernels_agree_on_long_batches(sb):
+    """fft 2048 / hop 512 complex64: the register-FFT kernel against the double
+    interior kernel over many runs per clip, explicit lengths and a ragged tail."""
+    import torch
+    c = sb.Stft.Config.create(fft_size=2048, hop=512)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    z = torch.randn((5, 1025, 431), dtype=torch.complex64, device="cuda", generator=g)
+    for length in (None, 220500, 100000, 230000, 1):
+        c.set_path("fast")
+        fast = sb.Stft.invert(c, z, length=length)
+        c.set_path("generic")
+        ref = sb.Stft.invert(c, z, length=length)
+        assert fast.shape == ref.shape
+        err = (fast - ref).abs().max().item() / ref.abs().max().item()
+        assert err <= FAST_TOL, (length, err)
+    c.set_path("auto")
 
 
 def test_round_trip_at_headline_geometry(sb):
