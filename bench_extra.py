@@ -104,6 +104,51 @@ def main():
         report("resample_stft_mel", f"{clips} clips x 10 s @44.1 kHz -> 22.05 kHz -> mel 128",
                ms, clips * (n * 4 + 128 * frames * 4), clips * 10.0, per)
 
+    # ---- config 1 outputs at batch scale: complex spectrum and power spectrogram, 1024 clips
+    if not args.only or "spectrum" in args.only:
+        clips = max(1, int(1024 * args.scale))
+        n = 220500
+        from soundml_b200 import synth
+        x = synth.clips_torch(clips, n, device=dev)
+        sc = sb.Stft.Config.create(fft_size=2048, hop=512)
+        frames = sb.Stft.frames(sc, n)
+        for name, fn, width in (("stft_power", sb.Stft.power_spectrum, 4),
+                                ("stft_complex", sb.Stft.transform, 8)):
+            out = fn(sc, x)
+            c0 = sb.kernel_launch_count()
+            ms = timed(lambda: fn(sc, x, out=out), args.steps, 2)
+            per = (sb.kernel_launch_count() - c0) // (args.steps + 2)
+            report(name, f"{clips} clips x 10 s @22.05 kHz, fft 2048 hop 512 -> [1025, {frames}]",
+                   ms, clips * (n * 4 + 1025 * frames * width), clips * 10.0, per)
+            del out
+        del x
+
+    # ---- SURVEY 8f rank 1 and the standalone Mel.apply: 1024 clips
+    if not args.only or "epilogue" in args.only:
+        clips = max(1, int(1024 * args.scale))
+        n = 220500
+        from soundml_b200 import synth
+        x = synth.clips_torch(clips, n, device=dev)
+        sc = sb.Stft.Config.create(fft_size=2048, hop=512)
+        mc = sb.Mel.Config.create(n_mels=128, sample_rate=22050, fft_size=2048)
+        frames = sb.Stft.frames(sc, n)
+        for name, fn, out_rows in (("mfcc20", lambda: sb.mfcc(sc, mc, x, n_mfcc=20), 20),
+                                   ("logmel_db", lambda: sb.Convert.power_to_db(
+                                       sb.mel_spectrogram(sc, mc, x), top_db=80.0), 128)):
+            c0 = sb.kernel_launch_count()
+            ms = timed(fn, args.steps, 2)
+            per = (sb.kernel_launch_count() - c0) // (args.steps + 2)
+            report(name, f"{clips} clips x 10 s @22.05 kHz -> [{out_rows}, {frames}]", ms,
+                   clips * (n * 4 + out_rows * frames * 4), clips * 10.0, per)
+        s_pow = sb.Stft.power_spectrum(sc, x)
+        del x
+        c0 = sb.kernel_launch_count()
+        ms = timed(lambda: sb.Mel.apply(mc, s_pow), args.steps, 2)
+        per = (sb.kernel_launch_count() - c0) // (args.steps + 2)
+        report("mel_apply", f"{clips} x [1025, {frames}] f32 power spectrogram -> [128, {frames}]", ms,
+               clips * frames * (1025 + 128) * 4, clips * 10.0, per)
+        del s_pow
+
     # ---- analysis + least-squares synthesis round trip, 1024 x 10 s clips
     if not args.only or "istft" in args.only:
         clips = max(1, int(1024 * args.scale))

@@ -230,6 +230,226 @@ def invert(c, z, length=None, dtype=None):
     return out
 
 
+# ---- streaming analysis ------------------------------------------------------
+
+def _last(t):
+    return int(t.shape[-1])
+
+
+def _cat(parts):
+    if len(parts) == 1:
+        return parts[0]
+    if _lib.is_torch(parts[0]):
+        import torch
+        return torch.cat(parts, dim=-1)
+    return np.concatenate(parts, axis=-1)
+
+
+def _copy(t):
+    return t.clone() if _lib.is_torch(t) else np.array(t, copy=True)
+
+
+def _take(t, idx):
+    """``take_last`` (stft.ml:307-312): gather along the time axis."""
+    if _lib.is_torch(t):
+        import torch
+        return t.index_select(-1, torch.as_tensor(idx, dtype=torch.int64, device=t.device))
+    return np.take(t, np.asarray(idx, dtype=np.int64), axis=-1)
+
+
+def _full(t, count, value):
+    shape = tuple(t.shape[:-1]) + (count,)
+    if _lib.is_torch(t):
+        import torch
+        return torch.full(shape, value, dtype=t.dtype, device=t.device)
+    return np.full(shape, value, dtype=t.dtype)
+
+
+class Kernel:
+    """``Stft.Kernel`` (stft.ml:375-622): the chunked form of ``transform``.
+
+    ``step`` feeds a chunk ``[..., m]`` and returns the frames it completed
+    (``[..., bins, frames]``) or ``None``; ``flush`` installs the right boundary
+    extension and returns the remaining frames.  Concatenating everything
+    returned, for any partition of the signal into chunks, equals
+    ``transform c x`` -- bit for bit here too, because a frame's arithmetic on
+    the GPU does not depend on which call carries it.
+
+    The state is the reference's: the padded stream not yet consumed
+    (``pending``), the raw prelude kept until the left extension is computable
+    (``left + 1`` samples under reflection, one otherwise), the last
+    ``right + 1`` raw samples for the right extension, and ``skip`` for hops
+    wider than the frame.  Frames are evaluated by a left-aligned twin of the
+    configuration (same analysis window) over the pending stream.
+    """
+
+    def __init__(self, c, channels, max_block, _analyse=None):
+        if channels < 1:
+            raise ValueError(
+                f"prepare: cannot analyse {channels} channels (channels must be at least 1)")
+        if max_block < 1:
+            raise ValueError(
+                f"prepare: cannot accept blocks of {max_block} samples "
+                "(max_block must be at least 1)")
+        self.cfg = c
+        self.fft, self.hop = c.fft_size, c.hop
+        self.left = {"centered": self.fft // 2, "left": 0, "right": self.fft - 1}[c.alignment]
+        self.right = self.fft // 2 if c.alignment == "centered" else 0
+        self._analyse = _analyse
+        self._twin = None
+        self.reset()
+
+    @classmethod
+    def prepare(cls, c, *, channels, max_block):
+        """``Kernel.prepare cdtype c dtype ~channels ~max_block``; the dtypes are
+        those of the chunks fed."""
+        return cls(c, channels, max_block)
+
+    def reset(self):
+        """``Kernel.reset`` (stft.ml:403-411)."""
+        self.started = self.drained = False
+        self.received = 0
+        self.prelude, self.pending = [], []
+        self.pending_len = 0
+        self.tail = None
+        self.skip = 0
+
+    # frames of a left-aligned stream: the twin plan shares the analysis window
+    def _frames_of(self, samples, count):
+        span = (count - 1) * self.hop + self.fft
+        if _last(samples) != span:
+            samples = samples[..., :span]
+        if self._analyse is not None:
+            return self._analyse(samples, count)
+        if self._twin is None:
+            h = C.c_void_p()
+            w = self.cfg.analysis_window
+            _lib.check(_lib.lib.smb_stft_plan_create_with_window(
+                C.byref(h), self.fft, self.hop, _lib.ALIGNMENTS["left"], _lib.PADS["constant"],
+                0.0, w.ctypes.data_as(C.POINTER(C.c_double))))
+            self._twin = Config(h, self.cfg.window, "left", "constant", 0.0, self.cfg.scale)
+        return transform(self._twin, samples)
+
+    def _process(self, extra, extra_len):                     # stft.ml:417-446
+        total = self.pending_len + extra_len
+        count = 0 if total < self.fft else 1 + (total - self.fft) // self.hop
+        if count == 0:
+            self.pending += [_copy(t) for t in extra if _last(t) > 0]
+            self.pending_len = total
+            return None
+        samples = _cat(self.pending + list(extra))
+        out = self._frames_of(samples, count)
+        next_start = count * self.hop
+        if next_start >= total:
+            self.skip += next_start - total
+            self.pending, self.pending_len = [], 0
+        else:
+            self.pending = [_copy(samples[..., next_start:total])]
+            self.pending_len = total - next_start
+        return out
+
+    def _install_threshold(self):                              # stft.ml:452-458
+        return self.left + 1 if self.cfg.pad == "reflect" else 1
+
+    def _left_pad(self, x):                                    # stft.ml:463-480
+        if self.left == 0:
+            return None
+        if self.cfg.pad == "constant":
+            return _full(x, self.left, self.cfg.pad_value)
+        if self.cfg.pad == "reflect":
+            return _take(x, [self.left - j for j in range(self.left)])
+        return _take(x, [0] * self.left)
+
+    def _install(self, x):                                     # stft.ml:485-497
+        n = _last(x)
+        if self.right > 0:
+            keep = min(self.right + 1, n)
+            self.tail = _copy(x[..., n - keep:n])
+        self.started = True
+        self.prelude = []
+        lp = self._left_pad(x)
+        if lp is None:
+            return self._process([x], n)
+        return self._process([lp, x], self.left + n)
+
+    def _update_tail(self, chunk):                             # stft.ml:501-513
+        keep = self.right + 1
+        m = _last(chunk)
+        if m >= keep:
+            self.tail = _copy(chunk[..., m - keep:m])
+        else:
+            combined = chunk if self.tail is None else _cat([self.tail, chunk])
+            cm = _last(combined)
+            self.tail = _copy(combined[..., max(0, cm - keep):cm])
+
+    def _right_pad(self):                                      # stft.ml:517-530
+        tl = _last(self.tail)
+        if self.cfg.pad == "constant":
+            return _full(self.tail, self.right, self.cfg.pad_value)
+        if self.cfg.pad == "reflect":
+            return _take(self.tail, [tl - 2 - i for i in range(self.right)])
+        return _take(self.tail, [tl - 1] * self.right)
+
+    def step(self, chunk):
+        """``Kernel.step k chunk`` (stft.ml:532-569)."""
+        if self.drained:
+            raise ValueError("step: cannot feed a drained kernel (flush consumed the tail; "
+                             "reset before reusing)")
+        if any(int(d) == 0 for d in chunk.shape[:-1]):
+            raise ValueError("step: cannot analyse a chunk with a zero-size leading axis "
+                             "(channels must be at least 1)")
+        m = _last(chunk)
+        if m == 0:
+            return None
+        self.received += m
+        if not self.started:
+            if self.received >= self._install_threshold():
+                return self._install(_cat(self.prelude + [chunk]))
+            self.prelude.append(_copy(chunk))
+            return None
+        if self.right > 0:
+            self._update_tail(chunk)
+        if self.skip >= m:
+            self.skip -= m
+            return None
+        dropped, self.skip = self.skip, 0
+        if dropped:
+            chunk = chunk[..., dropped:m]
+        return self._process([chunk], m - dropped)
+
+    def flush(self):
+        """``Kernel.flush k`` (stft.ml:571-606)."""
+        if self.drained:
+            return None
+        self.drained = True
+        out = None
+        if not self.started:
+            if self.received > 0:
+                x = _cat(self.prelude)
+                idx = self.cfg.source_indices(_last(x))        # pad_signal, stft.ml:318-338
+                padded = _take(x, np.maximum(idx, 0))
+                if (idx < 0).any():                            # constant extension
+                    fill = np.nonzero(idx < 0)[0]
+                    if _lib.is_torch(padded):
+                        import torch
+                        fill = torch.as_tensor(fill, dtype=torch.int64, device=padded.device)
+                    padded[..., fill] = self.cfg.pad_value
+                self.started, self.prelude = True, []
+                out = self._process([padded], _last(padded))
+        elif self.right > 0:
+            rp = self._right_pad()
+            r = _last(rp)
+            if self.skip >= r:
+                self.skip -= r
+            else:
+                dropped, self.skip = self.skip, 0
+                if dropped:
+                    rp = rp[..., dropped:r]
+                out = self._process([rp], r - dropped)
+        self.pending, self.pending_len = [], 0
+        return out
+
+
 def times(c, sample_rate, n, dtype=np.float64):
     """``Stft.times`` (stft.ml:245-254)."""
     if sample_rate < 1:

@@ -1,0 +1,72 @@
+"""Stft.Kernel through the CUDA kernels: chunked analysis equals the offline
+transform bit for bit, on host arrays and on device tensors.
+``pytest -m gpu``."""
+import numpy as np
+import pytest
+
+from golden_util import STFT_SEED, lcg_signal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb(lib):
+    import torch
+    assert torch.cuda.is_available()
+    return lib
+
+
+def run_chunks(k, x, sizes, cat):
+    outs, at = [], 0
+    for m in sizes:
+        o = k.step(x[..., at:at + m])
+        at += m
+        if o is not None:
+            outs.append(o)
+    o = k.flush()
+    if o is not None:
+        outs.append(o)
+    return cat(outs) if outs else None
+
+
+@pytest.mark.parametrize("case", [
+    dict(fft_size=64, hop=16, alignment="centered", pad="reflect"),
+    dict(fft_size=100, hop=30, win_length=80, alignment="right", pad="edge"),
+    dict(fft_size=16, hop=40, alignment="centered", pad=("constant", 0.5)),
+    dict(fft_size=2048, hop=512, alignment="centered", pad="reflect"),
+    dict(fft_size=2048, hop=500, win_length=1200, alignment="left", pad="reflect"),
+])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_partition_law_on_gpu(sb, case, dtype):
+    c = sb.Stft.Config.create(**case)
+    rng = np.random.default_rng(11)
+    big = case["fft_size"] == 2048
+    for n in ((1, 700, 5000, 20011) if big else (1, 33, 517, 4000)):
+        x = lcg_signal(2 * n, STFT_SEED).reshape(2, n).astype(dtype)
+        want = sb.Stft.transform(c, x)
+        for _ in range(3):
+            cuts = np.sort(rng.integers(0, n + 1, size=rng.integers(0, 6)))
+            sizes = list(np.diff(np.concatenate([[0], cuts, [n]])))
+            k = sb.Stft.Kernel.prepare(c, channels=2, max_block=n)
+            got = run_chunks(k, x, sizes, lambda o: np.concatenate(o, axis=-1))
+            if want.shape[-1] == 0:
+                assert got is None
+            else:
+                assert got.dtype == want.dtype and got.shape == want.shape, (n, sizes)
+                assert np.array_equal(got, want), (n, sizes)
+
+
+def test_device_chunks_match_offline_transform(sb):
+    import torch
+    from soundml_b200 import synth
+    c = sb.Stft.Config.create(fft_size=2048, hop=512)
+    x = synth.clips_torch(8, 220500, device="cuda")
+    want = sb.Stft.transform(c, x)
+    k = sb.Stft.Kernel.prepare(c, channels=8, max_block=65536)
+    sizes = [1000, 24, 65536, 50000, 1, 65536, 220500 - 1000 - 24 - 65536 - 50000 - 1 - 65536]
+    got = run_chunks(k, x, sizes, lambda o: torch.cat(o, dim=-1))
+    assert got.is_cuda and got.shape == want.shape
+    assert torch.equal(got, want)
+    k.reset()
+    again = run_chunks(k, x, [220500], lambda o: torch.cat(o, dim=-1))
+    assert torch.equal(again, want)
