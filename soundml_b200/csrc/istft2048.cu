@@ -14,11 +14,10 @@
 //     conj Y[1024-k]) for the bin pair each lane holds, the 1024-k halves moved
 //     into place by warp shuffle, then the 32 x 32 forward FFT of conj(Zinv)
 //     (the tile's memory is reused for the transposes),
-//   * windowed (1/2048 folded into the window) and added into the run's
-//     accumulator in C phases -- frames of one residue class modulo C never
-//     overlap, so each phase is collision-free and the summation order is fixed
-//     (deterministic output),
-//   * divided by the envelope and written once.
+//   * windowed (1/2048 folded into the window) and left in the warp's transpose
+//     buffer; after one barrier every output position gathers the taps of the
+//     frames that reach it, newest first (fixed order, deterministic), divides
+//     by the envelope and is written once.
 // 3 of every 16 transforms (hop 512) are recomputed by the neighbouring run.
 #include <cstdint>
 
@@ -97,7 +96,7 @@ istft2048_kernel(const Istft2048Params p) {
   float2* sTwBase = sTwPass + 1024;                                   // [32]
   float* sWindow = reinterpret_cast<float*>(sTwBase + 32);            // [2048]
   float* sWork = sWindow + kN;                 // spectrum tile [1025][17] float2, then 16 transposes
-  float* sAcc = sWork + kWorkFloats;           // [run_hops * hop]
+  float* sInvEnv = sWork + kWorkFloats;        // [hop] 1 / envelope of the fully covered positions
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const IstftArgs& a = p.a;
   for (int i = tid; i < 1024; i += blockDim.x) {
@@ -106,6 +105,10 @@ istft2048_kernel(const Istft2048Params p) {
   }
   if (tid < 32) sTwBase[tid] = p.tw_base[tid];
   for (int i = tid; i < kN; i += blockDim.x) sWindow[i] = p.window[i];
+  for (int i = tid; i < p.a.hop; i += blockDim.x) {
+    const double e = p.a.folded[i];
+    sInvEnv[i] = (float)(1.0 / (e == 0.0 ? 1.0 : e));
+  }
   __syncthreads();
 
   float2* tile = reinterpret_cast<float2*>(sWork);
@@ -133,7 +136,6 @@ istft2048_kernel(const Istft2048Params p) {
     }
     const int nf = (int)(p_hi - p_lo + 1);                             // <= 16 by construction
 
-    for (int i = tid; i < run_len; i += blockDim.x) sAcc[i] = 0.0f;
     // ---- spectrum tile: bins x nf frames, frames contiguous in global memory
     for (int i = tid; i < kBins * 16; i += blockDim.x) {
       const int k = i >> 4, t = i & 15;
@@ -188,50 +190,53 @@ istft2048_kernel(const Istft2048Params p) {
       }
       fft1024(v, ex, tw4, lane);
       // v[q] = conj(z[n]), n = lane + 32 q:  y[2n] = v.x, y[2n+1] = -v.y; window now
+      // windowed frame -> this warp's (now idle) transpose buffer, natural order
       const float2* w2 = reinterpret_cast<const float2*>(sWindow);
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
         const float2 w = w2[lane + 32 * q];
-        v[q] = make_float2(v[q].x * w.x, -v[q].y * w.y);
+        ex[lane + 32 * q] = make_float2(v[q].x * w.x, -v[q].y * w.y);
       }
     }
-    // ---- overlap-add in C collision-free phases
-    const long long frame = p_lo + warp;
-    const long long off = frame * hop - q0;                            // run position of the frame's tap 0
-    for (int c = p.classes - 1; c >= 0; --c) {
-      if (active && (int)(frame % p.classes) == c) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const long long i0 = off + 2 * (lane + 32 * q);
-          if (i0 >= 0 && i0 < q1 - q0) sAcc[i0] += v[q].x;
-          if (i0 + 1 >= 0 && i0 + 1 < q1 - q0) sAcc[i0 + 1] += v[q].y;
-        }
-      }
-      __syncthreads();
-    }
-    // ---- envelope division, trim, zero extension (stft.ml:846-894)
+    __syncthreads();
+    // ---- overlap-add as a gather: every output position sums the taps of the
+    // frames that reach it, newest frame first (the order in which the
+    // reference's block planes arrive, stft.ml:806-838), then the envelope
+    // division, trim and zero extension (stft.ml:846-894)
     const long long head = min(span, (long long)(kN - hop));
     const long long stop = max(head, min(span, a.count * (long long)hop));
-    for (long long m = m0 + tid; m < m1; m += blockDim.x) {
-      const long long q = m + a.left;
+    const int n_out = (int)(m1 - m0);
+    const long long full_lo = max(head, q0), full_hi = min(stop, q0 + n_out);
+    const int rel0 = (int)(q0 - p_lo * hop);          // run position 0 relative to frame p_lo's tap 0
+    int res = (int)((q0 + tid) % hop);
+    const int rstep = (int)(blockDim.x % hop);
+    for (int i = tid; i < n_out; i += blockDim.x) {
+      const long long q = q0 + i;
       float val = 0.0f;
       if (q < span) {
-        double e;
-        if (q >= head && q < stop) {
-          e = a.folded[q % hop];
+        const int rel = rel0 + i;
+        int t = min(nf - 1, rel / hop);                // newest frame reaching the position
+        int j = rel - t * hop;
+        float sum = 0.0f;
+        for (; t >= 0 && j < kN; --t, j += hop) sum += sWork[t * kExFloats + j];
+        if (q >= full_lo && q < full_hi) {
+          // every residue class reaches the position completely: tabulated reciprocal
+          val = sum * sInvEnv[res];
         } else {
           const long long first = max(0LL, ceil_div_ll(q - kN + 1, hop));
           const long long last = min(a.count - 1, q / hop);
-          e = 0.0;
+          double e = 0.0;
           for (long long pp = first; pp <= last; ++pp) {
             const double w = a.window[q - pp * hop];
             e += w * w;
           }
+          if (e == 0.0) e = 1.0;
+          val = (float)((double)sum / e);
         }
-        if (e == 0.0) e = 1.0;
-        val = (float)((double)sAcc[m - m0] / e);
       }
-      out[m] = val;
+      out[m0 + i] = val;
+      res += rstep;
+      if (res >= hop) res -= hop;
     }
     __syncthreads();
   }
@@ -244,8 +249,7 @@ bool istft2048_supports(const IstftArgs& a) {
   const int classes = (kN + a.hop - 1) / a.hop;
   const int run_hops = 16 - classes + (a.left % a.hop == 0 ? 1 : 0);
   if (run_hops < 1) return false;
-  // accumulator must fit beside the tile / transpose space
-  return (size_t)run_hops * a.hop * 4 <= 64 * 1024;
+  return true;
 }
 
 cudaError_t launch_istft2048(const IstftArgs& a, const float* window_scaled, const float2* tw_pass,
@@ -263,7 +267,7 @@ cudaError_t launch_istft2048(const IstftArgs& a, const float* window_scaled, con
   p.runs_per_signal = (a.out_len + run_len - 1) / run_len;
   p.total_runs = p.runs_per_signal * batch;
   const size_t smem = (size_t)(1024 + 32) * sizeof(float2) + (size_t)kN * 4 +
-                      (size_t)kWorkFloats * 4 + (size_t)run_len * 4;
+                      (size_t)kWorkFloats * 4 + (size_t)a.hop * 4;
   cudaError_t e = cudaFuncSetAttribute(istft2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
