@@ -10,6 +10,10 @@
      Mel.apply             mel.ml:202-231    -> B200.mel_apply
      Soundml.mel_spectrogram soundml.ml:22-24 -> B200.mel_spectrogram (fused)
      Resample.apply        resample.ml:1913-1936 -> B200.resample_apply
+     Stft.transform_range  stft.ml:652-666   -> B200.transform_range
+     Stft.invert           stft.ml:937-939   -> B200.invert
+     Convert.power_to_db / amplitude_to_db  convert.ml:20-56 -> B200.to_db
+     Soundml.mfcc          soundml.ml:50-95  -> B200.mfcc
 
    Config.create stays in OCaml: the plan is built from the float64 window /
    weights the config already owns, so the two sides cannot disagree. *)
@@ -49,6 +53,31 @@ external resample_apply_c :
   resample_plan -> (float, Bigarray.float32_elt) ba -> int -> int
   -> (float, Bigarray.float32_elt) ba -> unit
   = "soundml_b200_resample_apply"
+
+external resample_apply_f64_c :
+  resample_plan -> (float, Bigarray.float64_elt) ba -> int -> int
+  -> (float, Bigarray.float64_elt) ba -> unit
+  = "soundml_b200_resample_apply_f64"
+
+external transform_range_c :
+  stft_plan -> (float, 'a) ba -> int -> int -> int -> int -> (Complex.t, 'c) ba -> unit
+  = "soundml_b200_transform_range_bc" "soundml_b200_transform_range"
+
+(* length < 0 stands for None *)
+external invert_c :
+  stft_plan -> (Complex.t, 'c) ba -> int -> int -> int -> (float, 'a) ba -> unit
+  = "soundml_b200_invert_bc" "soundml_b200_invert"
+
+(* amplitude -> x -> reference -> amin -> top_db (nan = None) -> out *)
+external to_db_c :
+  bool -> (float, 'a) ba -> float -> float -> float -> (float, 'a) ba -> unit
+  = "soundml_b200_to_db_bc" "soundml_b200_to_db"
+
+(* lifter = 0. stands for None *)
+external mfcc_c :
+  stft_plan -> mel_plan -> (float, 'a) ba -> int -> int -> int -> float -> (float, 'a) ba
+  -> unit
+  = "soundml_b200_mfcc_bc" "soundml_b200_mfcc"
 
 (* The flat storage of a contiguous tensor, shared (resample.ml:94). *)
 let array1_of t = Nx_buffer.to_bigarray1 (Nx.to_buffer t)
@@ -117,4 +146,48 @@ let resample_apply ~sample_rate ~target ~quality x =
   let out = Nx.zeros Nx.float32 (Array.append lead [|total|]) in
   if batch > 0 && n > 0 then
     resample_apply_c plan (array1_of (Nx.contiguous x)) batch n (array1_of out) ;
+  out
+
+(* Replacement body of Stft.invert: the preconditions (check_synthesis,
+   stft.ml:787) stay in OCaml; the library re-validates and raises the same
+   messages. *)
+let invert dtype c ?length z =
+  let rank = Nx.ndim z in
+  let frames = Nx.dim (rank - 1) z in
+  let lead = Array.sub (Nx.shape z) 0 (rank - 2) in
+  let batch = Array.fold_left ( * ) 1 lead in
+  let out_len =
+    match length with Some n -> n | None -> Stft.output_length c ~frames
+  in
+  let out = Nx.zeros dtype (Array.append lead [|out_len|]) in
+  if batch > 0 && out_len > 0 && frames > 0 then
+    invert_c (stft_plan_of c) (array1_of (Nx.contiguous z)) batch frames
+      (match length with Some n -> n | None -> -1)
+      (array1_of out) ;
+  out
+
+(* Replacement body of Convert.power_to_db / amplitude_to_db: elementwise over
+   the flat storage, the top_db clamp is one whole-tensor maximum on the GPU. *)
+let to_db ~amplitude ?(reference = 1.) ~amin ?top_db s =
+  let out = Nx.zeros (Nx.dtype s) (Nx.shape s) in
+  if Nx.numel s > 0 then
+    to_db_c amplitude (array1_of (Nx.contiguous s)) reference amin
+      (match top_db with Some t -> t | None -> Float.nan)
+      (array1_of out) ;
+  out
+
+let mfcc stft_config mel_config ?(n_mfcc = 20) ?lifter x =
+  let n = Nx.dim (Nx.ndim x - 1) x in
+  let lead = leading_shape x in
+  let batch = Array.fold_left ( * ) 1 lead in
+  let frames = Stft.frames stft_config ~n in
+  let out = Nx.zeros (Nx.dtype x) (Array.append lead [|n_mfcc; frames|]) in
+  ( if batch > 0 && frames > 0 then
+      let mel =
+        mel_create (Mel.Config.n_mels mel_config) (Mel.Config.fft_size mel_config)
+          (array1_of (Mel.filterbank Nx.float64 mel_config))
+      in
+      mfcc_c (stft_plan_of stft_config) mel (array1_of (Nx.contiguous x)) batch n n_mfcc
+        (match lifter with Some l -> l | None -> 0.)
+        (array1_of out) ) ;
   out

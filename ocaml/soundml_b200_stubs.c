@@ -207,3 +207,116 @@ CAMLprim value soundml_b200_resample_apply(value v_plan, value v_x, value v_batc
   smb_ml_raise(st);
   CAMLreturn(Val_unit);
 }
+
+/* Resample.apply for float64 audio (resample.ml:72-84 carries both widths). */
+CAMLprim value soundml_b200_resample_apply_f64(value v_plan, value v_x, value v_batch, value v_n,
+                                               value v_out) {
+  CAMLparam3(v_plan, v_x, v_out);
+  smb_resample_plan *h = HANDLE(v_plan);
+  const double *x = (const double *)Caml_ba_data_val(v_x);
+  double *out = (double *)Caml_ba_data_val(v_out);
+  const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
+  if ((int64_t)Caml_ba_array_val(v_out)->dim[0] < batch * smb_resample_output_frames(h, n))
+    caml_failwith("soundml_b200: output extent disagrees with geometry");
+  caml_release_runtime_system();
+  int st = smb_resample_apply_f64(h, x, batch, n, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+
+/* ---- entry points added after the first slice ------------------------------- */
+
+/* Stft.transform_range ~p0 ~p1 (stft.ml:652-666): out [batch; bins; p1 - p0]. */
+CAMLprim value soundml_b200_transform_range(value v_plan, value v_x, value v_batch, value v_n,
+                                            value v_p0, value v_p1, value v_out) {
+  CAMLparam3(v_plan, v_x, v_out);
+  smb_stft_plan *h = HANDLE(v_plan);
+  const void *x = Caml_ba_data_val(v_x);
+  void *out = Caml_ba_data_val(v_out);
+  const int dtype = dtype_of(v_x);
+  const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
+  const int64_t p0 = Long_val(v_p0), p1 = Long_val(v_p1);
+  caml_release_runtime_system();
+  int st = smb_stft_transform_range(h, x, batch, n, dtype, p0, p1, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value soundml_b200_transform_range_bc(value *argv, int argn) {
+  (void)argn;
+  return soundml_b200_transform_range(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5],
+                                      argv[6]);
+}
+
+/* Stft.invert dtype c ?length z (stft.ml:693-939): z [batch; bins; frames] complex ->
+ * out [batch; length].  length < 0 stands for None (the natural length). */
+CAMLprim value soundml_b200_invert(value v_plan, value v_z, value v_batch, value v_frames,
+                                   value v_length, value v_out) {
+  CAMLparam3(v_plan, v_z, v_out);
+  smb_stft_plan *h = HANDLE(v_plan);
+  const void *z = Caml_ba_data_val(v_z);
+  void *out = Caml_ba_data_val(v_out);
+  const int in_dtype = dtype_of(v_z), out_dtype = dtype_of(v_out);
+  const int64_t batch = Long_val(v_batch), frames = Long_val(v_frames);
+  const int64_t length = Long_val(v_length);
+  caml_release_runtime_system();
+  int st = smb_stft_invert(h, z, batch, frames, in_dtype, length >= 0, length >= 0 ? length : 0,
+                           out_dtype, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value soundml_b200_invert_bc(value *argv, int argn) {
+  (void)argn;
+  return soundml_b200_invert(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5]);
+}
+
+/* Convert.power_to_db / amplitude_to_db (convert.ml:20-56).  top_db = nan stands
+ * for None; amplitude selects the 20 log10 form. */
+CAMLprim value soundml_b200_to_db(value v_amplitude, value v_x, value v_reference, value v_amin,
+                                  value v_top_db, value v_out) {
+  CAMLparam2(v_x, v_out);
+  const void *x = Caml_ba_data_val(v_x);
+  void *out = Caml_ba_data_val(v_out);
+  const int dtype = dtype_of(v_x);
+  const int64_t count = Caml_ba_array_val(v_x)->dim[0];
+  const double reference = Double_val(v_reference), amin = Double_val(v_amin);
+  const double top_db = Double_val(v_top_db);
+  const int amplitude = Bool_val(v_amplitude);
+  caml_release_runtime_system();
+  int st = amplitude
+      ? smb_amplitude_to_db(x, count, dtype, reference, amin, top_db, out, SMB_MEM_HOST, SMB_STREAM_OWN)
+      : smb_power_to_db(x, count, dtype, reference, amin, top_db, out, SMB_MEM_HOST, SMB_STREAM_OWN);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value soundml_b200_to_db_bc(value *argv, int argn) {
+  (void)argn;
+  return soundml_b200_to_db(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5]);
+}
+
+/* Soundml.mfcc stft mel ?n_mfcc ?lifter x (soundml.ml:50-95): out [batch; n_mfcc; frames];
+ * lifter = 0 stands for None. */
+CAMLprim value soundml_b200_mfcc(value v_stft, value v_mel, value v_x, value v_batch, value v_n,
+                                 value v_n_mfcc, value v_lifter, value v_out) {
+  CAMLparam4(v_stft, v_mel, v_x, v_out);
+  smb_stft_plan *hs = HANDLE(v_stft);
+  smb_mel_plan *hm = HANDLE(v_mel);
+  const void *x = Caml_ba_data_val(v_x);
+  void *out = Caml_ba_data_val(v_out);
+  const int dtype = dtype_of(v_x);
+  const int64_t batch = Long_val(v_batch), n = Long_val(v_n), n_mfcc = Long_val(v_n_mfcc);
+  const double lifter = Double_val(v_lifter);
+  caml_release_runtime_system();
+  int st = smb_mfcc(hs, hm, x, batch, n, dtype, n_mfcc, lifter, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value soundml_b200_mfcc_bc(value *argv, int argn) {
+  (void)argn;
+  return soundml_b200_mfcc(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5], argv[6],
+                           argv[7]);
+}
