@@ -116,6 +116,140 @@ def apply(c, x, out=None):
     return out
 
 
+def _cat(parts):
+    if len(parts) == 1:
+        return parts[0]
+    if _lib.is_torch(parts[0]):
+        import torch
+        return torch.cat(parts, dim=-1)
+    return np.concatenate(parts, axis=-1)
+
+
+class Kernel:
+    """``Resample.Kernel`` (resample.ml:1343-1424, 1786-1909): the chunked form
+    of ``apply``.
+
+    ``step`` feeds a chunk ``[..., m]`` and returns the output samples that
+    became computable (or ``None``); ``flush`` emits the delayed tail.  The
+    concatenation of everything returned equals ``apply c x`` on the
+    concatenated input, with ``ceil(n*L/M)`` samples in total.
+
+    The reference threads per-stage histories through its executors; here the
+    state is the raw input still inside some future output's dependency cone,
+    and every step runs the offline kernels over a window of it whose origin sits
+    on a whole phase cycle of every stage (so each output is computed with the
+    same phase, taps and summation order as in the offline call) and keeps the
+    outputs whose cone lies inside the known samples.  With the direct executor
+    the result is bit-identical to ``apply`` for every partition; block executors
+    (overlap-save, tensor-core) agree to rounding, their block grids being
+    anchored to the window.
+    """
+
+    def __init__(self, c, channels, max_block, _apply=None):
+        if channels < 1:
+            raise ValueError(
+                f"prepare: cannot resample {channels} channels (channels must be at least 1)")
+        if max_block < 1:
+            raise ValueError(
+                f"prepare: cannot accept blocks of {max_block} samples "
+                "(max_block must be at least 1)")
+        self.cfg, self.channels, self.max_block = c, channels, max_block
+        self._apply = _apply if _apply is not None else (lambda x: apply(c, x))
+        self.l, self.m = c.l, c.m
+        st = c.stages()
+        # dependency cone of one output, in input samples either side of floor(i M / L)
+        if len(st) == 0:
+            self.reach, self.grain = 0, 1
+        elif len(st) == 1:
+            self.reach, self.grain = st[0]["k"] + 1, st[0]["m"]
+        else:
+            l1, m1, k1 = st[0]["l"], st[0]["m"], st[0]["k"]
+            m2, k2 = st[1]["m"], st[1]["k"]
+            self.reach = k1 + ((k2 + 2) * m1 + l1 - 1) // l1 + 2
+            g = m1                                  # window origin: whole cycles of both stages
+            while (g // m1 * l1) % m2:
+                g += m1
+            self.grain = g
+        self.reset()
+
+    @classmethod
+    def prepare(cls, c, *, channels, max_block):
+        """``Kernel.prepare c dtype ~channels ~max_block``; the dtype is that of
+        the chunks fed."""
+        return cls(c, channels, max_block)
+
+    def reset(self):
+        self.fed = self.emitted = self.base = 0
+        self.buf = []
+        self.drained = False
+
+    def _window(self, upto):
+        """Outputs [emitted, upto) from a window of the retained input."""
+        # origin: a whole number of grains at or before the first needed input
+        first = self.emitted * self.m // self.l - self.reach
+        a0 = max(0, first // self.grain * self.grain)
+        x = _cat(self.buf)
+        self.buf = [x]
+        y = self._apply(x[..., a0 - self.base:])
+        o0 = a0 * self.l // self.m                       # a0 is a whole number of input cycles
+        out = y[..., self.emitted - o0:upto - o0]
+        self.emitted = upto
+        # drop what no future output can reach (kept on a grain boundary)
+        keep = max(0, (self.emitted * self.m // self.l - self.reach) // self.grain * self.grain)
+        if keep > self.base:
+            self.buf = [x[..., keep - self.base:]]
+            if _lib.is_torch(x):
+                self.buf = [self.buf[0].clone()]
+            else:
+                self.buf = [np.array(self.buf[0], copy=True)]
+            self.base = keep
+        return out.contiguous() if _lib.is_torch(out) else np.ascontiguousarray(out)
+
+    def step(self, chunk):
+        """``Kernel.step k chunk`` (resample.ml:1844-1909)."""
+        if self.drained:
+            raise ValueError("step: cannot feed a drained kernel (flush consumed the tail; "
+                             "reset before reusing)")
+        if chunk.ndim < 1:
+            raise ValueError("step: cannot resample a rank-zero tensor (the time axis must exist)")
+        n = int(chunk.shape[-1])
+        if n > self.max_block:
+            raise ValueError(f"step: cannot feed a {n}-sample chunk (max_block is {self.max_block})")
+        channels = int(np.prod(chunk.shape[:-1], dtype=np.int64)) if chunk.ndim > 1 else 1
+        if channels != self.channels:
+            unit = "channel" if self.channels == 1 else "channels"
+            raise ValueError(f"step: cannot feed {channels}-channel chunks (the kernel was "
+                             f"prepared for {self.channels} {unit})")
+        if n == 0:
+            return None
+        self.buf.append(chunk.clone() if _lib.is_torch(chunk) else np.array(chunk, copy=True))
+        self.fed += n
+        if self.l == self.m:                                  # identity: forward a copy
+            out, self.buf, self.base = self.buf[-1], [], self.fed
+            self.emitted = self.fed
+            return out
+        # outputs whose cone floor(i M / L) + reach lies inside the fed samples
+        safe = self.fed - self.reach
+        avail = 0 if safe <= 0 else (safe * self.l + self.m - 1) // self.m
+        avail = min(avail, self.cfg.output_frames(self.fed))
+        if avail <= self.emitted:
+            return None
+        return self._window(avail)
+
+    def flush(self):
+        """``Kernel.flush k``: the delayed tail, ``ceil(n*L/M)`` samples in all."""
+        if self.drained:
+            return None
+        self.drained = True
+        total = self.cfg.output_frames(self.fed) if self.fed else 0
+        if total <= self.emitted:
+            self.buf = []
+            return None
+        out = self._window(total)
+        self.buf = []
+        return out
+
+
 class Fir:
     """Odd-length FIR with its group delay compensated:
     ``y[i] = sum_t h[t] x[i + (taps-1)/2 - t]`` — the resampler's direct stage

@@ -70,3 +70,41 @@ def test_device_chunks_match_offline_transform(sb):
     k.reset()
     again = run_chunks(k, x, [220500], lambda o: torch.cat(o, dim=-1))
     assert torch.equal(again, want)
+
+
+# ---- Resample.Kernel ----------------------------------------------------------
+
+@pytest.mark.parametrize("sr,target,executor", [
+    (44100, 16000, "direct"), (44100, 16000, "planned"), (44100, 22050, "direct"),
+    (44100, 22050, "planned"), (22050, 44100, "planned"), (48000, 44100, "direct"),
+    (8000, 48000, "planned"), (44100, 48000, "direct"),
+])
+def test_resample_kernel_partition_law_on_gpu(sb, sr, target, executor):
+    """Chunked resampling equals apply: bit for bit with the direct executor,
+    to 1e-5 of peak where block executors (overlap-save, tcgen05) are planned."""
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target).set_executor(executor)
+    rng = np.random.default_rng(sr)
+    for n in (1, 900, 30011):
+        x = rng.uniform(-1, 1, (2, n)).astype(np.float32)
+        want = sb.Resample.apply(cfg, x)
+        for _ in range(2):
+            cuts = np.sort(rng.integers(0, n + 1, size=rng.integers(0, 5)))
+            sizes = list(np.diff(np.concatenate([[0], cuts, [n]])))
+            k = sb.Resample.Kernel.prepare(cfg, channels=2, max_block=n)
+            got = run_chunks(k, x, sizes, lambda o: np.concatenate(o, axis=-1))
+            assert got is not None and got.shape == want.shape, (n, sizes)
+            if executor == "direct":
+                assert np.array_equal(got, want), (n, sizes)
+            else:
+                assert np.abs(got - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-3), (n, sizes)
+
+
+def test_resample_kernel_device_stream(sb):
+    import torch
+    cfg = sb.Resample.Config.create(sample_rate=44100, target=22050)
+    x = torch.rand((4, 200000), device="cuda") * 2 - 1
+    want = sb.Resample.apply(cfg, x)
+    k = sb.Resample.Kernel.prepare(cfg, channels=4, max_block=70000)
+    got = run_chunks(k, x, [65536, 1, 65536, 200000 - 2 * 65536 - 1], lambda o: torch.cat(o, dim=-1))
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()

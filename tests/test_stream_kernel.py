@@ -76,3 +76,53 @@ def test_prepare_errors(lib):
     k = lib.Stft.Kernel.prepare(c, channels=1, max_block=16)
     with pytest.raises(ValueError, match="zero-size leading axis"):
         k.step(np.zeros((0, 5)))
+
+
+# ---- Resample.Kernel ----------------------------------------------------------
+
+from oracle import resample_oracle as R                      # noqa: E402
+from test_resample_oracle import RATE_PAIRS, oracle_stages   # noqa: E402
+
+
+@pytest.mark.parametrize("sr,target", RATE_PAIRS + [(22050, 22050)])
+def test_resample_kernel_partition_law_host_logic(lib, sr, target):
+    """step/flush over the oracle's apply: concatenated chunks == offline apply,
+    ceil(n L / M) samples, for every partition (resample.mli:296-317)."""
+    cfg = lib.Resample.Config.create(sample_rate=sr, target=target)
+    st = oracle_stages(cfg) if sr != target else []
+    offline = (lambda x: R.apply_plan(x, st, cfg.l, cfg.m)) if st else (lambda x: x.copy())
+    rng = np.random.default_rng(sr + target)
+    for n in (0, 1, 5, 700, 4001):
+        x = rng.uniform(-1, 1, (2, n))
+        want = offline(x)
+        assert want.shape[-1] == cfg.output_frames(n)
+        for sizes in chunkings(n, rng):
+            k = lib.Resample.Kernel(cfg, 2, 8192, _apply=offline)
+            outs, at = [], 0
+            for m in sizes:
+                o = k.step(x[:, at:at + m])
+                at += m
+                if o is not None:
+                    outs.append(o)
+            o = k.flush()
+            if o is not None:
+                outs.append(o)
+            assert k.flush() is None
+            got = np.concatenate(outs, axis=-1) if outs else np.zeros((2, 0))
+            assert got.shape == want.shape, (n, sizes)
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
+            with pytest.raises(ValueError, match="drained kernel"):
+                k.step(x[:, :1])
+
+
+def test_resample_kernel_errors(lib):
+    cfg = lib.Resample.Config.create(sample_rate=44100, target=22050)
+    with pytest.raises(ValueError, match="channels must be at least 1"):
+        lib.Resample.Kernel.prepare(cfg, channels=0, max_block=16)
+    with pytest.raises(ValueError, match="max_block must be at least 1"):
+        lib.Resample.Kernel.prepare(cfg, channels=1, max_block=0)
+    k = lib.Resample.Kernel.prepare(cfg, channels=2, max_block=16)
+    with pytest.raises(ValueError, match=r"17-sample chunk \(max_block is 16\)"):
+        k.step(np.zeros((2, 17), np.float32))
+    with pytest.raises(ValueError, match="3-channel chunks"):
+        k.step(np.zeros((3, 4), np.float32))
