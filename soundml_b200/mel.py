@@ -43,7 +43,7 @@ class Config:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and getattr(_lib, "lib", None) is not None:      # not during interpreter teardown
             _lib.lib.smb_mel_plan_destroy(h)
 
     n_mels = property(lambda self: int(_lib.lib.smb_mel_n_mels(self._h)))

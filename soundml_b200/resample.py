@@ -35,7 +35,7 @@ class Config:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and getattr(_lib, "lib", None) is not None:      # not during interpreter teardown
             _lib.lib.smb_resample_plan_destroy(h)
 
     l = property(lambda self: int(_lib.lib.smb_resample_l(self._h)))
@@ -273,7 +273,7 @@ class Fir:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and getattr(_lib, "lib", None) is not None:      # not during interpreter teardown
             _lib.lib.smb_fir_plan_destroy(h)
 
     def apply(self, x, method="direct", out=None):

@@ -48,7 +48,7 @@ class Config:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and getattr(_lib, "lib", None) is not None:      # not during interpreter teardown
             _lib.lib.smb_stft_plan_destroy(h)
 
     fft_size = property(lambda self: int(_lib.lib.smb_stft_fft_size(self._h)))
