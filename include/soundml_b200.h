@@ -155,6 +155,15 @@ int smb_stft_invert(smb_stft_plan* plan, const void* z, int64_t batch, int64_t f
                     int in_dtype, int has_length, int64_t length, int out_dtype, void* out,
                     int mem);
 
+/* Stft.griffin_lim ?n_iter ?momentum ?init ?length c s (stft.ml:964-1025): fast
+ * Griffin-Lim phase reconstruction.  s [batch, bins, frames] magnitudes (dtype);
+ * init_phase NULL (`Zero_phase) or phases of the same shape and dtype; the loop
+ * runs in complex128 at the natural synthesis length on the device, the result
+ * out [batch, length] is rounded into dtype. */
+int smb_stft_griffin_lim(smb_stft_plan* plan, const void* s, int64_t batch, int64_t frames,
+                         int dtype, int64_t n_iter, double momentum, const void* init_phase,
+                         int has_length, int64_t length, void* out, int mem);
+
 /* ---- mel ----------------------------------------------------------------- */
 /* Mel.Config.create; f_max = NaN means "Nyquist" (the OCaml default). */
 int smb_mel_plan_create(smb_mel_plan** plan, int64_t n_mels, int64_t sample_rate,

@@ -115,3 +115,49 @@ def invert(c, z, length=None, dtype=np.float64):
     out = np.zeros(lead + (out_len,), dtype=np.float64)
     out[..., :stop - left] = acc[..., left:stop]
     return out.astype(dtype)
+
+
+def griffin_lim(c, s, n_iter=32, momentum=0.99, init_phase=None, length=None):
+    """``Stft.griffin_lim ?n_iter ?momentum ?init ?length c s`` (stft.ml:964-1025):
+    fast Griffin-Lim phase reconstruction of a magnitude spectrogram ``[..., bins,
+    frames]``; the loop runs in complex128 at the natural synthesis length, the
+    result is rounded into the dtype of ``s``."""
+    from . import stft_oracle
+    s = np.asarray(s)
+    if s.ndim < 2:
+        raise ValueError(
+            f"griffin_lim: cannot invert a rank-{s.ndim} tensor (the bin and frame axes must exist)")
+    if s.shape[-2] != c.bins:
+        raise ValueError(
+            f"griffin_lim: cannot invert {s.shape[-2]} frequency bins of a {c.fft_size}-point "
+            f"transform (the bin axis must hold fft_size / 2 + 1 = {c.bins} values)")
+    if length is not None and length < 0:
+        raise ValueError(
+            f"griffin_lim: cannot synthesise a signal of length {length} "
+            "(length must be non-negative)")
+    check_invertible("griffin_lim", c)
+    if n_iter < 1:
+        raise ValueError(
+            f"griffin_lim: cannot run {n_iter} iterations (n_iter must be at least 1)")
+    if momentum < 0:
+        raise ValueError(
+            f"griffin_lim: cannot use a momentum of {momentum:g} (momentum must be non-negative)")
+    mags = s.astype(np.float64).astype(np.complex128)
+    if init_phase is None:
+        angles = np.ones(s.shape, dtype=np.complex128)
+    else:
+        p = np.asarray(init_phase, dtype=np.float64)
+        if p.shape != s.shape:
+            raise ValueError("griffin_lim: the initial phase must have the shape of the magnitudes")
+        angles = np.cos(p) + 1j * np.sin(p)
+    frames = s.shape[-1]
+    beta = momentum / (1.0 + momentum)
+    iterate = output_length(c, frames) > 0 and frames > 0 and 0 not in s.shape[:-2]
+    previous = None
+    tiny = np.finfo(np.float64).tiny                   # Float.min_float
+    for _ in range(n_iter if iterate else 0):
+        rebuilt = stft_oracle.transform(c, invert(c, mags * angles))[..., :frames]
+        extrapolated = rebuilt if previous is None else rebuilt - previous * beta
+        angles = extrapolated / (np.abs(extrapolated) + tiny)
+        previous = rebuilt
+    return invert(c, mags * angles, length=length, dtype=s.dtype)

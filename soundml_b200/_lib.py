@@ -79,6 +79,8 @@ SIGNATURES = {
     "smb_stft_nola": (_int, [_vp]),
     "smb_stft_output_length": (_i64, [_vp, _i64]),
     "smb_stft_invert": (_int, [_vp, _vp, _i64, _i64, _int, _int, _i64, _int, _vp, _int]),
+    "smb_stft_griffin_lim": (_int, [_vp, _vp, _i64, _i64, _int, _i64, _dbl, _vp, _int, _i64,
+                                    _vp, _int]),
     "smb_stft_power_spectrum": (_int, [_vp, _vp, _i64, _i64, _int, _dbl, _vp, _int]),
     "smb_mel_plan_create": (_int, [_pvp, _i64, _i64, _i64, _dbl, _dbl, _int, _int]),
     "smb_mel_plan_create_with_weights": (_int, [_pvp, _i64, _i64, _pd]),

@@ -1018,6 +1018,127 @@ int smb_stft_invert(smb_stft_plan* plan, const void* z, int64_t batch, int64_t f
   });
 }
 
+int smb_stft_griffin_lim(smb_stft_plan* plan, const void* s, int64_t batch, int64_t frames,
+                         int dtype, int64_t n_iter, double momentum, const void* init_phase,
+                         int has_length, int64_t length, void* out, int mem) {
+  return guarded([&] {
+    smb_stft_plan* p = plan;
+    if (batch < 0 || frames < 0)
+      throw smb::invalid_argument("griffin_lim: batch and frame counts must be non-negative");
+    if (has_length && length < 0)
+      throw smb::invalid_argument(smb::format(
+          "griffin_lim: cannot synthesise a signal of length %lld (length must be non-negative)",
+          (long long)length));
+    if (!p->nola())
+      throw smb::invalid_argument(smb::format(
+          "griffin_lim: cannot invert a %lld-point window advanced by %lld samples inside a "
+          "%lld-point frame (the overlap-added squared window must stay above 1e-10 of its "
+          "largest value at every position)",
+          (long long)p->geom.win_length, (long long)p->geom.hop, (long long)p->geom.fft));
+    if (n_iter < 1)
+      throw smb::invalid_argument(smb::format(
+          "griffin_lim: cannot run %lld iterations (n_iter must be at least 1)",
+          (long long)n_iter));
+    if (momentum < 0.0)
+      throw smb::invalid_argument(smb::format(
+          "griffin_lim: cannot use a momentum of %g (momentum must be non-negative)", momentum));
+    const size_t esz = dtype_size(dtype);
+    const int64_t bins = p->geom.bins(), left = p->geom.left_width(), hop = p->geom.hop;
+    const int64_t natural = p->output_length(frames);
+    const int64_t out_len = has_length ? length : natural;
+    if (batch == 0 || out_len == 0) return;
+    if (mem != SMB_MEM_DEVICE && mem != SMB_MEM_HOST)
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    if (frames == 0) {
+      if (mem == SMB_MEM_HOST) std::memset(out, 0, (size_t)batch * (size_t)out_len * esz);
+      else { p->ensure_device(); CK(cudaMemsetAsync(out, 0, (size_t)batch * (size_t)out_len * esz, p->stream.use)); }
+      return;
+    }
+    p->ensure_device();
+    cudaStream_t st = p->stream.use;
+    if (!p->d_folded) p->d_folded = upload(p->folded_square_window());
+    const size_t cells = (size_t)batch * (size_t)bins * (size_t)frames;
+    // the whole problem stays resident across the iterations
+    struct Temp {                       // freed when the call returns or throws
+      void* ptr = nullptr;
+      void reserve(size_t bytes) { CK(cudaMalloc(&ptr, bytes ? bytes : 1)); }
+      ~Temp() { if (ptr) cudaFree(ptr); }
+    } d_s, d_phase, d_spec, d_a, d_b, d_y, d_out;
+    const void* mags = s;
+    const void* phase = init_phase;
+    void* dout = out;
+    if (mem == SMB_MEM_HOST) {
+      d_s.reserve(cells * esz);
+      CK(cudaMemcpyAsync(d_s.ptr, s, cells * esz, cudaMemcpyHostToDevice, st));
+      mags = d_s.ptr;
+      if (init_phase) {
+        d_phase.reserve(cells * esz);
+        CK(cudaMemcpyAsync(d_phase.ptr, init_phase, cells * esz, cudaMemcpyHostToDevice, st));
+        phase = d_phase.ptr;
+      }
+      d_out.reserve((size_t)batch * (size_t)out_len * esz);
+      dout = d_out.ptr;
+    }
+    d_spec.reserve(cells * sizeof(double2));
+    double2* spec = (double2*)d_spec.ptr;
+    auto synth = [&](int64_t len, bool named, int out_dtype, void* dst) {
+      int64_t count = frames;
+      if (named) count = std::min(frames, (len + left + hop - 1) / hop);
+      if (count == 0) {
+        CK(cudaMemsetAsync(dst, 0, (size_t)batch * (size_t)len * dtype_size(out_dtype), st));
+        return;
+      }
+      smb::IstftArgs a{};
+      a.z = spec;
+      a.out = dst;
+      a.frames = frames;
+      a.count = count;
+      a.out_len = len;
+      a.fft = (int)p->geom.fft;
+      a.hop = (int)hop;
+      a.left = (int)left;
+      a.window = p->d_window64;
+      a.twiddle = p->d_twiddle64;
+      a.folded = p->d_folded;
+      a.in_f64 = 1;
+      a.out_f64 = out_dtype == SMB_F64;
+      CK(smb::launch_istft(a, batch, st));
+    };
+    CK(smb::launch_gl_project(mags, phase, dtype == SMB_F64, nullptr, nullptr, 0.0, 1,
+                              (long long)cells, spec, st));
+    // the loop runs at the natural length, the one geometry that re-analyses to
+    // exactly `frames` frames (stft.ml:1000-1008)
+    if (natural > 0) {
+      d_a.reserve(cells * sizeof(double2));
+      d_b.reserve(cells * sizeof(double2));
+      d_y.reserve((size_t)batch * (size_t)natural * sizeof(double));
+      double2* rebuilt = (double2*)d_a.ptr;
+      double2* previous = (double2*)d_b.ptr;
+      const double beta = momentum / (1.0 + momentum);
+      smb::FrameGeom g = p->frame_geom(natural);
+      if (g.frames != frames)
+        throw smb::invalid_argument("griffin_lim: the natural length does not re-analyse to the "
+                                    "given frame count");
+      for (int64_t k = 0; k < n_iter; ++k) {
+        synth(natural, false, SMB_F64, d_y.ptr);
+        CK(smb::launch_stft_generic(d_y.ptr, SMB_F64, batch, g, p->d_window64, p->d_twiddle64,
+                                    smb::kModeComplex, 1.0, rebuilt, st));
+        CK(smb::launch_gl_project(mags, nullptr, dtype == SMB_F64, rebuilt,
+                                  k == 0 ? nullptr : previous, beta, 0, (long long)cells, spec, st));
+        std::swap(rebuilt, previous);
+      }
+    }
+    synth(out_len, has_length != 0, dtype, dout);
+    if (mem == SMB_MEM_HOST) {
+      CK(cudaMemcpyAsync(out, dout, (size_t)batch * (size_t)out_len * esz, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    } else {
+      // the temporaries die with this call: wait for the work that uses them
+      CK(cudaStreamSynchronize(st));
+    }
+  });
+}
+
 // ---- mel ---------------------------------------------------------------------
 
 int smb_mel_plan_create(smb_mel_plan** plan, int64_t n_mels, int64_t sample_rate,

@@ -195,3 +195,62 @@ cudaError_t launch_istft(const IstftArgs& a, long long batch, cudaStream_t st) {
 }
 
 }  // namespace smb
+
+// ---- Griffin-Lim projections (stft.ml:941-1025) --------------------------------
+namespace smb {
+
+namespace {
+
+// spec = magnitudes * angles with angles = unit(rebuilt - beta * previous)
+// (unit: divide by |.| + the smallest positive normal double, stft.ml:959-962);
+// first = 1 builds the initial spectrum from the starting phase instead (unit
+// phase when phase == nullptr).
+template <typename T>
+__global__ void gl_project_kernel(const T* __restrict__ mags, const T* __restrict__ phase,
+                                  const double2* __restrict__ rebuilt,
+                                  const double2* __restrict__ previous, double beta, int first,
+                                  long long count, double2* __restrict__ spec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double m = (double)mags[i];
+  double2 a;
+  if (first) {
+    if (phase) {
+      const double p = (double)phase[i];
+      a = make_double2(cos(p), sin(p));
+    } else {
+      a = make_double2(1.0, 0.0);
+    }
+  } else {
+    double2 e = rebuilt[i];
+    if (previous) {
+      const double2 q = previous[i];
+      e.x -= q.x * beta;
+      e.y -= q.y * beta;
+    }
+    const double d = hypot(e.x, e.y) + 2.2250738585072014e-308;
+    a = make_double2(e.x / d, e.y / d);
+  }
+  spec[i] = make_double2(m * a.x, m * a.y);
+}
+
+}  // namespace
+
+cudaError_t launch_gl_project(const void* mags, const void* phase, int dtype,
+                              const double2* rebuilt, const double2* previous, double beta,
+                              int first, long long count, double2* spec, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  const int threads = 256;
+  const long long blocks = (count + threads - 1) / threads;
+  if (blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
+  if (dtype == 0)
+    gl_project_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(
+        (const float*)mags, (const float*)phase, rebuilt, previous, beta, first, count, spec);
+  else
+    gl_project_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(
+        (const double*)mags, (const double*)phase, rebuilt, previous, beta, first, count, spec);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+}  // namespace smb

@@ -47,6 +47,10 @@ struct IstftArgs {
   int in_f64, out_f64;
 };
 cudaError_t launch_istft(const IstftArgs& a, long long batch, cudaStream_t st);
+// Griffin-Lim: spec = mags * unit(rebuilt - beta * previous), or the initial spectrum
+cudaError_t launch_gl_project(const void* mags, const void* phase, int dtype,
+                              const double2* rebuilt, const double2* previous, double beta,
+                              int first, long long count, double2* spec, cudaStream_t st);
 // fft 2048, complex64 -> float32 on the register FFT (istft2048.cu)
 bool istft2048_supports(const IstftArgs& a);
 cudaError_t launch_istft2048(const IstftArgs& a, const float* window_scaled, const float2* tw_pass,

@@ -230,6 +230,55 @@ def invert(c, z, length=None, dtype=None):
     return out
 
 
+def griffin_lim(c, s, n_iter=32, momentum=0.99, init=None, length=None):
+    """``Stft.griffin_lim ?n_iter ?momentum ?init ?length c s`` (stft.ml:964-1025):
+    fast Griffin-Lim phase reconstruction of a magnitude spectrogram ``[..., bins,
+    frames]`` (float32 or float64) into ``[..., length]`` samples of the same
+    dtype.  ``init`` is ``None`` (zero phase) or a tensor of starting phases with
+    the shape of ``s``."""
+    if s.ndim < 2:
+        raise ValueError(
+            f"griffin_lim: cannot invert a rank-{s.ndim} tensor (the bin and frame axes must exist)")
+    bins, count = int(s.shape[-2]), int(s.shape[-1])
+    if bins != c.bins:
+        raise ValueError(
+            f"griffin_lim: cannot invert {bins} frequency bins of a {c.fft_size}-point transform "
+            f"(the bin axis must hold fft_size / 2 + 1 = {c.bins} values)")
+    s = _lib.contiguous(s)
+    ptr, mem, dtype = _lib.describe(s)
+    pptr = None
+    if init is not None:
+        if tuple(init.shape) != tuple(s.shape):
+            shape = lambda t: "; ".join(str(int(d)) for d in t.shape)
+            raise ValueError(
+                f"griffin_lim: cannot start from a [{shape(init)}] phase for a [{shape(s)}] "
+                "spectrogram (the initial phase must have the shape of the magnitudes)")
+        init = _lib.contiguous(init)
+        pptr, pmem, pdtype = _lib.describe(init)
+        if pmem != mem or pdtype != dtype:
+            raise ValueError("griffin_lim: the initial phase must live where the magnitudes "
+                             "live and share their dtype")
+    lead = tuple(int(d) for d in s.shape[:-2])
+    batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    # precondition order of the reference: length, invertibility, n_iter, momentum
+    probe = _lib.lib.smb_stft_griffin_lim(c._h, None, 0, 0, dtype, int(n_iter), float(momentum),
+                                          None, 0 if length is None else 1,
+                                          0 if length is None else int(length), None, mem)
+    _lib.check(probe)
+    out_len = output_length(c, count) if length is None else int(length)
+    out = _lib.empty_like_kind(s, lead + (out_len,))
+    if batch == 0 or out_len == 0:
+        return out
+    stream = _lib.current_stream(s)
+    if stream is not None:
+        _lib.check(_lib.lib.smb_stft_plan_set_stream(c._h, stream))
+    _lib.check(_lib.lib.smb_stft_griffin_lim(
+        c._h, ptr, batch, count, dtype, int(n_iter), float(momentum), pptr,
+        0 if length is None else 1, 0 if length is None else int(length),
+        _lib.out_pointer(out), mem))
+    return out
+
+
 # ---- streaming analysis ------------------------------------------------------
 
 def _last(t):

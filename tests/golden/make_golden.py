@@ -12,7 +12,7 @@ Reads the librosa-0.11 / SoXR golden JSON files of the reference test suites
     soundml/test/stft/vectors/*.json
     soundml/test/mel/vectors/{filterbank,mel_spectrogram,mfcc}.json
     soundml/test/db/vectors/*.json
-    soundml/test/istft/vectors/{inverse_*,lengths}.json
+    soundml/test/istft/vectors/{inverse_*,lengths,griffinlim_*}.json
     soundml/test/resample/vectors/soxr_reference.json
 
 and writes ``tests/golden/reference_vectors.npz``: one float64 array per case
@@ -39,6 +39,7 @@ SUITES = {
     "db": sorted(glob.glob(f"{REF}/db/vectors/*.json")),
     "istft": sorted(glob.glob(f"{REF}/istft/vectors/inverse_*.json")) +
              [f"{REF}/istft/vectors/lengths.json"],
+    "griffinlim": sorted(glob.glob(f"{REF}/istft/vectors/griffinlim_*.json")),
     "resample": [f"{REF}/resample/vectors/soxr_reference.json"],
 }
 

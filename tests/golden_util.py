@@ -44,6 +44,14 @@ def istft_spectrum(fft_size, frames, dtype):
     return z.astype(np.complex64 if dtype == "float32" else np.complex128)
 
 
+def griffin_lim_magnitudes(fft_size, frames, dtype):
+    """Magnitudes of the reference's Griffin-Lim goldens: LCG + 1, so strictly
+    positive (soundml/test/istft/gl_goldens.ml:35-37)."""
+    bins = fft_size // 2 + 1
+    m = (lcg_signal(bins * frames, ISTFT_SEED_RE) + 1.0).reshape(bins, frames)
+    return m.astype(np.float32 if dtype == "float32" else np.float64)
+
+
 class Goldens:
     def __init__(self):
         z = np.load(os.path.join(HERE, "golden", "reference_vectors.npz"))

@@ -4,8 +4,8 @@ import numpy as np
 import pytest
 
 from golden_util import (F32_ATOL, F32_RTOL, F64_ATOL, F64_RTOL, MEL_SEED, STFT_SEED,
-                         WINDOW_ATOL, WINDOW_RTOL, assert_close, istft_spectrum, lcg_signal,
-                         window_spec)
+                         WINDOW_ATOL, WINDOW_RTOL, assert_close, griffin_lim_magnitudes,
+                         istft_spectrum, lcg_signal, window_spec)
 from oracle import istft_oracle, mel_oracle, stft_oracle, window_oracle
 
 
@@ -182,3 +182,21 @@ def test_istft_round_trip_and_errors():
     c = stft_oracle.StftConfig(64, hop=16)
     assert istft_oracle.output_length(c, 0) == 0 and istft_oracle.output_length(c, 9) == 128
     assert istft_oracle.invert(c, np.zeros((33, 0), complex)).shape == (0,)
+
+
+def test_griffin_lim_goldens(goldens):
+    """Stft.griffin_lim against librosa (soundml/test/istft/gl_goldens.ml:49-78):
+    1 to 32 iterations, momentum 0 / 0.5 / 0.99, three geometries."""
+    n = 0
+    for key, stem, name, e in goldens.cases("griffinlim"):
+        p = e["params"]
+        c = stft_oracle.StftConfig(p["fft_size"], hop=p["hop"], win_length=p["win_length"],
+                                   alignment=p["alignment"], pad="constant", pad_value=0.0)
+        mags = griffin_lim_magnitudes(p["fft_size"], p["frames"], p["dtype"])
+        f32 = p["dtype"] == "float32"
+        got = istft_oracle.griffin_lim(c, mags, n_iter=p["n_iter"], momentum=p["momentum"])
+        assert got.dtype == mags.dtype
+        assert_close(got, goldens.values(key), F32_RTOL if f32 else F64_RTOL,
+                     F32_ATOL if f32 else F64_ATOL, key)
+        n += 1
+    assert n == 42
