@@ -191,8 +191,12 @@ def main():
 
     sc = sb.Stft.Config.create(fft_size=FFT, hop=HOP)
     mc = sb.Mel.Config.create(n_mels=N_MELS, sample_rate=SR, fft_size=FFT)
-    # rank r owns clips [r*BATCH, (r+1)*BATCH): independent units, no exchange
-    x = synth.clips_torch(BATCH, N, dev, SR, first_clip=rank * BATCH)
+    # rank r owns clips [r*BATCH, (r+1)*BATCH) of the global batch: independent
+    # units, no exchange (the same split tests/test_parallel_gloo.py checks)
+    from soundml_b200.parallel import max_over_ranks, my_shard
+    lo, hi = my_shard(world * BATCH, rank, world)
+    assert hi - lo == BATCH
+    x = synth.clips_torch(BATCH, N, dev, SR, first_clip=lo)
     out = torch.empty((BATCH, N_MELS, FRAMES), dtype=torch.float32, device=dev)
 
     def barrier():
@@ -219,11 +223,7 @@ def main():
     barrier()
     t_wall1 = time.time()
     launches = sb.kernel_launch_count() - launches0
-    ms = start.elapsed_time(end)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(start.elapsed_time(end), device=dev)   # the slowest rank defines the step
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     ms_per_step = ms / args.steps
     value = world * BATCH * CLIP_SECONDS / (ms_per_step * 1e-3)
@@ -243,11 +243,7 @@ def main():
         for _ in range(e2e_steps):
             sb.mel_spectrogram(sc, mc, xh_np, out=oh_np)     # returns after D2H lands
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0, device=dev)
         e2e = {"value": world * BATCH * CLIP_SECONDS * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": BATCH * N * 4, "d2h_bytes_per_step": BATCH * N_MELS * FRAMES * 4,
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
@@ -267,7 +263,7 @@ def main():
     except Exception:
         pass
     cpu = None
-    if world >= 1:
+    if world == 1:                      # reported on rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         clips = 32
         v, passes, dt = time_cpu(clips, args.cpu_seconds, cores)
