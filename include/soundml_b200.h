@@ -249,7 +249,9 @@ int smb_resample_apply_f64(smb_resample_plan* plan, const double* x, int64_t bat
 
 /* ---- FIR ------------------------------------------------------------------ */
 /* y[c,i] = sum_t h[t] * x[c, i + (taps-1)/2 - t], zeros outside, taps odd.
- * method: SMB_EXEC_DIRECT or SMB_EXEC_OLS (overlap-save on the rFFT kernels). */
+ * method: SMB_EXEC_DIRECT, SMB_EXEC_OLS (overlap-save on the FFT kernels) or
+ * SMB_EXEC_PLANNED (overlap-save from 17 taps up when the filter fits a block,
+ * else direct -- the measured crossover on B200). */
 int smb_fir_plan_create(smb_fir_plan** plan, const double* h, int64_t taps);
 int smb_fir_plan_destroy(smb_fir_plan* plan);
 int smb_fir_plan_set_stream(smb_fir_plan* plan, void* cuda_stream);

@@ -1590,10 +1590,13 @@ int smb_fir_apply(smb_fir_plan* plan, const float* x, int64_t batch, int64_t n, 
                   int method, int mem) {
   return guarded([&] {
     if (batch < 0 || n < 0) throw smb::invalid_argument("fir: negative extent");
-    if (method != SMB_EXEC_DIRECT && method != SMB_EXEC_OLS)
-      throw smb::invalid_argument("fir: method must be SMB_EXEC_DIRECT or SMB_EXEC_OLS");
+    if (method != SMB_EXEC_DIRECT && method != SMB_EXEC_OLS && method != SMB_EXEC_PLANNED)
+      throw smb::invalid_argument(
+          "fir: method must be SMB_EXEC_DIRECT, SMB_EXEC_OLS or SMB_EXEC_PLANNED");
     if (batch == 0 || n == 0) return;
     plan->ensure_device();
+    if (method == SMB_EXEC_PLANNED)
+      method = plan->ols.plan.ok && plan->k >= 8 ? SMB_EXEC_OLS : SMB_EXEC_DIRECT;
     if (method == SMB_EXEC_OLS && !plan->ols.plan.ok)
       throw smb::invalid_argument(
           "fir: this filter is too long for the overlap-save kernel (use the direct method)");

@@ -276,7 +276,9 @@ class Fir:
         if h and getattr(_lib, "lib", None) is not None:      # not during interpreter teardown
             _lib.lib.smb_fir_plan_destroy(h)
 
-    def apply(self, x, method="direct", out=None):
+    def apply(self, x, method="auto", out=None):
+        """``method``: ``"auto"`` (overlap-save from 17 taps up, else the direct
+        kernel), ``"ols"`` or ``"direct"``."""
         x = _lib.contiguous(x)
         ptr, mem, _ = _check("fir", x)
         n = int(x.shape[-1])
@@ -288,6 +290,6 @@ class Fir:
         stream = _lib.current_stream(x)
         if stream is not None:
             _lib.check(_lib.lib.smb_fir_plan_set_stream(self._h, stream))
-        code = {"direct": _lib.EXEC_DIRECT, "ols": _lib.EXEC_OLS}[method]
+        code = {"direct": _lib.EXEC_DIRECT, "ols": _lib.EXEC_OLS, "auto": _lib.EXEC_PLANNED}[method]
         _lib.check(_lib.lib.smb_fir_apply(self._h, ptr, batch, n, _lib.out_pointer(out), code, mem))
         return out

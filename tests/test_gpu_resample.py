@@ -132,12 +132,17 @@ def test_fir_direct_matches_oracle(sb, k):
     np.testing.assert_allclose(fir.taps, R.design_prototype(1, k, 0.25, R.kaiser_beta(126.0)),
                                rtol=1e-12, atol=1e-18)
     x = noise((2, 2, 9000), k)
-    got = fir.apply(x)
+    got = fir.apply(x, method="direct")
     want = R.fir_apply(x, fir.taps)
     assert got.shape == x.shape
     assert peak_rel_err(got, want) <= RESAMPLE_TOL
+    # the default picks overlap-save from 17 taps up, the direct kernel below
+    auto = fir.apply(x)
+    assert np.array_equal(auto, fir.apply(x, method="ols" if k >= 8 else "direct"))
+    assert peak_rel_err(auto, want) <= RESAMPLE_TOL
     for n in (1, 2, k, 2 * k + 1):
         xs = noise((n,), n)
+        assert peak_rel_err(fir.apply(xs, method="direct"), R.fir_apply(xs, fir.taps)) <= RESAMPLE_TOL
         assert peak_rel_err(fir.apply(xs), R.fir_apply(xs, fir.taps)) <= RESAMPLE_TOL
 
 
