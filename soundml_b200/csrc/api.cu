@@ -511,6 +511,8 @@ struct OlsDevice {
     a.tw = d_tw;
     if (fast && d_tw_pass && smb::ols2048_supports(a))
       CK(smb::launch_ols2048(a, d_tw_pass, d_tw_base, batch, sm_count, st));
+    else if (plan.full_inverse)
+      throw smb::invalid_argument("soundml_b200: this overlap-save plan needs the N = 2048 kernel");
     else
       CK(smb::launch_ols(a, batch, st));
   }

@@ -680,15 +680,17 @@ int64_t OlsPlan::blocks_for(int64_t n_out) const {
 
 static OlsPlan finish_ols(OlsPlan p, const std::vector<double>& proto) {
   const int64_t len = p.l > 1 ? p.n * p.l : p.n;             // resample.ml:858
-  p.w = p.l > 1 ? p.n * p.l : p.n / p.m;
+  p.w = p.l > 1 ? p.n * p.l : (p.full_inverse ? p.n : p.n / p.m);
   const int64_t longest = std::max(p.n, p.w);
   if (!is_pow2(p.n) || !is_pow2(p.w) || longest > 16384 || (int64_t)proto.size() > len ||
-      p.b < 1 || (p.m > 1 && p.n % p.m != 0))
+      p.b < 1 || (p.m > 1 && !p.full_inverse && p.n % p.m != 0))
     return p;
   std::vector<double> re((size_t)len, 0.0), im((size_t)len, 0.0);
   std::copy(proto.begin(), proto.end(), re.begin());          // padded at the tail
   fft_pow2(re, im);
-  const double scale = (p.m > 1 ? 1.0 / double(p.m) : 1.0) / double(p.w);
+  // 1/M of the alias fold and 1/W of the inverse; a full-length inverse carries 1/N
+  const double scale = p.full_inverse ? 1.0 / double(p.n)
+                                      : (p.m > 1 ? 1.0 / double(p.m) : 1.0) / double(p.w);
   const int64_t bins = (p.l > 1 ? p.w : p.n) / 2 + 1;
   p.spectrum_re.resize((size_t)bins);
   p.spectrum_im.resize((size_t)bins);
@@ -705,6 +707,14 @@ OlsPlan ols_plan_for_stage(const ResampleStage& s) {
   if (s.exec != kExecOls || (s.l > 1 && s.m > 1)) return p;
   p.l = s.l; p.m = s.m; p.k = s.k;
   p.n = s.ols_n; p.b = s.ols_b; p.delta = s.ols_delta;
+  if (s.l == 1 && s.m > 1 && 2 * s.k + s.m <= 1024) {
+    // the warp-per-block kernel: block length 2048, hop a multiple of m, and the
+    // reference's delta rule (resample.ml:279-300) so kept samples land on i m
+    p.n = 2048;
+    p.b = (2048 - 2 * s.k) / s.m * s.m;
+    p.delta = (s.m - (3 * s.k % s.m)) % s.m;
+    p.full_inverse = true;
+  }
   return finish_ols(p, s.proto);
 }
 

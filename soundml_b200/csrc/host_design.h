@@ -92,12 +92,17 @@ std::vector<double> bank_of_prototype(int64_t l, int64_t k, const std::vector<do
 struct OlsPlan {
   bool ok = false;
   int64_t n = 0, b = 0, delta = 0, w = 0, l = 1, m = 1, k = 0;
+  // true: the block is inverted at full length n and every m-th sample kept
+  // (ols2048_kernel), so n / m need not be a transform length
+  bool full_inverse = false;
   std::vector<double> spectrum_re, spectrum_im;   // W/2+1 (xL) or N/2+1 bins, 1/M and 1/W folded in
   int64_t blocks_for(int64_t n_out) const;         // blocks whose runs cover [0, n_out)
   int64_t hi(int64_t block) const;                 // last output block `block` completes
 };
 // GPU-executable OLS plan for a stage, or ok = false when the transform lengths
 // are not powers of two / too long for one CTA (the direct kernel runs instead).
+// Decimating stages whose filter fits take the GPU's own block length 2048
+// (any m), whatever length the planner priced for the CPU.
 OlsPlan ols_plan_for_stage(const ResampleStage& s);
 // FIR as an L = M = 1 stage: N = 2048 up to 1025 taps, else the smallest power of
 // two >= 10 K.

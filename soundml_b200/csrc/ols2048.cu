@@ -2,9 +2,10 @@
 //
 // Same filter and block geometry as ols_kernels.cu (reference: resample.ml:279-300,
 // 1309-1319, 1456-1599; spectrum shaping resample_stubs.c:329-372), specialised
-// to the block length the planner picks for filters of up to ~200 taps per side
-// (44.1 -> 22.05 kHz: N = 2048, K = 190) and that this build picks for FIRs of up
-// to 1025 taps.  Plain (L = M = 1) and decimating (/M, M | 2048) stages.
+// to block length 2048: what the planner picks for 44.1 -> 22.05 kHz (K = 190),
+// and what this build picks for every decimating stage whose filter fits (any M:
+// 48 -> 16 kHz is /3) and for FIRs of up to 1025 taps.  Plain (L = M = 1) and /M
+// stages.
 //
 // A warp owns a block from the first load to the last store -- no CTA-level
 // synchronisation, so the 16 warps of an SM drift apart and overlap each other's
@@ -230,19 +231,18 @@ ols2048_kernel(const Ols2048Params p) {
         if (i >= lo && i <= hi) out[i] = v[q].x;
       }
     } else {
+      // any other M: lay the block out in the (now idle) transpose buffer and let
+      // consecutive lanes pick consecutive outputs, i.e. every M-th sample
+      float2* yb2 = ex;
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const long long d0 = 2LL * (lane + 32 * q) - cpos;
-        if (d0 >= 0 && d0 % a.M == 0) {
-          const long long i = d0 / a.M;
-          if (i >= lo && i <= hi) out[i] = v[q].x;
-        }
-        const long long d1 = d0 + 1;
-        if (d1 >= 0 && d1 % a.M == 0) {
-          const long long i = d1 / a.M;
-          if (i >= lo && i <= hi) out[i] = -v[q].y;
-        }
-      }
+      for (int q = 0; q < 32; ++q) yb2[lane + 32 * q] = make_float2(v[q].x, -v[q].y);
+      __syncwarp();
+      const float* yb = reinterpret_cast<const float*>(ex);
+      const long long ibase = -cpos / a.M;                    // exact: M divides cpos
+      const long long i_first = max(lo, ibase);
+      const long long i_last = min(hi, ibase + (kN - 1) / a.M);
+      for (long long i = i_first + lane; i <= i_last; i += 32)
+        out[i] = yb[(int)(i - ibase) * a.M];
     }
     __syncwarp();
   }
@@ -251,8 +251,8 @@ ols2048_kernel(const Ols2048Params p) {
 }  // namespace
 
 bool ols2048_supports(const OlsArgs& a) {
-  return a.N == kN && a.L == 1 && a.M >= 1 && kN % a.M == 0 && a.W == kN / a.M &&
-         a.B >= 1 && 2 * a.K + a.delta < kN;
+  return a.N == kN && a.L == 1 && a.M >= 1 && a.B >= 1 && a.B % a.M == 0 &&
+         (3 * a.K + a.delta) % a.M == 0 && 2 * a.K + a.delta < kN;
 }
 
 cudaError_t launch_ols2048(const OlsArgs& a, const float2* tw_pass, const float2* tw_base,

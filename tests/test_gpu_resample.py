@@ -174,7 +174,8 @@ def test_fir_overlap_save_matches_oracle_and_direct(sb, k):
 
 
 @pytest.mark.parametrize("sr,target", [(44100, 22050), (22050, 44100), (48000, 8000), (8000, 48000),
-                                       (48000, 12000), (12000, 48000), (44100, 88200)])
+                                       (48000, 12000), (12000, 48000), (44100, 88200),
+                                       (48000, 16000), (16000, 48000), (96000, 32000)])
 def test_planned_ols_stages_match_direct_and_oracle(sb, sr, target):
     """Stages the planner tags for overlap-save (x2, x4, /2, /4) run the FFT
     kernel by default; forcing the direct kernel must give the same signal."""
