@@ -461,7 +461,7 @@ struct OlsDevice {
   void upload_from(const smb::OlsPlan& p) {
     plan = p;
     if (!p.ok) return;
-    if (p.n == 2048 && p.l == 1) {
+    if (p.n == 2048 && (p.l == 1 || p.polyphase)) {
       std::vector<float2> pass(1024), base(32);
       for (int k1 = 0; k1 < 32; ++k1)
         for (int n2 = 0; n2 < 32; ++n2) {
@@ -509,9 +509,10 @@ struct OlsDevice {
     a.N = (int)plan.n; a.B = (int)plan.b; a.delta = (int)plan.delta; a.W = (int)plan.w;
     a.H = d_h;
     a.tw = d_tw;
+    a.polyphase = plan.polyphase ? 1 : 0;
     if (fast && d_tw_pass && smb::ols2048_supports(a))
       CK(smb::launch_ols2048(a, d_tw_pass, d_tw_base, batch, sm_count, st));
-    else if (plan.full_inverse)
+    else if (plan.full_inverse || plan.polyphase)
       throw smb::invalid_argument("soundml_b200: this overlap-save plan needs the N = 2048 kernel");
     else
       CK(smb::launch_ols(a, batch, st));

@@ -678,6 +678,29 @@ int64_t OlsPlan::blocks_for(int64_t n_out) const {
   return blk + 1;
 }
 
+// xL stage as L branches: branch p filters the input with g_p[t] = proto[p + t L]
+// (bank[p][s] = h[p + (2K - s) L], resample.ml:165-179, read against t = 2K - s).
+static OlsPlan finish_polyphase(OlsPlan p, const std::vector<double>& proto) {
+  const int64_t bins = p.n / 2 + 1;
+  p.w = p.n;
+  p.spectrum_re.assign((size_t)(bins * p.l), 0.0);
+  p.spectrum_im.assign((size_t)(bins * p.l), 0.0);
+  for (int64_t ph = 0; ph < p.l; ++ph) {
+    std::vector<double> re((size_t)p.n, 0.0), im((size_t)p.n, 0.0);
+    for (int64_t t = 0; t <= 2 * p.k; ++t) {
+      const int64_t at = ph + t * p.l;
+      if (at < (int64_t)proto.size()) re[(size_t)t] = proto[(size_t)at];
+    }
+    fft_pow2(re, im);
+    for (int64_t i = 0; i < bins; ++i) {
+      p.spectrum_re[(size_t)(ph * bins + i)] = re[(size_t)i] / double(p.n);
+      p.spectrum_im[(size_t)(ph * bins + i)] = im[(size_t)i] / double(p.n);
+    }
+  }
+  p.ok = true;
+  return p;
+}
+
 static OlsPlan finish_ols(OlsPlan p, const std::vector<double>& proto) {
   const int64_t len = p.l > 1 ? p.n * p.l : p.n;             // resample.ml:858
   p.w = p.l > 1 ? p.n * p.l : (p.full_inverse ? p.n : p.n / p.m);
@@ -714,6 +737,14 @@ OlsPlan ols_plan_for_stage(const ResampleStage& s) {
     p.b = (2048 - 2 * s.k) / s.m * s.m;
     p.delta = (s.m - (3 * s.k % s.m)) % s.m;
     p.full_inverse = true;
+  }
+  if (s.m == 1 && s.l > 1 && s.l <= 8 && 2 * s.k + 1 <= 1024) {
+    // interpolating stage on the same kernel: L input-rate branches, block 2048
+    p.n = 2048;
+    p.b = 2048 - 2 * s.k;
+    p.delta = 0;
+    p.polyphase = true;
+    return finish_polyphase(p, s.proto);
   }
   return finish_ols(p, s.proto);
 }

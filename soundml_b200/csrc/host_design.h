@@ -95,6 +95,9 @@ struct OlsPlan {
   // true: the block is inverted at full length n and every m-th sample kept
   // (ols2048_kernel), so n / m need not be a transform length
   bool full_inverse = false;
+  // true: an xL stage as its L polyphase branches at the input rate, each a plain
+  // filter g_p[t] = h[p + t L] with its own n/2+1-bin spectrum (branch-major)
+  bool polyphase = false;
   std::vector<double> spectrum_re, spectrum_im;   // W/2+1 (xL) or N/2+1 bins, 1/M and 1/W folded in
   int64_t blocks_for(int64_t n_out) const;         // blocks whose runs cover [0, n_out)
   int64_t hi(int64_t block) const;                 // last output block `block` completes

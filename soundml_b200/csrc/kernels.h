@@ -118,7 +118,9 @@ struct OlsArgs {
   float* out;            // [batch, n_out]
   long long n, n_out, blocks;
   int L, M, K, N, B, delta, W;
-  const float2* H;       // plan spectrum: W/2+1 bins (xL) or N/2+1 (otherwise), scales folded in
+  const float2* H;       // plan spectrum: W/2+1 bins (xL) or N/2+1 (otherwise), scales folded in;
+                         // polyphase plans: L spectra of N/2+1 bins, one per branch
+  int polyphase;         // xL stage laid out as L input-rate branches (ols2048_kernel)
   const float2* tw;      // exp(-2 pi i j / max(N, W)), j < max(N, W)/2
 };
 size_t ols_smem_bytes(int N, int W);

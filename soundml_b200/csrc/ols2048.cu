@@ -4,8 +4,10 @@
 // 1309-1319, 1456-1599; spectrum shaping resample_stubs.c:329-372), specialised
 // to block length 2048: what the planner picks for 44.1 -> 22.05 kHz (K = 190),
 // and what this build picks for every decimating stage whose filter fits (any M:
-// 48 -> 16 kHz is /3) and for FIRs of up to 1025 taps.  Plain (L = M = 1) and /M
-// stages.
+// 48 -> 16 kHz is /3) and for FIRs of up to 1025 taps.  Plain (L = M = 1), /M and
+// xL stages; an interpolating stage runs as its L polyphase branches
+// y[jL + p] = sum_t x[j + K - t] g_p[t], g_p[t] = h[p + tL] -- L plain filters at
+// the input rate, one (block, branch) pair per warp, each with its own spectrum.
 //
 // A warp owns a block from the first load to the last store -- no CTA-level
 // synchronisation, so the 16 warps of an SM drift apart and overlap each other's
@@ -90,8 +92,8 @@ ols2048_kernel(const Ols2048Params p) {
   extern __shared__ __align__(16) float smem[];
   float2* sTwPass = reinterpret_cast<float2*>(smem);          // [16][32][2] pairs (k1, k1+1) per lane
   float2* sTwBase = sTwPass + 1024;                           // [32]
-  float2* sH = sTwBase + 32;                                  // [1025 (+1)] plan spectrum x 1/2
-  float* sEx = reinterpret_cast<float*>(sH + 1026);           // [16 warps][32][34] complex
+  float2* sH = sTwBase + 32;                                  // [L][1025 (+1)] plan spectra x 1/2
+  float* sEx = reinterpret_cast<float*>(sH + 1026 * p.a.L);   // [16 warps][32][34] complex
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 1024; i += blockDim.x) {
     const int l = i & 31, k1 = i >> 5;
@@ -99,9 +101,10 @@ ols2048_kernel(const Ols2048Params p) {
   }
   if (tid < 32) sTwBase[tid] = p.tw_base[tid];
   // the real split below yields 2 X[k]: the missing 1/2 rides on the spectrum
-  for (int i = tid; i <= kHalf; i += blockDim.x) {
+  for (int i = tid; i < 1025 * p.a.L; i += blockDim.x) {
+    const int ph = i / 1025, k = i - ph * 1025;
     const float2 h = p.a.H[i];
-    sH[i] = make_float2(0.5f * h.x, 0.5f * h.y);
+    sH[ph * 1026 + k] = make_float2(0.5f * h.x, 0.5f * h.y);
   }
   __syncthreads();
 
@@ -113,10 +116,14 @@ ols2048_kernel(const Ols2048Params p) {
   const long long wstride = (long long)gridDim.x * kWarps;
 
   for (long long id = (long long)blockIdx.x * kWarps + warp; id < p.total_blocks; id += wstride) {
-    const long long c = id / a.blocks;
-    const long long b = id - c * a.blocks;
+    // work item = (signal c, block b, polyphase branch ph)
+    const long long cb = id / a.L;
+    const int ph = (int)(id - cb * a.L);
+    const long long c = cb / a.blocks;
+    const long long b = cb - c * a.blocks;
     const float* xs = a.x + c * a.n;
     float* out = a.out + c * a.n_out;
+    const float2* sHp = sH + ph * 1026;
 
     // ---- block b reads stage inputs [b B - 2K - delta, +2048), zeros outside the signal
     const long long start = b * a.B - 2LL * a.K - a.delta;
@@ -158,7 +165,7 @@ ols2048_kernel(const Ols2048Params p) {
     float2 mid;
     {
       const float2 xm = make_float2(2.0f * v[16].x, -2.0f * v[16].y);   // 2 X[512]
-      const float2 ym = cmulf(xm, sH[512]);
+      const float2 ym = cmulf(xm, sHp[512]);
       mid = make_float2(2.0f * ym.x, 2.0f * ym.y);                       // conj(2 conj(Y)) = 2 Y
     }
 #pragma unroll
@@ -174,8 +181,8 @@ ols2048_kernel(const Ols2048Params p) {
       const float2 xk = make_float2(S.x + tr, S.y + ti);      // 2 X[k]
       const float2 xn = make_float2(S.x - tr, ti - S.y);      // 2 X[1024-k]
       const int k = lane + 32 * k2;
-      const float2 yk = cmulf(xk, sH[k]);                     // Y[k]
-      const float2 yn = cmulf(xn, sH[kHalf - k]);             // Y[1024-k]
+      const float2 yk = cmulf(xk, sHp[k]);                    // Y[k]
+      const float2 yn = cmulf(xn, sHp[kHalf - k]);            // Y[1024-k]
       // E = Y[k] + conj Y[nk], O = Y[k] - conj Y[nk]
       const float2 E = make_float2(yk.x + yn.x, yk.y - yn.y);
       const float2 O = make_float2(yk.x - yn.x, yk.y + yn.y);
@@ -210,7 +217,17 @@ ols2048_kernel(const Ols2048Params p) {
     if (hi >= a.n_out) hi = a.n_out - 1;
     // output i sits at full-rate block position i M + cpos (cpos divisible by M)
     const long long cpos = 3LL * a.K + a.delta - b * a.B;
-    if (a.M == 1) {
+    if (a.L > 1) {
+      // interpolating stage: branch ph of input-rate sample j lands on j L + ph
+      const long long hi_j = min(b * a.B + kN - 3LL * a.K - 1, a.n - 1);
+      const long long lo_j = b == 0 ? 0 : (b - 1) * a.B + kN - 3LL * a.K;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const long long j = 2LL * (lane + 32 * q) - cpos;
+        if (j >= lo_j && j <= hi_j) out[j * a.L + ph] = v[q].x;
+        if (j + 1 >= lo_j && j + 1 <= hi_j) out[(j + 1) * a.L + ph] = -v[q].y;
+      }
+    } else if (a.M == 1) {
       const bool vec = ((cpos & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
@@ -251,8 +268,9 @@ ols2048_kernel(const Ols2048Params p) {
 }  // namespace
 
 bool ols2048_supports(const OlsArgs& a) {
-  return a.N == kN && a.L == 1 && a.M >= 1 && a.B >= 1 && a.B % a.M == 0 &&
-         (3 * a.K + a.delta) % a.M == 0 && 2 * a.K + a.delta < kN;
+  if (a.N != kN || a.B < 1 || 2 * a.K + a.delta >= kN) return false;
+  if (a.L > 1) return a.M == 1 && a.delta == 0 && a.L <= 8 && a.polyphase;
+  return a.M >= 1 && a.B % a.M == 0 && (3 * a.K + a.delta) % a.M == 0;
 }
 
 cudaError_t launch_ols2048(const OlsArgs& a, const float2* tw_pass, const float2* tw_base,
@@ -262,8 +280,9 @@ cudaError_t launch_ols2048(const OlsArgs& a, const float2* tw_pass, const float2
   p.a = a;
   p.tw_pass = tw_pass;
   p.tw_base = tw_base;
-  p.total_blocks = a.blocks * batch;
-  const size_t smem = (size_t)(1024 + 32 + 1026) * sizeof(float2) + (size_t)kWarps * kExFloats * 4;
+  p.total_blocks = a.blocks * batch * a.L;
+  const size_t smem = (size_t)(1024 + 32 + 1026 * a.L) * sizeof(float2) +
+                      (size_t)kWarps * kExFloats * 4;
   cudaError_t e = cudaFuncSetAttribute(ols2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
