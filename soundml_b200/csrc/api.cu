@@ -521,74 +521,94 @@ struct OlsDevice {
 
 // Device image of G for the tensor-core executor of one phase-rich stage.
 struct GemmDevice {
+  // L <= 160 is one launch; wider stages (L = 320, 441, 640: the 44.1 k <-> 48 k
+  // family) are cut into column groups of <= 160, one launch each, because the
+  // three accumulators of a group must fit the 512 TMEM columns.
+  struct Group {
+    int col_begin = 0, width = 0, n_pad = 0, chunk_begin = 0, chunks = 0, tmem_cols = 0;
+    float* d_images = nullptr;
+    int4* d_meta = nullptr;
+  };
   bool ok = false;
-  int n_pad = 0, chunks = 0, tmem_cols = 0;
-  float* d_images = nullptr;
-  int4* d_meta = nullptr;
+  std::vector<Group> groups;
   void build(const smb::ResampleStage& s) {
     const int64_t l = s.l, m = s.m, k = s.k, taps = 2 * k + 1;
-    n_pad = (int)((l + 15) / 16 * 16);
-    if (s.exec != smb::kExecGemm || 3 * n_pad > 512) return;
-    const int64_t p_len = taps + ((l - 1) * m) / l;          // gemm_bank, resample.ml:215-226
-    chunks = (int)((p_len + 31) / 32);
-    tmem_cols = 32;
-    while (tmem_cols < 3 * n_pad) tmem_cols *= 2;
-    // G is banded: chunk ch (rows 32 ch .. 32 ch + 31 of G) only has nonzeros in a
-    // run of columns.  Store and multiply just that run, widened to multiples
-    // of 16 columns; chunks 0 and 1 keep the full width because their first
-    // products zero-initialise the accumulators.
-    std::vector<int> cmin((size_t)chunks, n_pad), cmax((size_t)chunks, -1);
-    for (int64_t r = 0; r < l; ++r) {
-      const int64_t d = (r * m) / l;
-      for (int64_t ch = d / 32; ch <= (d + taps - 1) / 32; ++ch) {
-        cmin[(size_t)ch] = std::min(cmin[(size_t)ch], (int)r);
-        cmax[(size_t)ch] = std::max(cmax[(size_t)ch], (int)r);
+    if (s.exec != smb::kExecGemm || l > 1024) return;
+    const int n_groups = (int)((l + 159) / 160);
+    const int base_width = (int)(((l + n_groups - 1) / n_groups + 15) / 16 * 16);
+    for (int c0 = 0; c0 < l; c0 += base_width) {
+      Group g;
+      g.col_begin = c0;
+      g.width = (int)std::min<int64_t>(base_width, l - c0);
+      g.n_pad = (g.width + 15) / 16 * 16;
+      // rows of G (K index) this group's columns touch: d(r) = floor(r M / L) .. + taps - 1
+      const int64_t d_first = ((int64_t)c0 * m) / l;
+      const int64_t d_last = ((int64_t)(c0 + g.width - 1) * m) / l + taps - 1;
+      g.chunk_begin = (int)(d_first / 32);
+      g.chunks = (int)(d_last / 32) - g.chunk_begin + 1;
+      g.tmem_cols = 32;
+      while (g.tmem_cols < 3 * g.n_pad) g.tmem_cols *= 2;
+      // G is banded: chunk ch only has nonzeros in a run of columns.  Store and
+      // multiply just that run, widened to multiples of 16 columns; the group's
+      // first two chunks keep the full width because their first products
+      // zero-initialise the accumulators.
+      std::vector<int> cmin((size_t)g.chunks, g.n_pad), cmax((size_t)g.chunks, -1);
+      for (int r = 0; r < g.width; ++r) {
+        const int64_t d = ((int64_t)(c0 + r) * m) / l;
+        for (int64_t ch = d / 32; ch <= (d + taps - 1) / 32; ++ch) {
+          const size_t rel = (size_t)(ch - g.chunk_begin);
+          cmin[rel] = std::min(cmin[rel], r);
+          cmax[rel] = std::max(cmax[rel], r);
+        }
       }
-    }
-    std::vector<int4> meta((size_t)chunks);
-    size_t total_floats = 0;
-    for (int ch = 0; ch < chunks; ++ch) {
-      int col0 = 0, ncols = n_pad;
-      if (ch >= 2 && cmax[(size_t)ch] >= 0) {
-        col0 = cmin[(size_t)ch] / 16 * 16;
-        ncols = (cmax[(size_t)ch] + 1 - col0 + 15) / 16 * 16;
-      } else if (ch >= 2) {
-        ncols = 16;                                          // empty chunk: a zero slice
+      std::vector<int4> meta((size_t)g.chunks);
+      size_t total_floats = 0;
+      for (int ch = 0; ch < g.chunks; ++ch) {
+        int col0 = 0, ncols = g.n_pad;
+        if (ch >= 2 && cmax[(size_t)ch] >= 0) {
+          col0 = cmin[(size_t)ch] / 16 * 16;
+          ncols = (cmax[(size_t)ch] + 1 - col0 + 15) / 16 * 16;
+        } else if (ch >= 2) {
+          ncols = 16;                                          // empty chunk: a zero slice
+        }
+        meta[(size_t)ch] = make_int4((int)(total_floats * 4), col0, ncols, 0);
+        total_floats += (size_t)2 * ncols * 32;
       }
-      meta[(size_t)ch] = make_int4((int)(total_floats * 4), col0, ncols, 0);
-      total_floats += (size_t)2 * ncols * 32;
-    }
-    std::vector<float> img(total_floats, 0.0f);
-    for (int64_t r = 0; r < l; ++r) {
-      const int64_t d = (r * m) / l, ph = (r * m) % l;
-      for (int64_t t = 0; t < taps; ++t) {
-        const int64_t j = d + t;                               // row of G
-        const double g = s.bank[(size_t)(ph * taps + t)];
-        const float gf = (float)g;
-        uint32_t bits;
-        std::memcpy(&bits, &gf, 4);
-        bits &= 0xFFFFE000u;                                   // tf32 piece, exact
-        float hi;
-        std::memcpy(&hi, &bits, 4);
-        const float lo = (float)(g - (double)hi);
-        const int64_t ch = j / 32, kk = j % 32;
-        const int4 mt = meta[(size_t)ch];
-        const int64_t rr = r - mt.y;                           // row inside the stored slice
-        const size_t cell = (size_t)(rr * 32 + ((((kk >> 2) ^ (rr & 7)) << 2) | (kk & 3)));
-        const size_t base = (size_t)mt.x / 4;
-        img[base + cell] = hi;
-        img[base + (size_t)mt.z * 32 + cell] = lo;
+      std::vector<float> img(total_floats, 0.0f);
+      for (int r = 0; r < g.width; ++r) {
+        const int64_t col = c0 + r;
+        const int64_t d = (col * m) / l, ph = (col * m) % l;
+        for (int64_t t = 0; t < taps; ++t) {
+          const int64_t j = d + t;                               // row of G
+          const double gv = s.bank[(size_t)(ph * taps + t)];
+          const float gf = (float)gv;
+          uint32_t bits;
+          std::memcpy(&bits, &gf, 4);
+          bits &= 0xFFFFE000u;                                   // tf32 piece, exact
+          float hi;
+          std::memcpy(&hi, &bits, 4);
+          const float lo = (float)(gv - (double)hi);
+          const int64_t ch = j / 32 - g.chunk_begin, kk = j % 32;
+          const int4 mt = meta[(size_t)ch];
+          const int64_t rr = r - mt.y;                           // row inside the stored slice
+          const size_t cell = (size_t)(rr * 32 + ((((kk >> 2) ^ (rr & 7)) << 2) | (kk & 3)));
+          const size_t base = (size_t)mt.x / 4;
+          img[base + cell] = hi;
+          img[base + (size_t)mt.z * 32 + cell] = lo;
+        }
       }
+      g.d_meta = upload(meta);
+      g.d_images = upload(img);
+      groups.push_back(g);
     }
-    d_meta = upload(meta);
-    d_images = upload(img);
     ok = true;
   }
   void release() {
-    cudaFree(d_images);
-    cudaFree(d_meta);
-    d_images = nullptr;
-    d_meta = nullptr;
+    for (Group& g : groups) {
+      cudaFree(g.d_images);
+      cudaFree(g.d_meta);
+    }
+    groups.clear();
   }
 };
 
@@ -599,7 +619,7 @@ struct smb_resample_plan {
   std::vector<float*> d_bank;        // per stage, [l][2k+1] float32
   std::vector<double*> d_bank64;     // the same banks uncast, for float64 audio
   std::vector<OlsDevice> ols;        // per stage; plan.ok only for OLS-tagged power-of-two stages
-  std::vector<GemmDevice> gemm;      // per stage; ok only for GEMM-tagged stages with L <= 160
+  std::vector<GemmDevice> gemm;      // per stage; ok only for GEMM-tagged stages
   int executor = SMB_EXEC_PLANNED;   // SMB_EXEC_DIRECT forces the dot-product kernel everywhere
   DeviceBuffer in, out, mid;
   void ensure_device() {
@@ -627,18 +647,24 @@ struct smb_resample_plan {
     if (executor != SMB_EXEC_DIRECT && ols[i].plan.ok) {
       ols[i].run(x, batch, n, n_out, out, st);
     } else if (executor != SMB_EXEC_DIRECT && gemm[i].ok) {
-      smb::GemmResampleArgs a{};
-      a.x = x;
-      a.out = out;
-      a.n = n;
-      a.n_out = n_out;
-      a.l = (int)s.l; a.m = (int)s.m; a.k = (int)s.k;
-      a.n_pad = gemm[i].n_pad;
-      a.chunks = gemm[i].chunks;
-      a.tmem_cols = gemm[i].tmem_cols;
-      a.b_images = gemm[i].d_images;
-      a.chunk_meta = gemm[i].d_meta;
-      CK(smb::launch_resample_gemm(a, batch, st));
+      for (const GemmDevice::Group& g : gemm[i].groups) {
+        smb::GemmResampleArgs a{};
+        a.x = x;
+        a.out = out;
+        a.n = n;
+        a.n_out = n_out;
+        a.l = g.width;
+        a.m = (int)s.m;
+        a.k = (int)s.k - 32 * g.chunk_begin;          // the group's first K-chunk is chunk 0
+        a.l_total = (int)s.l;
+        a.col_begin = g.col_begin;
+        a.n_pad = g.n_pad;
+        a.chunks = g.chunks;
+        a.tmem_cols = g.tmem_cols;
+        a.b_images = g.d_images;
+        a.chunk_meta = g.d_meta;
+        CK(smb::launch_resample_gemm(a, batch, st));
+      }
     } else
       CK(smb::launch_polyphase_direct(x, batch, n, d_bank[i], (int)s.l, (int)s.m, (int)s.k,
                                       n_out, out, st));

@@ -135,7 +135,8 @@ struct GemmResampleArgs {
   const float* x;          // [batch, n]
   float* out;              // [batch, n_out]
   long long n, n_out;
-  int l, m, k;             // stage factors and group delay
+  int l, m, k;             // columns of this launch, stage M, group delay less the skipped K-chunks
+  int l_total, col_begin;  // stage L (outputs per block-row) and this launch's first column
   int n_pad;               // l rounded up to a multiple of 16 (UMMA N)
   int chunks;              // ceil(P / 32) K-chunks
   int tmem_cols;           // power of two >= 3 * n_pad

@@ -296,24 +296,30 @@ resample_gemm_kernel(const GemmResampleArgs a) {
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kRows) : "memory");   // producers/epilogue warps only
-    const long long o_base = row0 * a.l;
-    const long long o_end = min(a.n_out, o_base + (long long)kRows * a.l);
-    if ((a.l & 3) == 0 && (reinterpret_cast<size_t>(out + o_base) & 15) == 0) {
+    // block-row r is the L_total consecutive outputs of one phase cycle; this
+    // launch owns columns [col_begin, col_begin + l) of it
+    const long long rows_total = (a.n_out + a.l_total - 1) / a.l_total;
+    const int rows_here = (int)min((long long)kRows, rows_total - row0);
+    const bool vec = ((a.l | a.l_total | a.col_begin) & 3) == 0 &&
+                     (reinterpret_cast<size_t>(out) & 15) == 0;
+    if (vec) {
       const int per_row = a.l >> 2;
-      const long long total4 = (o_end - o_base) >> 2;           // whole float4s in range
-      for (long long j = tid; j < total4; j += kRows) {
-        const int row = (int)(j / per_row), c4 = (int)(j - (long long)row * per_row);
-        reinterpret_cast<float4*>(out + o_base)[j] =
-            *reinterpret_cast<const float4*>(tile + row * pitch + 4 * c4);
-      }
-      for (long long o = o_base + (total4 << 2) + tid; o < o_end; o += kRows) {
-        const long long rel = o - o_base;
-        out[o] = tile[(rel / a.l) * pitch + (rel % a.l)];
+      for (int j = tid; j < rows_here * per_row; j += kRows) {
+        const int row = j / per_row, c4 = j - row * per_row;
+        const long long g = (row0 + row) * a.l_total + a.col_begin + 4 * c4;
+        const float4 val = *reinterpret_cast<const float4*>(tile + row * pitch + 4 * c4);
+        if (g + 3 < a.n_out) {
+          *reinterpret_cast<float4*>(out + g) = val;
+        } else {                                              // the signal ends inside this float4
+          const float e[4] = {val.x, val.y, val.z, val.w};
+          for (int t = 0; t < 4 && g + t < a.n_out; ++t) out[g + t] = e[t];
+        }
       }
     } else {
-      for (long long o = o_base + tid; o < o_end; o += kRows) {
-        const long long rel = o - o_base;
-        out[o] = tile[(rel / a.l) * pitch + (rel % a.l)];
+      for (int j = tid; j < rows_here * a.l; j += kRows) {
+        const int row = j / a.l, cc = j - row * a.l;
+        const long long g = (row0 + row) * a.l_total + a.col_begin + cc;
+        if (g < a.n_out) out[g] = tile[row * pitch + cc];
       }
     }
   }
@@ -338,7 +344,7 @@ cudaError_t launch_resample_gemm(const GemmResampleArgs& a, long long batch, cud
   cudaError_t e = cudaFuncSetAttribute(resample_gemm_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const long long rows = (a.n_out + a.l - 1) / a.l;
+  const long long rows = (a.n_out + a.l_total - 1) / a.l_total;
   const long long tiles = (rows + kRows - 1) / kRows;
   for (long long b0 = 0; b0 < batch; b0 += 65535) {
     const long long nb = batch - b0 < 65535 ? batch - b0 : 65535;

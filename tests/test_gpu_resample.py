@@ -41,6 +41,25 @@ def test_apply_matches_oracle(sb, sr, target):
 
 
 # resample_kernel.ml:28-52 — output length is ceil(n L / M), also for tiny inputs
+@pytest.mark.parametrize("sr,target", [(44100, 32000), (22050, 48000), (44100, 96000),
+                                       (11025, 48000), (16000, 44100)])
+def test_wide_phase_count_stages_run_on_the_tensor_cores(sb, sr, target):
+    """L = 320, 441, 640: the tcgen05 executor cuts the stage into column groups
+    of <= 160 phases; results must match the direct kernel and the oracle."""
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
+    assert any(s["exec"] == "gemm" and s["l"] > 160 for s in cfg.stages()), cfg.pp()
+    st = oracle_stages(cfg)
+    for n in (1, 500, 40013):
+        x = noise((2, n), n + target)
+        want = R.apply_plan(x, st, cfg.l, cfg.m)
+        planned = sb.Resample.apply(cfg.set_executor("planned"), x)
+        direct = sb.Resample.apply(cfg.set_executor("direct"), x)
+        assert planned.shape == direct.shape == want.shape
+        scale = max(np.abs(want).max(), 1e-3)
+        assert np.abs(planned - want).max() / scale <= RESAMPLE_TOL, (sr, target, n)
+        assert np.abs(direct - want).max() / scale <= RESAMPLE_TOL, (sr, target, n)
+
+
 @pytest.mark.parametrize("sr,target,l,m", [(44100, 48000, 160, 147), (48000, 44100, 147, 160),
                                             (44100, 16000, 160, 441), (44100, 22050, 1, 2),
                                             (22050, 44100, 2, 1), (3, 2, 2, 3)])
