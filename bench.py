@@ -104,9 +104,11 @@ def cpu_reference_pass(x, sc, mc, workers):
     return mel_oracle.mel_spectrogram(sc, mc, x, 2.0, workers=workers)
 
 
-def time_cpu(clips, min_seconds, workers):
+def time_cpu(clips, min_seconds, workers, keep=None):
     """Oracle on host cores: repeated passes over a `clips`-clip sample of the
-    workload until `min_seconds` of work; returns (audio-s/s, passes)."""
+    workload until `min_seconds` of work; returns (audio-s/s, passes, seconds).
+    `keep`, a list, receives the oracle's output for the sample so the caller can
+    state the GPU path's error against it next to the number."""
     from oracle import mel_oracle, stft_oracle
     from soundml_b200 import synth
     x = synth.clips_numpy(clips, N, SR)
@@ -115,7 +117,9 @@ def time_cpu(clips, min_seconds, workers):
     cpu_reference_pass(x[:2], sc, mc, workers)            # warm the FFT plan cache
     t0, passes = time.perf_counter(), 0
     while True:
-        cpu_reference_pass(x, sc, mc, workers)
+        y = cpu_reference_pass(x, sc, mc, workers)
+        if keep is not None and not keep:
+            keep.append(y)
         passes += 1
         dt = time.perf_counter() - t0
         if dt >= min_seconds:
@@ -262,14 +266,26 @@ def main():
         traffic = prof.get("stft2048_mel_dram_bytes_per_launch")
     except Exception:
         pass
-    cpu = None
+    cpu = parity = None
     if world == 1:                      # reported on rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         clips = 32
-        v, passes, dt = time_cpu(clips, args.cpu_seconds, cores)
+        kept = []
+        v, passes, dt = time_cpu(clips, args.cpu_seconds, cores, keep=kept)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{clips} of {BATCH} clips x {passes} passes ({dt:.1f} s), oracle "
                          "(numpy/scipy float64 restatement of stft.ml + mel.ml)"}
+        # the error metric that goes with the number: per clip
+        # max |got - ref| / max |ref| against the oracle's output for the same
+        # clips, and the elementwise pass rate at the reference's float32 gate
+        import numpy as np
+        want = np.asarray(kept[0], dtype=np.float64)
+        got = out[:clips].cpu().numpy().astype(np.float64)
+        per_clip = (np.abs(got - want).max(axis=(1, 2)) / np.abs(want).max(axis=(1, 2)))
+        gate = np.abs(got - want) <= 1e-7 + 1e-6 * np.abs(want)
+        parity = {"max_rel_err_per_clip": float(per_clip.max()), "tolerance": 1e-4,
+                  "f32_gate_pass_rate": float(gate.mean()),
+                  "sample": f"first {clips} clips against the oracle"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -282,6 +298,7 @@ def main():
                      "algorithmic_bytes_per_launch": ALGO_BYTES,
                      "kernel": "stft2048_kernel<mel>"},
         "cpu_baseline": cpu,
+        "parity": parity,
         "e2e": e2e,
         "gpu_launches": launches,
         "clocks": clocks,
