@@ -214,8 +214,9 @@ struct smb_stft_plan {
       tw[(size_t)j] = make_double2(std::cos(a), -std::sin(a));
     }
     d_twiddle64 = upload(tw);
-    if (n == 2048) {
-      std::vector<float> w32((size_t)n);
+    if (fast_step() > 0) {
+      // shorter frames run zero-padded to 2048: the window's tail is zero
+      std::vector<float> w32(2048, 0.0f);
       for (int64_t j = 0; j < n; ++j) w32[(size_t)j] = (float)window[(size_t)j];
       d_window32 = upload(w32);
       std::vector<float2> pass(1024), post(512);
@@ -255,6 +256,10 @@ struct smb_stft_plan {
     if (frames == 0) return 0;
     return (frames - 1) * geom.hop + geom.fft - geom.left_width() - geom.right_width();
   }
+  // 2048 / fft when the frame embeds in the fused kernel's 2048-point transform
+  int fast_step() const {
+    return geom.fft >= 128 && geom.fft <= 2048 && 2048 % geom.fft == 0 ? (int)(2048 / geom.fft) : 0;
+  }
   smb::FrameGeom frame_geom(int64_t n) const {
     smb::FrameGeom g;
     g.n = n;
@@ -292,6 +297,9 @@ struct smb_mel_plan {
   std::vector<float> vals;
   std::vector<smb::MelLane> mel_lanes;   // [kFastTile warps][mel_rounds][kFastRoundFilters]
   int mel_rounds = 0;
+  // 2048 / fft_size when the fused kernel can carry this filterbank (1 for fft
+  // 2048, 2 for 1024, ...), else 0
+  int fast_step = 0;
   bool device_ready = false;
   StreamOwner stream;
   double* d_weights = nullptr;
@@ -340,6 +348,10 @@ struct smb_mel_plan {
       band_hi[(size_t)m] = hi;
     }
     if (!small || bins + 3 > 32767) return;
+    // the fused kernel takes frames of 2048 / step samples, step a power of two
+    // (shorter frames run zero-padded and keep every step-th bin in the power row)
+    if (bins < 65 || bins > 1025 || 1024 % (bins - 1) != 0) return;
+    const int step = (int)(1024 / (bins - 1));
     // Schedule for the fused kernel.  Filters sorted by band length are cut into
     // rounds of kFastRoundFilters (two sets A and B); a warp lane is (filter j,
     // frame f) and walks its A and B filter together.  The bands of a round are
@@ -401,6 +413,7 @@ struct smb_mel_plan {
       }
     }
     if (!fits) { vals.clear(); return; }
+    fast_step = step;
     std::vector<std::vector<int>> lists((size_t)warps);
     std::vector<long long> load((size_t)warps, 0);
     for (int q = 0; q < rounds_total; ++q) {
@@ -857,9 +870,12 @@ void check_signal(const char* op, int64_t batch, int64_t n) {
 bool want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int out_kind,
                const smb_mel_plan* mel) {
   if (p->path == SMB_PATH_GENERIC) return false;
-  const bool ok = dtype == SMB_F32 && g.fft == 2048 &&
-                  (!mel || (mel->bins == 1025 && !mel->mel_lanes.empty())) &&
-                  smb::stft2048_supports(g, out_kind, mel ? (int)mel->n_mels : 0,
+  const int step = p->fast_step();
+  smb::FrameGeom gk = g;
+  gk.fft = 2048;
+  const bool ok = dtype == SMB_F32 && step > 0 &&
+                  (!mel || (mel->fast_step == step && !mel->mel_lanes.empty())) &&
+                  smb::stft2048_supports(gk, out_kind, mel ? (int)mel->n_mels : 0,
                                          mel ? (int)mel->vals.size() : 0,
                                          mel ? mel->mel_rounds : 0);
   if (!ok && p->path == SMB_PATH_FAST)
@@ -879,6 +895,8 @@ void run_spectrum(smb_stft_plan* p, const void* dx, int64_t batch, const smb::Fr
     a.out = (float*)dout;
     a.batch = batch;
     a.g = g;
+    a.g.fft = 2048;
+    a.bin_step = p->fast_step();
     a.window = p->d_window32;
     a.tw_pass = p->d_tw_pass;
     a.tw_post = p->d_tw_post;
@@ -1273,6 +1291,8 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
         a.out = (float*)dout;
         a.batch = nb;
         a.g = g;
+        a.g.fft = 2048;
+        a.bin_step = stft->fast_step();
         a.window = stft->d_window32;
         a.tw_pass = stft->d_tw_pass;
         a.tw_post = stft->d_tw_post;

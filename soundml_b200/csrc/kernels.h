@@ -86,6 +86,7 @@ struct Stft2048Args {
   int mel_rounds;              // rounds each warp walks
   const MelLane* mel_lanes;    // [kFastTile warps][mel_rounds][kFastRoundFilters]
   float power;
+  int bin_step;                // 2048 / fft_size: 1, or 2/4/8/16 for zero-padded shorter frames
 };
 // True when the fused kernel can take this geometry (hop small enough for the
 // shared-memory sample tile, mel tables small enough to be resident).

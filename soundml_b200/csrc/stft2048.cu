@@ -7,6 +7,12 @@
 // (stft.ml:356-364, 670-674; mel.ml:202-231) in one pass: the complex spectrum
 // and the power spectrogram never reach HBM on the mel path.
 //
+// Frame sizes 1024, 512, 256 and 128 ride on the same kernel: a frame zero-padded
+// to 2048 has the shorter transform's bin k at bin k * (2048 / fft), so the host
+// hands over a window whose tail is zero and `bin_step` = 2048 / fft; the real
+// split keeps every bin_step-th bin in the frame's row, and everything after it
+// (mel bands, write-out) sees a row of fft / 2 + 1 bins.
+//
 // Decomposition
 //   * One persistent CTA per SM, 16 warps in independent groups.  A group of
 //     kFastTile warps owns a tile of kFastTile consecutive frames of one signal:
@@ -37,7 +43,6 @@ namespace {
 
 constexpr int kFft = 2048;
 constexpr int kHalf = 1024;              // complex points
-constexpr int kBins = 1025;
 constexpr int kTile = kFastTile;         // frames per group tile, one warp each
 constexpr int kGroupThreads = 32 * kTile;
 constexpr int kGroupWarps = kTile;
@@ -186,6 +191,7 @@ stft2048_kernel(const Params p) {
   __syncthreads();
 
   const FrameGeom g = p.a.g;
+  const int bin_shift = 31 - __clz(p.a.bin_step), bin_mask = p.a.bin_step - 1;
   // tile indices fit 32 bits (checked by the launcher): cheap decode
   const int slot = blockIdx.x * kGroups + group;
   const int stride = gridDim.x * kGroups;
@@ -286,9 +292,10 @@ stft2048_kernel(const Params p) {
         const float2 xk = make_float2(S.x + tr, S.y + ti);
         const float2 xn = make_float2(S.x - tr, ti - S.y);
         const int k = lane + 32 * k2, nk = kHalf - k;
+        const bool keep_k = (k & bin_mask) == 0, keep_n = (nk & bin_mask) == 0;
         if (OUT == kFastComplex) {
-          rowc[k] = xk;
-          rowc[nk] = xn;
+          if (keep_k) rowc[k >> bin_shift] = xk;
+          if (keep_n) rowc[nk >> bin_shift] = xn;
         } else {
           float pk = xk.x * xk.x + xk.y * xk.y;
           float pn = xn.x * xn.x + xn.y * xn.y;
@@ -296,18 +303,19 @@ stft2048_kernel(const Params p) {
             if (p.a.power == 1.0f) { pk = sqrtf(pk); pn = sqrtf(pn); }
             else { pk = powf(sqrtf(pk), p.a.power); pn = powf(sqrtf(pn), p.a.power); }
           }
-          row[k] = pk;
-          row[nk] = pn;
+          if (keep_k) row[k >> bin_shift] = pk;
+          if (keep_n) row[nk >> bin_shift] = pn;
         }
       }
       if (lane == 0) {                            // k = 512 pairs with itself
         const float2 xm = make_float2(2.0f * a[16].x, -2.0f * a[16].y);
-        if (OUT == kFastComplex) rowc[512] = xm;
+        if (OUT == kFastComplex) rowc[512 >> bin_shift] = xm;
         else {
           float pm = xm.x * xm.x + xm.y * xm.y;
           if (!SQUARE) pm = p.a.power == 1.0f ? sqrtf(pm) : powf(sqrtf(pm), p.a.power);
-          row[512] = pm;
-          row[1025] = row[1026] = row[1027] = 0.0f;   // float4 padding read by the mel bands
+          row[512 >> bin_shift] = pm;
+          const int bins = (kHalf >> bin_shift) + 1;
+          row[bins] = row[bins + 1] = row[bins + 2] = 0.0f;   // float4 padding read by the mel bands
         }
       }
     }
@@ -370,16 +378,20 @@ stft2048_kernel(const Params p) {
           for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step)
             *ob = src[m];
         } else if (OUT == kFastPower) {
-          float* ob = p.a.out + ((long long)b * kBins + r0) * g.frames + p0 + f;
+          const int out_bins = kHalf / p.a.bin_step + 1;
+          float* ob = p.a.out + ((long long)b * out_bins + r0) * g.frames + p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float* src = sRows + f * kRowStride;
-          for (int k = r0; k < kBins; k += kGroupThreads / kTile, ob += step) *ob = src[k];
+          for (int r = r0; r < out_bins; r += kGroupThreads / kTile, ob += step)
+            *ob = src[r];
         } else {
-          float2* ob = reinterpret_cast<float2*>(p.a.out) + ((long long)b * kBins + r0) * g.frames +
+          const int out_bins = kHalf / p.a.bin_step + 1;
+          float2* ob = reinterpret_cast<float2*>(p.a.out) + ((long long)b * out_bins + r0) * g.frames +
                        p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float2* src = reinterpret_cast<const float2*>(sRows + f * kRowStride);
-          for (int k = r0; k < kBins; k += kGroupThreads / kTile, ob += step) *ob = src[k];
+          for (int r = r0; r < out_bins; r += kGroupThreads / kTile, ob += step)
+            *ob = src[r];
         }
       }
     }
@@ -406,7 +418,7 @@ static int span_needed(const FrameGeom& g) {
 }
 
 bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds) {
-  if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;
+  if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;   // g: the kernel's geometry
   if (out_kind == kFastMel && (n_mels < 1 || n_mels > kMaxMel || nnz > 65536)) return false;
   const bool mel = out_kind == kFastMel;
   return smem_layout(mel ? nnz : 0, mel ? mel_rounds : 0, span_needed(g), kMaxGroups / 2) <= kSmemLimit;
@@ -421,7 +433,7 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
     lo.batch = half;
     hi.batch = a.batch - half;
     hi.x = a.x + half * a.g.n;
-    const long long rows = out_kind == kFastMel ? a.n_mels : kBins;
+    const long long rows = out_kind == kFastMel ? a.n_mels : kHalf / a.bin_step + 1;
     hi.out = a.out + half * rows * a.g.frames * (out_kind == kFastComplex ? 2 : 1);
     cudaError_t e1 = launch_stft2048(lo, out_kind, sm_count, st);
     return e1 != cudaSuccess ? e1 : launch_stft2048(hi, out_kind, sm_count, st);

@@ -126,6 +126,45 @@ def test_fast_kernel_geometries(sb, hop, alignment):
     assert peak_rel_err(gotz.view(np.float32), refz.view(np.float32)) <= SPECTRUM_TOL
 
 
+@pytest.mark.parametrize("fft,hop,wl,n_mels", [(1024, 256, None, 80), (1024, 160, 800, 128),
+                                               (512, 128, None, 80), (512, 200, 400, 40),
+                                               (256, 64, None, 40), (128, 32, None, 20)])
+@pytest.mark.parametrize("alignment,pad", [("centered", "reflect"), ("left", "edge"),
+                                           ("right", ("constant", 0.25))])
+def test_shorter_frames_ride_the_fused_kernel(sb, fft, hop, wl, n_mels, alignment, pad):
+    """fft 1024 / 512 / 256 / 128 run zero-padded inside the fft-2048 kernel; power,
+    complex and mel outputs against the oracle, and the forced fast path must
+    accept them."""
+    name = pad if isinstance(pad, str) else pad[0]
+    val = 0.0 if isinstance(pad, str) else pad[1]
+    c = sb.Stft.Config.create(fft_size=fft, hop=hop, win_length=wl, alignment=alignment,
+                              pad=pad).set_path("fast")
+    o = stft_oracle.StftConfig(fft, hop, win_length=wl, alignment=alignment, pad=name,
+                               pad_value=val)
+    mc = sb.Mel.Config.create(n_mels=n_mels, sample_rate=16000, fft_size=fft)
+    mo = mel_oracle.MelConfig(n_mels, 16000, fft)
+    for n in (1, fft // 2, fft + 1, 7001):
+        x = np.stack([_signal(n, 1), _signal(n, 2) + 0.1])
+        ref = stft_oracle.power_spectrum(o, x)
+        got = sb.Stft.power_spectrum(c, x)
+        assert got.shape == ref.shape, (n, got.shape, ref.shape)
+        if ref.size == 0:
+            continue
+        for b in range(2):
+            assert peak_rel_err(got[b], ref[b]) <= SPECTRUM_TOL, (fft, hop, alignment, n, b)
+        refz = stft_oracle.transform(o, x)
+        gotz = sb.Stft.transform(c, x)
+        assert peak_rel_err(gotz.view(np.float32), refz.view(np.float32)) <= SPECTRUM_TOL
+        refm = mel_oracle.mel_spectrogram(o, mo, x)
+        gotm = sb.mel_spectrogram(c, mc, x)
+        assert gotm.shape == refm.shape
+        for b in range(2):
+            assert peak_rel_err(gotm[b], refm[b]) <= SPECTRUM_TOL, (fft, hop, alignment, n, b)
+        c.set_path("generic")
+        assert peak_rel_err(sb.mel_spectrogram(c, mc, x), gotm) <= SPECTRUM_TOL
+        c.set_path("fast")
+
+
 @pytest.mark.parametrize("pad", ["reflect", "edge", ("constant", 0.5)])
 @pytest.mark.parametrize("n", [1, 2, 700, 1024, 1025, 2047, 2048, 2049, 5000])
 def test_fast_kernel_short_signals_and_pads(sb, pad, n):
