@@ -17,10 +17,11 @@ from . import window as _window
 class Config:
     """``Stft.Config.t``.  Build with :meth:`create`."""
 
-    def __init__(self, handle, window, alignment, pad, pad_value, scale):
+    def __init__(self, handle, window, alignment, pad, pad_value, scale, win_length=None):
         self._h = handle
         self.window, self.alignment, self.pad = window, alignment, pad
         self.pad_value, self.scale = pad_value, scale
+        self._win_length = win_length
 
     @classmethod
     def create(cls, *, fft_size, window="hann", win_length=None, hop=None,
@@ -44,7 +45,7 @@ class Config:
             _lib.DEFAULT if win_length is None else int(win_length),
             kind, param, _lib.ALIGNMENTS[alignment], _lib.PADS[pad], pad_value,
             _lib.SCALES[scale]))
-        return cls(h, window, alignment, pad, pad_value, scale)
+        return cls(h, window, alignment, pad, pad_value, scale, win_length)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -52,6 +53,8 @@ class Config:
             _lib.lib.smb_stft_plan_destroy(h)
 
     fft_size = property(lambda self: int(_lib.lib.smb_stft_fft_size(self._h)))
+    win_length = property(lambda self: self.fft_size if self._win_length is None
+                          else int(self._win_length))
     hop = property(lambda self: int(_lib.lib.smb_stft_hop(self._h)))
     bins = property(lambda self: int(_lib.lib.smb_stft_bins(self._h)))
 
@@ -496,6 +499,142 @@ class Kernel:
                     rp = rp[..., dropped:r]
                 out = self._process([rp], r - dropped)
         self.pending, self.pending_len = [], 0
+        return out
+
+
+def synthesis_latency(c):
+    """``Config.synthesis_latency`` (stft.ml:152-153): output samples the streaming
+    synthesis trails by -- the head trim plus the tail holdback."""
+    fft, hop = c.fft_size, c.hop
+    left = {"centered": fft // 2, "left": 0, "right": fft - 1}[c.alignment]
+    right = fft // 2 if c.alignment == "centered" else 0
+    return left + max(0, hop + right - fft)
+
+
+class Synthesis:
+    """``Stft.Synthesis`` (stft.ml:1027-1296): the chunked form of ``invert``.
+
+    ``step`` feeds frames ``[..., bins, m]`` and returns the samples they
+    completed (``hop`` per frame once the head trim is paid) or ``None``;
+    ``flush`` releases the positions the last frame reaches.  Concatenating
+    everything returned equals ``invert`` at its default length on the
+    concatenated frames, for every partition of the frame sequence -- bit for bit,
+    because every position is computed from the same frames in the same order
+    with the same envelope value.
+
+    Padded position q is final once frame q / hop has arrived.  The state is the
+    spectra of the last frames that still reach an unreleased position (the
+    reference keeps their windowed inverses instead); each step inverts a window
+    of them with a left-aligned twin of the configuration, started early enough
+    that the released positions lie in the fully covered region of the window,
+    where the envelope is the same periodic tile as in the whole signal.
+    """
+
+    def __init__(self, c, channels, max_block, dtype=None, _invert=None):
+        if channels < 1:
+            raise ValueError(
+                f"prepare: cannot synthesise {channels} channels (channels must be at least 1)")
+        if max_block < 1:
+            raise ValueError(
+                f"prepare: cannot accept blocks of {max_block} frames "
+                "(max_block must be at least 1)")
+        if not nola(c):
+            raise ValueError(
+                f"prepare: cannot invert a {c.win_length}-point window advanced by {c.hop} "
+                f"samples inside a {c.fft_size}-point frame (the overlap-added squared window "
+                "must stay above 1e-10 of its largest value at every position)")
+        self.cfg, self.dtype = c, dtype
+        self.fft, self.hop = c.fft_size, c.hop
+        self.left = {"centered": self.fft // 2, "left": 0, "right": self.fft - 1}[c.alignment]
+        self.right = self.fft // 2 if c.alignment == "centered" else 0
+        self.hold = max(0, self.hop + self.right - self.fft)
+        self._invert = _invert
+        self._twin = None
+        self.reset()
+
+    @classmethod
+    def prepare(cls, c, *, channels, max_block, dtype=None):
+        """``Synthesis.prepare dtype c cdtype ~channels ~max_block``; ``dtype`` is
+        the output dtype (default: the component width of the frames fed)."""
+        return cls(c, channels, max_block, dtype)
+
+    def reset(self):
+        self.frames = 0            # frames fed
+        self.released = 0          # padded positions released so far
+        self.first = 0             # index of the first retained frame
+        self.hist = []             # spectra of frames [first, frames)
+        self.drained = False
+
+    def _window(self, lo, hi, final):
+        """Padded positions [lo, hi) from the retained frames."""
+        n, h = self.fft, self.hop
+        p0 = max(self.first, max(0, (lo - (n - h)) // h)) if lo >= n - h else 0
+        z = _cat(self.hist)
+        self.hist = [z]
+        zw = z[..., p0 - self.first:]
+        base = p0 * h
+        length = None if final else hi - base
+        if self._invert is not None:
+            y = self._invert(zw, length)
+        else:
+            if self._twin is None:
+                hdl = C.c_void_p()
+                w = self.cfg.analysis_window
+                _lib.check(_lib.lib.smb_stft_plan_create_with_window(
+                    C.byref(hdl), n, h, _lib.ALIGNMENTS["left"], _lib.PADS["constant"], 0.0,
+                    w.ctypes.data_as(C.POINTER(C.c_double))))
+                self._twin = Config(hdl, self.cfg.window, "left", "constant", 0.0, self.cfg.scale)
+            y = invert(self._twin, zw, length=length, dtype=self.dtype)
+        out = y[..., lo - base:hi - base]
+        return out.contiguous() if _lib.is_torch(out) else np.ascontiguousarray(out)
+
+    def step(self, z):
+        """``Synthesis.step k z`` (stft.ml:1168-1230)."""
+        if self.drained:
+            raise ValueError("step: cannot feed a drained kernel (flush consumed the tail; "
+                             "reset before reusing)")
+        if z.ndim < 2:
+            raise ValueError(
+                f"step: cannot invert a rank-{z.ndim} tensor (the bin and frame axes must exist)")
+        if int(z.shape[-2]) != self.cfg.bins:
+            raise ValueError(
+                f"step: cannot invert {int(z.shape[-2])} frequency bins of a {self.fft}-point "
+                f"transform (the bin axis must hold fft_size / 2 + 1 = {self.cfg.bins} values)")
+        if any(int(d) == 0 for d in z.shape[:-2]):
+            raise ValueError("step: cannot synthesise frames with a zero-size leading axis "
+                             "(channels must be at least 1)")
+        m = _last(z)
+        if m == 0:
+            return None
+        self.hist.append(_copy(z))
+        self.frames += m
+        # positions released after F frames = F H - max 0 (H + R - N)   (stft.mli:489-494)
+        upto = max(0, self.frames * self.hop - self.hold)
+        lo = max(self.released, self.left)
+        out = self._window(lo, upto, False) if upto > lo else None
+        self.released = max(self.released, upto)
+        # frames that still reach an unreleased position (or anchor the next window)
+        keep = max(0, (max(self.released, self.left) - (self.fft - self.hop)) // self.hop)
+        keep = min(keep, self.frames)
+        if keep > self.first:
+            zall = _cat(self.hist)
+            self.hist = [_copy(zall[..., keep - self.first:])]
+            self.first = keep
+        return out
+
+    def flush(self):
+        """``Synthesis.flush k`` (stft.ml:1232-1270): the positions the last frame
+        reaches, less the trailing trim."""
+        if self.drained:
+            return None
+        self.drained = True
+        out = None
+        if self.frames > 0:
+            span = (self.frames - 1) * self.hop + self.fft
+            lo, hi = max(self.released, self.left), span - self.right
+            if hi > lo:
+                out = self._window(lo, hi, True)
+        self.hist = []
         return out
 
 

@@ -126,3 +126,73 @@ def test_resample_kernel_errors(lib):
         k.step(np.zeros((2, 17), np.float32))
     with pytest.raises(ValueError, match="3-channel chunks"):
         k.step(np.zeros((3, 4), np.float32))
+
+
+# ---- Stft.Synthesis -------------------------------------------------------------
+
+from oracle import istft_oracle                                 # noqa: E402
+
+SYNTH_CASES = [
+    dict(fft_size=64, hop=16, alignment="centered"),
+    dict(fft_size=64, hop=16, alignment="left"),
+    dict(fft_size=64, hop=16, alignment="right"),
+    dict(fft_size=32, hop=7, win_length=20, alignment="centered"),
+    dict(fft_size=64, hop=64, window="rectangular", alignment="centered"),   # hold = hop + R - N > 0
+    dict(fft_size=31, hop=5, alignment="centered"),
+]
+
+
+@pytest.mark.parametrize("case", SYNTH_CASES)
+def test_synthesis_partition_law_host_logic(lib, case):
+    """Chunked synthesis == invert at its default length, bit for bit, for every
+    partition of the frame sequence (stft.mli:473-517), with the oracle standing in
+    for the GPU inverse."""
+    c = lib.Stft.Config.create(**case)
+    kw = dict(case)
+    fft = kw.pop("fft_size")
+    full = stft_oracle.StftConfig(fft, **kw)
+    kw["alignment"] = "left"
+    left = stft_oracle.StftConfig(fft, **kw)
+    rng = np.random.default_rng(3)
+    assert lib.Stft.synthesis_latency(c) == full.left_width() + max(
+        0, full.hop + full.right_width() - fft)
+    for frames in (0, 1, 2, 3, 9, 40):
+        z = rng.standard_normal((2, full.bins, frames)) + 1j * rng.standard_normal((2, full.bins, frames))
+        want = istft_oracle.invert(full, z)
+        for sizes in chunkings(frames, rng):
+            k = lib.Stft.Synthesis(c, 2, 4096,
+                                   _invert=lambda zw, length: istft_oracle.invert(left, zw, length=length))
+            outs, at, emitted = [], 0, 0
+            for m in sizes:
+                o = k.step(z[..., at:at + m])
+                at += m
+                if o is not None:
+                    outs.append(o)
+                    emitted += o.shape[-1]
+                # samples emitted after F frames = F H - synthesis_latency (stft.mli:489-494)
+                assert emitted == max(0, at * full.hop - lib.Stft.synthesis_latency(c))
+            o = k.flush()
+            if o is not None:
+                outs.append(o)
+            assert k.flush() is None
+            got = np.concatenate(outs, axis=-1) if outs else np.zeros((2, 0))
+            assert got.shape == want.shape, (frames, sizes, got.shape, want.shape)
+            assert np.array_equal(got, want), (frames, sizes)
+            with pytest.raises(ValueError, match="drained kernel"):
+                k.step(z[..., :1])
+
+
+def test_synthesis_prepare_errors(lib):
+    c = lib.Stft.Config.create(fft_size=64, hop=16)
+    with pytest.raises(ValueError, match="cannot synthesise 0 channels"):
+        lib.Stft.Synthesis.prepare(c, channels=0, max_block=4)
+    with pytest.raises(ValueError, match="blocks of 0 frames"):
+        lib.Stft.Synthesis.prepare(c, channels=1, max_block=0)
+    bad = lib.Stft.Config.create(fft_size=64, hop=65)
+    with pytest.raises(ValueError, match="prepare: cannot invert a 64-point window advanced by 65"):
+        lib.Stft.Synthesis.prepare(bad, channels=1, max_block=4)
+    k = lib.Stft.Synthesis.prepare(c, channels=1, max_block=4)
+    with pytest.raises(ValueError, match="frequency bins"):
+        k.step(np.zeros((32, 2), complex))
+    with pytest.raises(ValueError, match="zero-size leading axis"):
+        k.step(np.zeros((0, 33, 2), complex))
