@@ -1041,8 +1041,10 @@ int smb_stft_invert(smb_stft_plan* plan, const void* z, int64_t batch, int64_t f
             "soundml_b200: the fft-2048 synthesis kernel does not cover this geometry");
       if (fast) {
         if (!p->d_window_inv) {
-          std::vector<float> w((size_t)p->geom.fft);
-          for (size_t j = 0; j < w.size(); ++j) w[j] = (float)(p->window[j] / 2048.0);
+          // 1 / fft of the inverse folded in; frames shorter than 2048 leave a zero tail
+          std::vector<float> w(2048, 0.0f);
+          for (size_t j = 0; j < (size_t)p->geom.fft; ++j)
+            w[j] = (float)(p->window[j] / double(p->geom.fft));
           p->d_window_inv = upload(w);
         }
         CK(smb::launch_istft2048(a, p->d_window_inv, p->d_tw_pass, p->d_tw_post, nb, p->sm_count,

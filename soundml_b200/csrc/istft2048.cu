@@ -19,6 +19,12 @@
 //     frames that reach it, newest first (fixed order, deterministic), divides
 //     by the envelope and is written once.
 // 3 of every 16 transforms (hop 512) are recomputed by the neighbouring run.
+//
+// Frame sizes 1024 ... 128 ride along: the inverse of a 2048-point spectrum that
+// carries X[k] at bin k * (2048 / fft) and zeros elsewhere is the fft-point inverse
+// repeated, so the kernel spreads the fft / 2 + 1 input bins while it reads the
+// tile and uses the first fft samples of each frame (window tail zero, 1 / fft
+// folded into the window).
 #include <cstdint>
 
 #include "fft32.cuh"
@@ -89,6 +95,7 @@ struct Istft2048Params {
   long long runs_per_signal, total_runs;
 };
 
+template <int STEP>                                     // 2048 / fft_size
 __global__ void __launch_bounds__(kWarps * 32, 1)
 istft2048_kernel(const Istft2048Params p) {
   extern __shared__ __align__(16) float smem[];
@@ -118,7 +125,11 @@ istft2048_kernel(const Istft2048Params p) {
   const int partner = (32 - lane) & 31;
   const int hop = a.hop;
   const int run_len = p.run_hops * hop;
-  const long long span = (a.count - 1) * (long long)hop + kN;
+  constexpr int fft = kN / STEP;                          // frame length
+  constexpr int bin_mask = STEP - 1;
+  constexpr int bin_shift = STEP == 1 ? 0 : STEP == 2 ? 1 : STEP == 4 ? 2 : STEP == 8 ? 3 : 4;
+  constexpr int bins = fft / 2 + 1;
+  const long long span = (a.count - 1) * (long long)hop + fft;
   const unsigned tile_base = (unsigned)__cvta_generic_to_shared(tile);
 
   for (long long run = blockIdx.x; run < p.total_runs; run += gridDim.x) {
@@ -127,17 +138,17 @@ istft2048_kernel(const Istft2048Params p) {
     const long long m1 = min(m0 + run_len, a.out_len);
     const long long q0 = m0 + a.left;
     const long long q1 = min(m1 + a.left, span);                      // positions [q0, q1) receive taps
-    const float2* z = reinterpret_cast<const float2*>(a.z) + b * kBins * a.frames;
+    const float2* z = reinterpret_cast<const float2*>(a.z) + b * bins * a.frames;
     float* out = reinterpret_cast<float*>(a.out) + b * a.out_len;
     long long p_lo = 0, p_hi = -1;
     if (q1 > q0) {
       p_hi = min(a.count - 1, (q1 - 1) / hop);
-      p_lo = max(0LL, ceil_div_ll(q0 - kN + 1, hop));
+      p_lo = max(0LL, ceil_div_ll(q0 - fft + 1, hop));
     }
     const int nf = (int)(p_hi - p_lo + 1);                             // <= 16 by construction
 
     // ---- spectrum tile: bins x nf frames, frames contiguous in global memory
-    for (int i = tid; i < kBins * 16; i += blockDim.x) {
+    for (int i = tid; i < bins * 16; i += blockDim.x) {
       const int k = i >> 4, t = i & 15;
       if (t < nf)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_base + 8u * (k * kTileStride + t)),
@@ -154,11 +165,12 @@ istft2048_kernel(const Istft2048Params p) {
       // lane l, register k2 < 16 holds the bin pair k = l + 32 k2 and 1024 - k
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) {
-        const int k = lane + 32 * k2;
-        v[k2] = tile[k * kTileStride + warp];
-        r[k2] = tile[(kHalf - k) * kTileStride + warp];
+        const int k = lane + 32 * k2, nk = kHalf - k;
+        const float2 zero = make_float2(0.f, 0.f);
+        v[k2] = (k & bin_mask) == 0 ? tile[(k >> bin_shift) * kTileStride + warp] : zero;
+        r[k2] = (nk & bin_mask) == 0 ? tile[(nk >> bin_shift) * kTileStride + warp] : zero;
       }
-      mid = tile[512 * kTileStride + warp];
+      mid = tile[(512 >> bin_shift) * kTileStride + warp];
       if (lane == 0) { v[0].y = 0.0f; r[0].y = 0.0f; }                // DC and Nyquist are real
     }
     __syncthreads();                                                   // the tile becomes transpose space
@@ -203,7 +215,7 @@ istft2048_kernel(const Istft2048Params p) {
     // frames that reach it, newest frame first (the order in which the
     // reference's block planes arrive, stft.ml:806-838), then the envelope
     // division, trim and zero extension (stft.ml:846-894)
-    const long long head = min(span, (long long)(kN - hop));
+    const long long head = min(span, (long long)(fft - hop));
     const long long stop = max(head, min(span, a.count * (long long)hop));
     const int n_out = (int)(m1 - m0);
     const long long full_lo = max(head, q0), full_hi = min(stop, q0 + n_out);
@@ -218,12 +230,12 @@ istft2048_kernel(const Istft2048Params p) {
         int t = min(nf - 1, rel / hop);                // newest frame reaching the position
         int j = rel - t * hop;
         float sum = 0.0f;
-        for (; t >= 0 && j < kN; --t, j += hop) sum += sWork[t * kExFloats + j];
+        for (; t >= 0 && j < fft; --t, j += hop) sum += sWork[t * kExFloats + j];
         if (q >= full_lo && q < full_hi) {
           // every residue class reaches the position completely: tabulated reciprocal
           val = sum * sInvEnv[res];
         } else {
-          const long long first = max(0LL, ceil_div_ll(q - kN + 1, hop));
+          const long long first = max(0LL, ceil_div_ll(q - fft + 1, hop));
           const long long last = min(a.count - 1, q / hop);
           double e = 0.0;
           for (long long pp = first; pp <= last; ++pp) {
@@ -245,8 +257,9 @@ istft2048_kernel(const Istft2048Params p) {
 }  // namespace
 
 bool istft2048_supports(const IstftArgs& a) {
-  if (a.fft != kN || a.in_f64 || a.out_f64 || a.hop < 1 || a.hop > kN) return false;
-  const int classes = (kN + a.hop - 1) / a.hop;
+  if (a.fft < 128 || a.fft > kN || kN % a.fft != 0) return false;
+  if (a.in_f64 || a.out_f64 || a.hop < 1 || a.hop > a.fft) return false;
+  const int classes = (a.fft + a.hop - 1) / a.hop;
   const int run_hops = 16 - classes + (a.left % a.hop == 0 ? 1 : 0);
   if (run_hops < 1) return false;
   return true;
@@ -261,18 +274,29 @@ cudaError_t launch_istft2048(const IstftArgs& a, const float* window_scaled, con
   p.window = window_scaled;
   p.tw_pass = tw_pass;
   p.tw_base = tw_base;
-  p.classes = (kN + a.hop - 1) / a.hop;
+  p.classes = (a.fft + a.hop - 1) / a.hop;
   p.run_hops = 16 - p.classes + (a.left % a.hop == 0 ? 1 : 0);
   const long long run_len = (long long)p.run_hops * a.hop;
   p.runs_per_signal = (a.out_len + run_len - 1) / run_len;
   p.total_runs = p.runs_per_signal * batch;
   const size_t smem = (size_t)(1024 + 32) * sizeof(float2) + (size_t)kN * 4 +
                       (size_t)kWorkFloats * 4 + (size_t)a.hop * 4;
-  cudaError_t e = cudaFuncSetAttribute(istft2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
-  if (e != cudaSuccess) return e;
   const int grid = (int)(p.total_runs < sm_count ? p.total_runs : sm_count);
-  istft2048_kernel<<<grid, kWarps * 32, smem, st>>>(p);
+  cudaError_t e = cudaSuccess;
+#define SMB_LAUNCH_ISTFT2048(STEP)                                                          \
+  e = cudaFuncSetAttribute(istft2048_kernel<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)smem);                                                      \
+  if (e != cudaSuccess) return e;                                                           \
+  istft2048_kernel<STEP><<<grid, kWarps * 32, smem, st>>>(p);
+  switch (kN / a.fft) {
+    case 1: SMB_LAUNCH_ISTFT2048(1) break;
+    case 2: SMB_LAUNCH_ISTFT2048(2) break;
+    case 4: SMB_LAUNCH_ISTFT2048(4) break;
+    case 8: SMB_LAUNCH_ISTFT2048(8) break;
+    case 16: SMB_LAUNCH_ISTFT2048(16) break;
+    default: return cudaErrorInvalidConfiguration;
+  }
+#undef SMB_LAUNCH_ISTFT2048
   ++g_launch_count;
   return cudaGetLastError();
 }
