@@ -170,6 +170,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--path", default="auto", choices=["auto", "fast", "tensor"],
+                    help="which fused fft-2048 kernel: auto (the library's choice), the CUDA-core "
+                         "register FFT (fast) or the tcgen05 one (tensor)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 
@@ -193,7 +196,7 @@ def main():
     import soundml_b200 as sb
     from soundml_b200 import synth
 
-    sc = sb.Stft.Config.create(fft_size=FFT, hop=HOP)
+    sc = sb.Stft.Config.create(fft_size=FFT, hop=HOP).set_path(args.path)
     mc = sb.Mel.Config.create(n_mels=N_MELS, sample_rate=SR, fft_size=FFT)
     # rank r owns clips [r*BATCH, (r+1)*BATCH) of the global batch: independent
     # units, no exchange (the same split tests/test_parallel_gloo.py checks)

@@ -72,7 +72,7 @@ enum { SMB_NORM_SLANEY = 0, SMB_NORM_NONE = 1 };
 enum { SMB_QUALITY_FAST = 0, SMB_QUALITY_HIGH = 1, SMB_QUALITY_BEST = 2, SMB_QUALITY_CUSTOM = 3 };
 enum { SMB_EXEC_DIRECT = 0, SMB_EXEC_OLS = 1, SMB_EXEC_GEMM = 2, SMB_EXEC_PLANNED = 3 };
 /* Kernel selection for the STFT family (testing / benchmarking). */
-enum { SMB_PATH_AUTO = 0, SMB_PATH_GENERIC = 1, SMB_PATH_FAST = 2 };
+enum { SMB_PATH_AUTO = 0, SMB_PATH_GENERIC = 1, SMB_PATH_FAST = 2, SMB_PATH_TENSOR = 3 };
 
 typedef struct smb_stft_plan smb_stft_plan;
 typedef struct smb_mel_plan smb_mel_plan;

@@ -14,7 +14,7 @@ OK, EINVAL, ECUDA, ENOMEM = 0, 1, 2, 3
 MEM_DEVICE, MEM_HOST = 0, 1
 F32, F64 = 0, 1
 DEFAULT = -(2 ** 31)
-PATH_AUTO, PATH_GENERIC, PATH_FAST = 0, 1, 2
+PATH_AUTO, PATH_GENERIC, PATH_FAST, PATH_TENSOR = 0, 1, 2, 3
 EXEC_DIRECT, EXEC_OLS, EXEC_GEMM, EXEC_PLANNED = 0, 1, 2, 3
 
 WINDOWS = {"hann": 0, "hamming": 1, "blackman": 2, "blackman_harris": 3,

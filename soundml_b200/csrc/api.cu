@@ -5,6 +5,7 @@
 // Preconditions are checked in the reference's order and with its messages
 // (SMB_EINVAL = Invalid_argument); CUDA failures are SMB_ECUDA.  There is no
 // CPU execution path in this library.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -196,6 +197,7 @@ struct smb_stft_plan {
   float* d_window32 = nullptr;       // fast path tables (fft 2048 only)
   float2* d_tw_pass = nullptr;
   float2* d_tw_post = nullptr;
+  void* d_dft_images = nullptr;      // tensor-core kernel: split-fp16 images of the 32-point DFT
   HostPipe pipe;
   DeviceBuffer tmp;        // power spectrogram of the generic mel path
   DeviceBuffer cepstral;   // mel spectrogram (+ host-call output) of the MFCC path
@@ -232,6 +234,24 @@ struct smb_stft_plan {
         }
       d_tw_pass = upload(pass);
       d_tw_post = upload(post);
+      // The 32-point DFT in real arithmetic, F[n = (k, c')][j = (m, c)] with
+      // (re, im) interleaved: out_re = sum in_re cos + in_im sin, out_im = sum
+      // in_im cos - in_re sin (angle 2 pi m k / 32).  Two fp16 images (leading 11
+      // bits, remainder) in the K-major SWIZZLE_128B operand layout: row n is
+      // 128 bytes, its 16-byte chunk q sits at position q ^ (n mod 8).
+      std::vector<__half> images(2 * 64 * 64);
+      for (int n = 0; n < 64; ++n)
+        for (int j = 0; j < 64; ++j) {
+          const int k = n >> 1, co = n & 1, m = j >> 1, ci = j & 1;
+          const double a = kTwoPi * double((m * k) % 32) / 32.0;
+          const double v = ci == co ? std::cos(a) : (ci == 1 ? std::sin(a) : -std::sin(a));
+          const __half hi = __float2half_rn((float)v);
+          const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+          const size_t at = (size_t)n * 64 + (size_t)((((j >> 3) ^ (n & 7)) << 3) | (j & 7));
+          images[at] = hi;
+          images[64 * 64 + at] = lo;
+        }
+      d_dft_images = upload(images);
     }
     device_ready = true;
   }
@@ -280,6 +300,7 @@ struct smb_stft_plan {
     cudaFree(d_window32);
     cudaFree(d_tw_pass);
     cudaFree(d_tw_post);
+    cudaFree(d_dft_images);
     pipe.release();
     tmp.release();
     cepstral.release();
@@ -297,6 +318,11 @@ struct smb_mel_plan {
   std::vector<float> vals;
   std::vector<smb::MelLane> mel_lanes;   // [kFastTile warps][mel_rounds][kFastRoundFilters]
   int mel_rounds = 0;
+  // the same for the tensor-core kernel's 4-frame tiles
+  std::vector<float> vals_tc;               // [round][step][lane] float4 weights
+  std::vector<smb::MelPiece> pieces_tc;     // [kTcTile warps][mel_rounds_tc][32]
+  std::vector<unsigned short> pstart_tc;    // [n_mels + 1]
+  int mel_rounds_tc = 0, n_pieces_tc = 0;
   // 2048 / fft_size when the fused kernel can carry this filterbank (1 for fft
   // 2048, 2 for 1024, ...), else 0
   int fast_step = 0;
@@ -306,6 +332,9 @@ struct smb_mel_plan {
   int *d_band_lo = nullptr, *d_band_hi = nullptr;
   float* d_vals = nullptr;
   smb::MelLane* d_mel_lanes = nullptr;
+  float* d_vals_tc = nullptr;
+  smb::MelPiece* d_pieces_tc = nullptr;
+  unsigned short* d_pstart_tc = nullptr;
   DeviceBuffer in, out;
   // MFCC epilogue: DCT table of the last (n_mfcc, lifter) asked for, max scratch
   double* d_dct = nullptr;
@@ -352,9 +381,9 @@ struct smb_mel_plan {
     // (shorter frames run zero-padded and keep every step-th bin in the power row)
     if (bins < 65 || bins > 1025 || 1024 % (bins - 1) != 0) return;
     const int step = (int)(1024 / (bins - 1));
-    // Schedule for the fused kernel.  Filters sorted by band length are cut into
-    // rounds of kFastRoundFilters (two sets A and B); a warp lane is (filter j,
-    // frame f) and walks its A and B filter together.  The bands of a round are
+    // Schedule for the fused kernels.  Filters sorted by band length are cut into
+    // rounds of 2 * (32 / tile) filters (two sets A and B); a warp lane is (filter
+    // j, frame f) and walks its A and B filter together.  The bands of a round are
     // stored zero-padded to one common length (a whole number of 8-float steps,
     // starting on a float4 of the 16-byte aligned power row) and interleaved
     // [step][set][half][j] x float4, so every weight load of a warp is one
@@ -363,24 +392,143 @@ struct smb_mel_plan {
     // float4s apart, which with the kernel's row stride (8 mod 32) keeps the
     // power-row loads conflict-free.  Rounds go to the group's warps
     // longest-first onto the lightest warp.
+    if (!build_schedule(smb::kFastTile, vals, mel_lanes, mel_rounds) || !build_tc_schedule()) {
+      vals.clear();
+      vals_tc.clear();
+      mel_lanes.clear();
+      pieces_tc.clear();
+      return;
+    }
+    fast_step = step;
+  }
+  // Schedule of the tensor-core kernel (4-frame tiles).  Every filter's band,
+  // starting on a float4 of the power row, is cut into pieces of at most
+  // kTcPieceSteps float4 steps; a lane carries one piece for the four frames of
+  // the tile and leaves a partial sum in slot `pid` (the slots of a filter are
+  // consecutive: pstart).  Pieces sorted by length fill rounds of 32 lanes with one
+  // step count; inside a round the lanes of a quarter-warp get distinct start
+  // residues (start / 4 mod 8) where possible, so their 16-byte power-row loads
+  // fall in distinct bank groups.  Weights are stored [round][step][lane] x float4.
+  // Rounds go to the 4 warps longest-first onto the lightest warp.
+  bool build_tc_schedule() {
+    const int row_floats = (int)((bins + 3) / 4 * 4);
+    const int ps = smb::kTcPieceSteps;
+    struct Piece { int m, start, steps, pid; };
+    std::vector<Piece> pieces;
+    pstart_tc.assign((size_t)n_mels + 1, 0);
+    for (int64_t m = 0; m < n_mels; ++m) {
+      pstart_tc[(size_t)m] = (unsigned short)pieces.size();
+      const int lo = band_lo[(size_t)m] & ~3, hi = std::max(band_hi[(size_t)m], lo + 1);
+      const int total = (hi - lo + 3) / 4;
+      for (int s0 = 0; s0 < total; s0 += ps)
+        pieces.push_back(Piece{(int)m, lo + 4 * s0, std::min(ps, total - s0), (int)pieces.size()});
+      if (pieces.size() > 4000) return false;
+    }
+    pstart_tc[(size_t)n_mels] = (unsigned short)pieces.size();
+    n_pieces_tc = (int)pieces.size();
+    std::vector<int> order(pieces.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return pieces[(size_t)a].steps > pieces[(size_t)b].steps; });
+    const int rounds_total = (int)((pieces.size() + 31) / 32);
+    struct Round { int steps; size_t base; int member[32]; int start[32]; };
+    std::vector<Round> built((size_t)rounds_total);
+    for (int q = 0; q < rounds_total; ++q) {
+      Round& rd = built[(size_t)q];
+      std::vector<int> pool;
+      for (int t = 0; t < 32; ++t) {
+        const size_t at = (size_t)q * 32 + (size_t)t;
+        if (at < order.size()) pool.push_back(order[at]);
+      }
+      rd.steps = 1;
+      for (int id : pool) rd.steps = std::max(rd.steps, pieces[(size_t)id].steps);
+      if (rd.steps * 4 > row_floats) return false;
+      // the stored run [start, start + 4 steps) must stay inside the row
+      auto start_of = [&](int id) { return std::min(pieces[(size_t)id].start, row_floats - 4 * rd.steps); };
+      for (int t = 0; t < 32; ++t) rd.member[t] = -1;
+      // octets with distinct residues first, leftovers into the free lanes
+      std::vector<int> left;
+      std::vector<std::vector<int>> by_res(8);
+      for (int id : pool) by_res[(size_t)((start_of(id) >> 2) & 7)].push_back(id);
+      for (int o = 0; o < 4; ++o) {
+        int lane = o * 8;
+        for (int r = 0; r < 8; ++r)
+          if (!by_res[(size_t)r].empty()) {
+            rd.member[lane++] = by_res[(size_t)r].back();
+            by_res[(size_t)r].pop_back();
+          }
+      }
+      for (auto& v : by_res) for (int id : v) left.push_back(id);
+      for (int t = 0; t < 32 && !left.empty(); ++t)
+        if (rd.member[t] < 0) { rd.member[t] = left.back(); left.pop_back(); }
+      rd.base = vals_tc.size();
+      vals_tc.resize(rd.base + (size_t)rd.steps * 32 * 4, 0.0f);
+      for (int t = 0; t < 32; ++t) {
+        const int id = rd.member[t];
+        rd.start[t] = id >= 0 ? start_of(id) : 0;
+        if (id < 0) continue;
+        const Piece& pc = pieces[(size_t)id];
+        // the piece's own bins [pc.start, pc.start + 4 pc.steps), clipped to the band
+        for (int k = pc.start; k < pc.start + 4 * pc.steps; ++k) {
+          if (k >= bins || k < band_lo[(size_t)pc.m] || k >= band_hi[(size_t)pc.m]) continue;
+          const int u = k - rd.start[t];
+          vals_tc[rd.base + ((size_t)(u >> 2) * 32 + (size_t)t) * 4 + (size_t)(u & 3)] =
+              (float)weights[(size_t)((int64_t)pc.m * bins + k)];
+        }
+      }
+    }
+    const int warps = smb::kTcTile;
+    std::vector<std::vector<int>> lists((size_t)warps);
+    std::vector<long long> load((size_t)warps, 0);
+    for (int q = 0; q < rounds_total; ++q) {
+      const size_t w = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+      lists[w].push_back(q);
+      load[w] += built[(size_t)q].steps * 21 + 20;
+    }
+    mel_rounds_tc = 0;
+    for (const auto& l : lists) mel_rounds_tc = std::max(mel_rounds_tc, (int)l.size());
+    const size_t zero_off = vals_tc.size();            // idle rounds: one step over zero weights
+    vals_tc.insert(vals_tc.end(), (size_t)(32 * 4), 0.0f);
+    if (vals_tc.size() >= (1u << 24)) return false;
+    pieces_tc.assign((size_t)(warps * mel_rounds_tc * 32), smb::MelPiece{});
+    for (int w = 0; w < warps; ++w)
+      for (int r = 0; r < mel_rounds_tc; ++r)
+        for (int t = 0; t < 32; ++t) {
+          smb::MelPiece& out = pieces_tc[((size_t)w * (size_t)mel_rounds_tc + (size_t)r) * 32 + (size_t)t];
+          if ((size_t)r < lists[(size_t)w].size()) {
+            const Round& rd = built[(size_t)lists[(size_t)w][(size_t)r]];
+            out.off = (int)(rd.base + (size_t)t * 4) | (rd.steps << 24);
+            out.lo = (short)rd.start[t];
+            out.pid = (unsigned short)(rd.member[t] >= 0 ? pieces[(size_t)rd.member[t]].pid : n_pieces_tc);
+          } else {
+            out.off = (int)(zero_off + (size_t)t * 4) | (1 << 24);
+            out.lo = 0;
+            out.pid = (unsigned short)n_pieces_tc;
+          }
+        }
+    return true;
+  }
+  bool build_schedule(int tile, std::vector<float>& vals, std::vector<smb::MelLane>& mel_lanes,
+                      int& mel_rounds) const {
+    constexpr int kMaxRound = 16;
     const int row_floats = (int)((bins + 3) / 4 * 4);        // the kernel zeroes the row tail
     std::vector<int> order((size_t)n_mels);
     for (int64_t m = 0; m < n_mels; ++m) order[(size_t)m] = (int)m;
     auto span = [&](int m) { return band_hi[(size_t)m] - (band_lo[(size_t)m] & ~3); };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return span(a) > span(b); });
-    const int warps = smb::kFastTile, lf = smb::kFastLaneFilters, per_round = smb::kFastRoundFilters;
+    const int warps = tile, lf = 32 / tile, per_round = 2 * lf;
     const int rounds_total = (int)((n_mels + per_round - 1) / per_round);
-    struct Round { int n8; smb::MelLane lane[smb::kFastRoundFilters]; };
+    struct Round { int n8; smb::MelLane lane[kMaxRound]; };
     std::vector<Round> built((size_t)rounds_total);
-    bool fits = n_mels <= 255;
-    for (int q = 0; q < rounds_total && fits; ++q) {
-      int member[smb::kFastRoundFilters], slo[smb::kFastRoundFilters];
+    if (n_mels > 255 || per_round > kMaxRound) return false;
+    for (int q = 0; q < rounds_total; ++q) {
+      int member[kMaxRound], slo[kMaxRound];
       for (int t = 0; t < per_round; ++t) {
         const size_t at = (size_t)(q * per_round + t);
         member[t] = at < order.size() ? order[at] : -1;
         slo[t] = member[t] >= 0 ? (band_lo[(size_t)member[t]] & ~3) : 0;
       }
-      for (int t = 0; t < per_round && smb::kFastTile == 4; t += 2) {
+      for (int t = 0; t < per_round && tile == 4; t += 2) {
         if (member[t] < 0 || member[t + 1] < 0) continue;
         if ((((slo[t] ^ slo[t + 1]) >> 2) & 1) == 0) {
           if (slo[t + 1] >= 4) slo[t + 1] -= 4;
@@ -390,7 +538,7 @@ struct smb_mel_plan {
       int n8 = 1;
       for (int t = 0; t < per_round; ++t)
         if (member[t] >= 0) n8 = std::max(n8, (band_hi[(size_t)member[t]] - slo[t] + 7) / 8);
-      if (n8 * 8 > row_floats || n8 > 255) { fits = false; break; }
+      if (n8 * 8 > row_floats || n8 > 255) return false;
       built[(size_t)q].n8 = n8;
       const size_t base = vals.size();
       vals.resize(base + (size_t)n8 * 16 * lf, 0.0f);
@@ -412,8 +560,6 @@ struct smb_mel_plan {
         }
       }
     }
-    if (!fits) { vals.clear(); return; }
-    fast_step = step;
     std::vector<std::vector<int>> lists((size_t)warps);
     std::vector<long long> load((size_t)warps, 0);
     for (int q = 0; q < rounds_total; ++q) {
@@ -435,6 +581,7 @@ struct smb_mel_plan {
               (size_t)r < lists[(size_t)w].size() ? built[(size_t)lists[(size_t)w][(size_t)r]].lane[t]
                                                   : idle;
         }
+    return true;
   }
   void ensure_device() {
     if (device_ready) return;
@@ -445,6 +592,9 @@ struct smb_mel_plan {
     d_band_hi = upload(band_hi);
     d_vals = upload(vals);
     d_mel_lanes = upload(mel_lanes);
+    d_vals_tc = upload(vals_tc);
+    d_pieces_tc = upload(pieces_tc);
+    d_pstart_tc = upload(pstart_tc);
     CK(cudaMalloc(&d_max, sizeof(unsigned long long)));
     device_ready = true;
   }
@@ -455,6 +605,9 @@ struct smb_mel_plan {
     cudaFree(d_band_hi);
     cudaFree(d_vals);
     cudaFree(d_mel_lanes);
+    cudaFree(d_vals_tc);
+    cudaFree(d_pieces_tc);
+    cudaFree(d_pstart_tc);
     cudaFree(d_dct);
     cudaFree(d_max);
     in.release();
@@ -813,7 +966,7 @@ int smb_stft_plan_set_stream(smb_stft_plan* plan, void* s) {
 }
 int smb_stft_plan_set_path(smb_stft_plan* plan, int path) {
   return guarded([&] {
-    if (path < SMB_PATH_AUTO || path > SMB_PATH_FAST)
+    if (path < SMB_PATH_AUTO || path > SMB_PATH_TENSOR)
       throw smb::invalid_argument("set_path: unknown path");
     plan->path = path;
   });
@@ -859,6 +1012,9 @@ namespace {
 
 enum SpecKind { kSpecComplex, kSpecPower };
 
+// SMB_PATH_AUTO: the tensor-core kernel when it covers the call
+constexpr bool kAutoPrefersTensor = false;
+
 void check_signal(const char* op, int64_t batch, int64_t n) {
   if (n < 0)
     throw smb::invalid_argument(smb::format(
@@ -867,21 +1023,37 @@ void check_signal(const char* op, int64_t batch, int64_t n) {
   if (batch < 0) throw smb::invalid_argument(smb::format("%s: negative batch", op));
 }
 
-bool want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int out_kind,
-               const smb_mel_plan* mel) {
-  if (p->path == SMB_PATH_GENERIC) return false;
+// Which fused kernel takes the call: 0 none (generic path), SMB_PATH_FAST the
+// CUDA-core register-FFT kernel, SMB_PATH_TENSOR the tcgen05 kernel.
+int want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int out_kind,
+              const smb_mel_plan* mel) {
+  if (p->path == SMB_PATH_GENERIC) return 0;
   const int step = p->fast_step();
   smb::FrameGeom gk = g;
   gk.fft = 2048;
-  const bool ok = dtype == SMB_F32 && step > 0 &&
-                  (!mel || (mel->fast_step == step && !mel->mel_lanes.empty())) &&
-                  smb::stft2048_supports(gk, out_kind, mel ? (int)mel->n_mels : 0,
-                                         mel ? (int)mel->vals.size() : 0,
-                                         mel ? mel->mel_rounds : 0);
-  if (!ok && p->path == SMB_PATH_FAST)
-    throw smb::invalid_argument(
-        "soundml_b200: the fused fft-2048 kernel does not cover this geometry");
-  return ok;
+  const bool base = dtype == SMB_F32 && step > 0 &&
+                    (!mel || (mel->fast_step == step && !mel->mel_lanes.empty()));
+  const bool ok_tc = base && smb::stft2048tc_supports(gk, out_kind, mel ? (int)mel->n_mels : 0,
+                                                      mel ? (int)mel->vals_tc.size() : 0,
+                                                      mel ? mel->mel_rounds_tc : 0,
+                                                      mel ? mel->n_pieces_tc : 0);
+  const bool ok_cc = base && smb::stft2048_supports(gk, out_kind, mel ? (int)mel->n_mels : 0,
+                                                    mel ? (int)mel->vals.size() : 0,
+                                                    mel ? mel->mel_rounds : 0);
+  if (p->path == SMB_PATH_TENSOR) {
+    if (!ok_tc)
+      throw smb::invalid_argument(
+          "soundml_b200: the tensor-core fft-2048 kernel does not cover this geometry");
+    return SMB_PATH_TENSOR;
+  }
+  if (p->path == SMB_PATH_FAST) {
+    if (!ok_cc)
+      throw smb::invalid_argument(
+          "soundml_b200: the fused fft-2048 kernel does not cover this geometry");
+    return SMB_PATH_FAST;
+  }
+  if (ok_tc && kAutoPrefersTensor) return SMB_PATH_TENSOR;
+  return ok_cc ? SMB_PATH_FAST : (ok_tc ? SMB_PATH_TENSOR : 0);
 }
 
 // x (device) -> spectrum (device).  kind: complex or |X|^power.
@@ -889,7 +1061,7 @@ void run_spectrum(smb_stft_plan* p, const void* dx, int64_t batch, const smb::Fr
                   int dtype, SpecKind kind, double power, void* dout) {
   cudaStream_t st = p->stream.use;
   const int fast_kind = kind == kSpecComplex ? smb::kFastComplex : smb::kFastPower;
-  if (want_fast(p, dtype, g, fast_kind, nullptr)) {
+  if (const int which = want_fast(p, dtype, g, fast_kind, nullptr)) {
     smb::Stft2048Args a{};
     a.x = (const float*)dx;
     a.out = (float*)dout;
@@ -901,7 +1073,9 @@ void run_spectrum(smb_stft_plan* p, const void* dx, int64_t batch, const smb::Fr
     a.tw_pass = p->d_tw_pass;
     a.tw_post = p->d_tw_post;
     a.power = (float)power;
-    CK(smb::launch_stft2048(a, fast_kind, p->sm_count, st));
+    a.dft_images = p->d_dft_images;
+    if (which == SMB_PATH_TENSOR) CK(smb::launch_stft2048tc(a, fast_kind, p->sm_count, st));
+    else CK(smb::launch_stft2048(a, fast_kind, p->sm_count, st));
   } else {
     CK(smb::launch_stft_generic(dx, dtype, batch, g, p->d_window64, p->d_twiddle64,
                                 kind == kSpecComplex ? smb::kModeComplex : smb::kModePower,
@@ -1285,7 +1459,7 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
     stft->ensure_device();
     mel->ensure_device();
     cudaStream_t st = stft->stream.use;
-    const bool fast = want_fast(stft, dtype, g, smb::kFastMel, mel);
+    const int fast = want_fast(stft, dtype, g, smb::kFastMel, mel);
     auto run = [&](const void* din, void* dout, int64_t nb) {
       if (fast) {
         smb::Stft2048Args a{};
@@ -1299,12 +1473,23 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
         a.tw_pass = stft->d_tw_pass;
         a.tw_post = stft->d_tw_post;
         a.n_mels = (int)mel->n_mels;
-        a.nnz = (int)mel->vals.size();
-        a.vals = mel->d_vals;
-        a.mel_rounds = mel->mel_rounds;
-        a.mel_lanes = mel->d_mel_lanes;
         a.power = (float)power;
-        CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
+        a.dft_images = stft->d_dft_images;
+        if (fast == SMB_PATH_TENSOR) {
+          a.nnz = (int)mel->vals_tc.size();
+          a.vals = mel->d_vals_tc;
+          a.tc_pieces = mel->d_pieces_tc;
+          a.tc_pstart = mel->d_pstart_tc;
+          a.tc_rounds = mel->mel_rounds_tc;
+          a.tc_n_pieces = mel->n_pieces_tc;
+          CK(smb::launch_stft2048tc(a, smb::kFastMel, stft->sm_count, st));
+        } else {
+          a.nnz = (int)mel->vals.size();
+          a.vals = mel->d_vals;
+          a.mel_rounds = mel->mel_rounds;
+          a.mel_lanes = mel->d_mel_lanes;
+          CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
+        }
       } else {
         // two kernels through a plan-owned power spectrogram
         const size_t spec_bytes = (size_t)nb * stft->geom.bins() * g.frames * esz;

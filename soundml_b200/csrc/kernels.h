@@ -87,11 +87,32 @@ struct Stft2048Args {
   const MelLane* mel_lanes;    // [kFastTile warps][mel_rounds][kFastRoundFilters]
   float power;
   int bin_step;                // 2048 / fft_size: 1, or 2/4/8/16 for zero-padded shorter frames
+  // tensor-core variant (stft2048tc.cu) only: [hi, lo] fp16 images of the real 64 x 64
+  // form of the 32-point DFT, K-major SWIZZLE_128B; and its own mel schedule (vals / nnz
+  // then hold [round][step][lane] float4 weights)
+  const void* dft_images;
+  const struct MelPiece* tc_pieces;    // [kTcTile warps][tc_rounds][32 lanes]
+  const unsigned short* tc_pstart;     // [n_mels + 1] partial-sum slots of each filter
+  int tc_rounds, tc_n_pieces;
 };
+// One lane of a mel round of the tensor-core kernel: a piece (<= kTcPieceSteps float4
+// steps) of one filter's band, carried for the 4 frames of the tile.
+struct MelPiece {
+  int off;                 // weights: float offset of [step 0][lane] (low 24 bits), steps of the round (high 8)
+  short lo;                // first bin read (multiple of 4)
+  unsigned short pid;      // partial-sum slot (tc_n_pieces = scratch)
+};
+constexpr int kTcPieceSteps = 4;
 // True when the fused kernel can take this geometry (hop small enough for the
 // shared-memory sample tile, mel tables small enough to be resident).
 bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds);
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
+// Tensor-core variant: both 32-point passes as split-fp16 products on tcgen05, a
+// tile = kTcTile frames = 128 MMA rows per group of kTcTile warps.
+constexpr int kTcTile = 4;
+bool stft2048tc_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds,
+                         int n_pieces);
+cudaError_t launch_stft2048tc(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
 
 // ---- resampler / FIR ----------------------------------------------------------
 // One polyphase stage, direct form (resample_stubs.c:127-143):

@@ -69,7 +69,7 @@ class Config:
         """Testing hook: force the generic (double interior) or the fused
         fft-2048 kernel.  ``"auto"`` picks the fused kernel when it applies."""
         code = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC,
-                "fast": _lib.PATH_FAST}[path]
+                "fast": _lib.PATH_FAST, "tensor": _lib.PATH_TENSOR}[path]
         _lib.check(_lib.lib.smb_stft_plan_set_path(self._h, code))
         return self
 
