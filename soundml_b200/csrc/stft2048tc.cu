@@ -43,6 +43,7 @@
 #include "kernels.h"
 
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 namespace smb {
@@ -323,7 +324,7 @@ stft2048tc_kernel(const Params p) {
     for (int i = tid; i <= p.a.n_mels; i += blockDim.x) sPstart[i] = p.a.tc_pstart[i];
   }
   if (tid == 0) {
-    for (int gI = 0; gI < 2 * kGroups; ++gI) mbar_init(smem_u32(&bars[gI]), 1);
+    for (int gI = 0; gI < 2 * kMaxGroups; ++gI) mbar_init(smem_u32(&bars[gI]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr int kTmemCols = kGroups > 2 ? 512 : 256;
@@ -731,6 +732,7 @@ cudaError_t launch_stft2048tc(const Stft2048Args& a, int out_kind, int sm_count,
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
   p.total_tiles = p.tiles_per_signal * a.batch;
   int groups = 4;
+  if (const char* e = getenv("SMB_TC_GROUPS")) groups = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 4;   // experiments
   auto layout = [&](int gr) {
     return smem_layout(out_kind, p.a.n_mels, p.a.nnz, p.a.tc_rounds, p.a.tc_n_pieces, p.span_cap, gr);
   };
