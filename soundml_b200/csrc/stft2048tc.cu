@@ -43,6 +43,7 @@
 #include "kernels.h"
 
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cuda_fp16.h>
 
@@ -187,11 +188,12 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
                                              uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
+  // no "memory" clobber: these bytes are only read by the tensor core, after the
+  // proxy fence + barrier that follow; ordinary loads may move across the store
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 __device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t a) {
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a));
 }
 // fp16 pair (lo half = a, hi half = b), round to nearest
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -206,80 +208,95 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t h) {
 
 struct Params {
   Stft2048Args a;
+  long long* timing;         // [9] cycle totals (TIMING kernels only)
   int span_cap;              // floats reserved per group for samples (multiple of 4)
   int region_bytes;          // operand / row region per group (multiple of 1024)
   int row_stride;            // floats per output row of a frame
   long long tiles_per_signal, total_tiles;
 };
 
+// Tile geometry shared by the staging call and the consumer.
+struct TileRef {
+  int b, p0;                 // signal, first frame
+};
+// An interior tile whose source run is 16-byte aligned is brought in by one bulk
+// copy (TMA); everything else goes through cp.async and the boundary rule.
+__device__ __forceinline__ bool tile_is_bulk(const Params& p, TileRef t) {
+  const FrameGeom& g = p.a.g;
+  const int nf = (int)min((long long)kTile, g.frames - t.p0);
+  const int span = (nf - 1) * g.hop + kFft;
+  const long long s0 = (long long)t.p0 * g.hop - g.left;
+  const size_t addr = reinterpret_cast<size_t>(p.a.x + (long long)t.b * g.n + s0);
+  return s0 >= 0 && s0 + span <= g.n && (addr & 15) == 0 && (span & 3) == 0;
+}
 // Brings one tile's samples (padded stream positions p0*hop .. + span) into the
 // group's sample buffer; the tail up to span_cap is zeroed (the scale scan reads
-// the whole buffer).  An interior tile whose source run is 16-byte aligned is one
-// bulk copy (TMA) issued by a single thread and lands on `bar`: returns true,
-// the caller waits on the barrier.  Otherwise the rules of
-// stft2048.cu::stage_tile apply (cp.async for the real samples, the reference's
-// boundary rule stft.ml:300-338 for the border) and the caller waits for its
-// cp.async group.
-__device__ __forceinline__ bool stage_tile(const Params& p, int tile, float* sSamples, int gtid,
-                                           uint32_t bar) {
+// the whole buffer).  Run by ONE warp of the group.  Bulk tiles: lane 0 issues the
+// copy, which lands on `bar`.  Otherwise the rules of stft2048.cu::stage_tile
+// apply (cp.async for the real samples, the reference's boundary rule
+// stft.ml:300-338 for the border) and this warp waits for its cp.async group
+// before the group's barrier.
+__device__ __forceinline__ void stage_tile(const Params& p, TileRef t, bool bulk, float* sSamples,
+                                           int lane, uint32_t bar) {
   const FrameGeom& g = p.a.g;
-  const int tps = (int)p.tiles_per_signal;
-  const int b = tile / tps;
-  const int p0 = (tile - b * tps) * kTile;
-  const int nf = (int)min((long long)kTile, g.frames - p0);
+  const int nf = (int)min((long long)kTile, g.frames - t.p0);
   const int span = (nf - 1) * g.hop + kFft;
-  const long long q0 = (long long)p0 * g.hop;
+  const long long q0 = (long long)t.p0 * g.hop;
   const long long s0 = q0 - g.left;
-  const float* xs = p.a.x + (long long)b * g.n;
+  const float* xs = p.a.x + (long long)t.b * g.n;
   const float* src = xs + s0;                       // src + i is valid for i in [lo, hi)
   const unsigned base = (unsigned)__cvta_generic_to_shared(sSamples);
-  const size_t addr = reinterpret_cast<size_t>(src);
-  for (int i = span + gtid; i < p.span_cap; i += kGroupThreads) sSamples[i] = 0.0f;
-  if (s0 >= 0 && s0 + span <= g.n && (addr & 15) == 0 && (span & 3) == 0) {
-    if (gtid == 0) {
+  for (int i = span + lane; i < p.span_cap; i += 32) sSamples[i] = 0.0f;
+  if (bulk) {
+    if (lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(bar, 4u * (uint32_t)span);
       bulk_g2s(base, src, 4u * (uint32_t)span, bar);
     }
-    return true;
+    return;
   }
+  const size_t addr = reinterpret_cast<size_t>(src);
   const int lo = (int)max(0LL, min((long long)span, -s0));
   const int hi = (int)max((long long)lo, min((long long)span, g.n - s0));
-  for (int i = gtid; i < lo; i += kGroupThreads) {
+  for (int i = lane; i < lo; i += 32) {
     const long long s = src_index(g, q0 + i);
     sSamples[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
   }
-  for (int i = hi + gtid; i < span; i += kGroupThreads) {
+  for (int i = hi + lane; i < span; i += 32) {
     const long long s = src_index(g, q0 + i);
     sSamples[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
   }
   if ((addr & 15) == 0) {
     const int head = min(hi, (lo + 3) & ~3), tail = max(head, hi & ~3);
-    for (int i = lo + gtid; i < head; i += kGroupThreads)
+    for (int i = lo + lane; i < head; i += 32)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
-    for (int i = head + 4 * gtid; i < tail; i += 4 * kGroupThreads)
+    for (int i = head + 4 * lane; i < tail; i += 4 * 32)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
-    for (int i = tail + gtid; i < hi; i += kGroupThreads)
+    for (int i = tail + lane; i < hi; i += 32)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
   } else if ((addr & 7) == 0) {
     const int head = min(hi, (lo + 1) & ~1), tail = max(head, hi & ~1);
-    for (int i = lo + gtid; i < head; i += kGroupThreads)
+    for (int i = lo + lane; i < head; i += 32)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
-    for (int i = head + 2 * gtid; i < tail; i += 2 * kGroupThreads)
+    for (int i = head + 2 * lane; i < tail; i += 2 * 32)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
-    for (int i = tail + gtid; i < hi; i += kGroupThreads)
+    for (int i = tail + lane; i < hi; i += 32)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
   } else {
-    for (int i = lo + gtid; i < hi; i += kGroupThreads)
+    for (int i = lo + lane; i < hi; i += 32)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
   }
-  return false;
 }
 
 // STEP1: bin_step == 1 (fft 2048 proper): every bin is kept.
-template <int OUT, bool SQUARE, int kGroups, bool STEP1>
+template <int OUT, bool SQUARE, int kGroups, bool STEP1, bool TIMING = false>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 stft2048tc_kernel(const Params p) {
+  // TIMING: per-phase cycle totals of every group's first thread (profiling aid,
+  // SMB_TC_TIMING=1): wait, scale, build, mma1, convert, mma2, split, mel, write
+  long long tacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = 0;
+#define SMB_TC_MARK(i) if (TIMING) { const long long tnow = clock64(); tacc[i] += tnow - tprev; tprev = tnow; }
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxGroups];
   __shared__ uint32_t tmem_base_slot;
@@ -349,6 +366,12 @@ stft2048tc_kernel(const Params p) {
   const int slot = blockIdx.x * kGroups + group;
   const int stride = gridDim.x * kGroups;
   const int total_tiles = (int)p.total_tiles, tiles_per_signal = (int)p.tiles_per_signal;
+  // tile -> (signal, first frame) is kept incrementally: one division here only
+  const int stride_b = stride / tiles_per_signal, stride_t = stride - stride_b * tiles_per_signal;
+  TileRef cur;
+  cur.b = slot / tiles_per_signal;
+  int cur_t = slot - cur.b * tiles_per_signal;
+  cur.p0 = cur_t * kTile;
 
   float* sSamples = sSamplesAll + group * p.span_cap;
   const uint32_t region_addr = smem_addr + regions_off + group * p.region_bytes;
@@ -374,19 +397,32 @@ stft2048tc_kernel(const Params p) {
   float* row = sRows + warp * p.row_stride;
 
   bool bulk = false;
-  if (slot < total_tiles) bulk = stage_tile(p, slot, sSamples, gtid, sbar);
+  if (slot < total_tiles) {
+    bulk = tile_is_bulk(p, cur);
+    if (warp == 0) stage_tile(p, cur, bulk, sSamples, lane, sbar);
+  }
   for (int tile = slot; tile < total_tiles; tile += stride) {
-    const int b = tile / tiles_per_signal;
-    const int p0 = (tile - b * tiles_per_signal) * kTile;
+    const int b = cur.b, p0 = cur.p0;
     const int nf = (int)min((long long)kTile, g.frames - p0);
+    TileRef nxt;                                    // the tile after this one
+    {
+      int t = cur_t + stride_t;
+      nxt.b = cur.b + stride_b;
+      if (t >= tiles_per_signal) { t -= tiles_per_signal; ++nxt.b; }
+      cur_t = t;
+      nxt.p0 = t * kTile;
+    }
+    cur = nxt;
 
+    if (TIMING) tprev = clock64();
     if (bulk) {
       mbar_wait(sbar, sphase & 1);
       ++sphase;
-    } else {
+    } else if (warp == 0) {
       asm volatile("cp.async.wait_all;" ::: "memory");
     }
     group_sync(group);
+    SMB_TC_MARK(0)
 
     // ---- scale: largest sample magnitude of the tile -> power of two
     float scale, unscale;
@@ -397,8 +433,8 @@ stft2048tc_kernel(const Params p) {
         const float4 v = s4[i];
         m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      // non-negative floats order like their bit patterns: one REDUX per warp
+      m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));
       if (lane == 0) sMax[group * kTile + warp] = m;
       group_sync(group);
       const float4 mm = *reinterpret_cast<const float4*>(sMax + group * kTile);
@@ -410,6 +446,7 @@ stft2048tc_kernel(const Params p) {
       unscale = __uint_as_float((uint32_t)(254 - sb) << 23);
     }
 
+    SMB_TC_MARK(1)
     // ---- pass-1 operand: rows (f, n2 = lane), this warp's 16 K-columns
     {
       float2 ws[8];
@@ -442,6 +479,7 @@ stft2048tc_kernel(const Params p) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     group_sync(group);
+    SMB_TC_MARK(2)
 
     if (gtid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -455,11 +493,16 @@ stft2048tc_kernel(const Params p) {
       umma_commit(bar);
     }
     // ---- the sample buffer is free: fetch the next tile under the rest of this one
-    if (tile + stride < total_tiles) bulk = stage_tile(p, tile + stride, sSamples, gtid, sbar);
+    const bool more = tile + stride < total_tiles;
+    if (more) {
+      bulk = tile_is_bulk(p, nxt);
+      if (warp == 1) stage_tile(p, nxt, bulk, sSamples, lane, sbar);
+    }
 
     mbar_wait(bar, phase & 1);
     ++phase;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    SMB_TC_MARK(3)
 
     // ---- D1 row (f = warp, n2 = lane): twiddle, split, scatter into pass 2's
     // operand, rows (f, k1), K-column (n2, c)
@@ -492,9 +535,11 @@ stft2048tc_kernel(const Params p) {
         }
       }
     }
+    if (more && warp == 1 && !bulk) asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     group_sync(group);
+    SMB_TC_MARK(4)
 
     if (gtid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -510,12 +555,14 @@ stft2048tc_kernel(const Params p) {
     mbar_wait(bar, phase & 1);
     ++phase;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    SMB_TC_MARK(5)
 
     // ---- D2 row (f = warp, k1 = lane): a[k2] = s Z'[k1 + 32 k2]; real split as in
-    // stft2048.cu.  The tile's scale is undone here (it rides on S and on the
-    // twiddle), except on the mel path with |X|^2, where it is one multiply per
-    // mel value at write-out (the projection is linear).
-    const bool late_unscale = OUT == kFastMel && SQUARE;
+    // stft2048.cu.  For the complex spectrum the tile's scale is undone here (it
+    // rides on S and on the twiddle); |X|^p is taken on the scaled values (no
+    // underflow of the squares for faint signals) and the scale comes off as one
+    // multiply per value at write-out (the mel projection is linear).
+    const bool late_unscale = OUT != kFastComplex;
     {
       float2 a[32];
       {
@@ -547,6 +594,8 @@ stft2048tc_kernel(const Params p) {
           r[k2].y = -__shfl_sync(0xffffffffu, sy, partner);
         }
         float2* rowc = reinterpret_cast<float2*>(row);
+        // results first (the twiddle loads can all run ahead: no store in between),
+        // stores after: xk -> a[k2], conj X[N-k] -> r[k2] (or the two powers in a[k2])
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) {
           //   S = Z'[k] + conj Z'[N-k],  D = Z'[k] - conj Z'[N-k],  W = W2048^k
@@ -559,11 +608,9 @@ stft2048tc_kernel(const Params p) {
           const float2 T = make_float2(w.x * D.y + w.y * D.x, w.y * D.y - w.x * D.x);
           const float2 xk = add2(S, T);
           const float2 xm = sub2(S, T);                     // conj of X[N-k]
-          const int k = lane + 32 * k2, nk = kHalf - k;
-          const bool keep_k = STEP1 || (k & bin_mask) == 0, keep_n = STEP1 || (nk & bin_mask) == 0;
           if (OUT == kFastComplex) {
-            if (keep_k) rowc[k >> bin_shift] = xk;
-            if (keep_n) rowc[nk >> bin_shift] = make_float2(xm.x, -xm.y);
+            a[k2] = xk;
+            r[k2] = make_float2(xm.x, -xm.y);
           } else {
             float pk = xk.x * xk.x + xk.y * xk.y;
             float pn = xm.x * xm.x + xm.y * xm.y;
@@ -571,8 +618,19 @@ stft2048tc_kernel(const Params p) {
               if (p.a.power == 1.0f) { pk = sqrtf(pk); pn = sqrtf(pn); }
               else { pk = powf(sqrtf(pk), p.a.power); pn = powf(sqrtf(pn), p.a.power); }
             }
-            if (keep_k) row[k >> bin_shift] = pk;
-            if (keep_n) row[nk >> bin_shift] = pn;
+            a[k2] = make_float2(pk, pn);
+          }
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const int k = lane + 32 * k2, nk = kHalf - k;
+          const bool keep_k = STEP1 || (k & bin_mask) == 0, keep_n = STEP1 || (nk & bin_mask) == 0;
+          if (OUT == kFastComplex) {
+            if (keep_k) rowc[k >> bin_shift] = a[k2];
+            if (keep_n) rowc[nk >> bin_shift] = r[k2];
+          } else {
+            if (keep_k) row[k >> bin_shift] = a[k2].x;
+            if (keep_n) row[nk >> bin_shift] = a[k2].y;
           }
         }
         if (lane == 0) {                            // k = 512 pairs with itself
@@ -589,6 +647,7 @@ stft2048tc_kernel(const Params p) {
       }
     }
     group_sync(group);
+    SMB_TC_MARK(6)
 
     if (OUT == kFastMel) {
       // ---- mel projection over the tile's power rows.  A lane carries one piece
@@ -606,7 +665,31 @@ stft2048tc_kernel(const Params p) {
         const float4* v2 = reinterpret_cast<const float4*>(sRows + 2 * p.row_stride + q.lo);
         const float4* v3 = reinterpret_cast<const float4*>(sRows + 3 * p.row_stride + q.lo);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int i = 0; i < steps; ++i) {
+        // the step count is uniform over the warp; two steps at a time keeps ten
+        // 16-byte loads in flight ahead of the 32 FMAs that consume them
+        int i = 0;
+        for (; i + 2 <= steps; i += 2) {
+          const float4 ww = wq[32 * i], wz = wq[32 * i + 32];
+          const float4 x0 = v0[i], x1 = v1[i], x2 = v2[i], x3 = v3[i];
+          const float4 y0 = v0[i + 1], y1 = v1[i + 1], y2 = v2[i + 1], y3 = v3[i + 1];
+          a0 = fmaf(ww.x, x0.x, a0); a1 = fmaf(ww.x, x1.x, a1);
+          a2 = fmaf(ww.x, x2.x, a2); a3 = fmaf(ww.x, x3.x, a3);
+          a0 = fmaf(ww.y, x0.y, a0); a1 = fmaf(ww.y, x1.y, a1);
+          a2 = fmaf(ww.y, x2.y, a2); a3 = fmaf(ww.y, x3.y, a3);
+          a0 = fmaf(ww.z, x0.z, a0); a1 = fmaf(ww.z, x1.z, a1);
+          a2 = fmaf(ww.z, x2.z, a2); a3 = fmaf(ww.z, x3.z, a3);
+          a0 = fmaf(ww.w, x0.w, a0); a1 = fmaf(ww.w, x1.w, a1);
+          a2 = fmaf(ww.w, x2.w, a2); a3 = fmaf(ww.w, x3.w, a3);
+          a0 = fmaf(wz.x, y0.x, a0); a1 = fmaf(wz.x, y1.x, a1);
+          a2 = fmaf(wz.x, y2.x, a2); a3 = fmaf(wz.x, y3.x, a3);
+          a0 = fmaf(wz.y, y0.y, a0); a1 = fmaf(wz.y, y1.y, a1);
+          a2 = fmaf(wz.y, y2.y, a2); a3 = fmaf(wz.y, y3.y, a3);
+          a0 = fmaf(wz.z, y0.z, a0); a1 = fmaf(wz.z, y1.z, a1);
+          a2 = fmaf(wz.z, y2.z, a2); a3 = fmaf(wz.z, y3.z, a3);
+          a0 = fmaf(wz.w, y0.w, a0); a1 = fmaf(wz.w, y1.w, a1);
+          a2 = fmaf(wz.w, y2.w, a2); a3 = fmaf(wz.w, y3.w, a3);
+        }
+        if (i < steps) {
           const float4 ww = wq[32 * i];
           const float4 x0 = v0[i], x1 = v1[i], x2 = v2[i], x3 = v3[i];
           a0 = fmaf(ww.x, x0.x, a0); a1 = fmaf(ww.x, x1.x, a1);
@@ -625,20 +708,25 @@ stft2048tc_kernel(const Params p) {
       }
       group_sync(group);
     }
+    SMB_TC_MARK(7)
 
     // ---- write the tile along the frame axis: [batch, rows, frames]
     {
       const int f = gtid & (kTile - 1), r0 = gtid / kTile;
+      // |s X|^p = s^p |X|^p
+      const float post = SQUARE ? unscale * unscale
+                                : (p.a.power == 1.0f ? unscale : powf(unscale, p.a.power));
       if (f < nf) {
         if (OUT == kFastMel) {
           float* ob = p.a.out + ((long long)b * p.a.n_mels + r0) * g.frames + p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float* src = sRows + f * p.row_stride + kRowReal;
-          const float post = late_unscale ? unscale * unscale : 1.0f;
           for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step) {
-            const int q0 = sPstart[m], q1 = sPstart[m + 1];
-            float acc = src[q0];
-            for (int q = q0 + 1; q < q1; ++q) acc += src[q];
+            const int q0 = sPstart[m], cnt = sPstart[m + 1] - q0;
+            // the slots behind a filter's last one exist (padding of the partial area)
+            const float s0 = src[q0], s1 = src[q0 + 1], s2 = src[q0 + 2], s3 = src[q0 + 3];
+            float acc = (s0 + (cnt > 1 ? s1 : 0.0f)) + ((cnt > 2 ? s2 : 0.0f) + (cnt > 3 ? s3 : 0.0f));
+            for (int q = q0 + 4; q < q0 + cnt; ++q) acc += src[q];
             *ob = acc * post;
           }
         } else if (OUT == kFastPower) {
@@ -647,7 +735,7 @@ stft2048tc_kernel(const Params p) {
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float* src = sRows + f * p.row_stride;
           for (int r = r0; r < out_bins; r += kGroupThreads / kTile, ob += step)
-            *ob = src[r];
+            *ob = src[r] * post;
         } else {
           const int out_bins = kHalf / p.a.bin_step + 1;
           float2* ob = reinterpret_cast<float2*>(p.a.out) + ((long long)b * out_bins + r0) * g.frames +
@@ -660,7 +748,11 @@ stft2048tc_kernel(const Params p) {
       }
     }
     group_sync(group);
+    SMB_TC_MARK(8)
   }
+#undef SMB_TC_MARK
+  if (TIMING && gtid == 0)
+    for (int i = 0; i < 9; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(p.timing) + i, (unsigned long long)tacc[i]);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -679,7 +771,7 @@ static int span_needed(const FrameGeom& g) {
 static int row_floats(int out_kind, int n_pieces) {
   if (out_kind == kFastComplex) return kRowComplex;
   if (out_kind == kFastPower) return kRowReal;
-  return kRowReal + ((n_pieces + 1 + 3) & ~3);          // partial sums (+ one scratch slot)
+  return kRowReal + ((n_pieces + 1 + 3 + 3) & ~3);      // partial sums (+ one scratch slot, + 3 read past the end)
 }
 static int region_needed(int out_kind, int n_pieces) {
   const int rows = kTile * row_floats(out_kind, n_pieces) * 4;
@@ -725,6 +817,7 @@ cudaError_t launch_stft2048tc(const Stft2048Args& a, int out_kind, int sm_count,
   }
   Params p;
   p.a = a;
+  p.timing = nullptr;
   if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.tc_rounds = 0; p.a.tc_n_pieces = 0; }
   p.span_cap = span_needed(a.g);
   p.region_bytes = region_needed(out_kind, p.a.tc_n_pieces);
@@ -754,6 +847,28 @@ cudaError_t launch_stft2048tc(const Stft2048Args& a, int out_kind, int sm_count,
   else if (groups == 3) { SMB_LAUNCHTC_G(OUT, SQ, 3) }                                      \
   else { SMB_LAUNCHTC_G(OUT, SQ, 2) }
   const bool sq = a.power == 2.0f;
+  if (getenv("SMB_TC_TIMING") && out_kind == kFastMel && sq && groups == 4 && a.bin_step == 1) {
+    // profiling aid: per-phase cycle totals, printed per launch
+    static long long* d_timing = nullptr;
+    if (!d_timing) cudaMalloc(&d_timing, 9 * sizeof(long long));
+    cudaMemsetAsync(d_timing, 0, 9 * sizeof(long long), st);
+    p.timing = d_timing;
+    e = cudaFuncSetAttribute(stft2048tc_kernel<kFastMel, true, 4, true, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    stft2048tc_kernel<kFastMel, true, 4, true, true><<<grid, 4 * kGroupThreads, smem, st>>>(p);
+    long long h[9];
+    cudaMemcpyAsync(h, d_timing, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    static const char* names[9] = {"wait", "scale", "build", "mma1", "convert", "mma2", "split", "mel", "write"};
+    long long tot = 0;
+    for (int i = 0; i < 9; ++i) tot += h[i];
+    for (int i = 0; i < 9; ++i)
+      fprintf(stderr, "tc-timing %-8s %8.1f cycles/tile (%4.1f%%)\n", names[i],
+              (double)h[i] / (double)p.total_tiles, 100.0 * (double)h[i] / (double)tot);
+    ++g_launch_count;
+    return cudaGetLastError();
+  }
   if (out_kind == kFastMel) { if (sq) { SMB_LAUNCHTC(kFastMel, true) } else { SMB_LAUNCHTC(kFastMel, false) } }
   else if (out_kind == kFastPower) { if (sq) { SMB_LAUNCHTC(kFastPower, true) } else { SMB_LAUNCHTC(kFastPower, false) } }
   else { SMB_LAUNCHTC(kFastComplex, true) }

@@ -25,6 +25,13 @@ def sb(lib):
     return lib
 
 
+@pytest.fixture(params=["fast", "tensor"])
+def fused(request):
+    """The two fused fft-2048 kernels: the CUDA-core register FFT ("fast") and the
+    tcgen05 one ("tensor"); both are held to the same bar."""
+    return request.param
+
+
 def _signal(n, seed=7):
     rng = np.random.default_rng(seed)
     t = np.arange(n)
@@ -74,7 +81,7 @@ def test_mel_spectrogram_goldens_on_gpu(sb, goldens):
 
 # ------------------------------------------------ config 1: one 10 s clip ----
 
-@pytest.mark.parametrize("path", ["fast", "generic"])
+@pytest.mark.parametrize("path", ["fast", "tensor", "generic"])
 def test_config1_clip_against_oracle(sb, path):
     from soundml_b200 import synth
     x = synth.clips_numpy(1, 220500)[0]
@@ -97,24 +104,40 @@ def test_config1_clip_against_oracle(sb, path):
     assert peak_rel_err(mel, mel_oracle.apply(mo, ref_p)) <= SPECTRUM_TOL
 
 
-def test_fast_kernel_error_is_float32_class(sb):
-    """The fused kernel is float32 inside; report how close it lands."""
+def test_fast_kernel_error_is_float32_class(sb, fused):
+    """The fused kernels are float32 inside (the tensor-core one through split
+    fp16 operands, 22 significant bits); report how close they land."""
     x = _signal(50000)
-    c = sb.Stft.Config.create(fft_size=2048, hop=512).set_path("fast")
+    c = sb.Stft.Config.create(fft_size=2048, hop=512).set_path(fused)
     o = stft_oracle.StftConfig(2048, 512)
     err = peak_rel_err(sb.Stft.power_spectrum(c, x), stft_oracle.power_spectrum(o, x))
-    assert err <= 2e-6, err
+    assert err <= (2e-6 if fused == "fast" else 6e-6), err
+
+
+@pytest.mark.parametrize("amp", [1e-30, 1e-12, 1e-3, 37.0, 32768.0, 1e12])
+def test_tensor_kernel_is_scale_free(sb, amp):
+    """fp16 operands have 5 exponent bits: the kernel rescales every tile by a
+    power of two, so the error does not depend on the signal's level."""
+    rng = np.random.default_rng(11)
+    x = (rng.uniform(-1, 1, 20000) * amp).astype(np.float32)
+    c = sb.Stft.Config.create(fft_size=2048, hop=512).set_path("tensor")
+    o = stft_oracle.StftConfig(2048, 512)
+    z, ref = sb.Stft.transform(c, x), stft_oracle.transform(o, x)
+    assert peak_rel_err(z.view(np.float32), ref.view(np.float32)) <= 3e-6
+    p = sb.Stft.power_spectrum(c, x, power=1.0)
+    assert peak_rel_err(p, stft_oracle.power_spectrum(o, x, 1.0)) <= 3e-6
+    assert not np.abs(sb.Stft.power_spectrum(c, np.zeros(5000, np.float32))).any()
 
 
 # ------------------------------------------- geometry sweep, fast kernel ----
 
 @pytest.mark.parametrize("hop", [512, 500, 333, 128, 1, 600])
 @pytest.mark.parametrize("alignment", ["centered", "left", "right"])
-def test_fast_kernel_geometries(sb, hop, alignment):
+def test_fast_kernel_geometries(sb, hop, alignment, fused):
     x = np.stack([_signal(9000, 1), _signal(9000, 2), _signal(9000, 3)])
     if hop == 1:
         x = x[:, :2600]
-    c = sb.Stft.Config.create(fft_size=2048, hop=hop, alignment=alignment).set_path("fast")
+    c = sb.Stft.Config.create(fft_size=2048, hop=hop, alignment=alignment).set_path(fused)
     o = stft_oracle.StftConfig(2048, hop, alignment=alignment)
     ref = stft_oracle.power_spectrum(o, x)
     got = sb.Stft.power_spectrum(c, x)
@@ -131,14 +154,14 @@ def test_fast_kernel_geometries(sb, hop, alignment):
                                                (256, 64, None, 40), (128, 32, None, 20)])
 @pytest.mark.parametrize("alignment,pad", [("centered", "reflect"), ("left", "edge"),
                                            ("right", ("constant", 0.25))])
-def test_shorter_frames_ride_the_fused_kernel(sb, fft, hop, wl, n_mels, alignment, pad):
+def test_shorter_frames_ride_the_fused_kernel(sb, fft, hop, wl, n_mels, alignment, pad, fused):
     """fft 1024 / 512 / 256 / 128 run zero-padded inside the fft-2048 kernel; power,
     complex and mel outputs against the oracle, and the forced fast path must
     accept them."""
     name = pad if isinstance(pad, str) else pad[0]
     val = 0.0 if isinstance(pad, str) else pad[1]
     c = sb.Stft.Config.create(fft_size=fft, hop=hop, win_length=wl, alignment=alignment,
-                              pad=pad).set_path("fast")
+                              pad=pad).set_path(fused)
     o = stft_oracle.StftConfig(fft, hop, win_length=wl, alignment=alignment, pad=name,
                                pad_value=val)
     mc = sb.Mel.Config.create(n_mels=n_mels, sample_rate=16000, fft_size=fft)
@@ -162,17 +185,17 @@ def test_shorter_frames_ride_the_fused_kernel(sb, fft, hop, wl, n_mels, alignmen
             assert peak_rel_err(gotm[b], refm[b]) <= SPECTRUM_TOL, (fft, hop, alignment, n, b)
         c.set_path("generic")
         assert peak_rel_err(sb.mel_spectrogram(c, mc, x), gotm) <= SPECTRUM_TOL
-        c.set_path("fast")
+        c.set_path(fused)
 
 
 @pytest.mark.parametrize("pad", ["reflect", "edge", ("constant", 0.5)])
 @pytest.mark.parametrize("n", [1, 2, 700, 1024, 1025, 2047, 2048, 2049, 5000])
-def test_fast_kernel_short_signals_and_pads(sb, pad, n):
+def test_fast_kernel_short_signals_and_pads(sb, pad, n, fused):
     """n <= fft/2 exercises multi-reflection (stft.ml:297-305)."""
     x = _signal(n, 5) + 0.25
     name = pad if isinstance(pad, str) else pad[0]
     val = 0.0 if isinstance(pad, str) else pad[1]
-    c = sb.Stft.Config.create(fft_size=2048, hop=512, pad=pad).set_path("fast")
+    c = sb.Stft.Config.create(fft_size=2048, hop=512, pad=pad).set_path(fused)
     o = stft_oracle.StftConfig(2048, 512, pad=name, pad_value=val)
     ref = stft_oracle.power_spectrum(o, x)
     got = sb.Stft.power_spectrum(c, x)
@@ -183,19 +206,19 @@ def test_fast_kernel_short_signals_and_pads(sb, pad, n):
 @pytest.mark.parametrize("window,win_length,scale", [
     ("hamming", None, "none"), (("kaiser", 8.6), 1200, "magnitude"), ("blackman", 2000, "psd"),
     (("tukey", 0.25), None, "none"), ("rectangular", 512, "none")])
-def test_fast_kernel_windows(sb, window, win_length, scale):
+def test_fast_kernel_windows(sb, window, win_length, scale, fused):
     x = _signal(12000, 9)
     c = sb.Stft.Config.create(fft_size=2048, hop=500, window=window, win_length=win_length,
-                              scale=scale).set_path("fast")
+                              scale=scale).set_path(fused)
     name, param = (window, 0.0) if isinstance(window, str) else window
     o = stft_oracle.StftConfig(2048, 500, win_length, window=name, window_param=param, scale=scale)
     assert peak_rel_err(sb.Stft.power_spectrum(c, x), stft_oracle.power_spectrum(o, x)) <= SPECTRUM_TOL
 
 
-def test_fast_mel_matches_oracle_on_batch(sb):
+def test_fast_mel_matches_oracle_on_batch(sb, fused):
     from soundml_b200 import synth
     x = synth.clips_numpy(5, 30000, first_clip=57)
-    c = sb.Stft.Config.create(fft_size=2048, hop=512).set_path("fast")
+    c = sb.Stft.Config.create(fft_size=2048, hop=512).set_path(fused)
     o = stft_oracle.StftConfig(2048, 512)
     for n_mels, kw in [(128, {}), (40, dict(scale="htk", norm="none")), (80, dict(f_min=300.0, f_max=8000.0))]:
         mc = sb.Mel.Config.create(n_mels=n_mels, sample_rate=22050, fft_size=2048, **kw)
