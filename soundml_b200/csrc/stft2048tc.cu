@@ -167,6 +167,28 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same, the descriptors given by their low words (start address field) over the
+// common high word: the K-steps of a batch only move the start address
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc,
+                                            bool accumulate) {
+  constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
+  if (accumulate)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(kDescHi), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(kDescHi), "r"(idesc)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                ::"r"(bar) : "memory");
@@ -181,6 +203,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
         "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() {
@@ -378,6 +409,10 @@ stft2048tc_kernel(const Params p) {
   float* sRows = reinterpret_cast<float*>(smem + regions_off + group * p.region_bytes);
   const uint32_t a_hi = region_addr, a_lo = region_addr + kABytes;
   const uint32_t f_hi = smem_addr, f_lo = smem_addr + kBBytes;
+  // low words of the operand descriptors (start address in 16-byte units, LBO = 1);
+  // a K-step of 16 halves moves the start by 32 bytes = 2 units
+  const uint32_t dl_a_hi = ((a_hi >> 4) & 0x3FFF) | (1u << 16), dl_a_lo = ((a_lo >> 4) & 0x3FFF) | (1u << 16);
+  const uint32_t dl_f_hi = ((f_hi >> 4) & 0x3FFF) | (1u << 16), dl_f_lo = ((f_lo >> 4) & 0x3FFF) | (1u << 16);
   // instruction descriptor: D f32, A/B f16, both K-major, N = 64, M = 128
   constexpr uint32_t kIdesc = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -456,17 +491,26 @@ stft2048tc_kernel(const Params p) {
       const uint32_t sw = (uint32_t)lane & 7u;
       const uint32_t c0 = (((uint32_t)(2 * warp) ^ sw) << 4), c1 = (((uint32_t)(2 * warp + 1) ^ sw) << 4);
       const bool even = (g.hop & 1) == 0;
-      for (int f = 0; f < nf; ++f) {
-        const float* fs = sSamples + f * g.hop + 64 * (8 * warp) + 2 * lane;
+      const float* fs0 = sSamples + 64 * (8 * warp) + 2 * lane;
+      // software pipeline: the samples of frame f + 1 are requested before frame f
+      // is converted, so the shared-memory latency hides under the arithmetic
+      auto load_frame = [&](int f, float2 (&v)[8]) {
+        const float* fs = fs0 + f * g.hop;
+        if (even || (f & 1) == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float2*>(fs + 64 * i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = make_float2(fs[64 * i], fs[64 * i + 1]);
+        }
+      };
+      auto convert_frame = [&](int f, const float2 (&v)[8]) {
         uint32_t hw[8], lw[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float2 v;
-          if (even || (f & 1) == 0) v = *reinterpret_cast<const float2*>(fs + 64 * i);
-          else v = make_float2(fs[64 * i], fs[64 * i + 1]);
-          v = mul2(v, ws[i]);
-          hw[i] = pack_half2(v.x, v.y);
-          const float2 l = sub2(v, unpack_half2(hw[i]));
+          const float2 u = mul2(v[i], ws[i]);
+          hw[i] = pack_half2(u.x, u.y);
+          const float2 l = sub2(u, unpack_half2(hw[i]));
           lw[i] = pack_half2(l.x, l.y);
         }
         const uint32_t rowoff = (uint32_t)(32 * f + lane) * 128u;
@@ -474,7 +518,16 @@ stft2048tc_kernel(const Params p) {
         st_shared_v4(a_hi + rowoff + c1, hw[4], hw[5], hw[6], hw[7]);
         st_shared_v4(a_lo + rowoff + c0, lw[0], lw[1], lw[2], lw[3]);
         st_shared_v4(a_lo + rowoff + c1, lw[4], lw[5], lw[6], lw[7]);
-      }
+      };
+      float2 va[8], vb[8];
+      load_frame(0, va);
+      if (nf > 1) load_frame(1, vb);
+      convert_frame(0, va);
+      if (nf > 2) load_frame(2, va);
+      if (nf > 1) convert_frame(1, vb);
+      if (nf > 3) load_frame(3, vb);
+      if (nf > 2) convert_frame(2, va);
+      if (nf > 3) convert_frame(3, vb);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -486,9 +539,9 @@ stft2048tc_kernel(const Params p) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const uint32_t off = ks * 32;               // 16 halves = 32 bytes along K
-        umma_f16(acc1, umma_desc(a_hi + off), umma_desc(f_hi + off), kIdesc, ks > 0);
-        umma_f16(acc1, umma_desc(a_lo + off), umma_desc(f_hi + off), kIdesc, 1);
-        umma_f16(acc1, umma_desc(a_hi + off), umma_desc(f_lo + off), kIdesc, 1);
+        umma_f16_lo(acc1, dl_a_hi + 2 * ks, dl_f_hi + 2 * ks, kIdesc, ks > 0);
+        umma_f16_lo(acc1, dl_a_lo + 2 * ks, dl_f_hi + 2 * ks, kIdesc, true);
+        umma_f16_lo(acc1, dl_a_hi + 2 * ks, dl_f_lo + 2 * ks, kIdesc, true);
       }
       umma_commit(bar);
     }
@@ -507,33 +560,48 @@ stft2048tc_kernel(const Params p) {
     // ---- D1 row (f = warp, n2 = lane): twiddle, split, scatter into pass 2's
     // operand, rows (f, k1), K-column (n2, c)
     {
-      const float4* t4 = reinterpret_cast<const float4*>(sTwPass);
+      const float4* t4 = reinterpret_cast<const float4*>(sTwPass) + lane;
       const uint32_t base_hi = a_hi + (uint32_t)(32 * warp) * 128u + lane_chunk;
-      uint32_t d0[32], d1[32];
-      tmem_ld32(acc1 + lane_base, d0);
-      tmem_ld32(acc1 + lane_base + 32, d1);
-      tmem_ld_wait();
+      // chunk q = columns 16 q .. 16 q + 15 = k1 8 q .. 8 q + 7, four float4 of twiddles.
+      // TMEM loads and twiddle loads run one chunk ahead of the arithmetic.
+      auto load_tw = [&](int q, float4 (&t)[4]) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+        for (int j = 0; j < 4; ++j) t[j] = t4[(4 * q + j) * 32];
+      };
+      auto convert_chunk = [&](int q, const uint32_t (&d)[16], const float4 (&t)[4]) {
 #pragma unroll
-        for (int kk = 0; kk < 16; kk += 2) {
-          const int k1 = 16 * half + kk;
-          const uint32_t* d = half ? d1 : d0;
-          const float4 t = t4[(k1 >> 1) * 32 + lane];
-          const float yr0 = __uint_as_float(d[2 * kk]), yi0 = __uint_as_float(d[2 * kk + 1]);
-          const float yr1 = __uint_as_float(d[2 * kk + 2]), yi1 = __uint_as_float(d[2 * kk + 3]);
-          const float2 z0 = make_float2(yr0 * t.x - yi0 * t.y, yr0 * t.y + yi0 * t.x);
-          const float2 z1 = make_float2(yr1 * t.z - yi1 * t.w, yr1 * t.w + yi1 * t.z);
+        for (int j = 0; j < 4; ++j) {
+          const int k1 = 8 * q + 2 * j;             // (k1 mod 8) = 2 j
+          const float yr0 = __uint_as_float(d[4 * j]), yi0 = __uint_as_float(d[4 * j + 1]);
+          const float yr1 = __uint_as_float(d[4 * j + 2]), yi1 = __uint_as_float(d[4 * j + 3]);
+          const float2 z0 = make_float2(yr0 * t[j].x - yi0 * t[j].y, yr0 * t[j].y + yi0 * t[j].x);
+          const float2 z1 = make_float2(yr1 * t[j].z - yi1 * t[j].w, yr1 * t[j].w + yi1 * t[j].z);
           const uint32_t h0 = pack_half2(z0.x, z0.y), h1 = pack_half2(z1.x, z1.y);
           const float2 l0 = sub2(z0, unpack_half2(h0)), l1 = sub2(z1, unpack_half2(h1));
-          const uint32_t o0 = (base_hi ^ ((uint32_t)(k1 & 7) << 4)) + (uint32_t)k1 * 128u;
-          const uint32_t o1 = (base_hi ^ ((uint32_t)((k1 + 1) & 7) << 4)) + (uint32_t)(k1 + 1) * 128u;
+          const uint32_t o0 = (base_hi ^ ((uint32_t)(2 * j) << 4)) + (uint32_t)k1 * 128u;
+          const uint32_t o1 = (base_hi ^ ((uint32_t)(2 * j + 1) << 4)) + (uint32_t)(k1 + 1) * 128u;
           st_shared_b32(o0, h0);
           st_shared_b32(o0 + kABytes, pack_half2(l0.x, l0.y));
           st_shared_b32(o1, h1);
           st_shared_b32(o1 + kABytes, pack_half2(l1.x, l1.y));
         }
-      }
+      };
+      uint32_t da[16], db[16];
+      float4 ta[4], tb[4];
+      tmem_ld16(acc1 + lane_base, da);
+      tmem_ld16(acc1 + lane_base + 16, db);
+      load_tw(0, ta);
+      tmem_ld_wait();
+      load_tw(1, tb);
+      convert_chunk(0, da, ta);
+      tmem_ld16(acc1 + lane_base + 32, da);
+      load_tw(2, ta);
+      convert_chunk(1, db, tb);
+      tmem_ld16(acc1 + lane_base + 48, db);
+      tmem_ld_wait();
+      load_tw(3, tb);
+      convert_chunk(2, da, ta);
+      convert_chunk(3, db, tb);
     }
     if (more && warp == 1 && !bulk) asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -546,9 +614,9 @@ stft2048tc_kernel(const Params p) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const uint32_t off = ks * 32;
-        umma_f16(acc2, umma_desc(a_hi + off), umma_desc(f_hi + off), kIdesc, ks > 0);
-        umma_f16(acc2, umma_desc(a_lo + off), umma_desc(f_hi + off), kIdesc, 1);
-        umma_f16(acc2, umma_desc(a_hi + off), umma_desc(f_lo + off), kIdesc, 1);
+        umma_f16_lo(acc2, dl_a_hi + 2 * ks, dl_f_hi + 2 * ks, kIdesc, ks > 0);
+        umma_f16_lo(acc2, dl_a_lo + 2 * ks, dl_f_hi + 2 * ks, kIdesc, true);
+        umma_f16_lo(acc2, dl_a_hi + 2 * ks, dl_f_lo + 2 * ks, kIdesc, true);
       }
       umma_commit(bar);
     }
@@ -721,13 +789,28 @@ stft2048tc_kernel(const Params p) {
           float* ob = p.a.out + ((long long)b * p.a.n_mels + r0) * g.frames + p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float* src = sRows + f * p.row_stride + kRowReal;
-          for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step) {
-            const int q0 = sPstart[m], cnt = sPstart[m + 1] - q0;
-            // the slots behind a filter's last one exist (padding of the partial area)
-            const float s0 = src[q0], s1 = src[q0 + 1], s2 = src[q0 + 2], s3 = src[q0 + 3];
-            float acc = (s0 + (cnt > 1 ? s1 : 0.0f)) + ((cnt > 2 ? s2 : 0.0f) + (cnt > 3 ? s3 : 0.0f));
-            for (int q = q0 + 4; q < q0 + cnt; ++q) acc += src[q];
-            *ob = acc * post;
+          // four filters per trip, all their loads ahead of the adds and the stores
+          // (the slots behind a filter's last one exist: padding of the partial area)
+          for (int m0 = r0; m0 < p.a.n_mels; m0 += 4 * (kGroupThreads / kTile), ob += 4 * step) {
+            int q0[4], cnt[4];
+            float v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int m = min(m0 + u * (kGroupThreads / kTile), p.a.n_mels - 1);
+              q0[u] = sPstart[m];
+              cnt[u] = sPstart[m + 1] - q0[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int t = 0; t < 4; ++t) v[u][t] = src[q0[u] + t];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float acc = (v[u][0] + (cnt[u] > 1 ? v[u][1] : 0.0f)) +
+                          ((cnt[u] > 2 ? v[u][2] : 0.0f) + (cnt[u] > 3 ? v[u][3] : 0.0f));
+              for (int q = q0[u] + 4; q < q0[u] + cnt[u]; ++q) acc += src[q];
+              if (m0 + u * (kGroupThreads / kTile) < p.a.n_mels) ob[u * step] = acc * post;
+            }
           }
         } else if (OUT == kFastPower) {
           const int out_bins = kHalf / p.a.bin_step + 1;
