@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsoundml_b200.so")
+# SOUNDML_B200_LIB: load another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("SOUNDML_B200_LIB") or os.path.join(HERE, "libsoundml_b200.so")
 
 OK, EINVAL, ECUDA, ENOMEM = 0, 1, 2, 3
 MEM_DEVICE, MEM_HOST = 0, 1

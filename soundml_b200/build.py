@@ -43,25 +43,26 @@ def needs_build():
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA translation unit for sm_100a and link the library."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every CUDA translation unit for sm_100a and link the library.
+    ``defines`` / ``out`` build a variant (e.g. -DSMB_FFT32_PACKED=1) next to it."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if out is None else "build_variant")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     for src in CUDA_SOURCES + HOST_SOURCES:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, src), "-o", obj]
         if src.endswith(".cpp"):
             cmd.insert(1, "-x")
             cmd.insert(2, "cu")
         _run(cmd, verbose)
         objs.append(obj)
-    _run([nvcc, "-shared", "-o", LIB] + objs + ["-cudart", "static"], verbose)
-    return LIB
+    _run([nvcc, "-shared", "-o", out or LIB] + objs + ["-cudart", "static"], verbose)
+    return out or LIB
 
 
 def _run(cmd, verbose):
@@ -75,4 +76,7 @@ def _run(cmd, verbose):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs,
+                out=outs[0] if outs else None))

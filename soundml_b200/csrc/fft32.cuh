@@ -97,21 +97,22 @@ __device__ __forceinline__ void fft32_row(const float2 (&y)[32], float2 (&x)[32]
 // 32-point forward DFT in registers, natural order in and out:
 // n = 8a + b, k = c + 4d  ->  4-point DFTs over a, twiddle W32^(bc), 8-point over b.
 // One float32 instruction per real operation.
-__device__ __forceinline__ void fft32(float2 (&x)[32]) {
+__device__ __forceinline__ void fft32_scalar(float2 (&x)[32]) {
   float2 y[32];
   fft32_column<0>(x, y); fft32_column<1>(x, y); fft32_column<2>(x, y); fft32_column<3>(x, y);
   fft32_column<4>(x, y); fft32_column<5>(x, y); fft32_column<6>(x, y); fft32_column<7>(x, y);
   fft32_row<0>(y, x); fft32_row<1>(y, x); fft32_row<2>(y, x); fft32_row<3>(y, x);
 }
 
-// ---- packed form (measured, not used by the kernels) -------------------------------
+// ---- packed form --------------------------------------------------------------------
 // sm_100 issues float32 adds, multiplies and FMAs on register PAIRS (FADD2 / FMUL2 /
 // FFMA2: two lanes per issue slot).  tools/bench_f32x2.cu shows they run at half the
-// instruction rate of the scalar forms (0.49 against 0.98 per clock per scheduler), so
-// they free issue slots, not the FMA pipe: the packed transform below takes 512 cycles
-// per warp against 533 (tools/bench_fft32.cu) and leaves the fused kernels unchanged
-// (1.47 ms against 1.44-1.47 ms), whose register FFTs already saturate that pipe.  It
-// stays here with its benchmark as the record of that experiment.  A C2 carries two complex numbers side by side,
+// instruction rate of the scalar forms (0.49 against 0.98 per clock per scheduler): they
+// free issue slots, not the FMA pipe.  Alone the packed transform takes 512 cycles per
+// warp against 533 (tools/bench_fft32.cu); inside the fused STFT kernel, whose other
+// phases compete for the same issue slots, it is worth 7 % (1.58 -> 1.47 ms, same box,
+// back to back), so stft2048.cu calls it.  The OLS and iSTFT kernels measured slower
+// with it (4.50 -> 4.55 ms, 3.43 -> 3.62 ms) and keep the scalar form.  A C2 carries two complex numbers side by side,
 // the real parts in one pair and the imaginary parts in another, so that every
 // butterfly -- including the rotations by -i, which only swap the roles of the two
 // pairs -- runs on both at once.  The pairing is chosen so that no value ever has to
@@ -242,6 +243,15 @@ __device__ __forceinline__ void fft32_packed(float2 (&x)[32]) {
     x[4 * d + 1] = make_float2(v13[d].re.x, v13[d].im.x);
     x[4 * d + 3] = make_float2(v13[d].re.y, v13[d].im.y);
   }
+}
+
+// The transform the kernels call (-DSMB_FFT32_PACKED=1 selects the packed form).
+__device__ __forceinline__ void fft32(float2 (&x)[32]) {
+#if defined(SMB_FFT32_PACKED) && SMB_FFT32_PACKED
+  fft32_packed(x);
+#else
+  fft32_scalar(x);
+#endif
 }
 
 }  // namespace fft32impl

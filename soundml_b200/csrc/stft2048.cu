@@ -26,7 +26,9 @@
 //     32 x 32: pass 1 (lane = n2) is a 32-point FFT held entirely in
 //     registers over the stride-32 samples, the twiddled result is transposed
 //     through a padded, warp-private shared buffer, pass 2 (lane = k1) is the
-//     second register FFT.  The even/odd split that turns Z into the real
+//     second register FFT (both in the packed float32x2 form of fft32.cuh: FADD2 /
+//     FMUL2 / FFMA2 halve their issue slots; measured 1.58 -> 1.47 ms on the headline
+//     workload).  The even/odd split that turns Z into the real
 //     spectrum pairs bin k with 1024-k, which live in lanes l and 32-l: the
 //     partner values move by warp shuffle, each lane finishing 16 pairs.
 //   * Mel: the filterbank is >98 % zeros (each bin feeds at most two
@@ -147,7 +149,8 @@ __device__ __forceinline__ void stage_tile(const Params& p, int tile, float* sSa
   }
 }
 
-template <int OUT, bool SQUARE, int kGroups>
+// STEP1: bin_step == 1 (fft 2048 proper): every bin is kept, no per-bin tests.
+template <int OUT, bool SQUARE, int kGroups, bool STEP1>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 stft2048_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
@@ -191,7 +194,7 @@ stft2048_kernel(const Params p) {
   __syncthreads();
 
   const FrameGeom g = p.a.g;
-  const int bin_shift = 31 - __clz(p.a.bin_step), bin_mask = p.a.bin_step - 1;
+  const int bin_shift = STEP1 ? 0 : 31 - __clz(p.a.bin_step), bin_mask = STEP1 ? 0 : p.a.bin_step - 1;
   // tile indices fit 32 bits (checked by the launcher): cheap decode
   const int slot = blockIdx.x * kGroups + group;
   const int stride = gridDim.x * kGroups;
@@ -233,7 +236,7 @@ stft2048_kernel(const Params p) {
                                   fs[64 * (n1 + 1) + 2 * lane + 1] * w.w);
         }
       }
-      fft32(a);                                   // a[k1] = Y[n2 = lane][k1]
+      fft32_packed(a);                            // a[k1] = Y[n2 = lane][k1]
       // twiddle W1024^(k1 n2) and transpose through the padded buffer
       {
         const float4* t4 = reinterpret_cast<const float4*>(sTwPass);
@@ -259,7 +262,7 @@ stft2048_kernel(const Params p) {
         }
       }
       __syncwarp();                               // the buffer becomes the output row
-      fft32(a);
+      fft32_packed(a);
 
       // ---- real-spectrum split.  With Z' = Z/2 (window pre-scaled):
       //   S = Z'[k] + conj Z'[N-k],  D = Z'[k] - conj Z'[N-k],  W = W2048^k
@@ -292,7 +295,7 @@ stft2048_kernel(const Params p) {
         const float2 xk = make_float2(S.x + tr, S.y + ti);
         const float2 xn = make_float2(S.x - tr, ti - S.y);
         const int k = lane + 32 * k2, nk = kHalf - k;
-        const bool keep_k = (k & bin_mask) == 0, keep_n = (nk & bin_mask) == 0;
+        const bool keep_k = STEP1 || (k & bin_mask) == 0, keep_n = STEP1 || (nk & bin_mask) == 0;
         if (OUT == kFastComplex) {
           if (keep_k) rowc[k >> bin_shift] = xk;
           if (keep_n) rowc[nk >> bin_shift] = xn;
@@ -452,11 +455,13 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
   long long want = (p.total_tiles + groups - 1) / groups;
   const int grid = (int)(want < sm_count ? want : sm_count);
   cudaError_t e;
-#define SMB_LAUNCH2048_G(OUT, SQ, G)                                                         \
-  e = cudaFuncSetAttribute(stft2048_kernel<OUT, SQ, G>,                                      \
+#define SMB_LAUNCH2048_GS(OUT, SQ, G, S1)                                                    \
+  e = cudaFuncSetAttribute(stft2048_kernel<OUT, SQ, G, S1>,                                  \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
   if (e != cudaSuccess) return e;                                                            \
-  stft2048_kernel<OUT, SQ, G><<<grid, G * kGroupThreads, smem, st>>>(p);
+  stft2048_kernel<OUT, SQ, G, S1><<<grid, G * kGroupThreads, smem, st>>>(p);
+#define SMB_LAUNCH2048_G(OUT, SQ, G)                                                         \
+  if (a.bin_step == 1) { SMB_LAUNCH2048_GS(OUT, SQ, G, true) } else { SMB_LAUNCH2048_GS(OUT, SQ, G, false) }
 #define SMB_LAUNCH2048(OUT, SQ)                                                              \
   if (groups == kMaxGroups) { SMB_LAUNCH2048_G(OUT, SQ, kMaxGroups) }                       \
   else { SMB_LAUNCH2048_G(OUT, SQ, kMaxGroups / 2) }
@@ -466,6 +471,7 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
   else { SMB_LAUNCH2048(kFastComplex, true) }
 #undef SMB_LAUNCH2048
 #undef SMB_LAUNCH2048_G
+#undef SMB_LAUNCH2048_GS
   ++g_launch_count;
   return cudaGetLastError();
 }

@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(512, 1) k(float* out, int iters) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) a[i] = make_float2(threadIdx.x * 1e-3f + i, blockIdx.x * 1e-3f - i);
   for (int it = 0; it < iters; ++it) {
-    if (PACKED) fft32_packed(a); else fft32(a);
+    if (PACKED) fft32_packed(a); else fft32_scalar(a);
 #pragma unroll
     for (int i = 0; i < 32; ++i) { a[i].x *= 0.17f; a[i].y *= 0.17f; }
   }
