@@ -266,7 +266,8 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get("stft2048_mel_dram_bytes_per_launch")
+        traffic = prof.get("stft2048tc_mel_dram_bytes_per_launch" if args.path == "tensor"
+                           else "stft2048_mel_dram_bytes_per_launch")
     except Exception:
         pass
     cpu = parity = None
@@ -299,7 +300,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                      "algorithmic_bytes_per_launch": ALGO_BYTES,
-                     "kernel": "stft2048_kernel<mel>"},
+                     "kernel": "stft2048tc_kernel<mel>" if args.path == "tensor"
+                               else "stft2048_kernel<mel>"},
         "cpu_baseline": cpu,
         "parity": parity,
         "e2e": e2e,
