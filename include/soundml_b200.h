@@ -71,7 +71,11 @@ enum { SMB_MEL_SLANEY = 0, SMB_MEL_HTK = 1 };
 enum { SMB_NORM_SLANEY = 0, SMB_NORM_NONE = 1 };
 enum { SMB_QUALITY_FAST = 0, SMB_QUALITY_HIGH = 1, SMB_QUALITY_BEST = 2, SMB_QUALITY_CUSTOM = 3 };
 enum { SMB_EXEC_DIRECT = 0, SMB_EXEC_OLS = 1, SMB_EXEC_GEMM = 2, SMB_EXEC_PLANNED = 3 };
-/* Kernel selection for the STFT family (testing / benchmarking). */
+/* Kernel selection for the STFT family (testing / benchmarking): AUTO picks the
+ * fused fft-2048 kernel when the geometry allows it, else the double-interior
+ * generic kernel; FAST forces the fused CUDA-core kernel (register FFT), TENSOR the
+ * fused tcgen05 kernel (both 32-point FFT passes as split-fp16 products in TMEM);
+ * a forced kernel that does not cover the call is SMB_EINVAL. */
 enum { SMB_PATH_AUTO = 0, SMB_PATH_GENERIC = 1, SMB_PATH_FAST = 2, SMB_PATH_TENSOR = 3 };
 
 typedef struct smb_stft_plan smb_stft_plan;

@@ -66,8 +66,9 @@ class Config:
         return out
 
     def set_path(self, path):
-        """Testing hook: force the generic (double interior) or the fused
-        fft-2048 kernel.  ``"auto"`` picks the fused kernel when it applies."""
+        """Testing hook: force the generic (double interior) kernel, the fused
+        fft-2048 CUDA-core kernel (``"fast"``) or the fused tcgen05 kernel
+        (``"tensor"``).  ``"auto"`` picks the fused CUDA-core kernel when it applies."""
         code = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC,
                 "fast": _lib.PATH_FAST, "tensor": _lib.PATH_TENSOR}[path]
         _lib.check(_lib.lib.smb_stft_plan_set_path(self._h, code))
