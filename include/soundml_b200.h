@@ -265,6 +265,26 @@ int smb_fir_apply(smb_fir_plan* plan, const float* x, int64_t batch, int64_t n,
  * (resample.ml:145-163): taps = 2K+1, cutoff in Nyquist units. */
 int smb_fir_design_lowpass(int64_t k, double cutoff, double attenuation, double* out);
 
+/* ---- soundml-io device ingest -------------------------- */
+/* The layout pass of soundml-io's decode path on the device: a decoded block,
+ * interleaved [frames][channels] as sf_readf_float / sf_readf_double fill the
+ * reference's staging block (soundml-io/lib/soundml_io_stubs.c:832-872,
+ * soundml_io_read_planar_*), becomes planar -- channel c at out + c * out_total +
+ * out_off -- or, with SMB_INGEST_DOWNMIX, one mono line at out + out_off (channels
+ * added in order, one multiply by 1 / channels: the reference's arithmetic, bit for
+ * bit).  mem_in / mem_out say where the block and the destination live
+ * (SMB_MEM_HOST in + SMB_MEM_DEVICE out is the ingest direction: the block goes up
+ * asynchronously on `cuda_stream` (NULL = default stream) and the call returns when
+ * it has been consumed).  The result feeds Resample.Kernel.step on arrival, as
+ * decode_step does (soundml-io/lib/soundml_io.ml:742-782). */
+enum { SMB_INGEST_PLANAR = 1, SMB_INGEST_DOWNMIX = 2 };
+int smb_ingest_layout(const void* interleaved, int64_t frames, int64_t channels, int mode,
+                      int dtype, void* out, int64_t out_total, int64_t out_off,
+                      int mem_in, int mem_out, void* cuda_stream);
+/* decode_block_frames ~channels ~elt ~advertised (soundml_io.ml:532-536): frames
+ * per decode block of the fused read. */
+int64_t smb_ingest_block_frames(int64_t channels, int64_t elt, int64_t advertised);
+
 #ifdef __cplusplus
 }
 #endif

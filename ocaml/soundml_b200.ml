@@ -79,6 +79,12 @@ external mfcc_c :
   -> unit
   = "soundml_b200_mfcc_bc" "soundml_b200_mfcc"
 
+(* soundml-io: the layout pass after stub_readf (soundml_io_stubs.c:832-872) on the
+   device; mode 1 = planar, 2 = downmix. *)
+external ingest_layout_c :
+  (float, 'a) ba -> int -> int -> int -> (float, 'a) ba -> int -> int -> unit
+  = "soundml_b200_ingest_layout_bc" "soundml_b200_ingest_layout"
+
 (* The flat storage of a contiguous tensor, shared (resample.ml:94). *)
 let array1_of t = Nx_buffer.to_bigarray1 (Nx.to_buffer t)
 

@@ -320,3 +320,29 @@ CAMLprim value soundml_b200_mfcc_bc(value *argv, int argn) {
   return soundml_b200_mfcc(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5], argv[6],
                            argv[7]);
 }
+
+/* soundml-io device ingest: the layout pass of stub_readf's staging block on the
+ * device (soundml_io_stubs.c:832-872).  staging: the interleaved block libsndfile
+ * just filled (host Bigarray, [frames * channels]); dst: the planar destination
+ * (host Bigarray here; a device pointer when the caller keeps the signal on the
+ * GPU for Resample.Kernel.step).  mode: 1 planar, 2 downmix, as SOUNDML_IO_MODE_*. */
+CAMLprim value soundml_b200_ingest_layout(value v_staging, value v_frames, value v_channels,
+                                          value v_mode, value v_dst, value v_total, value v_off) {
+  CAMLparam2(v_staging, v_dst);
+  const void *staging = Caml_ba_data_val(v_staging);
+  void *dst = Caml_ba_data_val(v_dst);
+  const int dtype = dtype_of(v_staging);
+  const int64_t frames = Long_val(v_frames), channels = Long_val(v_channels);
+  const int64_t total = Long_val(v_total), off = Long_val(v_off);
+  const int mode = Int_val(v_mode);
+  caml_release_runtime_system();
+  int st = smb_ingest_layout(staging, frames, channels, mode, dtype, dst, total, off,
+                             SMB_MEM_HOST, SMB_MEM_HOST, NULL);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value soundml_b200_ingest_layout_bc(value *argv, int argn) {
+  (void)argn;
+  return soundml_b200_ingest_layout(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5], argv[6]);
+}

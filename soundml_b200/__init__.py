@@ -9,7 +9,7 @@ import numpy as np
 
 import math
 
-from . import _lib, convert, mel, stft, window
+from . import _lib, convert, io, mel, stft, window
 from . import resample as _resample_mod
 from ._lib import SoundmlError
 
@@ -19,8 +19,9 @@ Window = window
 Convert = convert
 Resample = _resample_mod
 Fir = _resample_mod.Fir
+Io = io
 
-__all__ = ["Stft", "Mel", "Window", "Convert", "Resample", "Fir", "mel_spectrogram", "mfcc",
+__all__ = ["Stft", "Mel", "Window", "Convert", "Resample", "Fir", "Io", "mel_spectrogram", "mfcc",
            "resample",
            "kernel_launch_count", "SoundmlError"]
 

@@ -17,6 +17,7 @@ F32, F64 = 0, 1
 DEFAULT = -(2 ** 31)
 PATH_AUTO, PATH_GENERIC, PATH_FAST, PATH_TENSOR = 0, 1, 2, 3
 EXEC_DIRECT, EXEC_OLS, EXEC_GEMM, EXEC_PLANNED = 0, 1, 2, 3
+INGEST_PLANAR, INGEST_DOWNMIX = 1, 2
 
 WINDOWS = {"hann": 0, "hamming": 1, "blackman": 2, "blackman_harris": 3,
            "nuttall": 4, "bartlett": 5, "kaiser": 6, "gaussian": 7, "tukey": 8,
@@ -116,6 +117,8 @@ SIGNATURES = {
     "smb_fir_plan_set_stream": (_int, [_vp, _vp]),
     "smb_fir_apply": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _int]),
     "smb_fir_design_lowpass": (_int, [_i64, _dbl, _dbl, _pd]),
+    "smb_ingest_layout": (_int, [_vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _int, _int, _vp]),
+    "smb_ingest_block_frames": (_i64, [_i64, _i64, _i64]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

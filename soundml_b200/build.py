@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsoundml_b200.so")
 
 CUDA_SOURCES = ["api.cu", "kernels_generic.cu", "stft2048.cu", "stft2048tc.cu", "resample_kernels.cu",
-                "ols_kernels.cu", "ols2048.cu", "resample_gemm.cu", "db_kernels.cu", "istft_kernels.cu", "istft2048.cu"]
+                "ols_kernels.cu", "ols2048.cu", "resample_gemm.cu", "db_kernels.cu", "istft_kernels.cu", "istft2048.cu", "ingest_kernels.cu"]
 HOST_SOURCES = ["host_design.cpp"]
 HEADERS = ["host_design.h", "kernels.h", "fft32.cuh", os.path.join("..", "..", "include", "soundml_b200.h")]
 

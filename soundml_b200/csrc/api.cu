@@ -1858,6 +1858,57 @@ int smb_fir_apply(smb_fir_plan* plan, const float* x, int64_t batch, int64_t n, 
     }
   });
 }
+// ---- soundml-io device ingest ------------------------------------------------------
+int64_t smb_ingest_block_frames(int64_t channels, int64_t elt, int64_t advertised) {
+  // soundml_io.ml:532-536
+  if (channels < 1 || elt < 1) return -1;
+  const int64_t budget = 4194304 / (channels * elt);
+  const int64_t block = std::min<int64_t>(1048576, std::max<int64_t>(4096, budget));
+  return advertised > 0 ? std::min(block, std::max<int64_t>(4096, advertised)) : block;
+}
+int smb_ingest_layout(const void* interleaved, int64_t frames, int64_t channels, int mode,
+                      int dtype, void* out, int64_t out_total, int64_t out_off, int mem_in,
+                      int mem_out, void* cuda_stream) {
+  return guarded([&] {
+    // geometry, as soundml_io_check_geometry (soundml_io_stubs.c:1150-1172)
+    if (mode != SMB_INGEST_PLANAR && mode != SMB_INGEST_DOWNMIX)
+      throw smb::invalid_argument("ingest: mode must be SMB_INGEST_PLANAR or SMB_INGEST_DOWNMIX");
+    if (channels < 1 || channels > 65535)
+      throw smb::invalid_argument("ingest: channels must lie in [1, 65535]");
+    if (frames < 0 || out_off < 0 || out_total < 0 || out_off + frames > out_total)
+      throw smb::invalid_argument("ingest: the block does not fit the destination "
+                                  "(need 0 <= out_off, out_off + frames <= out_total)");
+    const size_t esz = dtype_size(dtype);
+    if ((mem_in != SMB_MEM_HOST && mem_in != SMB_MEM_DEVICE) ||
+        (mem_out != SMB_MEM_HOST && mem_out != SMB_MEM_DEVICE))
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    if (frames == 0) return;
+    require_device();
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int64_t width = mode == SMB_INGEST_PLANAR ? channels : 1;
+    static thread_local DeviceBuffer stage_in, stage_out;
+    const void* din = interleaved;
+    if (mem_in == SMB_MEM_HOST) {
+      void* up = stage_in.ensure((size_t)frames * channels * esz);
+      CK(cudaMemcpyAsync(up, interleaved, (size_t)frames * channels * esz, cudaMemcpyHostToDevice, st));
+      din = up;
+    }
+    if (mem_out == SMB_MEM_DEVICE) {
+      CK(smb::launch_ingest_layout(din, dtype, frames, (int)channels, mode == SMB_INGEST_DOWNMIX,
+                                   (char*)out + (size_t)out_off * esz, out_total, st));
+      if (mem_in == SMB_MEM_HOST) CK(cudaStreamSynchronize(st));   // the host block may be reused
+    } else {
+      void* dn = stage_out.ensure((size_t)frames * width * esz);
+      CK(smb::launch_ingest_layout(din, dtype, frames, (int)channels, mode == SMB_INGEST_DOWNMIX, dn,
+                                   frames, st));
+      CK(cudaMemcpy2DAsync((char*)out + (size_t)out_off * esz, (size_t)out_total * esz, dn,
+                           (size_t)frames * esz, (size_t)frames * esz, (size_t)width,
+                           cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  });
+}
+
 int smb_fir_design_lowpass(int64_t k, double cutoff, double attenuation, double* out) {
   return guarded([&] {
     if (k < 1) throw smb::invalid_argument("fir: k must be at least 1");

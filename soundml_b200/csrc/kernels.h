@@ -134,6 +134,11 @@ cudaError_t launch_mfcc(const void* mel, int dtype, long long batch, int n_mels,
                         int n_mfcc, const double* dct, unsigned long long* max_slot, double amin,
                         double scale, double offset, double range, void* out, cudaStream_t st);
 
+// soundml-io's layout pass (soundml_io_stubs.c:832-872): interleaved [frames][channels]
+// -> planar (channel c at out + c * out_total) or the mono downmix.
+cudaError_t launch_ingest_layout(const void* in, int dtype, long long frames, int channels,
+                                 int downmix, void* out, long long out_total, cudaStream_t st);
+
 // Overlap-save stage (FIR, xL, /M) on half-length complex FFTs.
 struct OlsArgs {
   const float* x;        // [batch, n]

@@ -200,3 +200,22 @@ def test_griffin_lim_goldens(goldens):
                      F32_ATOL if f32 else F64_ATOL, key)
         n += 1
     assert n == 42
+
+
+def test_io_layout_oracle_and_block_sizing():
+    """soundml-io layout pass restated (soundml_io_stubs.c:832-872): planar scatter and
+    the in-order downmix; decode_block_frames (soundml_io.ml:532-536) known answers."""
+    import numpy as np
+    from oracle import io_oracle
+    b = np.array([[1.0, 2.0, 4.0], [0.5, -0.5, 1.0]], dtype=np.float32)
+    assert np.array_equal(io_oracle.layout(b, "planar"), b.T)
+    third = np.float32(1) / np.float32(3)
+    want = np.array([[np.float32(7.0) * third, np.float32(1.0) * third]], dtype=np.float32)
+    assert np.array_equal(io_oracle.layout(b, "mono"), want)
+    s = np.array([[0.25, 0.5]], dtype=np.float64)
+    assert io_oracle.layout(s, "mono")[0, 0] == 0.375
+    assert io_oracle.decode_block_frames(2, 4) == 524288
+    assert io_oracle.decode_block_frames(1, 4) == 1048576
+    assert io_oracle.decode_block_frames(64, 8) == 8192
+    assert io_oracle.decode_block_frames(2, 4, 100) == 4096
+    assert io_oracle.decode_block_frames(2, 4, 50000) == 50000
