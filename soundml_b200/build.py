@@ -71,6 +71,10 @@ def _run(cmd, verbose):
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+    else:   # compiler warnings are never silent (a missing return once hung a kernel)
+        warn = [l for l in (res.stdout + res.stderr).splitlines() if "warning" in l.lower()]
+        if warn:
+            sys.stderr.write("\n".join(warn) + "\n")
     if res.returncode != 0:
         raise RuntimeError(f"build failed: {' '.join(cmd)}")
 

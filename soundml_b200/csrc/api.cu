@@ -314,15 +314,22 @@ struct smb_mel_plan {
   int scale = 0, norm = 0;
   std::vector<double> weights;       // [n_mels][bins]
   std::vector<int> band_lo, band_hi;
-  // band storage for the fused kernel: filter m keeps bins [lo, lo+len)
-  std::vector<float> vals;
-  std::vector<smb::MelLane> mel_lanes;   // [kFastTile warps][mel_rounds][kFastRoundFilters]
-  int mel_rounds = 0;
-  // the same for the tensor-core kernel's 4-frame tiles
-  std::vector<float> vals_tc;               // [round][step][lane] float4 weights
-  std::vector<smb::MelPiece> pieces_tc;     // [kTcTile warps][mel_rounds_tc][32]
-  std::vector<unsigned short> pstart_tc;    // [n_mels + 1]
-  int mel_rounds_tc = 0, n_pieces_tc = 0;
+  // Mel schedule of a fused kernel: every filter's band cut into pieces of at most
+  // `ps` float4 steps, a lane carries one piece for all the frames of the tile.
+  struct PieceSchedule {
+    std::vector<float> vals;               // [round][step][lane] float4 weights
+    std::vector<smb::MelPiece> pieces;     // [warps][rounds][32]
+    std::vector<unsigned short> pstart;    // [n_mels + 1]: partial-sum slots of each filter
+    int rounds = 0, n_pieces = 0;
+    float* d_vals = nullptr;
+    smb::MelPiece* d_pieces = nullptr;
+    unsigned short* d_pstart = nullptr;
+    void clear() { vals.clear(); pieces.clear(); pstart.clear(); rounds = n_pieces = 0; }
+    void to_device() { d_vals = upload(vals); d_pieces = upload(pieces); d_pstart = upload(pstart); }
+    void free_device() { cudaFree(d_vals); cudaFree(d_pieces); cudaFree(d_pstart); }
+  };
+  PieceSchedule sched_cc;   // CUDA-core kernel: kFastTile warps, 8 frames per lane
+  PieceSchedule sched_tc;   // tensor-core kernel: kTcTile warps, 4 frames per lane
   // 2048 / fft_size when the fused kernel can carry this filterbank (1 for fft
   // 2048, 2 for 1024, ...), else 0
   int fast_step = 0;
@@ -330,11 +337,6 @@ struct smb_mel_plan {
   StreamOwner stream;
   double* d_weights = nullptr;
   int *d_band_lo = nullptr, *d_band_hi = nullptr;
-  float* d_vals = nullptr;
-  smb::MelLane* d_mel_lanes = nullptr;
-  float* d_vals_tc = nullptr;
-  smb::MelPiece* d_pieces_tc = nullptr;
-  unsigned short* d_pstart_tc = nullptr;
   DeviceBuffer in, out;
   // MFCC epilogue: DCT table of the last (n_mfcc, lifter) asked for, max scratch
   double* d_dct = nullptr;
@@ -381,205 +383,137 @@ struct smb_mel_plan {
     // (shorter frames run zero-padded and keep every step-th bin in the power row)
     if (bins < 65 || bins > 1025 || 1024 % (bins - 1) != 0) return;
     const int step = (int)(1024 / (bins - 1));
-    // Schedule for the fused kernels.  Filters sorted by band length are cut into
-    // rounds of 2 * (32 / tile) filters (two sets A and B); a warp lane is (filter
-    // j, frame f) and walks its A and B filter together.  The bands of a round are
-    // stored zero-padded to one common length (a whole number of 8-float steps,
-    // starting on a float4 of the 16-byte aligned power row) and interleaved
-    // [step][set][half][j] x float4, so every weight load of a warp is one
-    // contiguous run.  With 4-frame tiles two neighbouring filters (j even, j
-    // odd) share a quarter-warp: their band starts are then kept an odd number of
-    // float4s apart, which with the kernel's row stride (8 mod 32) keeps the
-    // power-row loads conflict-free.  Rounds go to the group's warps
-    // longest-first onto the lightest warp.
-    if (!build_schedule(smb::kFastTile, vals, mel_lanes, mel_rounds) || !build_tc_schedule()) {
-      vals.clear();
-      vals_tc.clear();
-      mel_lanes.clear();
-      pieces_tc.clear();
+    // the CUDA-core kernel trades a few padded steps for conflict-free octets
+    // (whole list as the window); the tensor-core kernel has no shared memory to
+    // spare for longer weight tables and keeps the strict longest-first rounds
+    if (!build_schedule(sched_cc, smb::kFastTile, smb::kFastPieceSteps, 1 << 30) ||
+        !build_schedule(sched_tc, smb::kTcTile, smb::kTcPieceSteps, 32)) {
+      sched_cc.clear();
+      sched_tc.clear();
       return;
     }
     fast_step = step;
   }
-  // Schedule of the tensor-core kernel (4-frame tiles).  Every filter's band,
-  // starting on a float4 of the power row, is cut into pieces of at most
-  // kTcPieceSteps float4 steps; a lane carries one piece for the four frames of
-  // the tile and leaves a partial sum in slot `pid` (the slots of a filter are
-  // consecutive: pstart).  Pieces sorted by length fill rounds of 32 lanes with one
-  // step count; inside a round the lanes of a quarter-warp get distinct start
-  // residues (start / 4 mod 8) where possible, so their 16-byte power-row loads
-  // fall in distinct bank groups.  Weights are stored [round][step][lane] x float4.
-  // Rounds go to the 4 warps longest-first onto the lightest warp.
-  bool build_tc_schedule() {
-    const int row_floats = (int)((bins + 3) / 4 * 4);
-    const int ps = smb::kTcPieceSteps;
+  // Mel schedule of the fused kernels.  Every filter's band, starting on a float4
+  // of the power row, is cut into pieces of at most `ps` float4 steps; a lane
+  // carries one piece for all the frames of its tile (one weight load feeds 4 FMAs
+  // per frame) and leaves a partial sum in slot `pid` (the slots of a filter are
+  // consecutive: pstart; the write-out adds them up).  Rounds of 32 lanes share one
+  // step count.  They are filled longest pieces first out of a window of
+  // candidates, so that the lanes of a quarter-warp get distinct start residues
+  // (start / 4 mod 8) where the window allows: their 16-byte power-row loads then
+  // fall in distinct bank groups.  Weights are stored
+  // [round][step][lane] x float4, a contiguous run per warp-wide load.  Rounds go
+  // to the group's warps longest-first onto the lightest warp.
+  bool build_schedule(PieceSchedule& sc, int warps, int ps, int window) const {
+    sc.clear();
+    const int row_floats = (int)((bins + 3) / 4 * 4);        // the kernel zeroes the row tail
     struct Piece { int m, start, steps, pid; };
     std::vector<Piece> pieces;
-    pstart_tc.assign((size_t)n_mels + 1, 0);
+    sc.pstart.assign((size_t)n_mels + 1, 0);
     for (int64_t m = 0; m < n_mels; ++m) {
-      pstart_tc[(size_t)m] = (unsigned short)pieces.size();
+      sc.pstart[(size_t)m] = (unsigned short)pieces.size();
       const int lo = band_lo[(size_t)m] & ~3, hi = std::max(band_hi[(size_t)m], lo + 1);
       const int total = (hi - lo + 3) / 4;
       for (int s0 = 0; s0 < total; s0 += ps)
         pieces.push_back(Piece{(int)m, lo + 4 * s0, std::min(ps, total - s0), (int)pieces.size()});
       if (pieces.size() > 4000) return false;
     }
-    pstart_tc[(size_t)n_mels] = (unsigned short)pieces.size();
-    n_pieces_tc = (int)pieces.size();
-    std::vector<int> order(pieces.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(),
+    sc.pstart[(size_t)n_mels] = (unsigned short)pieces.size();
+    sc.n_pieces = (int)pieces.size();
+    // pieces longest first; a round is picked from the first `window` of them
+    std::vector<int> rest(pieces.size());
+    for (size_t i = 0; i < rest.size(); ++i) rest[i] = (int)i;
+    std::stable_sort(rest.begin(), rest.end(),
                      [&](int a, int b) { return pieces[(size_t)a].steps > pieces[(size_t)b].steps; });
-    const int rounds_total = (int)((pieces.size() + 31) / 32);
     struct Round { int steps; size_t base; int member[32]; int start[32]; };
-    std::vector<Round> built((size_t)rounds_total);
-    for (int q = 0; q < rounds_total; ++q) {
-      Round& rd = built[(size_t)q];
-      std::vector<int> pool;
-      for (int t = 0; t < 32; ++t) {
-        const size_t at = (size_t)q * 32 + (size_t)t;
-        if (at < order.size()) pool.push_back(order[at]);
-      }
-      rd.steps = 1;
-      for (int id : pool) rd.steps = std::max(rd.steps, pieces[(size_t)id].steps);
-      if (rd.steps * 4 > row_floats) return false;
-      // the stored run [start, start + 4 steps) must stay inside the row
-      auto start_of = [&](int id) { return std::min(pieces[(size_t)id].start, row_floats - 4 * rd.steps); };
+    std::vector<Round> built;
+    while (!rest.empty()) {
+      Round rd;
       for (int t = 0; t < 32; ++t) rd.member[t] = -1;
-      // octets with distinct residues first, leftovers into the free lanes
-      std::vector<int> left;
-      std::vector<std::vector<int>> by_res(8);
-      for (int id : pool) by_res[(size_t)((start_of(id) >> 2) & 7)].push_back(id);
+      const size_t nc = std::min(rest.size(), (size_t)window);
+      std::vector<char> used(nc, 0);
+      // four octets, each scanning the candidates for eight distinct residues ...
       for (int o = 0; o < 4; ++o) {
+        unsigned seen = 0;
         int lane = o * 8;
-        for (int r = 0; r < 8; ++r)
-          if (!by_res[(size_t)r].empty()) {
-            rd.member[lane++] = by_res[(size_t)r].back();
-            by_res[(size_t)r].pop_back();
-          }
+        for (size_t c = 0; c < nc && lane < o * 8 + 8; ++c) {
+          if (used[c]) continue;
+          const unsigned r = (unsigned)((pieces[(size_t)rest[c]].start >> 2) & 7);
+          if (seen & (1u << r)) continue;
+          seen |= 1u << r;
+          used[c] = 1;
+          rd.member[lane++] = rest[c];
+        }
       }
-      for (auto& v : by_res) for (int id : v) left.push_back(id);
-      for (int t = 0; t < 32 && !left.empty(); ++t)
-        if (rd.member[t] < 0) { rd.member[t] = left.back(); left.pop_back(); }
-      rd.base = vals_tc.size();
-      vals_tc.resize(rd.base + (size_t)rd.steps * 32 * 4, 0.0f);
+      // ... then the free lanes take the longest candidates left
+      for (int t = 0; t < 32; ++t) {
+        if (rd.member[t] >= 0) continue;
+        size_t c = 0;
+        while (c < nc && used[c]) ++c;
+        if (c == nc) break;
+        used[c] = 1;
+        rd.member[t] = rest[c];
+      }
+      std::vector<int> keep;
+      for (size_t c = 0; c < rest.size(); ++c)
+        if (c >= nc || !used[c]) keep.push_back(rest[c]);
+      rest.swap(keep);
+      rd.steps = 1;
+      for (int t = 0; t < 32; ++t)
+        if (rd.member[t] >= 0) rd.steps = std::max(rd.steps, pieces[(size_t)rd.member[t]].steps);
+      if (rd.steps * 4 > row_floats) return false;
+      rd.base = sc.vals.size();
+      sc.vals.resize(rd.base + (size_t)rd.steps * 32 * 4, 0.0f);
       for (int t = 0; t < 32; ++t) {
         const int id = rd.member[t];
-        rd.start[t] = id >= 0 ? start_of(id) : 0;
+        rd.start[t] = 0;
         if (id < 0) continue;
         const Piece& pc = pieces[(size_t)id];
+        // the stored run [start, start + 4 steps) must stay inside the row
+        rd.start[t] = std::min(pc.start, row_floats - 4 * rd.steps);
         // the piece's own bins [pc.start, pc.start + 4 pc.steps), clipped to the band
         for (int k = pc.start; k < pc.start + 4 * pc.steps; ++k) {
           if (k >= bins || k < band_lo[(size_t)pc.m] || k >= band_hi[(size_t)pc.m]) continue;
           const int u = k - rd.start[t];
-          vals_tc[rd.base + ((size_t)(u >> 2) * 32 + (size_t)t) * 4 + (size_t)(u & 3)] =
+          sc.vals[rd.base + ((size_t)(u >> 2) * 32 + (size_t)t) * 4 + (size_t)(u & 3)] =
               (float)weights[(size_t)((int64_t)pc.m * bins + k)];
         }
       }
+      built.push_back(rd);
     }
-    const int warps = smb::kTcTile;
+    const int rounds_total = (int)built.size();
+    std::vector<int> by_len((size_t)rounds_total);
+    for (int q = 0; q < rounds_total; ++q) by_len[(size_t)q] = q;
+    std::stable_sort(by_len.begin(), by_len.end(),
+                     [&](int a, int b) { return built[(size_t)a].steps > built[(size_t)b].steps; });
     std::vector<std::vector<int>> lists((size_t)warps);
     std::vector<long long> load((size_t)warps, 0);
-    for (int q = 0; q < rounds_total; ++q) {
+    for (int q : by_len) {
       const size_t w = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
       lists[w].push_back(q);
       load[w] += built[(size_t)q].steps * 21 + 20;
     }
-    mel_rounds_tc = 0;
-    for (const auto& l : lists) mel_rounds_tc = std::max(mel_rounds_tc, (int)l.size());
-    const size_t zero_off = vals_tc.size();            // idle rounds: one step over zero weights
-    vals_tc.insert(vals_tc.end(), (size_t)(32 * 4), 0.0f);
-    if (vals_tc.size() >= (1u << 24)) return false;
-    pieces_tc.assign((size_t)(warps * mel_rounds_tc * 32), smb::MelPiece{});
+    sc.rounds = 0;
+    for (const auto& l : lists) sc.rounds = std::max(sc.rounds, (int)l.size());
+    const size_t zero_off = sc.vals.size();            // idle rounds: one step over zero weights
+    sc.vals.insert(sc.vals.end(), (size_t)(32 * 4), 0.0f);
+    if (sc.vals.size() >= (1u << 24)) return false;
+    sc.pieces.assign((size_t)(warps * sc.rounds * 32), smb::MelPiece{});
     for (int w = 0; w < warps; ++w)
-      for (int r = 0; r < mel_rounds_tc; ++r)
+      for (int r = 0; r < sc.rounds; ++r)
         for (int t = 0; t < 32; ++t) {
-          smb::MelPiece& out = pieces_tc[((size_t)w * (size_t)mel_rounds_tc + (size_t)r) * 32 + (size_t)t];
+          smb::MelPiece& out = sc.pieces[((size_t)w * (size_t)sc.rounds + (size_t)r) * 32 + (size_t)t];
           if ((size_t)r < lists[(size_t)w].size()) {
             const Round& rd = built[(size_t)lists[(size_t)w][(size_t)r]];
             out.off = (int)(rd.base + (size_t)t * 4) | (rd.steps << 24);
             out.lo = (short)rd.start[t];
-            out.pid = (unsigned short)(rd.member[t] >= 0 ? pieces[(size_t)rd.member[t]].pid : n_pieces_tc);
+            out.pid = (unsigned short)(rd.member[t] >= 0 ? pieces[(size_t)rd.member[t]].pid : sc.n_pieces);
           } else {
             out.off = (int)(zero_off + (size_t)t * 4) | (1 << 24);
             out.lo = 0;
-            out.pid = (unsigned short)n_pieces_tc;
+            out.pid = (unsigned short)sc.n_pieces;
           }
-        }
-    return true;
-  }
-  bool build_schedule(int tile, std::vector<float>& vals, std::vector<smb::MelLane>& mel_lanes,
-                      int& mel_rounds) const {
-    constexpr int kMaxRound = 16;
-    const int row_floats = (int)((bins + 3) / 4 * 4);        // the kernel zeroes the row tail
-    std::vector<int> order((size_t)n_mels);
-    for (int64_t m = 0; m < n_mels; ++m) order[(size_t)m] = (int)m;
-    auto span = [&](int m) { return band_hi[(size_t)m] - (band_lo[(size_t)m] & ~3); };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return span(a) > span(b); });
-    const int warps = tile, lf = 32 / tile, per_round = 2 * lf;
-    const int rounds_total = (int)((n_mels + per_round - 1) / per_round);
-    struct Round { int n8; smb::MelLane lane[kMaxRound]; };
-    std::vector<Round> built((size_t)rounds_total);
-    if (n_mels > 255 || per_round > kMaxRound) return false;
-    for (int q = 0; q < rounds_total; ++q) {
-      int member[kMaxRound], slo[kMaxRound];
-      for (int t = 0; t < per_round; ++t) {
-        const size_t at = (size_t)(q * per_round + t);
-        member[t] = at < order.size() ? order[at] : -1;
-        slo[t] = member[t] >= 0 ? (band_lo[(size_t)member[t]] & ~3) : 0;
-      }
-      for (int t = 0; t < per_round && tile == 4; t += 2) {
-        if (member[t] < 0 || member[t + 1] < 0) continue;
-        if ((((slo[t] ^ slo[t + 1]) >> 2) & 1) == 0) {
-          if (slo[t + 1] >= 4) slo[t + 1] -= 4;
-          else if (slo[t] >= 4) slo[t] -= 4;
-        }
-      }
-      int n8 = 1;
-      for (int t = 0; t < per_round; ++t)
-        if (member[t] >= 0) n8 = std::max(n8, (band_hi[(size_t)member[t]] - slo[t] + 7) / 8);
-      if (n8 * 8 > row_floats || n8 > 255) return false;
-      built[(size_t)q].n8 = n8;
-      const size_t base = vals.size();
-      vals.resize(base + (size_t)n8 * 16 * lf, 0.0f);
-      for (int t = 0; t < per_round; ++t) {
-        const int ab = t / lf, j = t % lf, m = member[t];
-        smb::MelLane& ln = built[(size_t)q].lane[t];
-        ln.n8 = (unsigned char)n8;
-        ln.off = (int)base + (ab * 2 * lf + j) * 4;   // + 16 lf per step, + 4 lf for the second half
-        // stored band [lo, lo + 8 n8): inside the row, covering the filter's band
-        const int lo = std::min(slo[t], row_floats - n8 * 8);
-        ln.lo = (short)lo;
-        ln.out = (unsigned char)(m >= 0 ? m : n_mels);
-        if (m < 0) continue;
-        for (int u = 0; u < n8 * 8; ++u) {
-          const int k = lo + u;
-          const size_t at = base + (size_t)(u / 8) * 16 * lf +
-                            (size_t)(ab * 2 * lf + ((u / 4) & 1) * lf + j) * 4 + (size_t)(u & 3);
-          vals[at] = k < bins ? (float)weights[(size_t)((int64_t)m * bins + k)] : 0.0f;
-        }
-      }
-    }
-    std::vector<std::vector<int>> lists((size_t)warps);
-    std::vector<long long> load((size_t)warps, 0);
-    for (int q = 0; q < rounds_total; ++q) {
-      const size_t w = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
-      lists[w].push_back(q);
-      load[w] += built[(size_t)q].n8 + 2;
-    }
-    mel_rounds = 0;
-    for (const auto& l : lists) mel_rounds = std::max(mel_rounds, (int)l.size());
-    // idle rounds: one step over zero weights into the scratch row
-    const int zero_off = (int)vals.size();
-    vals.insert(vals.end(), (size_t)(16 * lf), 0.0f);
-    mel_lanes.assign((size_t)(warps * mel_rounds * per_round), smb::MelLane{});
-    for (int w = 0; w < warps; ++w)
-      for (int r = 0; r < mel_rounds; ++r)
-        for (int t = 0; t < per_round; ++t) {
-          const smb::MelLane idle{zero_off + ((t / lf) * 2 * lf + t % lf) * 4, 0, (unsigned char)n_mels, 1};
-          mel_lanes[((size_t)w * mel_rounds + (size_t)r) * per_round + (size_t)t] =
-              (size_t)r < lists[(size_t)w].size() ? built[(size_t)lists[(size_t)w][(size_t)r]].lane[t]
-                                                  : idle;
         }
     return true;
   }
@@ -590,11 +524,8 @@ struct smb_mel_plan {
     d_weights = upload(weights);
     d_band_lo = upload(band_lo);
     d_band_hi = upload(band_hi);
-    d_vals = upload(vals);
-    d_mel_lanes = upload(mel_lanes);
-    d_vals_tc = upload(vals_tc);
-    d_pieces_tc = upload(pieces_tc);
-    d_pstart_tc = upload(pstart_tc);
+    sched_cc.to_device();
+    sched_tc.to_device();
     CK(cudaMalloc(&d_max, sizeof(unsigned long long)));
     device_ready = true;
   }
@@ -603,11 +534,8 @@ struct smb_mel_plan {
     cudaFree(d_weights);
     cudaFree(d_band_lo);
     cudaFree(d_band_hi);
-    cudaFree(d_vals);
-    cudaFree(d_mel_lanes);
-    cudaFree(d_vals_tc);
-    cudaFree(d_pieces_tc);
-    cudaFree(d_pstart_tc);
+    sched_cc.free_device();
+    sched_tc.free_device();
     cudaFree(d_dct);
     cudaFree(d_max);
     in.release();
@@ -1032,14 +960,15 @@ int want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int ou
   smb::FrameGeom gk = g;
   gk.fft = 2048;
   const bool base = dtype == SMB_F32 && step > 0 &&
-                    (!mel || (mel->fast_step == step && !mel->mel_lanes.empty()));
+                    (!mel || (mel->fast_step == step && !mel->sched_cc.pieces.empty()));
   const bool ok_tc = base && smb::stft2048tc_supports(gk, out_kind, mel ? (int)mel->n_mels : 0,
-                                                      mel ? (int)mel->vals_tc.size() : 0,
-                                                      mel ? mel->mel_rounds_tc : 0,
-                                                      mel ? mel->n_pieces_tc : 0);
+                                                      mel ? (int)mel->sched_tc.vals.size() : 0,
+                                                      mel ? mel->sched_tc.rounds : 0,
+                                                      mel ? mel->sched_tc.n_pieces : 0);
   const bool ok_cc = base && smb::stft2048_supports(gk, out_kind, mel ? (int)mel->n_mels : 0,
-                                                    mel ? (int)mel->vals.size() : 0,
-                                                    mel ? mel->mel_rounds : 0);
+                                                    mel ? (int)mel->sched_cc.vals.size() : 0,
+                                                    mel ? mel->sched_cc.rounds : 0,
+                                                    mel ? mel->sched_cc.n_pieces : 0);
   if (p->path == SMB_PATH_TENSOR) {
     if (!ok_tc)
       throw smb::invalid_argument(
@@ -1475,21 +1404,15 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
         a.n_mels = (int)mel->n_mels;
         a.power = (float)power;
         a.dft_images = stft->d_dft_images;
-        if (fast == SMB_PATH_TENSOR) {
-          a.nnz = (int)mel->vals_tc.size();
-          a.vals = mel->d_vals_tc;
-          a.tc_pieces = mel->d_pieces_tc;
-          a.tc_pstart = mel->d_pstart_tc;
-          a.tc_rounds = mel->mel_rounds_tc;
-          a.tc_n_pieces = mel->n_pieces_tc;
-          CK(smb::launch_stft2048tc(a, smb::kFastMel, stft->sm_count, st));
-        } else {
-          a.nnz = (int)mel->vals.size();
-          a.vals = mel->d_vals;
-          a.mel_rounds = mel->mel_rounds;
-          a.mel_lanes = mel->d_mel_lanes;
-          CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
-        }
+        const auto& sc = fast == SMB_PATH_TENSOR ? mel->sched_tc : mel->sched_cc;
+        a.nnz = (int)sc.vals.size();
+        a.vals = sc.d_vals;
+        a.mel_pieces = sc.d_pieces;
+        a.mel_pstart = sc.d_pstart;
+        a.mel_rounds = sc.rounds;
+        a.mel_n_pieces = sc.n_pieces;
+        if (fast == SMB_PATH_TENSOR) CK(smb::launch_stft2048tc(a, smb::kFastMel, stft->sm_count, st));
+        else CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
       } else {
         // two kernels through a plan-owned power spectrogram
         const size_t spec_bytes = (size_t)nb * stft->geom.bins() * g.frames * esz;

@@ -58,19 +58,18 @@ cudaError_t launch_istft2048(const IstftArgs& a, const float* window_scaled, con
                              cudaStream_t st);
 
 // ---- fast path: fft 2048, float32, fused frame+window+rFFT+|X|^p(+mel) -------
-// Tile shape of the fused kernel, shared with the host-side mel schedule: a group
-// of kFastTile warps transforms kFastTile consecutive frames, one per warp.  In the
-// mel step a lane is (filter j of kFastLaneFilters, frame f) and carries two
-// filters (octet A and B) at a time, so a round covers kFastRoundFilters filters.
+// Tile shape of the fused CUDA-core kernel: a group of kFastTile warps transforms
+// kFastTile consecutive frames, one per warp.
 constexpr int kFastTile = 8;
-constexpr int kFastLaneFilters = 32 / kFastTile;
-constexpr int kFastRoundFilters = 2 * kFastLaneFilters;
-struct MelLane {           // one filter of a mel round (lane j = slot % LaneFilters, octet = slot / LaneFilters)
-  int off;                 // the filter's first float4 in the round's interleaved weights
-  short lo;                // first bin of the stored band (multiple of 4)
-  unsigned char out;       // output filter; n_mels = scratch row (padding entry)
-  unsigned char n8;        // 8-float steps, the same for all filters of a round
+// One lane of a mel round of the fused kernels: a piece (a few float4 steps) of one
+// filter's band, carried for all the frames of the tile.
+struct MelPiece {
+  int off;                 // weights: float offset of [step 0][lane] (low 24 bits), steps of the round (high 8)
+  short lo;                // first bin read (multiple of 4)
+  unsigned short pid;      // partial-sum slot (mel_n_pieces = scratch)
 };
+constexpr int kFastPieceSteps = 3;     // float4 steps per piece, CUDA-core kernel (8 frames per lane)
+constexpr int kTcPieceSteps = 4;       // tensor-core kernel (4 frames per lane)
 enum FastOut { kFastComplex = 0, kFastPower = 1, kFastMel = 2 };
 struct Stft2048Args {
   const float* x;          // [batch, n]
@@ -80,32 +79,22 @@ struct Stft2048Args {
   const float* window;     // [2048]
   const float2* tw_pass;   // [32][32]  W_1024^(k1*n2), index k1*32 + n2
   const float2* tw_post;   // [16][32]  W_2048^(l + 32 j), index j*32 + l
-  // band-stored mel filterbank (kFastMel only)
+  // piece-wise mel schedule (kFastMel only; one per kernel, see api.cu build_schedule)
   int n_mels, nnz;
-  const float* vals;           // [nnz] zero-padded band weights
-  int mel_rounds;              // rounds each warp walks
-  const MelLane* mel_lanes;    // [kFastTile warps][mel_rounds][kFastRoundFilters]
+  const float* vals;               // [nnz] weights, [round][step][lane] x float4
+  const MelPiece* mel_pieces;      // [warps of a group][mel_rounds][32 lanes]
+  const unsigned short* mel_pstart;   // [n_mels + 1] partial-sum slots of each filter
+  int mel_rounds, mel_n_pieces;
   float power;
   int bin_step;                // 2048 / fft_size: 1, or 2/4/8/16 for zero-padded shorter frames
   // tensor-core variant (stft2048tc.cu) only: [hi, lo] fp16 images of the real 64 x 64
-  // form of the 32-point DFT, K-major SWIZZLE_128B; and its own mel schedule (vals / nnz
-  // then hold [round][step][lane] float4 weights)
+  // form of the 32-point DFT, K-major SWIZZLE_128B
   const void* dft_images;
-  const struct MelPiece* tc_pieces;    // [kTcTile warps][tc_rounds][32 lanes]
-  const unsigned short* tc_pstart;     // [n_mels + 1] partial-sum slots of each filter
-  int tc_rounds, tc_n_pieces;
 };
-// One lane of a mel round of the tensor-core kernel: a piece (<= kTcPieceSteps float4
-// steps) of one filter's band, carried for the 4 frames of the tile.
-struct MelPiece {
-  int off;                 // weights: float offset of [step 0][lane] (low 24 bits), steps of the round (high 8)
-  short lo;                // first bin read (multiple of 4)
-  unsigned short pid;      // partial-sum slot (tc_n_pieces = scratch)
-};
-constexpr int kTcPieceSteps = 4;
 // True when the fused kernel can take this geometry (hop small enough for the
 // shared-memory sample tile, mel tables small enough to be resident).
-bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds);
+bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds,
+                       int n_pieces);
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
 // Tensor-core variant: both 32-point passes as split-fp16 products on tcgen05, a
 // tile = kTcTile frames = 128 MMA rows per group of kTcTile warps.

@@ -32,10 +32,19 @@
 //     spectrum pairs bin k with 1024-k, which live in lanes l and 32-l: the
 //     partner values move by warp shuffle, each lane finishing 16 pairs.
 //   * Mel: the filterbank is >98 % zeros (each bin feeds at most two
-//     triangles), so the projection runs as a lane-balanced sparse product
-//     over the frame's power row in shared memory, in float32 FMAs.
+//     triangles), so the projection runs as a band product over the tile's power
+//     rows in shared memory, in float32 FMAs: every filter's band is cut into
+//     pieces of a few float4 steps, a lane carries one piece for all the frames of
+//     the tile (one 16-byte weight load feeds 4 FMAs per frame), partial sums are
+//     added at write-out.
+//   * Interior tiles are brought in by one bulk copy (TMA) per tile, issued by
+//     one thread and awaited on the group's mbarrier; boundary tiles go through
+//     cp.async and the reference's index rule.
 //   * Outputs are staged per tile so global writes run along the contiguous
 //     frame axis.
+#include <cstdint>
+#include <cstdlib>
+
 #include "fft32.cuh"
 #include "kernels.h"
 
@@ -48,15 +57,13 @@ constexpr int kHalf = 1024;              // complex points
 constexpr int kTile = kFastTile;         // frames per group tile, one warp each
 constexpr int kGroupThreads = 32 * kTile;
 constexpr int kGroupWarps = kTile;
-constexpr int kLF = kFastLaneFilters;    // filters side by side in a warp's mel step
 constexpr int kMaxGroups = kTile == 8 ? 2 : 4;
 static_assert(kTile == 8 || kTile == 4, "tile shapes the lane maps are written for");
 // floats per warp region: holds [32][34] complex; 16-byte rows; the frames of a
 // tile land 4 banks apart (8 frames) or 8 banks apart (4 frames)
 constexpr int kRowStride = kTile == 8 ? 2180 : 2184;
-constexpr int kMelOutOff = 1032;         // mel results of a frame sit behind its power row
+constexpr int kMelOutOff = 1032;         // the mel partial sums of a frame sit behind its power row
 constexpr int kExStride = 34;            // padded transpose row (complex): 16-byte rows, conflict-free
-constexpr int kMaxMel = 128;
 
 using namespace fft32impl;
 
@@ -91,8 +98,38 @@ __device__ __forceinline__ void group_sync(int group) {
   asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
 struct Params {
   Stft2048Args a;
+  int use_bulk;              // interior tiles by one bulk copy (SMB_NO_BULK=1 turns it off)
   int span_cap;              // floats reserved per group for samples
   long long tiles_per_signal, total_tiles;
 };
@@ -102,8 +139,11 @@ struct Params {
 // cp.async (16 bytes per request when source and destination are both 16-byte
 // aligned, else 8 or 4); border positions are resolved by the reference's
 // boundary rule (stft.ml:300-338) and stored directly.  Completion is awaited
-// by the caller (cp.async.wait_all + group barrier).
-__device__ __forceinline__ void stage_tile(const Params& p, int tile, float* sSamples, int gtid) {
+// by the caller (cp.async.wait_all + group barrier).  An interior tile whose source
+// run is 16-byte aligned is one bulk copy (TMA) issued by the group's first thread
+// onto `bar`: returns true and the caller waits on the mbarrier instead.
+__device__ __forceinline__ bool stage_tile(const Params& p, int tile, float* sSamples, int gtid,
+                                           uint32_t bar) {
   const FrameGeom& g = p.a.g;
   const int tps = (int)p.tiles_per_signal;
   const int b = tile / tps;
@@ -113,6 +153,14 @@ __device__ __forceinline__ void stage_tile(const Params& p, int tile, float* sSa
   const long long q0 = p0 * g.hop;
   const long long s0 = q0 - g.left;
   const float* xs = p.a.x + (long long)b * g.n;
+  if (p.use_bulk && s0 >= 0 && s0 + span <= g.n && (reinterpret_cast<size_t>(xs + s0) & 15) == 0 && (span & 3) == 0) {
+    if (gtid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, 4u * (uint32_t)span);
+      bulk_g2s(smem_u32(sSamples), xs + s0, 4u * (uint32_t)span, bar);
+    }
+    return true;
+  }
   // [lo, hi): positions of the span that are real samples
   const int lo = (int)max(0LL, min((long long)span, -s0));
   const int hi = (int)max((long long)lo, min((long long)span, g.n - s0));
@@ -147,6 +195,7 @@ __device__ __forceinline__ void stage_tile(const Params& p, int tile, float* sSa
     for (int i = lo + gtid; i < hi; i += kGroupThreads)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(base + 4u * i), "l"(src + i) : "memory");
   }
+  return false;
 }
 
 // STEP1: bin_step == 1 (fft 2048 proper): every bin is kept, no per-bin tests.
@@ -159,13 +208,16 @@ stft2048_kernel(const Params p) {
   float* sWindow = smem;                                        // [16][32] x {w(n1), w(n1+1)} float2 pairs, x 1/2
   float2* sTwPass = reinterpret_cast<float2*>(sWindow + kFft);  // [16][32][2]  W_1024^(k1 n2), k1 = 2 pair + {0,1}
   float2* sTwPost = sTwPass + 1024;                             // [32]         W_2048^l
-  float* sMelVals = reinterpret_cast<float*>(sTwPost + 32);     // band weights, round by round
+  float* sMelVals = reinterpret_cast<float*>(sTwPost + 32);     // band weights [round][step][lane] x float4
   const int nnz_pad = (p.a.nnz + 3) & ~3;
-  MelLane* sMelLanes = reinterpret_cast<MelLane*>(sMelVals + nnz_pad);   // [warps][rounds][2 kLF]
+  MelPiece* sPieces = reinterpret_cast<MelPiece*>(sMelVals + nnz_pad);   // [warps][rounds][32]
+  unsigned short* sPstart = reinterpret_cast<unsigned short*>(sPieces + kGroupWarps * p.a.mel_rounds * 32);
+  __shared__ __align__(8) uint64_t sbars[kMaxGroups];          // bulk copy of a group's samples landed
   // offsets stay integers so every pointer keeps its shared-memory provenance
   // (generic LD/ST would go through the slower generic path)
   const int tables_bytes = (kFft + 2 * 1024 + 2 * 32 + nnz_pad) * 4 +
-                           kGroupWarps * p.a.mel_rounds * 2 * kLF * (int)sizeof(MelLane);
+                           kGroupWarps * p.a.mel_rounds * 32 * (int)sizeof(MelPiece) +
+                           (((p.a.n_mels + 2) * 2 + 3) & ~3);
   float* groups_base = smem + (((tables_bytes + 15) & ~15) >> 2);
   const int group_floats = p.span_cap + kTile * kRowStride;
 
@@ -189,9 +241,16 @@ stft2048_kernel(const Params p) {
   if (tid < 32) sTwPost[tid] = p.a.tw_post[tid];
   if (OUT == kFastMel) {
     for (int i = tid; i < p.a.nnz; i += blockDim.x) sMelVals[i] = p.a.vals[i];
-    for (int i = tid; i < kGroupWarps * p.a.mel_rounds * 2 * kLF; i += blockDim.x) sMelLanes[i] = p.a.mel_lanes[i];
+    for (int i = tid; i < kGroupWarps * p.a.mel_rounds * 32; i += blockDim.x) sPieces[i] = p.a.mel_pieces[i];
+    for (int i = tid; i <= p.a.n_mels; i += blockDim.x) sPstart[i] = p.a.mel_pstart[i];
+  }
+  if (tid == 0) {
+    for (int gI = 0; gI < kMaxGroups; ++gI) mbar_init(smem_u32(&sbars[gI]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  const uint32_t sbar = smem_u32(&sbars[group]);
+  uint32_t sphase = 0;
 
   const FrameGeom g = p.a.g;
   const int bin_shift = STEP1 ? 0 : 31 - __clz(p.a.bin_step), bin_mask = STEP1 ? 0 : p.a.bin_step - 1;
@@ -202,7 +261,8 @@ stft2048_kernel(const Params p) {
   float* row = sRows + warp * kRowStride;
   float2* ex = reinterpret_cast<float2*>(row);
 
-  if (slot < total_tiles) stage_tile(p, slot, sSamples, gtid);
+  bool bulk = false;
+  if (slot < total_tiles) bulk = stage_tile(p, slot, sSamples, gtid, sbar);
   for (int tile = slot; tile < total_tiles; tile += stride) {
     const int b = tile / tiles_per_signal;
     const long long p0 = (long long)(tile - b * tiles_per_signal) * kTile;
@@ -210,7 +270,12 @@ stft2048_kernel(const Params p) {
 
     // ---- the tile's samples were requested one iteration ago (or just above
     // the loop): wait for this thread's copies, then for the group's.
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (bulk) {
+      mbar_wait(sbar, sphase & 1);
+      ++sphase;
+    } else {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
     group_sync(group);
 
     if (warp < nf) {
@@ -326,45 +391,39 @@ stft2048_kernel(const Params p) {
 
     // ---- the sample buffer is free: start fetching the next tile's samples
     // under the mel / write-out phases.
-    if (tile + stride < total_tiles) stage_tile(p, tile + stride, sSamples, gtid);
+    if (tile + stride < total_tiles) bulk = stage_tile(p, tile + stride, sSamples, gtid, sbar);
 
     if (OUT == kFastMel) {
-      // ---- mel projection over the tile's power rows.  A warp takes 2 kLF
-      // filters of near-equal band length at a time: lane = (filter j of kLF,
-      // frame f) and carries filter j of set A and of set B side by side (two
-      // independent accumulator sets hide the shared-memory latency).  Weights
-      // are interleaved [step][set][half][j] so a warp-wide load is one
-      // contiguous run; power rows are 16-byte aligned and kRowStride spreads
-      // the frames of a tile over the banks (with 4-frame tiles the host also
-      // starts neighbouring filters an odd number of float4s apart), so the value
-      // loads are conflict-free too.
-      const int f = lane & (kTile - 1), j = lane / kTile;
-      const float4* prow4 = reinterpret_cast<const float4*>(sRows + f * kRowStride);
-      float* mel_out = sRows + f * kRowStride + kMelOutOff;
-      const MelLane* mine = sMelLanes + warp * p.a.mel_rounds * (2 * kLF) + j;
+      // ---- mel projection over the tile's power rows.  A lane carries one piece
+      // (a few float4 steps of one filter's band) for all the frames of the tile:
+      // the weight load is one contiguous run per warp, the rows' loads fall in
+      // distinct bank groups across a quarter-warp (host schedule); a warp's
+      // pieces in a round share one step count, so there is no divergence.
+      const MelPiece* mine = sPieces + warp * p.a.mel_rounds * 32 + lane;
+      float* part = sRows + kMelOutOff;
       for (int r = 0; r < p.a.mel_rounds; ++r) {
-        const MelLane qa = mine[r * 2 * kLF], qb = mine[r * 2 * kLF + kLF];
-        const float4* wa = reinterpret_cast<const float4*>(sMelVals + qa.off);
-        const float4* wb = reinterpret_cast<const float4*>(sMelVals + qb.off);
-        const float4* va = prow4 + (qa.lo >> 2);
-        const float4* vb = prow4 + (qb.lo >> 2);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-        // the trip count is the same for the whole warp: no divergence
-        for (int i = 0; i < qa.n8; ++i) {
-          const float4 w0 = wa[4 * kLF * i], w1 = wa[4 * kLF * i + kLF], x0 = va[2 * i], x1 = va[2 * i + 1];
-          const float4 u0 = wb[4 * kLF * i], u1 = wb[4 * kLF * i + kLF], y0 = vb[2 * i], y1 = vb[2 * i + 1];
-          a0 = fmaf(w0.x, x0.x, a0); a1 = fmaf(w0.y, x0.y, a1);
-          a2 = fmaf(w0.z, x0.z, a2); a3 = fmaf(w0.w, x0.w, a3);
-          b0 = fmaf(u0.x, y0.x, b0); b1 = fmaf(u0.y, y0.y, b1);
-          b2 = fmaf(u0.z, y0.z, b2); b3 = fmaf(u0.w, y0.w, b3);
-          a0 = fmaf(w1.x, x1.x, a0); a1 = fmaf(w1.y, x1.y, a1);
-          a2 = fmaf(w1.z, x1.z, a2); a3 = fmaf(w1.w, x1.w, a3);
-          b0 = fmaf(u1.x, y1.x, b0); b1 = fmaf(u1.y, y1.y, b1);
-          b2 = fmaf(u1.z, y1.z, b2); b3 = fmaf(u1.w, y1.w, b3);
+        const MelPiece q = mine[r * 32];
+        const int steps = (int)((unsigned)q.off >> 24);
+        const float4* wq = reinterpret_cast<const float4*>(sMelVals + (q.off & 0xFFFFFF));
+        const float4* v = reinterpret_cast<const float4*>(sRows + q.lo);
+        float acc[kTile];
+#pragma unroll
+        for (int f = 0; f < kTile; ++f) acc[f] = 0.0f;
+        for (int i = 0; i < steps; ++i) {
+          const float4 ww = wq[32 * i];
+          float4 x[kTile];
+#pragma unroll
+          for (int f = 0; f < kTile; ++f) x[f] = v[f * (kRowStride / 4) + i];
+#pragma unroll
+          for (int f = 0; f < kTile; ++f) {
+            acc[f] = fmaf(ww.x, x[f].x, acc[f]);
+            acc[f] = fmaf(ww.y, x[f].y, acc[f]);
+            acc[f] = fmaf(ww.z, x[f].z, acc[f]);
+            acc[f] = fmaf(ww.w, x[f].w, acc[f]);
+          }
         }
-        mel_out[qa.out] = (a0 + a1) + (a2 + a3);
-        mel_out[qb.out] = (b0 + b1) + (b2 + b3);
+#pragma unroll
+        for (int f = 0; f < kTile; ++f) part[f * kRowStride + q.pid] = acc[f];
       }
       group_sync(group);
     }
@@ -378,8 +437,15 @@ stft2048_kernel(const Params p) {
           float* ob = p.a.out + ((long long)b * p.a.n_mels + r0) * g.frames + p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float* src = sRows + f * kRowStride + kMelOutOff;
-          for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step)
-            *ob = src[m];
+          // a filter's partial sums sit in consecutive slots (the slots behind its
+          // last one exist: padding of the partial area)
+          for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step) {
+            const int q0 = sPstart[m], cnt = sPstart[m + 1] - q0;
+            const float s0 = src[q0], s1 = src[q0 + 1], s2 = src[q0 + 2], s3 = src[q0 + 3];
+            float acc = (s0 + (cnt > 1 ? s1 : 0.0f)) + ((cnt > 2 ? s2 : 0.0f) + (cnt > 3 ? s3 : 0.0f));
+            for (int q = q0 + 4; q < q0 + cnt; ++q) acc += src[q];
+            *ob = acc;
+          }
         } else if (OUT == kFastPower) {
           const int out_bins = kHalf / p.a.bin_step + 1;
           float* ob = p.a.out + ((long long)b * out_bins + r0) * g.frames + p0 + f;
@@ -404,11 +470,12 @@ stft2048_kernel(const Params p) {
 
 }  // namespace
 
-static size_t smem_layout(int nnz, int mel_rounds, int span_cap, int groups) {
+static size_t smem_layout(int n_mels, int nnz, int mel_rounds, int span_cap, int groups) {
   const int nnz_pad = (nnz + 3) & ~3;
   size_t bytes = (size_t)(kFft + 2 * 1024 + 2 * 32) * 4;         // window, tw_pass, tw_post
   bytes += (size_t)nnz_pad * 4;                                    // band weights
-  bytes += (size_t)kGroupWarps * mel_rounds * 2 * kLF * sizeof(MelLane);      // warp schedule
+  bytes += (size_t)kGroupWarps * mel_rounds * 32 * sizeof(MelPiece);          // warp schedule
+  bytes += (size_t)(((n_mels + 2) * 2 + 3) & ~3);                  // partial-sum slots of each filter
   bytes = (bytes + 15) & ~(size_t)15;
   bytes += (size_t)groups * (span_cap + kTile * kRowStride) * 4;
   return bytes;
@@ -420,11 +487,16 @@ static int span_needed(const FrameGeom& g) {
   return (((kTile - 1) * g.hop + kFft) + 3) & ~3;
 }
 
-bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds) {
+bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds,
+                       int n_pieces) {
   if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;   // g: the kernel's geometry
-  if (out_kind == kFastMel && (n_mels < 1 || n_mels > kMaxMel || nnz > 65536)) return false;
+  // the partial sums of a frame live behind its power row, inside the row stride
+  if (out_kind == kFastMel && (n_mels < 1 || n_mels > 255 || nnz >= (1 << 24) ||
+                               kMelOutOff + n_pieces + 1 + 3 > kRowStride))
+    return false;
   const bool mel = out_kind == kFastMel;
-  return smem_layout(mel ? nnz : 0, mel ? mel_rounds : 0, span_needed(g), kMaxGroups / 2) <= kSmemLimit;
+  return smem_layout(mel ? n_mels : 0, mel ? nnz : 0, mel ? mel_rounds : 0, span_needed(g),
+                     kMaxGroups / 2) <= kSmemLimit;
 }
 
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st) {
@@ -443,14 +515,15 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
   }
   Params p;
   p.a = a;
-  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; }
+  p.use_bulk = getenv("SMB_NO_BULK") ? 0 : 1;
+  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; p.a.mel_n_pieces = 0; }
   p.span_cap = span_needed(a.g);
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
   p.total_tiles = p.tiles_per_signal * a.batch;
   // the full complement of groups per SM when their tiles fit shared memory, else half
-  const int groups = smem_layout(p.a.nnz, p.a.mel_rounds, p.span_cap, kMaxGroups) <= kSmemLimit
+  const int groups = smem_layout(p.a.n_mels, p.a.nnz, p.a.mel_rounds, p.span_cap, kMaxGroups) <= kSmemLimit
                          ? kMaxGroups : kMaxGroups / 2;
-  const size_t smem = smem_layout(p.a.nnz, p.a.mel_rounds, p.span_cap, groups);
+  const size_t smem = smem_layout(p.a.n_mels, p.a.nnz, p.a.mel_rounds, p.span_cap, groups);
   if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
   long long want = (p.total_tiles + groups - 1) / groups;
   const int grid = (int)(want < sm_count ? want : sm_count);

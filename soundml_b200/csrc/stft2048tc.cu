@@ -64,17 +64,6 @@ constexpr int kABytes = 128 * 128;        // one split of a pass's A operand
 constexpr int kBBytes = 64 * 128;         // one split of F
 constexpr int kMaxGroups = 4;
 
-__device__ constexpr float kW64C[16] = {
-    1.0f, 0.9951847266721969f, 0.9807852804032304f, 0.9569403357322088f,
-    0.9238795325112867f, 0.881921264348355f, 0.8314696123025452f, 0.773010453362737f,
-    0.7071067811865476f, 0.6343932841636455f, 0.5555702330196023f, 0.4713967368259978f,
-    0.38268343236508984f, 0.29028467725446233f, 0.19509032201612833f, 0.09801714032956077f};
-__device__ constexpr float kW64S[16] = {
-    0.0f, -0.0980171403295606f, -0.19509032201612825f, -0.2902846772544623f,
-    -0.3826834323650898f, -0.47139673682599764f, -0.5555702330196022f, -0.6343932841636455f,
-    -0.7071067811865475f, -0.773010453362737f, -0.8314696123025452f, -0.8819212643483549f,
-    -0.9238795325112867f, -0.9569403357322089f, -0.9807852804032304f, -0.9951847266721968f};
-
 __device__ __forceinline__ long long src_index(const FrameGeom& g, long long q) {
   long long s = q - g.left;
   if (s >= 0 && s < g.n) return s;
@@ -148,26 +137,7 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
   return r;
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                         uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// the same, the descriptors given by their low words (start address field) over the
+// tcgen05.mma, K-major SWIZZLE_128B operands (8-row groups 1024 B apart), the descriptors given by their low words (start address field) over the
 // common high word: the K-steps of a batch only move the start address
 __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc,
                                             bool accumulate) {
@@ -348,7 +318,7 @@ stft2048tc_kernel(const Params p) {
   float* sMelVals = sSamplesAll + kGroups * p.span_cap;
   const int nnz_pad = (p.a.nnz + 3) & ~3;
   MelPiece* sPieces = reinterpret_cast<MelPiece*>(sMelVals + nnz_pad);       // [warps][rounds][32]
-  unsigned short* sPstart = reinterpret_cast<unsigned short*>(sPieces + kTile * p.a.tc_rounds * 32);
+  unsigned short* sPstart = reinterpret_cast<unsigned short*>(sPieces + kTile * p.a.mel_rounds * 32);
 
   const int tid = threadIdx.x;
   const int group = tid / kGroupThreads;
@@ -368,8 +338,8 @@ stft2048tc_kernel(const Params p) {
   for (int i = tid; i < 512; i += blockDim.x) sTwPost[i] = p.a.tw_post[i];
   if (OUT == kFastMel) {
     for (int i = tid; i < p.a.nnz; i += blockDim.x) sMelVals[i] = p.a.vals[i];
-    for (int i = tid; i < kTile * p.a.tc_rounds * 32; i += blockDim.x) sPieces[i] = p.a.tc_pieces[i];
-    for (int i = tid; i <= p.a.n_mels; i += blockDim.x) sPstart[i] = p.a.tc_pstart[i];
+    for (int i = tid; i < kTile * p.a.mel_rounds * 32; i += blockDim.x) sPieces[i] = p.a.mel_pieces[i];
+    for (int i = tid; i <= p.a.n_mels; i += blockDim.x) sPstart[i] = p.a.mel_pstart[i];
   }
   if (tid == 0) {
     for (int gI = 0; gI < 2 * kMaxGroups; ++gI) mbar_init(smem_u32(&bars[gI]), 1);
@@ -722,9 +692,9 @@ stft2048tc_kernel(const Params p) {
       // (at most 4 float4 steps of one filter's band) for the four frames: the
       // weight load is one contiguous run per warp, every power value is read
       // once per filter it feeds; a warp's pieces in a round have one step count.
-      const MelPiece* mine = sPieces + warp * p.a.tc_rounds * 32 + lane;
+      const MelPiece* mine = sPieces + warp * p.a.mel_rounds * 32 + lane;
       float* part = sRows + kRowReal;
-      for (int r = 0; r < p.a.tc_rounds; ++r) {
+      for (int r = 0; r < p.a.mel_rounds; ++r) {
         const MelPiece q = mine[r * 32];
         const int steps = (int)((unsigned)q.off >> 24);
         const float4* wq = reinterpret_cast<const float4*>(sMelVals + (q.off & 0xFFFFFF));
@@ -901,16 +871,16 @@ cudaError_t launch_stft2048tc(const Stft2048Args& a, int out_kind, int sm_count,
   Params p;
   p.a = a;
   p.timing = nullptr;
-  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.tc_rounds = 0; p.a.tc_n_pieces = 0; }
+  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; p.a.mel_n_pieces = 0; }
   p.span_cap = span_needed(a.g);
-  p.region_bytes = region_needed(out_kind, p.a.tc_n_pieces);
-  p.row_stride = row_floats(out_kind, p.a.tc_n_pieces);
+  p.region_bytes = region_needed(out_kind, p.a.mel_n_pieces);
+  p.row_stride = row_floats(out_kind, p.a.mel_n_pieces);
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
   p.total_tiles = p.tiles_per_signal * a.batch;
   int groups = 4;
   if (const char* e = getenv("SMB_TC_GROUPS")) groups = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 4;   // experiments
   auto layout = [&](int gr) {
-    return smem_layout(out_kind, p.a.n_mels, p.a.nnz, p.a.tc_rounds, p.a.tc_n_pieces, p.span_cap, gr);
+    return smem_layout(out_kind, p.a.n_mels, p.a.nnz, p.a.mel_rounds, p.a.mel_n_pieces, p.span_cap, gr);
   };
   while (groups > 2 && layout(groups) > kSmemLimit) --groups;
   const size_t smem = layout(groups);
