@@ -319,14 +319,14 @@ struct smb_mel_plan {
   struct PieceSchedule {
     std::vector<float> vals;               // [round][step][lane] float4 weights
     std::vector<smb::MelPiece> pieces;     // [warps][rounds][32]
-    std::vector<unsigned short> pstart;    // [n_mels + 1]: partial-sum slots of each filter
-    int rounds = 0, n_pieces = 0;
+    std::vector<unsigned char> pcnt;       // [n_mels]: pieces (= partial sums) of each filter, 1..4
+    int rounds = 0, mpad = 0;              // partial-sum slot of (piece j, filter m) = j * mpad + m
     float* d_vals = nullptr;
     smb::MelPiece* d_pieces = nullptr;
-    unsigned short* d_pstart = nullptr;
-    void clear() { vals.clear(); pieces.clear(); pstart.clear(); rounds = n_pieces = 0; }
-    void to_device() { d_vals = upload(vals); d_pieces = upload(pieces); d_pstart = upload(pstart); }
-    void free_device() { cudaFree(d_vals); cudaFree(d_pieces); cudaFree(d_pstart); }
+    unsigned char* d_pcnt = nullptr;
+    void clear() { vals.clear(); pieces.clear(); pcnt.clear(); rounds = mpad = 0; }
+    void to_device() { d_vals = upload(vals); d_pieces = upload(pieces); d_pcnt = upload(pcnt); }
+    void free_device() { cudaFree(d_vals); cudaFree(d_pieces); cudaFree(d_pcnt); }
   };
   PieceSchedule sched_cc;   // CUDA-core kernel: kFastTile warps, 8 frames per lane
   PieceSchedule sched_tc;   // tensor-core kernel: kTcTile warps, 4 frames per lane
@@ -397,8 +397,9 @@ struct smb_mel_plan {
   // Mel schedule of the fused kernels.  Every filter's band, starting on a float4
   // of the power row, is cut into pieces of at most `ps` float4 steps; a lane
   // carries one piece for all the frames of its tile (one weight load feeds 4 FMAs
-  // per frame) and leaves a partial sum in slot `pid` (the slots of a filter are
-  // consecutive: pstart; the write-out adds them up).  Rounds of 32 lanes share one
+  // per frame) and leaves a partial sum in slot `pid` = j * mpad + m for the j-th
+  // piece of filter m (at most four per filter: `ps` grows with the longest band;
+  // the write-out adds the pcnt[m] of them up).  Rounds of 32 lanes share one
   // step count.  They are filled longest pieces first out of a window of
   // candidates, so that the lanes of a quarter-warp get distinct start residues
   // (start / 4 mod 8) where the window allows: their 16-byte power-row loads then
@@ -410,17 +411,24 @@ struct smb_mel_plan {
     const int row_floats = (int)((bins + 3) / 4 * 4);        // the kernel zeroes the row tail
     struct Piece { int m, start, steps, pid; };
     std::vector<Piece> pieces;
-    sc.pstart.assign((size_t)n_mels + 1, 0);
+    sc.pcnt.assign((size_t)n_mels, 1);
+    sc.mpad = (int)((n_mels + 7) / 8 * 8);
+    int longest = 1;
     for (int64_t m = 0; m < n_mels; ++m) {
-      sc.pstart[(size_t)m] = (unsigned short)pieces.size();
+      const int lo = band_lo[(size_t)m] & ~3, hi = std::max(band_hi[(size_t)m], lo + 1);
+      longest = std::max(longest, (hi - lo + 3) / 4);
+    }
+    ps = std::max(ps, (longest + 3) / 4);                // no filter in more than four pieces
+    if (ps > 255) return false;
+    for (int64_t m = 0; m < n_mels; ++m) {
       const int lo = band_lo[(size_t)m] & ~3, hi = std::max(band_hi[(size_t)m], lo + 1);
       const int total = (hi - lo + 3) / 4;
-      for (int s0 = 0; s0 < total; s0 += ps)
-        pieces.push_back(Piece{(int)m, lo + 4 * s0, std::min(ps, total - s0), (int)pieces.size()});
-      if (pieces.size() > 4000) return false;
+      int j = 0;
+      for (int s0 = 0; s0 < total; s0 += ps, ++j)
+        pieces.push_back(Piece{(int)m, lo + 4 * s0, std::min(ps, total - s0), j * sc.mpad + (int)m});
+      sc.pcnt[(size_t)m] = (unsigned char)j;
     }
-    sc.pstart[(size_t)n_mels] = (unsigned short)pieces.size();
-    sc.n_pieces = (int)pieces.size();
+    const int scratch = 4 * sc.mpad;                     // idle lanes drop their zeros here
     // pieces longest first; a round is picked from the first `window` of them
     std::vector<int> rest(pieces.size());
     for (size_t i = 0; i < rest.size(); ++i) rest[i] = (int)i;
@@ -508,11 +516,11 @@ struct smb_mel_plan {
             const Round& rd = built[(size_t)lists[(size_t)w][(size_t)r]];
             out.off = (int)(rd.base + (size_t)t * 4) | (rd.steps << 24);
             out.lo = (short)rd.start[t];
-            out.pid = (unsigned short)(rd.member[t] >= 0 ? pieces[(size_t)rd.member[t]].pid : sc.n_pieces);
+            out.pid = (unsigned short)(rd.member[t] >= 0 ? pieces[(size_t)rd.member[t]].pid : scratch);
           } else {
             out.off = (int)(zero_off + (size_t)t * 4) | (1 << 24);
             out.lo = 0;
-            out.pid = (unsigned short)sc.n_pieces;
+            out.pid = (unsigned short)scratch;
           }
         }
     return true;
@@ -964,11 +972,11 @@ int want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int ou
   const bool ok_tc = base && smb::stft2048tc_supports(gk, out_kind, mel ? (int)mel->n_mels : 0,
                                                       mel ? (int)mel->sched_tc.vals.size() : 0,
                                                       mel ? mel->sched_tc.rounds : 0,
-                                                      mel ? mel->sched_tc.n_pieces : 0);
+                                                      mel ? mel->sched_tc.mpad : 0);
   const bool ok_cc = base && smb::stft2048_supports(gk, out_kind, mel ? (int)mel->n_mels : 0,
                                                     mel ? (int)mel->sched_cc.vals.size() : 0,
                                                     mel ? mel->sched_cc.rounds : 0,
-                                                    mel ? mel->sched_cc.n_pieces : 0);
+                                                    mel ? mel->sched_cc.mpad : 0);
   if (p->path == SMB_PATH_TENSOR) {
     if (!ok_tc)
       throw smb::invalid_argument(
@@ -1408,9 +1416,9 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
         a.nnz = (int)sc.vals.size();
         a.vals = sc.d_vals;
         a.mel_pieces = sc.d_pieces;
-        a.mel_pstart = sc.d_pstart;
+        a.mel_pcnt = sc.d_pcnt;
         a.mel_rounds = sc.rounds;
-        a.mel_n_pieces = sc.n_pieces;
+        a.mel_mpad = sc.mpad;
         if (fast == SMB_PATH_TENSOR) CK(smb::launch_stft2048tc(a, smb::kFastMel, stft->sm_count, st));
         else CK(smb::launch_stft2048(a, smb::kFastMel, stft->sm_count, st));
       } else {

@@ -66,7 +66,7 @@ constexpr int kFastTile = 8;
 struct MelPiece {
   int off;                 // weights: float offset of [step 0][lane] (low 24 bits), steps of the round (high 8)
   short lo;                // first bin read (multiple of 4)
-  unsigned short pid;      // partial-sum slot (mel_n_pieces = scratch)
+  unsigned short pid;      // partial-sum slot j * mel_mpad + m (4 * mel_mpad = scratch)
 };
 constexpr int kFastPieceSteps = 3;     // float4 steps per piece, CUDA-core kernel (8 frames per lane)
 constexpr int kTcPieceSteps = 4;       // tensor-core kernel (4 frames per lane)
@@ -83,8 +83,8 @@ struct Stft2048Args {
   int n_mels, nnz;
   const float* vals;               // [nnz] weights, [round][step][lane] x float4
   const MelPiece* mel_pieces;      // [warps of a group][mel_rounds][32 lanes]
-  const unsigned short* mel_pstart;   // [n_mels + 1] partial-sum slots of each filter
-  int mel_rounds, mel_n_pieces;
+  const unsigned char* mel_pcnt;   // [n_mels] partial sums of each filter (1..4)
+  int mel_rounds, mel_mpad;        // partial-sum slot of (piece j, filter m) = j * mel_mpad + m
   float power;
   int bin_step;                // 2048 / fft_size: 1, or 2/4/8/16 for zero-padded shorter frames
   // tensor-core variant (stft2048tc.cu) only: [hi, lo] fp16 images of the real 64 x 64
@@ -94,13 +94,13 @@ struct Stft2048Args {
 // True when the fused kernel can take this geometry (hop small enough for the
 // shared-memory sample tile, mel tables small enough to be resident).
 bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds,
-                       int n_pieces);
+                       int mpad);
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
 // Tensor-core variant: both 32-point passes as split-fp16 products on tcgen05, a
 // tile = kTcTile frames = 128 MMA rows per group of kTcTile warps.
 constexpr int kTcTile = 4;
 bool stft2048tc_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds,
-                         int n_pieces);
+                         int mpad);
 cudaError_t launch_stft2048tc(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
 
 // ---- resampler / FIR ----------------------------------------------------------

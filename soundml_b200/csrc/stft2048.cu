@@ -211,13 +211,13 @@ stft2048_kernel(const Params p) {
   float* sMelVals = reinterpret_cast<float*>(sTwPost + 32);     // band weights [round][step][lane] x float4
   const int nnz_pad = (p.a.nnz + 3) & ~3;
   MelPiece* sPieces = reinterpret_cast<MelPiece*>(sMelVals + nnz_pad);   // [warps][rounds][32]
-  unsigned short* sPstart = reinterpret_cast<unsigned short*>(sPieces + kGroupWarps * p.a.mel_rounds * 32);
+  unsigned char* sPcnt = reinterpret_cast<unsigned char*>(sPieces + kGroupWarps * p.a.mel_rounds * 32);
   __shared__ __align__(8) uint64_t sbars[kMaxGroups];          // bulk copy of a group's samples landed
   // offsets stay integers so every pointer keeps its shared-memory provenance
   // (generic LD/ST would go through the slower generic path)
   const int tables_bytes = (kFft + 2 * 1024 + 2 * 32 + nnz_pad) * 4 +
                            kGroupWarps * p.a.mel_rounds * 32 * (int)sizeof(MelPiece) +
-                           (((p.a.n_mels + 2) * 2 + 3) & ~3);
+                           ((p.a.n_mels + 3) & ~3);
   float* groups_base = smem + (((tables_bytes + 15) & ~15) >> 2);
   const int group_floats = p.span_cap + kTile * kRowStride;
 
@@ -242,7 +242,7 @@ stft2048_kernel(const Params p) {
   if (OUT == kFastMel) {
     for (int i = tid; i < p.a.nnz; i += blockDim.x) sMelVals[i] = p.a.vals[i];
     for (int i = tid; i < kGroupWarps * p.a.mel_rounds * 32; i += blockDim.x) sPieces[i] = p.a.mel_pieces[i];
-    for (int i = tid; i <= p.a.n_mels; i += blockDim.x) sPstart[i] = p.a.mel_pstart[i];
+    for (int i = tid; i < p.a.n_mels; i += blockDim.x) sPcnt[i] = p.a.mel_pcnt[i];
   }
   if (tid == 0) {
     for (int gI = 0; gI < kMaxGroups; ++gI) mbar_init(smem_u32(&sbars[gI]), 1);
@@ -437,14 +437,13 @@ stft2048_kernel(const Params p) {
           float* ob = p.a.out + ((long long)b * p.a.n_mels + r0) * g.frames + p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float* src = sRows + f * kRowStride + kMelOutOff;
-          // a filter's partial sums sit in consecutive slots (the slots behind its
-          // last one exist: padding of the partial area)
+          // the j-th partial sum of filter m sits at j * mpad + m (up to four; slots a
+          // filter does not use hold stale bits and are masked out, never added)
+          const int mpad = p.a.mel_mpad;
           for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step) {
-            const int q0 = sPstart[m], cnt = sPstart[m + 1] - q0;
-            const float s0 = src[q0], s1 = src[q0 + 1], s2 = src[q0 + 2], s3 = src[q0 + 3];
-            float acc = (s0 + (cnt > 1 ? s1 : 0.0f)) + ((cnt > 2 ? s2 : 0.0f) + (cnt > 3 ? s3 : 0.0f));
-            for (int q = q0 + 4; q < q0 + cnt; ++q) acc += src[q];
-            *ob = acc;
+            const int cnt = sPcnt[m];
+            const float s0 = src[m], s1 = src[mpad + m], s2 = src[2 * mpad + m], s3 = src[3 * mpad + m];
+            *ob = (s0 + (cnt > 1 ? s1 : 0.0f)) + ((cnt > 2 ? s2 : 0.0f) + (cnt > 3 ? s3 : 0.0f));
           }
         } else if (OUT == kFastPower) {
           const int out_bins = kHalf / p.a.bin_step + 1;
@@ -475,7 +474,7 @@ static size_t smem_layout(int n_mels, int nnz, int mel_rounds, int span_cap, int
   size_t bytes = (size_t)(kFft + 2 * 1024 + 2 * 32) * 4;         // window, tw_pass, tw_post
   bytes += (size_t)nnz_pad * 4;                                    // band weights
   bytes += (size_t)kGroupWarps * mel_rounds * 32 * sizeof(MelPiece);          // warp schedule
-  bytes += (size_t)(((n_mels + 2) * 2 + 3) & ~3);                  // partial-sum slots of each filter
+  bytes += (size_t)((n_mels + 3) & ~3);                            // partial sums per filter
   bytes = (bytes + 15) & ~(size_t)15;
   bytes += (size_t)groups * (span_cap + kTile * kRowStride) * 4;
   return bytes;
@@ -488,11 +487,11 @@ static int span_needed(const FrameGeom& g) {
 }
 
 bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds,
-                       int n_pieces) {
+                       int mpad) {
   if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;   // g: the kernel's geometry
   // the partial sums of a frame live behind its power row, inside the row stride
   if (out_kind == kFastMel && (n_mels < 1 || n_mels > 255 || nnz >= (1 << 24) ||
-                               kMelOutOff + n_pieces + 1 + 3 > kRowStride))
+                               kMelOutOff + 4 * mpad + 1 > kRowStride))
     return false;
   const bool mel = out_kind == kFastMel;
   return smem_layout(mel ? n_mels : 0, mel ? nnz : 0, mel ? mel_rounds : 0, span_needed(g),
@@ -516,7 +515,7 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
   Params p;
   p.a = a;
   p.use_bulk = getenv("SMB_NO_BULK") ? 0 : 1;
-  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; p.a.mel_n_pieces = 0; }
+  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; p.a.mel_mpad = 0; }
   p.span_cap = span_needed(a.g);
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
   p.total_tiles = p.tiles_per_signal * a.batch;

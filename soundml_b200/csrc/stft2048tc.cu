@@ -58,8 +58,6 @@ constexpr int kGroupThreads = 32 * kTile;
 static_assert(kTile == 4, "one warp per frame, 128 TMEM lanes per tile");
 constexpr int kRowReal = 1032;            // floats per power row (mel partial sums follow it)
 constexpr int kRowComplex = 2056;         // floats per complex row, = 8 mod 32
-constexpr int kMelOutOff = 1032;
-constexpr int kMaxMel = 128;
 constexpr int kABytes = 128 * 128;        // one split of a pass's A operand
 constexpr int kBBytes = 64 * 128;         // one split of F
 constexpr int kMaxGroups = 4;
@@ -309,7 +307,7 @@ stft2048tc_kernel(const Params p) {
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   const uint32_t smem_addr = raw_addr + pad;
-  // [F hi | F lo] [regions x groups] [tw_pass] [tw_post] [samples x groups] [mel vals] [pieces] [pstart]
+  // [F hi | F lo] [regions x groups] [tw_pass] [tw_post] [samples x groups] [mel vals] [pieces] [pcnt]
   const uint32_t regions_off = 2 * kBBytes;
   const uint32_t tables_off = regions_off + kGroups * p.region_bytes;
   float2* sTwPass = reinterpret_cast<float2*>(smem + tables_off);           // [16][32][2] W_1024^(k1 n2)
@@ -318,7 +316,7 @@ stft2048tc_kernel(const Params p) {
   float* sMelVals = sSamplesAll + kGroups * p.span_cap;
   const int nnz_pad = (p.a.nnz + 3) & ~3;
   MelPiece* sPieces = reinterpret_cast<MelPiece*>(sMelVals + nnz_pad);       // [warps][rounds][32]
-  unsigned short* sPstart = reinterpret_cast<unsigned short*>(sPieces + kTile * p.a.mel_rounds * 32);
+  unsigned char* sPcnt = reinterpret_cast<unsigned char*>(sPieces + kTile * p.a.mel_rounds * 32);
 
   const int tid = threadIdx.x;
   const int group = tid / kGroupThreads;
@@ -339,7 +337,7 @@ stft2048tc_kernel(const Params p) {
   if (OUT == kFastMel) {
     for (int i = tid; i < p.a.nnz; i += blockDim.x) sMelVals[i] = p.a.vals[i];
     for (int i = tid; i < kTile * p.a.mel_rounds * 32; i += blockDim.x) sPieces[i] = p.a.mel_pieces[i];
-    for (int i = tid; i <= p.a.n_mels; i += blockDim.x) sPstart[i] = p.a.mel_pstart[i];
+    for (int i = tid; i < p.a.n_mels; i += blockDim.x) sPcnt[i] = p.a.mel_pcnt[i];
   }
   if (tid == 0) {
     for (int gI = 0; gI < 2 * kMaxGroups; ++gI) mbar_init(smem_u32(&bars[gI]), 1);
@@ -508,7 +506,6 @@ stft2048tc_kernel(const Params p) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t off = ks * 32;               // 16 halves = 32 bytes along K
         umma_f16_lo(acc1, dl_a_hi + 2 * ks, dl_f_hi + 2 * ks, kIdesc, ks > 0);
         umma_f16_lo(acc1, dl_a_lo + 2 * ks, dl_f_hi + 2 * ks, kIdesc, true);
         umma_f16_lo(acc1, dl_a_hi + 2 * ks, dl_f_lo + 2 * ks, kIdesc, true);
@@ -583,7 +580,6 @@ stft2048tc_kernel(const Params p) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t off = ks * 32;
         umma_f16_lo(acc2, dl_a_hi + 2 * ks, dl_f_hi + 2 * ks, kIdesc, ks > 0);
         umma_f16_lo(acc2, dl_a_lo + 2 * ks, dl_f_hi + 2 * ks, kIdesc, true);
         umma_f16_lo(acc2, dl_a_hi + 2 * ks, dl_f_lo + 2 * ks, kIdesc, true);
@@ -759,28 +755,13 @@ stft2048tc_kernel(const Params p) {
           float* ob = p.a.out + ((long long)b * p.a.n_mels + r0) * g.frames + p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float* src = sRows + f * p.row_stride + kRowReal;
-          // four filters per trip, all their loads ahead of the adds and the stores
-          // (the slots behind a filter's last one exist: padding of the partial area)
-          for (int m0 = r0; m0 < p.a.n_mels; m0 += 4 * (kGroupThreads / kTile), ob += 4 * step) {
-            int q0[4], cnt[4];
-            float v[4][4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int m = min(m0 + u * (kGroupThreads / kTile), p.a.n_mels - 1);
-              q0[u] = sPstart[m];
-              cnt[u] = sPstart[m + 1] - q0[u];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-              for (int t = 0; t < 4; ++t) v[u][t] = src[q0[u] + t];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float acc = (v[u][0] + (cnt[u] > 1 ? v[u][1] : 0.0f)) +
-                          ((cnt[u] > 2 ? v[u][2] : 0.0f) + (cnt[u] > 3 ? v[u][3] : 0.0f));
-              for (int q = q0[u] + 4; q < q0[u] + cnt[u]; ++q) acc += src[q];
-              if (m0 + u * (kGroupThreads / kTile) < p.a.n_mels) ob[u * step] = acc * post;
-            }
+          // the j-th partial sum of filter m sits at j * mpad + m (up to four; slots a
+          // filter does not use hold stale bits and are masked out, never added)
+          const int mpad = p.a.mel_mpad;
+          for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step) {
+            const int cnt = sPcnt[m];
+            const float s0 = src[m], s1 = src[mpad + m], s2 = src[2 * mpad + m], s3 = src[3 * mpad + m];
+            *ob = ((s0 + (cnt > 1 ? s1 : 0.0f)) + ((cnt > 2 ? s2 : 0.0f) + (cnt > 3 ? s3 : 0.0f))) * post;
           }
         } else if (OUT == kFastPower) {
           const int out_bins = kHalf / p.a.bin_step + 1;
@@ -821,38 +802,38 @@ static const size_t kSmemLimit = 232448;   // 227 KB opt-in maximum per CTA
 static int span_needed(const FrameGeom& g) {
   return (((kTile - 1) * g.hop + kFft) + 3) & ~3;
 }
-static int row_floats(int out_kind, int n_pieces) {
+static int row_floats(int out_kind, int mpad) {
   if (out_kind == kFastComplex) return kRowComplex;
   if (out_kind == kFastPower) return kRowReal;
-  return kRowReal + ((n_pieces + 1 + 3 + 3) & ~3);      // partial sums (+ one scratch slot, + 3 read past the end)
+  return kRowReal + ((4 * mpad + 1 + 3) & ~3);          // partial sums [4][mpad] + one scratch slot
 }
-static int region_needed(int out_kind, int n_pieces) {
-  const int rows = kTile * row_floats(out_kind, n_pieces) * 4;
+static int region_needed(int out_kind, int mpad) {
+  const int rows = kTile * row_floats(out_kind, mpad) * 4;
   const int need = rows > 2 * kABytes ? rows : 2 * kABytes;
   return (need + 1023) & ~1023;
 }
-static size_t smem_layout(int out_kind, int n_mels, int nnz, int mel_rounds, int n_pieces, int span_cap,
+static size_t smem_layout(int out_kind, int n_mels, int nnz, int mel_rounds, int mpad, int span_cap,
                           int groups) {
   const int nnz_pad = (nnz + 3) & ~3;
   size_t bytes = 1024;                                             // alignment slack
   bytes += 2 * kBBytes;
-  bytes += (size_t)groups * region_needed(out_kind, n_pieces);
+  bytes += (size_t)groups * region_needed(out_kind, mpad);
   bytes += (size_t)(2 * 1024 + 2 * 512) * 4;                       // tw_pass, tw_post
   bytes += (size_t)groups * span_cap * 4;
   bytes += (size_t)nnz_pad * 4;
   bytes += (size_t)kTile * mel_rounds * 32 * sizeof(MelPiece);
-  bytes += (size_t)(n_mels + 2) * sizeof(unsigned short);
+  bytes += (size_t)((n_mels + 3) & ~3);
   return bytes;
 }
 
 bool stft2048tc_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds,
-                         int n_pieces) {
+                         int mpad) {
   if (g.fft != kFft || g.hop < 1 || g.hop > 4096) return false;
-  if (out_kind == kFastMel && (n_mels < 1 || n_mels > 255 || nnz >= (1 << 24) || n_pieces > 4000))
+  if (out_kind == kFastMel && (n_mels < 1 || n_mels > 255 || nnz >= (1 << 24) || mpad > 256))
     return false;
   const bool mel = out_kind == kFastMel;
   return smem_layout(out_kind, mel ? n_mels : 0, mel ? nnz : 0, mel ? mel_rounds : 0,
-                     mel ? n_pieces : 0, span_needed(g), 2) <= kSmemLimit;
+                     mel ? mpad : 0, span_needed(g), 2) <= kSmemLimit;
 }
 
 cudaError_t launch_stft2048tc(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st) {
@@ -871,16 +852,16 @@ cudaError_t launch_stft2048tc(const Stft2048Args& a, int out_kind, int sm_count,
   Params p;
   p.a = a;
   p.timing = nullptr;
-  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; p.a.mel_n_pieces = 0; }
+  if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; p.a.mel_mpad = 0; }
   p.span_cap = span_needed(a.g);
-  p.region_bytes = region_needed(out_kind, p.a.mel_n_pieces);
-  p.row_stride = row_floats(out_kind, p.a.mel_n_pieces);
+  p.region_bytes = region_needed(out_kind, p.a.mel_mpad);
+  p.row_stride = row_floats(out_kind, p.a.mel_mpad);
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
   p.total_tiles = p.tiles_per_signal * a.batch;
   int groups = 4;
   if (const char* e = getenv("SMB_TC_GROUPS")) groups = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 4;   // experiments
   auto layout = [&](int gr) {
-    return smem_layout(out_kind, p.a.n_mels, p.a.nnz, p.a.mel_rounds, p.a.mel_n_pieces, p.span_cap, gr);
+    return smem_layout(out_kind, p.a.n_mels, p.a.nnz, p.a.mel_rounds, p.a.mel_mpad, p.span_cap, gr);
   };
   while (groups > 2 && layout(groups) > kSmemLimit) --groups;
   const size_t smem = layout(groups);
