@@ -463,7 +463,9 @@ stft2048_kernel(const Params p) {
         }
       }
     }
-    group_sync(group);
+    // no barrier here: nothing writes shared memory before the group barrier at the
+    // top of the next iteration, which orders these row reads before the next
+    // tile's transposes
   }
 }
 
