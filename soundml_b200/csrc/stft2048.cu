@@ -132,6 +132,12 @@ struct Params {
   int use_bulk;              // interior tiles by one bulk copy (SMB_NO_BULK=1 turns it off)
   int span_cap;              // floats reserved per group for samples
   long long tiles_per_signal, total_tiles;
+  // bin-major outputs (power / complex): a group walks a contiguous run of tiles and
+  // keeps the frames that do not fill a 32-byte sector of an output row until the
+  // next tile completes it (see the write-out); carry_cap = floats per group, 0 = off
+  int carry_cap;
+  int carry_period;              // carried elements per S consecutive rows
+  unsigned long long carry_prefix;   // byte i: carried elements of the rows before row i of a period
 };
 
 // Brings one tile's samples (padded stream positions p0*hop .. + span) into the
@@ -219,7 +225,7 @@ stft2048_kernel(const Params p) {
                            kGroupWarps * p.a.mel_rounds * 32 * (int)sizeof(MelPiece) +
                            ((p.a.n_mels + 3) & ~3);
   float* groups_base = smem + (((tables_bytes + 15) & ~15) >> 2);
-  const int group_floats = p.span_cap + kTile * kRowStride;
+  const int group_floats = p.span_cap + kTile * kRowStride + p.carry_cap;
 
   const int tid = threadIdx.x;
   const int group = tid / kGroupThreads;
@@ -228,6 +234,7 @@ stft2048_kernel(const Params p) {
   const int lane = tid & 31;
   float* sSamples = groups_base + group * group_floats;
   float* sRows = sSamples + p.span_cap;
+  float* sCarry = sRows + kTile * kRowStride;
 
   for (int i = tid; i < kFft; i += blockDim.x) {
     // source index j = 2 (32 n1 + l) + c  ->  ((n1/2) * 32 + l) * 4 + (n1 & 1) * 2 + c
@@ -261,9 +268,17 @@ stft2048_kernel(const Params p) {
   float* row = sRows + warp * kRowStride;
   float2* ex = reinterpret_cast<float2*>(row);
 
+  // mel: tiles dealt round-robin; bin-major outputs with a carry: contiguous runs
+  int first = slot, last = total_tiles, tstep = stride;
+  if (OUT != kFastMel && p.carry_cap) {
+    const int run = (total_tiles + stride - 1) / stride;
+    first = min(slot * run, total_tiles);
+    last = min(first + run, total_tiles);
+    tstep = 1;
+  }
   bool bulk = false;
-  if (slot < total_tiles) bulk = stage_tile(p, slot, sSamples, gtid, sbar);
-  for (int tile = slot; tile < total_tiles; tile += stride) {
+  if (first < last) bulk = stage_tile(p, first, sSamples, gtid, sbar);
+  for (int tile = first; tile < last; tile += tstep) {
     const int b = tile / tiles_per_signal;
     const long long p0 = (long long)(tile - b * tiles_per_signal) * kTile;
     const int nf = (int)min((long long)kTile, g.frames - p0);
@@ -391,7 +406,7 @@ stft2048_kernel(const Params p) {
 
     // ---- the sample buffer is free: start fetching the next tile's samples
     // under the mel / write-out phases.
-    if (tile + stride < total_tiles) bulk = stage_tile(p, tile + stride, sSamples, gtid, sbar);
+    if (tile + tstep < last) bulk = stage_tile(p, tile + tstep, sSamples, gtid, sbar);
 
     if (OUT == kFastMel) {
       // ---- mel projection over the tile's power rows.  A lane carries one piece
@@ -432,8 +447,8 @@ stft2048_kernel(const Params p) {
     // consecutive lanes carry the tile's frames of one output row.
     {
       const int f = gtid & (kTile - 1), r0 = gtid / kTile;
-      if (f < nf) {
-        if (OUT == kFastMel) {
+      if (OUT == kFastMel) {
+        if (f < nf) {
           float* ob = p.a.out + ((long long)b * p.a.n_mels + r0) * g.frames + p0 + f;
           const long long step = (long long)(kGroupThreads / kTile) * g.frames;
           const float* src = sRows + f * kRowStride + kMelOutOff;
@@ -445,21 +460,51 @@ stft2048_kernel(const Params p) {
             const float s0 = src[m], s1 = src[mpad + m], s2 = src[2 * mpad + m], s3 = src[3 * mpad + m];
             *ob = (s0 + (cnt > 1 ? s1 : 0.0f)) + ((cnt > 2 ? s2 : 0.0f) + (cnt > 3 ? s3 : 0.0f));
           }
-        } else if (OUT == kFastPower) {
-          const int out_bins = kHalf / p.a.bin_step + 1;
-          float* ob = p.a.out + ((long long)b * out_bins + r0) * g.frames + p0 + f;
-          const long long step = (long long)(kGroupThreads / kTile) * g.frames;
-          const float* src = sRows + f * kRowStride;
-          for (int r = r0; r < out_bins; r += kGroupThreads / kTile, ob += step)
-            *ob = src[r];
-        } else {
-          const int out_bins = kHalf / p.a.bin_step + 1;
-          float2* ob = reinterpret_cast<float2*>(p.a.out) + ((long long)b * out_bins + r0) * g.frames +
-                       p0 + f;
-          const long long step = (long long)(kGroupThreads / kTile) * g.frames;
-          const float2* src = reinterpret_cast<const float2*>(sRows + f * kRowStride);
-          for (int r = r0; r < out_bins; r += kGroupThreads / kTile, ob += step)
-            *ob = src[r];
+        }
+      }
+      if (OUT != kFastMel) {
+        // Rows are frames-contiguous and a tile's 8 frames start anywhere inside a
+        // 32-byte sector of the row (row length is odd at the headline shape), so a
+        // plain write leaves a partial sector at both ends of every run; L2 writes
+        // those back before the neighbouring tile fills them (ncu: +1.5 GB DRAM read,
+        // +0.9 GB write at 1024 clips).  Instead every row writes the 8 elements that
+        // start q = (row offset mod sector) before the tile: q carried over from the
+        // previous tile of the same clip (kept by the same thread, no barrier) plus
+        // its own first 8-q, and parks its last q.  First / last tiles of a clip or
+        // of the group's run write what they have.
+        typedef typename std::conditional<OUT == kFastComplex, float2, float>::type T;
+        constexpr int S = 32 / (int)sizeof(T);               // elements per sector
+        const int out_bins = kHalf / p.a.bin_step + 1;
+        const long long R0 = (long long)b * out_bins;
+        const int fm = (int)(g.frames & (S - 1));
+        const bool carrying = p.carry_cap != 0;
+        const bool has_carry = carrying && tile != first && p0 != 0;
+        const bool park = carrying && tile + tstep < last && p0 + kTile < g.frames;   // then nf == kTile
+        T* carry = reinterpret_cast<T*>(sCarry);
+        const T* src = reinterpret_cast<const T*>(sRows);
+        constexpr int kRowT = kRowStride * 4 / (int)sizeof(T);
+        T* out = reinterpret_cast<T*>(p.a.out);
+        // a thread's rows are kGroupThreads / kTile apart, a multiple of S: its phase
+        // in the sector period, hence q and its side of the split, never change
+        constexpr int kRows = kGroupThreads / kTile;
+        static_assert(kRows % S == 0, "row step keeps the sector phase");
+        const int ph = (int)((R0 + r0) & (S - 1));
+        const int q = carrying ? (ph * fm) & (S - 1) : 0;
+        const bool own = f >= q;
+        const int j0 = f - q, j1 = kTile - q + f;             // first-store frame / parked frame
+        const bool w = own ? j0 < nf : has_carry;
+        const bool tail = !own && j1 < nf;
+        int cs = p.carry_period * (int)(((R0 + r0) / S) - (R0 / S)) + (int)((p.carry_prefix >> (8 * ph)) & 0xff) + f;
+        const int cstep = p.carry_period * (kRows / S);
+        T* orow = out + (R0 + r0) * g.frames + p0;
+        const long long ostep = (long long)kRows * g.frames;
+        const T* s0 = src + (own ? j0 : 0) * kRowT, *s1 = src + (tail ? j1 : 0) * kRowT;
+        for (int r = r0; r < out_bins; r += kRows, orow += ostep, cs += cstep) {
+          if (w) orow[j0] = own ? s0[r] : carry[cs];
+          if (tail) {
+            if (park) carry[cs] = s1[r];
+            else orow[j1] = s1[r];
+          }
         }
       }
     }
@@ -524,8 +569,27 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
   // the full complement of groups per SM when their tiles fit shared memory, else half
   const int groups = smem_layout(p.a.n_mels, p.a.nnz, p.a.mel_rounds, p.span_cap, kMaxGroups) <= kSmemLimit
                          ? kMaxGroups : kMaxGroups / 2;
-  const size_t smem = smem_layout(p.a.n_mels, p.a.nnz, p.a.mel_rounds, p.span_cap, groups);
+  size_t smem = smem_layout(p.a.n_mels, p.a.nnz, p.a.mel_rounds, p.span_cap, groups);
   if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+  p.carry_cap = p.carry_period = 0;
+  p.carry_prefix = 0;
+  if (out_kind != kFastMel && !getenv("SMB_NO_CARRY")) {
+    // sector carry of the bin-major write-out: q(row) = (row * frames) mod S elements
+    const int S = out_kind == kFastComplex ? 4 : 8;
+    const int fm = (int)(a.g.frames & (S - 1));
+    int period = 0;
+    for (int i = 0; i < S; ++i) {
+      p.carry_prefix |= (unsigned long long)period << (8 * i);
+      period += (i * fm) & (S - 1);
+    }
+    const int out_bins = kHalf / a.bin_step + 1;
+    const int cap = ((period * (out_bins / S + 2) * (out_kind == kFastComplex ? 2 : 1)) + 3) & ~3;
+    if (period > 0 && smem + (size_t)groups * cap * 4 <= kSmemLimit) {
+      p.carry_cap = cap;
+      p.carry_period = period;
+      smem += (size_t)groups * cap * 4;
+    }
+  }
   long long want = (p.total_tiles + groups - 1) / groups;
   const int grid = (int)(want < sm_count ? want : sm_count);
   cudaError_t e;

@@ -366,3 +366,33 @@ def test_transform_range_tiles_the_full_transform(sb, fft, hop, path):
         sb.Stft.transform_range(c, x, 3, 2)
     with pytest.raises(ValueError, match=r"the range must satisfy 0 <= p0 <= p1 <= frames"):
         sb.Stft.transform_range(c, x, 0, total + 1)
+
+
+@pytest.mark.parametrize("frames", [431, 100, 101, 102, 104, 57, 9, 8, 3])
+@pytest.mark.parametrize("fft", [2048, 512])
+def test_bin_major_write_out_carries_sectors_across_tiles(sb, frames, fft, monkeypatch):
+    """The power / complex write-out of the fused kernel parks the frames that do
+    not fill a 32-byte sector of an output row and writes them with the next tile
+    of the same clip (stft2048.cu, write-out).  Batches large enough that a group
+    walks several tiles and crosses clip boundaries, row lengths of every phase
+    mod 8: same bits as the plain write-out, and the oracle's values."""
+    hop = fft // 4
+    n = (frames - 1) * hop + 3
+    batch = 19 if frames > 200 else 90            # > 296 tiles whenever frames > 8*4
+    x = np.stack([_signal(n, 100 + s) for s in range(batch)])
+    c = sb.Stft.Config.create(fft_size=fft, hop=hop).set_path("fast")
+    assert sb.Stft.frames(c, n) == frames
+    got_p = sb.Stft.power_spectrum(c, x)
+    got_z = sb.Stft.transform(c, x)
+    monkeypatch.setenv("SMB_NO_CARRY", "1")
+    plain_p = sb.Stft.power_spectrum(c, x)
+    plain_z = sb.Stft.transform(c, x)
+    monkeypatch.delenv("SMB_NO_CARRY")
+    assert np.array_equal(got_p, plain_p)
+    assert np.array_equal(got_z.view(np.float32), plain_z.view(np.float32))
+    o = stft_oracle.StftConfig(fft, hop)
+    ref = stft_oracle.power_spectrum(o, x[:8])
+    for b in range(8):
+        assert peak_rel_err(got_p[b], ref[b]) <= SPECTRUM_TOL, b
+    refz = stft_oracle.transform(o, x[-3:])
+    assert peak_rel_err(got_z[-3:].view(np.float32), refz.view(np.float32)) <= SPECTRUM_TOL

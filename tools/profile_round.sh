@@ -7,9 +7,8 @@ SMB_TC_TIMING=1 timeout 120 python bench.py --path tensor --no-e2e --steps 3 --w
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:stft2048 -c 20 --csv --log-file gpurun_out/launches.csv python bench.py --steps 10 --warmup 3 --no-e2e --cpu-seconds 0.5 > gpurun_out/launches.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:stft2048 -c 20 --csv --log-file gpurun_out/launches_tensor.csv python bench.py --path tensor --steps 10 --warmup 3 --no-e2e --cpu-seconds 0.5 > gpurun_out/launches_tensor.log 2>&1
 # full captures of both fused kernels
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:stft2048_kernel -s 3 -c 1 -o gpurun_out/r1i python bench.py --steps 3 --warmup 3 --no-e2e --cpu-seconds 0.5 > gpurun_out/r1i.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:stft2048tc -s 3 -c 1 -o gpurun_out/tc_d python bench.py --path tensor --steps 3 --warmup 3 --no-e2e --cpu-seconds 0.5 > gpurun_out/tc_d.log 2>&1
-tools/bench_umma_batch.bin > gpurun_out/umma_batch.txt 2>&1
-tools/bench_f32x2.bin > gpurun_out/f32x2.txt 2>&1
-tools/bench_fft32.bin > gpurun_out/fft32.txt 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:stft2048_kernel -s 3 -c 1 -o gpurun_out/r1k python bench.py --steps 3 --warmup 3 --no-e2e --cpu-seconds 0.5 > gpurun_out/r1k.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:stft2048tc -s 3 -c 1 -o gpurun_out/tc_e python bench.py --path tensor --steps 3 --warmup 3 --no-e2e --cpu-seconds 0.5 > gpurun_out/tc_e.log 2>&1
 tail -1 gpurun_out/bench_line.json | cut -c1-200
+timeout 600 python bench_extra.py > gpurun_out/bench_extra.jsonl 2> gpurun_out/bench_extra_err.log
+timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_line_reference.json 2>> gpurun_out/bench_err.log
