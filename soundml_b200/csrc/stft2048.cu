@@ -219,6 +219,7 @@ stft2048_kernel(const Params p) {
   MelPiece* sPieces = reinterpret_cast<MelPiece*>(sMelVals + nnz_pad);   // [warps][rounds][32]
   unsigned char* sPcnt = reinterpret_cast<unsigned char*>(sPieces + kGroupWarps * p.a.mel_rounds * 32);
   __shared__ __align__(8) uint64_t sbars[kMaxGroups];          // bulk copy of a group's samples landed
+  __shared__ unsigned char sCarryMap[32];                       // carry slot within a period -> row phase | k << 4
   // offsets stay integers so every pointer keeps its shared-memory provenance
   // (generic LD/ST would go through the slower generic path)
   const int tables_bytes = (kFft + 2 * 1024 + 2 * 32 + nnz_pad) * 4 +
@@ -251,6 +252,14 @@ stft2048_kernel(const Params p) {
     for (int i = tid; i < kGroupWarps * p.a.mel_rounds * 32; i += blockDim.x) sPieces[i] = p.a.mel_pieces[i];
     for (int i = tid; i < p.a.n_mels; i += blockDim.x) sPcnt[i] = p.a.mel_pcnt[i];
   }
+  if (OUT != kFastMel && p.carry_cap) {
+    const int S = OUT == kFastComplex ? 4 : 8;
+    if (tid < S) {
+      const int q = (tid * (int)(p.a.g.frames & (S - 1))) & (S - 1);
+      const int at = (int)((p.carry_prefix >> (8 * tid)) & 0xff);
+      for (int k = 0; k < q; ++k) sCarryMap[at + k] = (unsigned char)(tid | (k << 4));
+    }
+  }
   if (tid == 0) {
     for (int gI = 0; gI < kMaxGroups; ++gI) mbar_init(smem_u32(&sbars[gI]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -268,6 +277,10 @@ stft2048_kernel(const Params p) {
   float* row = sRows + warp * kRowStride;
   float2* ex = reinterpret_cast<float2*>(row);
 
+  // where a thread starts in the carry slots, and how a step of kGroupThreads moves it
+  const int cper = OUT != kFastMel && p.carry_cap ? p.carry_period : 1;
+  const int park_g4 = gtid / cper, park_idx = gtid % cper;
+  const int park_dq = kGroupThreads / cper, park_dr = kGroupThreads % cper;
   // mel: tiles dealt round-robin; bin-major outputs with a carry: contiguous runs
   int first = slot, last = total_tiles, tstep = stride;
   if (OUT != kFastMel && p.carry_cap) {
@@ -494,23 +507,44 @@ stft2048_kernel(const Params p) {
         const int j0 = f - q, j1 = kTile - q + f;             // first-store frame / parked frame
         const bool w = own ? j0 < nf : has_carry;
         const bool tail = !own && j1 < nf;
-        int cs = p.carry_period * (int)(((R0 + r0) / S) - (R0 / S)) + (int)((p.carry_prefix >> (8 * ph)) & 0xff) + f;
+        const int cs = p.carry_period * (int)(((R0 + r0) / S) - (R0 / S)) + (int)((p.carry_prefix >> (8 * ph)) & 0xff) + f;
         const int cstep = p.carry_period * (kRows / S);
         T* orow = out + (R0 + r0) * g.frames + p0;
         const long long ostep = (long long)kRows * g.frames;
-        const T* s0 = src + (own ? j0 : 0) * kRowT, *s1 = src + (tail ? j1 : 0) * kRowT;
-        for (int r = r0; r < out_bins; r += kRows, orow += ostep, cs += cstep) {
-          if (w) orow[j0] = own ? s0[r] : carry[cs];
-          if (tail) {
-            if (park) carry[cs] = s1[r];
-            else orow[j1] = s1[r];
+        // one load per row position whichever side the thread is on
+        const T* ld = own ? src + j0 * kRowT + r0 : carry + cs;
+        const int ldstep = own ? kRows : cstep;
+        if (park) {
+          if (w)
+            for (int r = r0; r < out_bins; r += kRows, orow += ostep, ld += ldstep) orow[j0] = *ld;
+          group_sync(group);                                  // the old carry has been read
+          // park the tile's last q frames of every row: carry slot e <-> (row, frame)
+          // through the per-period map, dense over the group's threads
+          const int r_off = (int)(R0 & (S - 1));
+          const int total = ((int)((R0 + out_bins - 1) / S - R0 / S) + 1) * p.carry_period;
+          int g4 = park_g4, idx = park_idx;
+          for (int e = gtid; e < total; e += kGroupThreads) {
+            const int m = sCarryMap[idx];
+            const int mph = m & 15, k = m >> 4;
+            const int r = g4 * S + mph - r_off;
+            const int mq = (mph * fm) & (S - 1);
+            if (r >= 0 && r < out_bins) carry[e] = src[(kTile - mq + k) * kRowT + r];
+            idx += park_dr;
+            g4 += park_dq;
+            if (idx >= p.carry_period) { idx -= p.carry_period; ++g4; }
+          }
+        } else {
+          const T* s1 = src + (tail ? j1 : 0) * kRowT;
+          for (int r = r0; r < out_bins; r += kRows, orow += ostep, ld += ldstep) {
+            if (w) orow[j0] = *ld;
+            if (tail) orow[j1] = s1[r];
           }
         }
       }
     }
-    // no barrier here: nothing writes shared memory before the group barrier at the
-    // top of the next iteration, which orders these row reads before the next
-    // tile's transposes
+    // no barrier here: nothing writes the rows before the group barrier at the top
+    // of the next iteration, which orders these row reads before the next tile's
+    // transposes (and the parked carry before its readers)
   }
 }
 
@@ -584,7 +618,7 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
     }
     const int out_bins = kHalf / a.bin_step + 1;
     const int cap = ((period * (out_bins / S + 2) * (out_kind == kFastComplex ? 2 : 1)) + 3) & ~3;
-    if (period > 0 && smem + (size_t)groups * cap * 4 <= kSmemLimit) {
+    if (period > 0 && smem + (size_t)groups * cap * 4 + 64 <= kSmemLimit) {   // 64: the static tables
       p.carry_cap = cap;
       p.carry_period = period;
       smem += (size_t)groups * cap * 4;
