@@ -14,3 +14,11 @@ for path in ("tensor", "fast"):
         p = sb.Stft.power_spectrum(c, x)
         z = sb.Stft.transform(c, x)
         print(path, hop, m.shape, float(np.abs(m).max()), float(np.abs(p).max()), float(np.abs(z).max()))
+
+# bin-major write-out with the sector carry: enough tiles (> 2 * 148 groups) that a
+# group walks consecutive tiles of a clip and crosses clip boundaries
+x = synth.clips_numpy(40, 100 * 512 + 3)
+c = sb.Stft.Config.create(fft_size=2048, hop=512).set_path("fast")
+p = sb.Stft.power_spectrum(c, x)
+z = sb.Stft.transform(c, x)
+print("carry", p.shape, float(np.abs(p).max()), float(np.abs(z).max()))
