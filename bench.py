@@ -109,21 +109,24 @@ def time_cpu(clips, min_seconds, workers, keep=None):
     workload until `min_seconds` of work; returns (audio-s/s, passes, seconds).
     `keep`, a list, receives the oracle's output for the sample so the caller can
     state the GPU path's error against it next to the number."""
+    os.environ["OMP_NUM_THREADS"] = str(workers)         # see run_reference
     from oracle import mel_oracle, stft_oracle
     from soundml_b200 import synth
+    from threadpoolctl import threadpool_limits
     x = synth.clips_numpy(clips, N, SR)
     sc = stft_oracle.StftConfig(FFT, HOP)
     mc = mel_oracle.MelConfig(N_MELS, SR, FFT)
-    cpu_reference_pass(x[:2], sc, mc, workers)            # warm the FFT plan cache
-    t0, passes = time.perf_counter(), 0
-    while True:
-        y = cpu_reference_pass(x, sc, mc, workers)
-        if keep is not None and not keep:
-            keep.append(y)
-        passes += 1
-        dt = time.perf_counter() - t0
-        if dt >= min_seconds:
-            return clips * CLIP_SECONDS * passes / dt, passes, dt
+    with threadpool_limits(limits=workers):
+        cpu_reference_pass(x[:2], sc, mc, workers)        # warm the FFT plan cache
+        t0, passes = time.perf_counter(), 0
+        while True:
+            y = cpu_reference_pass(x, sc, mc, workers)
+            if keep is not None and not keep:
+                keep.append(y)
+            passes += 1
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds:
+                return clips * CLIP_SECONDS * passes / dt, passes, dt
 
 
 def run_reference(args, rank, world):
@@ -134,6 +137,11 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     clips = 64
     steps = max(1, args.steps)
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; scipy.fft's worker pool and
+    # the BLAS behind the oracle's matmul both size themselves from it.  This arm
+    # is the CPU path on all host threads at every N: undo the cap before either
+    # library starts its pool (and see threadpool_limits below).
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     from oracle import mel_oracle, stft_oracle
     from soundml_b200 import synth
     x = synth.clips_numpy(clips, N, SR)
@@ -142,10 +150,13 @@ def run_reference(args, rank, world):
     for _ in range(max(1, min(args.warmup, 3))):
         cpu_reference_pass(x[:8], sc, mc, cores)
     steps = min(steps, 20)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_reference_pass(x, sc, mc, cores)
-    dt = time.perf_counter() - t0
+    # a BLAS that was loaded before the line above keeps its one thread otherwise
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=cores):
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_reference_pass(x, sc, mc, cores)
+        dt = time.perf_counter() - t0
     value = clips * CLIP_SECONDS * steps / dt
     sample = f"{clips} of {BATCH} clips per step (same signal recipe), {steps} steps"
     line = {
