@@ -148,12 +148,10 @@ struct Params {
 // by the caller (cp.async.wait_all + group barrier).  An interior tile whose source
 // run is 16-byte aligned is one bulk copy (TMA) issued by the group's first thread
 // onto `bar`: returns true and the caller waits on the mbarrier instead.
-__device__ __forceinline__ bool stage_tile(const Params& p, int tile, float* sSamples, int gtid,
+__device__ __forceinline__ bool stage_tile(const Params& p, int b, int t, float* sSamples, int gtid,
                                            uint32_t bar) {
   const FrameGeom& g = p.a.g;
-  const int tps = (int)p.tiles_per_signal;
-  const int b = tile / tps;
-  const long long p0 = (long long)(tile - b * tps) * kTile;
+  const long long p0 = (long long)t * kTile;              // tile t of clip b
   const int nf = (int)min((long long)kTile, g.frames - p0);
   const int span = (nf - 1) * g.hop + kFft;
   const long long q0 = p0 * g.hop;
@@ -289,11 +287,17 @@ stft2048_kernel(const Params p) {
     last = min(first + run, total_tiles);
     tstep = 1;
   }
+  // (clip, tile of the clip) walk the deal without a division per tile
+  const int step_b = tstep / tiles_per_signal, step_t = tstep - step_b * tiles_per_signal;
+  int nb = first / tiles_per_signal, nt = first - nb * tiles_per_signal;
   bool bulk = false;
-  if (first < last) bulk = stage_tile(p, first, sSamples, gtid, sbar);
+  if (first < last) bulk = stage_tile(p, nb, nt, sSamples, gtid, sbar);
   for (int tile = first; tile < last; tile += tstep) {
-    const int b = tile / tiles_per_signal;
-    const long long p0 = (long long)(tile - b * tiles_per_signal) * kTile;
+    const int b = nb;
+    const long long p0 = (long long)nt * kTile;
+    nb += step_b;
+    nt += step_t;
+    if (nt >= tiles_per_signal) { nt -= tiles_per_signal; ++nb; }
     const int nf = (int)min((long long)kTile, g.frames - p0);
 
     // ---- the tile's samples were requested one iteration ago (or just above
@@ -419,7 +423,7 @@ stft2048_kernel(const Params p) {
 
     // ---- the sample buffer is free: start fetching the next tile's samples
     // under the mel / write-out phases.
-    if (tile + tstep < last) bulk = stage_tile(p, tile + tstep, sSamples, gtid, sbar);
+    if (tile + tstep < last) bulk = stage_tile(p, nb, nt, sSamples, gtid, sbar);
 
     if (OUT == kFastMel) {
       // ---- mel projection over the tile's power rows.  A lane carries one piece
@@ -468,6 +472,7 @@ stft2048_kernel(const Params p) {
           // the j-th partial sum of filter m sits at j * mpad + m (up to four; slots a
           // filter does not use hold stale bits and are masked out, never added)
           const int mpad = p.a.mel_mpad;
+#pragma unroll 4
           for (int m = r0; m < p.a.n_mels; m += kGroupThreads / kTile, ob += step) {
             const int cnt = sPcnt[m];
             const float s0 = src[m], s1 = src[mpad + m], s2 = src[2 * mpad + m], s3 = src[3 * mpad + m];
