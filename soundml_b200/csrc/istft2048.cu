@@ -222,15 +222,19 @@ istft2048_kernel(const Istft2048Params p) {
     const int rel0 = (int)(q0 - p_lo * hop);          // run position 0 relative to frame p_lo's tap 0
     int res = (int)((q0 + tid) % hop);
     const int rstep = (int)(blockDim.x % hop);
+    // newest frame reaching position i and the tap it lands on, walked without a
+    // division per sample: (tq, tj) = divmod(rel0 + i, hop), i advancing by blockDim.x
+    const int tq_step = (int)(blockDim.x / hop);
+    int tq = (rel0 + tid) / hop, tj = (rel0 + tid) - tq * hop;
     for (int i = tid; i < n_out; i += blockDim.x) {
       const long long q = q0 + i;
       float val = 0.0f;
       if (q < span) {
-        const int rel = rel0 + i;
-        int t = min(nf - 1, rel / hop);                // newest frame reaching the position
-        int j = rel - t * hop;
+        int t = min(nf - 1, tq);
+        int j = tj + (tq - t) * hop;
         float sum = 0.0f;
-        for (; t >= 0 && j < fft; --t, j += hop) sum += sWork[t * kExFloats + j];
+        const float* tap = sWork + t * kExFloats + j;
+        for (; t >= 0 && j < fft; --t, j += hop, tap -= kExFloats - hop) sum += *tap;
         if (q >= full_lo && q < full_hi) {
           // every residue class reaches the position completely: tabulated reciprocal
           val = sum * sInvEnv[res];
@@ -249,6 +253,9 @@ istft2048_kernel(const Istft2048Params p) {
       out[m0 + i] = val;
       res += rstep;
       if (res >= hop) res -= hop;
+      tq += tq_step;
+      tj += rstep;
+      if (tj >= hop) { tj -= hop; ++tq; }
     }
     __syncthreads();
   }
