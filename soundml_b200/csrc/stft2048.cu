@@ -42,6 +42,7 @@
 //     cp.async and the reference's index rule.
 //   * Outputs are staged per tile so global writes run along the contiguous
 //     frame axis.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 
@@ -129,7 +130,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 struct Params {
   Stft2048Args a;
-  int use_bulk;              // interior tiles by one bulk copy (SMB_NO_BULK=1 turns it off)
+  // interior tiles by one bulk copy (SMB_NO_BULK=1 turns it off): tiles t in
+  // [bulk_t_lo, bulk_t_hi] of a clip b with (b * bulk_nmod + bulk_c0) % 4 == 0
+  int bulk_t_lo, bulk_t_hi;
+  unsigned bulk_nmod, bulk_c0;
   int span_cap;              // floats reserved per group for samples
   long long tiles_per_signal, total_tiles;
   // bin-major outputs (power / complex): a group walks a contiguous run of tiles and
@@ -151,20 +155,25 @@ struct Params {
 __device__ __forceinline__ bool stage_tile(const Params& p, int b, int t, float* sSamples, int gtid,
                                            uint32_t bar) {
   const FrameGeom& g = p.a.g;
+  // interior full tile with a 16-byte aligned source run: the launcher worked the
+  // tile range and the clip-phase rule out once (a handful of 32-bit operations
+  // here instead of the 64-bit bounds and address tests in every thread)
+  if (t >= p.bulk_t_lo && t <= p.bulk_t_hi && (((unsigned)b * p.bulk_nmod + p.bulk_c0) & 3u) == 0) {
+    if (gtid == 0) {
+      const uint32_t span = (uint32_t)((kTile - 1) * g.hop + kFft);
+      const float* src = p.a.x + (long long)b * g.n + ((long long)t * kTile * g.hop - g.left);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, 4u * span);
+      bulk_g2s(smem_u32(sSamples), src, 4u * span, bar);
+    }
+    return true;
+  }
   const long long p0 = (long long)t * kTile;              // tile t of clip b
   const int nf = (int)min((long long)kTile, g.frames - p0);
   const int span = (nf - 1) * g.hop + kFft;
   const long long q0 = p0 * g.hop;
   const long long s0 = q0 - g.left;
   const float* xs = p.a.x + (long long)b * g.n;
-  if (p.use_bulk && s0 >= 0 && s0 + span <= g.n && (reinterpret_cast<size_t>(xs + s0) & 15) == 0 && (span & 3) == 0) {
-    if (gtid == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, 4u * (uint32_t)span);
-      bulk_g2s(smem_u32(sSamples), xs + s0, 4u * (uint32_t)span, bar);
-    }
-    return true;
-  }
   // [lo, hi): positions of the span that are real samples
   const int lo = (int)max(0LL, min((long long)span, -s0));
   const int hi = (int)max((long long)lo, min((long long)span, g.n - s0));
@@ -600,7 +609,23 @@ cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, c
   }
   Params p;
   p.a = a;
-  p.use_bulk = getenv("SMB_NO_BULK") ? 0 : 1;
+  p.bulk_t_lo = 0;
+  p.bulk_t_hi = -1;
+  p.bulk_nmod = p.bulk_c0 = 0;
+  if (!getenv("SMB_NO_BULK") && (a.g.hop & 3) == 0 && (reinterpret_cast<size_t>(a.x) & 3) == 0) {
+    // full tile t reads source samples [t*T*hop - left, ... + span): inside the clip, and
+    // 16-byte aligned when (x/4 + b*n - left) % 4 == 0 (T*hop is a multiple of 4)
+    const long long th = (long long)kTile * a.g.hop, span = (long long)(kTile - 1) * a.g.hop + kFft;
+    const long long lo = (a.g.left + th - 1) / th;
+    const long long hi = std::min<long long>((a.g.n + a.g.left - span >= 0 ? (a.g.n + a.g.left - span) / th : -1),
+                                  a.g.frames / kTile - 1);
+    if (lo <= hi) {
+      p.bulk_t_lo = (int)lo;
+      p.bulk_t_hi = (int)hi;
+      p.bulk_nmod = (unsigned)(a.g.n & 3);
+      p.bulk_c0 = (unsigned)(((reinterpret_cast<size_t>(a.x) >> 2) + 4 - (size_t)(a.g.left & 3)) & 3);
+    }
+  }
   if (out_kind != kFastMel) { p.a.nnz = 0; p.a.n_mels = 0; p.a.mel_rounds = 0; p.a.mel_mpad = 0; }
   p.span_cap = span_needed(a.g);
   p.tiles_per_signal = (a.g.frames + kTile - 1) / kTile;
