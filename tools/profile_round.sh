@@ -9,6 +9,10 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:s
 # full captures of both fused kernels
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:stft2048_kernel -s 3 -c 1 -o gpurun_out/r1k python bench.py --steps 3 --warmup 3 --no-e2e --cpu-seconds 0.5 > gpurun_out/r1k.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:stft2048tc -s 3 -c 1 -o gpurun_out/tc_e python bench.py --path tensor --steps 3 --warmup 3 --no-e2e --cpu-seconds 0.5 > gpurun_out/tc_e.log 2>&1
-tail -1 gpurun_out/bench_line.json | cut -c1-200
 timeout 600 python bench_extra.py > gpurun_out/bench_extra.jsonl 2> gpurun_out/bench_extra_err.log
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_line_reference.json 2>> gpurun_out/bench_err.log
+# the bin-major outputs (Stft.transform / power_spectrum): full capture of the complex kernel
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:stft2048_kernel -s 6 -c 1 -o gpurun_out/cplx_c python bench_extra.py --only spectrum --steps 2 > gpurun_out/cplx_c.log 2>&1
+# library yardstick (cuFFT + cuBLAS) beside the fused kernel
+timeout 200 python tools/bench_library_stft.py > gpurun_out/library_stft.json 2> gpurun_out/library_stft_err.log
+tail -1 gpurun_out/bench_line.json | cut -c1-200
