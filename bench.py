@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--path", default="auto", choices=["auto", "fast", "tensor"],
+    ap.add_argument("--path", default="auto", choices=["auto", "fast", "tensor", "pair"],
                     help="which fused fft-2048 kernel: auto (the library's choice), the CUDA-core "
                          "register FFT (fast) or the tcgen05 one (tensor)")
     args = ap.parse_args()

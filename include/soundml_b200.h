@@ -74,9 +74,12 @@ enum { SMB_EXEC_DIRECT = 0, SMB_EXEC_OLS = 1, SMB_EXEC_GEMM = 2, SMB_EXEC_PLANNE
 /* Kernel selection for the STFT family (testing / benchmarking): AUTO picks the
  * fused fft-2048 kernel when the geometry allows it, else the double-interior
  * generic kernel; FAST forces the fused CUDA-core kernel (register FFT), TENSOR the
- * fused tcgen05 kernel (both 32-point FFT passes as split-fp16 products in TMEM);
+ * fused tcgen05 kernel (both 32-point FFT passes as split-fp16 products in TMEM),
+ * PAIR the frame-pair kernel (two frames per warp in float32x2 lanes; mel output of
+ * fft 2048, what AUTO picks for smb_mel_spectrogram when it applies);
  * a forced kernel that does not cover the call is SMB_EINVAL. */
-enum { SMB_PATH_AUTO = 0, SMB_PATH_GENERIC = 1, SMB_PATH_FAST = 2, SMB_PATH_TENSOR = 3 };
+enum { SMB_PATH_AUTO = 0, SMB_PATH_GENERIC = 1, SMB_PATH_FAST = 2, SMB_PATH_TENSOR = 3,
+       SMB_PATH_PAIR = 4 };
 
 typedef struct smb_stft_plan smb_stft_plan;
 typedef struct smb_mel_plan smb_mel_plan;
@@ -191,6 +194,12 @@ int smb_mel_apply(smb_mel_plan* plan, const void* s, int64_t batch, int64_t fram
 int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x,
                         int64_t batch, int64_t n, int dtype, double power, void* out,
                         int mem);
+/* Measurement hook, not part of the drop-in surface: the transform alone on the
+ * frame-pair kernel's skeleton (staging, window, both FFT passes, transposition; no
+ * split, no |X|^2, no mel).  bench.py reports its time as roofline.compute_floor_ms.
+ * x: device float32 [batch, n]; scratch: device, ..._scratch_bytes() bytes. */
+int64_t smb_stft_fft_ceiling_scratch_bytes(const smb_stft_plan* plan, int64_t batch, int64_t n);
+int smb_stft_fft_ceiling(smb_stft_plan* stft, const void* x, int64_t batch, int64_t n, void* scratch);
 
 /* ---- dB conversion and MFCC ------------------------- */
 /* Convert.power_to_db / amplitude_to_db ?reference ?amin ?top_db (convert.ml:20-56):

@@ -15,7 +15,7 @@ OK, EINVAL, ECUDA, ENOMEM = 0, 1, 2, 3
 MEM_DEVICE, MEM_HOST = 0, 1
 F32, F64 = 0, 1
 DEFAULT = -(2 ** 31)
-PATH_AUTO, PATH_GENERIC, PATH_FAST, PATH_TENSOR = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_FAST, PATH_TENSOR, PATH_PAIR = 0, 1, 2, 3, 4
 EXEC_DIRECT, EXEC_OLS, EXEC_GEMM, EXEC_PLANNED = 0, 1, 2, 3
 INGEST_PLANAR, INGEST_DOWNMIX = 1, 2
 
@@ -93,6 +93,8 @@ SIGNATURES = {
     "smb_mel_filterbank": (_int, [_vp, _pd]),
     "smb_mel_apply": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _int]),
     "smb_mel_spectrogram": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _dbl, _vp, _int]),
+    "smb_stft_fft_ceiling_scratch_bytes": (_i64, [_vp, _i64, _i64]),
+    "smb_stft_fft_ceiling": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "smb_power_to_db": (_int, [_vp, _i64, _int, _dbl, _dbl, _dbl, _vp, _int, _vp]),
     "smb_amplitude_to_db": (_int, [_vp, _i64, _int, _dbl, _dbl, _dbl, _vp, _int, _vp]),
     "smb_mfcc": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _i64, _dbl, _vp, _int]),

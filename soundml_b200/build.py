@@ -15,10 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsoundml_b200.so")
 
-CUDA_SOURCES = ["api.cu", "kernels_generic.cu", "stft2048.cu", "stft2048tc.cu", "resample_kernels.cu",
+CUDA_SOURCES = ["api.cu", "kernels_generic.cu", "stft2048.cu", "stft2048p.cu", "stft2048tc.cu", "resample_kernels.cu",
                 "ols_kernels.cu", "ols2048.cu", "resample_gemm.cu", "db_kernels.cu", "istft_kernels.cu", "istft2048.cu", "ingest_kernels.cu"]
 HOST_SOURCES = ["host_design.cpp"]
-HEADERS = ["host_design.h", "kernels.h", "fft32.cuh", os.path.join("..", "..", "include", "soundml_b200.h")]
+HEADERS = ["host_design.h", "kernels.h", "fft32.cuh", "fft32x2.cuh", "stft_stage.cuh", os.path.join("..", "..", "include", "soundml_b200.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -51,16 +51,26 @@ def build(force=False, verbose=False, defines=(), out=None):
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build" if out is None else "build_variant")
     os.makedirs(objdir, exist_ok=True)
-    objs = []
+    objs, jobs = [], []
+    newest_header = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
     for src in CUDA_SOURCES + HOST_SOURCES:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        # an object newer than its source and every header is kept (variants and
+        # forced builds recompile everything)
+        if (out is None and not force and os.path.exists(obj) and
+                os.path.getmtime(obj) > max(os.path.getmtime(os.path.join(CSRC, src)), newest_header)):
+            continue
         cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, src), "-o", obj]
         if src.endswith(".cpp"):
             cmd.insert(1, "-x")
             cmd.insert(2, "cu")
-        _run(cmd, verbose)
-        objs.append(obj)
+        jobs.append(cmd)
+    # translation units are independent: compile them side by side
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1) or 1) as pool:
+        list(pool.map(lambda c: _run(c, verbose), jobs))
     _run([nvcc, "-shared", "-o", out or LIB] + objs + ["-cudart", "static"], verbose)
     return out or LIB
 

@@ -328,6 +328,19 @@ struct smb_mel_plan {
     void to_device() { d_vals = upload(vals); d_pieces = upload(pieces); d_pcnt = upload(pcnt); }
     void free_device() { cudaFree(d_vals); cudaFree(d_pieces); cudaFree(d_pcnt); }
   };
+  // Mel schedule of the frame-pair kernel (stft2048p.cu): whole filters, eight per
+  // round, a lane = (filter, frame pair); rounds dealt to the group's four warps.
+  struct PairSchedule {
+    std::vector<float> w;                  // [round][step][8 filters] x float4
+    std::vector<smb::PairMelItem> items;   // [4 warps][rounds][8]
+    int rounds = 0;
+    float* d_w = nullptr;
+    smb::PairMelItem* d_items = nullptr;
+    void clear() { w.clear(); items.clear(); rounds = 0; }
+    void to_device() { if (!items.empty()) { d_w = upload(w); d_items = upload(items); } }
+    void free_device() { cudaFree(d_w); cudaFree(d_items); }
+  };
+  PairSchedule sched_pair;
   PieceSchedule sched_cc;   // CUDA-core kernel: kFastTile warps, 8 frames per lane
   PieceSchedule sched_tc;   // tensor-core kernel: kTcTile warps, 4 frames per lane
   // 2048 / fft_size when the fused kernel can carry this filterbank (1 for fft
@@ -383,6 +396,7 @@ struct smb_mel_plan {
     // (shorter frames run zero-padded and keep every step-th bin in the power row)
     if (bins < 65 || bins > 1025 || 1024 % (bins - 1) != 0) return;
     const int step = (int)(1024 / (bins - 1));
+    if (step == 1 && !build_pair_schedule(sched_pair)) sched_pair.clear();
     // the CUDA-core kernel trades a few padded steps for conflict-free octets
     // (whole list as the window); the tensor-core kernel has no shared memory to
     // spare for longer weight tables and keeps the strict longest-first rounds
@@ -393,6 +407,84 @@ struct smb_mel_plan {
       return;
     }
     fast_step = step;
+  }
+  // Mel schedule of the frame-pair kernel.  Filter m's band [band_lo, band_hi) is read
+  // in 4-bin steps from an even bin b0 <= band_lo; eight consecutive filters make a
+  // round (neighbouring bands have similar lengths), lane (i, j) of the round's warp
+  // carries filter i for frame pair j.  The two filters of a quarter-warp start on
+  // 16-byte groups of opposite parity (b0 / 2 odd against even; one of them moves two
+  // bins down, weights zero there) so that the eight 16-byte loads of a quarter-warp,
+  // whose four frame pairs sit 32 bytes apart, fall in eight distinct bank groups.
+  // Weights are stored [round][step][filter] x float4 = one 128-byte run per warp
+  // load.  Rounds go longest-first onto the lightest of the four warps.
+  bool build_pair_schedule(PairSchedule& sc) const {
+    sc.clear();
+    const int kBins = 1032;                                  // power row incl. zeroed tail (stft2048p.cu)
+    if (bins != 1025 || n_mels > 32767) return false;
+    const int rounds_total = (int)((n_mels + 7) / 8);
+    struct Round { int steps; size_t base; int b0[8]; int m[8]; };
+    std::vector<Round> built((size_t)rounds_total);
+    for (int q = 0; q < rounds_total; ++q) {
+      Round& rd = built[(size_t)q];
+      int hi[8];
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = (int64_t)q * 8 + i;
+        rd.m[i] = m < n_mels ? (int)m : -1;
+        rd.b0[i] = m < n_mels ? band_lo[(size_t)m] & ~1 : 0;
+        hi[i] = m < n_mels ? std::max(band_hi[(size_t)m], rd.b0[i]) : 0;
+      }
+      for (int i = 0; i < 8; i += 2) {
+        if (rd.m[i] < 0 || rd.m[i + 1] < 0) continue;
+        if ((((rd.b0[i] >> 1) + (rd.b0[i + 1] >> 1)) & 1) != 0) continue;
+        if (rd.b0[i + 1] >= 2) rd.b0[i + 1] -= 2;
+        else if (rd.b0[i] >= 2) rd.b0[i] -= 2;
+      }
+      rd.steps = 1;                                        // 0 marks an idle round in the kernel
+      for (int i = 0; i < 8; ++i)
+        if (rd.m[i] >= 0) rd.steps = std::max(rd.steps, (hi[i] - rd.b0[i] + 3) / 4);
+      rd.steps = (rd.steps + 1) & ~1;                      // the kernel runs two steps per iteration
+      if (rd.steps > 510 || 4 * rd.steps > kBins) return false;
+      // every lane runs the round's step count: keep its reads inside the row
+      for (int i = 0; i < 8; ++i) rd.b0[i] = std::min(rd.b0[i], (kBins - 4 * rd.steps) & ~1);
+      rd.base = sc.w.size();
+      sc.w.resize(rd.base + (size_t)rd.steps * 8 * 4, 0.0f);
+      for (int i = 0; i < 8; ++i) {
+        if (rd.m[i] < 0) continue;
+        for (int k = band_lo[(size_t)rd.m[i]]; k < band_hi[(size_t)rd.m[i]]; ++k) {
+          const int u = k - rd.b0[i];
+          sc.w[rd.base + ((size_t)(u >> 2) * 8 + (size_t)i) * 4 + (size_t)(u & 3)] =
+              (float)weights[(size_t)((int64_t)rd.m[i] * bins + k)];
+        }
+      }
+    }
+    sc.w.resize(sc.w.size() + 8 * 4, 0.0f);                // the kernel's prefetch reads one step ahead
+    if (sc.w.size() >= (1u << 24)) return false;
+    const int warps = smb::kPairTile / 2;
+    std::vector<int> by_len((size_t)rounds_total);
+    for (int q = 0; q < rounds_total; ++q) by_len[(size_t)q] = q;
+    std::stable_sort(by_len.begin(), by_len.end(),
+                     [&](int a, int b) { return built[(size_t)a].steps > built[(size_t)b].steps; });
+    std::vector<std::vector<int>> lists((size_t)warps);
+    std::vector<long long> load((size_t)warps, 0);
+    for (int q : by_len) {
+      const size_t wi = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+      lists[wi].push_back(q);
+      load[wi] += built[(size_t)q].steps * 10 + 30;
+    }
+    sc.rounds = 0;
+    for (const auto& l : lists) sc.rounds = std::max(sc.rounds, (int)l.size());
+    sc.items.assign((size_t)(warps * sc.rounds * 8), smb::PairMelItem{0, 0, -1});   // idle: no steps
+    for (int wi = 0; wi < warps; ++wi)
+      for (size_t r = 0; r < lists[(size_t)wi].size(); ++r) {
+        const Round& rd = built[(size_t)lists[(size_t)wi][r]];
+        for (int i = 0; i < 8; ++i) {
+          smb::PairMelItem& it = sc.items[((size_t)wi * (size_t)sc.rounds + r) * 8 + (size_t)i];
+          it.w4_steps = (int)(rd.base / 4 + (size_t)i) | ((rd.steps / 2) << 24);
+          it.h0 = (unsigned short)(rd.b0[i] >> 1);
+          it.m = (short)rd.m[i];
+        }
+      }
+    return true;
   }
   // Mel schedule of the fused kernels.  Every filter's band, starting on a float4
   // of the power row, is cut into pieces of at most `ps` float4 steps; a lane
@@ -534,6 +626,7 @@ struct smb_mel_plan {
     d_band_hi = upload(band_hi);
     sched_cc.to_device();
     sched_tc.to_device();
+    sched_pair.to_device();
     CK(cudaMalloc(&d_max, sizeof(unsigned long long)));
     device_ready = true;
   }
@@ -544,6 +637,7 @@ struct smb_mel_plan {
     cudaFree(d_band_hi);
     sched_cc.free_device();
     sched_tc.free_device();
+    sched_pair.free_device();
     cudaFree(d_dct);
     cudaFree(d_max);
     in.release();
@@ -902,7 +996,7 @@ int smb_stft_plan_set_stream(smb_stft_plan* plan, void* s) {
 }
 int smb_stft_plan_set_path(smb_stft_plan* plan, int path) {
   return guarded([&] {
-    if (path < SMB_PATH_AUTO || path > SMB_PATH_TENSOR)
+    if (path < SMB_PATH_AUTO || path > SMB_PATH_PAIR)
       throw smb::invalid_argument("set_path: unknown path");
     plan->path = path;
   });
@@ -969,6 +1063,18 @@ int want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int ou
   gk.fft = 2048;
   const bool base = dtype == SMB_F32 && step > 0 &&
                     (!mel || (mel->fast_step == step && !mel->sched_cc.pieces.empty()));
+  // the frame-pair kernel: mel output of fft 2048 proper
+  const bool ok_pair = dtype == SMB_F32 && step == 1 && mel && out_kind == smb::kFastMel &&
+                       !mel->sched_pair.items.empty() &&
+                       smb::stft2048p_supports(gk, (int)mel->n_mels, (int)mel->sched_pair.w.size(),
+                                               mel->sched_pair.rounds);
+  if (p->path == SMB_PATH_PAIR) {
+    if (!ok_pair)
+      throw smb::invalid_argument(
+          "soundml_b200: the frame-pair fft-2048 kernel does not cover this call");
+    return SMB_PATH_PAIR;
+  }
+  if (p->path == SMB_PATH_AUTO && ok_pair) return SMB_PATH_PAIR;
   const bool ok_tc = base && smb::stft2048tc_supports(gk, out_kind, mel ? (int)mel->n_mels : 0,
                                                       mel ? (int)mel->sched_tc.vals.size() : 0,
                                                       mel ? mel->sched_tc.rounds : 0,
@@ -991,6 +1097,28 @@ int want_fast(const smb_stft_plan* p, int dtype, const smb::FrameGeom& g, int ou
   }
   if (ok_tc && kAutoPrefersTensor) return SMB_PATH_TENSOR;
   return ok_cc ? SMB_PATH_FAST : (ok_tc ? SMB_PATH_TENSOR : 0);
+}
+
+smb::Stft2048PairArgs pair_args(const smb_stft_plan* stft, const smb_mel_plan* mel, const void* din,
+                                void* dout, int64_t nb, const smb::FrameGeom& g, double power) {
+  smb::Stft2048PairArgs a{};
+  a.x = (const float*)din;
+  a.out = (float*)dout;
+  a.batch = nb;
+  a.g = g;
+  a.g.fft = 2048;
+  a.window = stft->d_window32;
+  a.tw_pass = stft->d_tw_pass;
+  a.tw_post = stft->d_tw_post;
+  a.power = (float)power;
+  if (mel) {
+    a.n_mels = (int)mel->n_mels;
+    a.mel_w = mel->sched_pair.d_w;
+    a.mel_w_floats = (int)mel->sched_pair.w.size();
+    a.mel_items = mel->sched_pair.d_items;
+    a.mel_rounds = mel->sched_pair.rounds;
+  }
+  return a;
 }
 
 // x (device) -> spectrum (device).  kind: complex or |X|^power.
@@ -1398,7 +1526,10 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
     cudaStream_t st = stft->stream.use;
     const int fast = want_fast(stft, dtype, g, smb::kFastMel, mel);
     auto run = [&](const void* din, void* dout, int64_t nb) {
-      if (fast) {
+      if (fast == SMB_PATH_PAIR) {
+        CK(smb::launch_stft2048p(pair_args(stft, mel, din, dout, nb, g, power), false,
+                                 stft->sm_count, st));
+      } else if (fast) {
         smb::Stft2048Args a{};
         a.x = (const float*)din;
         a.out = (float*)dout;
@@ -1438,6 +1569,33 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
     } else {
       throw smb::invalid_argument("soundml_b200: unknown memory kind");
     }
+  });
+}
+
+// Measurement only: the transform alone on the frame-pair kernel's skeleton (tile
+// staging, window, both register-FFT passes, the transposition between them, one
+// shared-memory store per value) -- no real-spectrum split, no |X|^2, no mel, nothing
+// but one float per thread and tile written to `scratch`.  bench.py times it beside the
+// real kernel as the kernel's compute floor.  x: device float32 [batch, n]; scratch:
+// device, smb_stft_fft_ceiling_scratch_bytes(plan, batch, n) bytes.
+int64_t smb_stft_fft_ceiling_scratch_bytes(const smb_stft_plan* plan, int64_t batch, int64_t n) {
+  int64_t r = -1;
+  guarded([&] {
+    const int64_t frames = plan->geom.frames(n);
+    r = (frames + smb::kPairTile - 1) / smb::kPairTile * batch * 128 * 4;
+  });
+  return r;
+}
+int smb_stft_fft_ceiling(smb_stft_plan* stft, const void* x, int64_t batch, int64_t n, void* scratch) {
+  return guarded([&] {
+    check_signal("fft_ceiling", batch, n);
+    const smb::FrameGeom g = stft->frame_geom(n);
+    if (stft->fast_step() != 1 || !smb::stft2048p_supports(g, 1, 0, 0))
+      throw smb::invalid_argument("fft_ceiling: the frame-pair kernel takes fft 2048 with an even hop");
+    if (batch == 0 || g.frames == 0) return;
+    stft->ensure_device();
+    CK(smb::launch_stft2048p(pair_args(stft, nullptr, x, scratch, batch, g, 2.0), true,
+                             stft->sm_count, stft->stream.use));
   });
 }
 

@@ -96,6 +96,37 @@ struct Stft2048Args {
 bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, int mel_rounds,
                        int mpad);
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
+// ---- frame-pair kernel (stft2048p.cu): two frames per warp in float32x2 lanes -----
+constexpr int kPairTile = 8;           // frames per group tile, two per warp
+// One filter of a mel round of the frame-pair kernel: lane (filter i, frame pair j)
+// walks `steps` 4-bin steps from bin b0 (even) of warp j's power rows.
+struct PairMelItem {
+  int w4_steps;            // weights: float4 index of [step 0][filter i] (low 24 bits), half the
+                           // (even) step count of the round (high 8)
+  unsigned short h0;       // first bin read / 2 (the band starts on an even bin)
+  short m;                 // filter the sum belongs to, -1 for an idle lane
+};
+struct Stft2048PairArgs {
+  const float* x;          // [batch, n]
+  float* out;              // [batch, n_mels, frames]
+  long long batch;
+  FrameGeom g;
+  const float* window;     // [2048]
+  const float2* tw_pass;   // [32][32]  W_1024^(k1*n2), index k1*32 + n2
+  const float2* tw_post;   // [32]      W_2048^l
+  int n_mels;
+  const float* mel_w;               // [round][step][8 filters] x float4 band weights, one
+                                    // readable step of padding behind the last round
+  int mel_w_floats;                 // multiple of 4
+  const PairMelItem* mel_items;     // [4 warps][mel_rounds][8 filters]
+  int mel_rounds;
+  float power;
+};
+bool stft2048p_supports(const FrameGeom& g, int n_mels, int mel_w_floats, int mel_rounds);
+// ceiling = true: the measurement floor of the transform alone (stage + window + both
+// register FFT passes + transposition, one store per value; no split, no |X|^2, no
+// mel); `out` then takes total_tiles * 128 floats of scratch.
+cudaError_t launch_stft2048p(const Stft2048PairArgs& a, bool ceiling, int sm_count, cudaStream_t st);
 // Tensor-core variant: both 32-point passes as split-fp16 products on tcgen05, a
 // tile = kTcTile frames = 128 MMA rows per group of kTcTile warps.
 constexpr int kTcTile = 4;

@@ -67,10 +67,13 @@ class Config:
 
     def set_path(self, path):
         """Testing hook: force the generic (double interior) kernel, the fused
-        fft-2048 CUDA-core kernel (``"fast"``) or the fused tcgen05 kernel
-        (``"tensor"``).  ``"auto"`` picks the fused CUDA-core kernel when it applies."""
+        fft-2048 CUDA-core kernel (``"fast"``), the fused tcgen05 kernel
+        (``"tensor"``) or the frame-pair kernel (``"pair"``: mel output of fft 2048).
+        ``"auto"`` picks the frame-pair kernel for mel spectrograms it covers, else
+        the fused CUDA-core kernel when it applies, else the generic one."""
         code = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC,
-                "fast": _lib.PATH_FAST, "tensor": _lib.PATH_TENSOR}[path]
+                "fast": _lib.PATH_FAST, "tensor": _lib.PATH_TENSOR,
+                "pair": _lib.PATH_PAIR}[path]
         _lib.check(_lib.lib.smb_stft_plan_set_path(self._h, code))
         return self
 
