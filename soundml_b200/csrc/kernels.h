@@ -115,11 +115,10 @@ struct Stft2048PairArgs {
   const float2* tw_pass;   // [32][32]  W_1024^(k1*n2), index k1*32 + n2
   const float2* tw_post;   // [32]      W_2048^l
   int n_mels;
-  const float* mel_w;               // [round][step][8 filters] x float4 band weights, one
-                                    // readable step of padding behind the last round
+  const float* mel_w;               // [round][step][8 filters] x float4 band weights
   int mel_w_floats;                 // multiple of 4
   const PairMelItem* mel_items;     // [4 warps][mel_rounds][8 filters]
-  int mel_rounds;
+  int mel_rounds;                   // even: rounds 2q, 2q + 1 of a warp run in lockstep, same step count
   float power;
 };
 bool stft2048p_supports(const FrameGeom& g, int n_mels, int mel_w_floats, int mel_rounds);

@@ -57,7 +57,10 @@ constexpr int kWarpBuf = 32 * kExPitch * 16;   // bytes: [32][33] x (re A, re B,
 constexpr int kPowerBins = 1032;            // bins per power row incl. the zeroed tail the mel steps may read
 static_assert(32 * (kGroupWarps - 1) + kPowerBins * 8 <= kWarpBuf, "power rows fit the transposition buffer");
 
-enum Mode { kModeMel = 0, kModeCeiling = 1 };
+// kModeFree: the ceiling with its warps running free -- the first tile's samples are
+// staged once and re-read, no group barrier, no staging inside the loop (what the
+// transform skeleton does when nothing couples the warps; measurement only)
+enum Mode { kModeMel = 0, kModeCeiling = 1, kModeFree = 2 };
 
 // W_64^k2 = exp(-2 pi i k2 / 64), k2 < 16: the split twiddle W_2048^(l + 32 k2) is the
 // lane's W_2048^l times one of these constants.
@@ -80,6 +83,43 @@ struct Params {
   int tiles_per_signal, total_tiles;
 };
 
+// ---- TMEM as a per-lane table store.  The window and the inter-pass twiddles are
+// per-lane constants (lane = n2 needs w[64 n1 + 2 n2 + c] and W1024^(k1 n2) for every
+// n1, k1): 128 floats per lane, too many for registers, and as shared-memory tables
+// they cost 64 of the kernel's ~400 wavefronts per frame on the pipe that bounds it.
+// Tensor memory is organised exactly that way -- 128 lanes x 512 32-bit columns, a
+// warp reading "its" 32 lanes with tcgen05.ld.32x32b -- and has its own datapath, so
+// the tables live there: columns [0, 64) window, [64, 128) twiddles, one copy per
+// 32-lane quarter (warps w and w + 4 share quarter w % 4).
+constexpr uint32_t kTmemCols = 128;
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+        "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// no "memory" clobber: tensor memory is invisible to C++ loads and stores, so the
+// compiler may move shared-memory traffic across the load; the wait names the
+// registers, which orders their first use behind it
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]),
+                 "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+
 __device__ __forceinline__ pk_t shfl_pk(pk_t v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
 }
@@ -99,7 +139,8 @@ __device__ __forceinline__ pk_t power_of(CP x, float power) {
 // starts hop samples = ROWS rows of 32 complex points after frame A, so row n1 of B
 // is row n1 + ROWS of A in the same lane: the pair needs 32 + ROWS sample loads
 // instead of 64.
-template <bool SQUARE, int MODE, int ROWS>
+// TT: window and twiddle tables in tensor memory (else in shared memory).
+template <bool SQUARE, int MODE, int ROWS, bool TT>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 stft2048p_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -111,6 +152,7 @@ stft2048p_kernel(const Params p) {
   float* sMelW = reinterpret_cast<float*>(smem_raw + 16640);
   PairMelItem* sItems = reinterpret_cast<PairMelItem*>(sMelW + p.a.mel_w_floats);
   __shared__ __align__(8) uint64_t sbars[kGroups];
+  __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
   const int group = tid / kGroupThreads;
@@ -123,14 +165,48 @@ stft2048p_kernel(const Params p) {
   unsigned char* ex = sBufs + warp * kWarpBuf;                 // this warp's
   float* prow = reinterpret_cast<float*>(ex + 32 * warp);      // its power rows, [bin][2]
 
-  for (int i = tid; i < 2048; i += blockDim.x) {
-    // source index j = 2 (32 n1 + l) + c  ->  ((n1/2) * 32 + l) * 4 + (n1 & 1) * 2 + c
-    const int c = i & 1, l = (i >> 1) & 31, n1 = i >> 6;
-    sWindow[(((n1 >> 1) * 32 + l) << 2) + ((n1 & 1) << 1) + c] = p.a.window[i] * 0.5f;
-  }
-  for (int i = tid; i < 1024; i += blockDim.x) {
-    const int l = i & 31, k1 = i >> 5;
-    reinterpret_cast<float2*>(sTwPass)[(((k1 >> 1) * 32 + l) << 1) + (k1 & 1)] = p.a.tw_pass[i];
+  uint32_t ttab = 0;                     // tensor-memory address of this warp's table rows
+  if (TT) {
+    if (tid < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    ttab = tmem_slot + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
+    if (tid < 128) {                     // one warp per 32-lane quarter fills it
+      uint32_t v[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)     // column 2 n1 + c: w[64 n1 + 2 lane + c] / 2
+          v[e] = __float_as_uint(p.a.window[64 * (8 * q + (e >> 1)) + 2 * lane + (e & 1)] * 0.5f);
+        tmem_st16(ttab + 16 * q, v);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {   // column 64 + 2 k1 + c: W1024^(k1 lane)
+          const float2 t = p.a.tw_pass[(8 * q + (e >> 1)) * 32 + lane];
+          v[e] = __float_as_uint((e & 1) ? t.y : t.x);
+        }
+        tmem_st16(ttab + 64 + 16 * q, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // ordered by the barrier below
+  } else {
+    for (int i = tid; i < 2048; i += blockDim.x) {
+      // source index j = 2 (32 n1 + l) + c  ->  ((n1/2) * 32 + l) * 4 + (n1 & 1) * 2 + c
+      const int c = i & 1, l = (i >> 1) & 31, n1 = i >> 6;
+      sWindow[(((n1 >> 1) * 32 + l) << 2) + ((n1 & 1) << 1) + c] = p.a.window[i] * 0.5f;
+    }
+    for (int i = tid; i < 1024; i += blockDim.x) {
+      const int l = i & 31, k1 = i >> 5;
+      reinterpret_cast<float2*>(sTwPass)[(((k1 >> 1) * 32 + l) << 1) + (k1 & 1)] = p.a.tw_pass[i];
+    }
   }
   if (tid < 32) sTwPost[tid] = p.a.tw_post[tid];
   if (MODE == kModeMel) {
@@ -142,6 +218,7 @@ stft2048p_kernel(const Params p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (TT) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t sbar = smem_u32(&sbars[group]);
   uint32_t sphase = 0;
 
@@ -166,13 +243,15 @@ stft2048p_kernel(const Params p) {
     const int nf = (int)min((long long)kTile, g.frames - p0);
 
     // ---- the tile's samples were requested one iteration ago
-    if (bulk) {
-      stage::mbar_wait(sbar, sphase & 1);
-      ++sphase;
-    } else {
-      asm volatile("cp.async.wait_all;" ::: "memory");
+    if (MODE != kModeFree || tile == slot) {
+      if (bulk) {
+        stage::mbar_wait(sbar, sphase & 1);
+        ++sphase;
+      } else {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+      }
+      named_sync(group + 1, kGroupThreads);
     }
-    named_sync(group + 1, kGroupThreads);
 
     {
       // ---- pass 1: lane = n2, registers = n1; z[n] = x[2n] + i x[2n+1], n = 32 n1 + n2.
@@ -186,24 +265,55 @@ stft2048p_kernel(const Params p) {
         float2 raw[32 + ROWS];
 #pragma unroll
         for (int r = 0; r < 32 + ROWS; ++r) raw[r] = sA[32 * r];
+        if (TT) {
 #pragma unroll
-        for (int n1 = 0; n1 < 32; n1 += 2) {
-          const float4 w = w4[(n1 >> 1) * 32];
-          a[n1] = CP{pk(raw[n1].x * w.x, raw[n1 + ROWS].x * w.x), pk(raw[n1].y * w.y, raw[n1 + ROWS].y * w.y)};
-          a[n1 + 1] = CP{pk(raw[n1 + 1].x * w.z, raw[n1 + 1 + ROWS].x * w.z),
-                         pk(raw[n1 + 1].y * w.w, raw[n1 + 1 + ROWS].y * w.w)};
+          for (int q = 0; q < 4; ++q) {
+            uint32_t wv[16];
+            tmem_ld16(ttab + 16 * q, wv);
+            tmem_wait16(wv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int n1 = 8 * q + e;
+              const float wx = __uint_as_float(wv[2 * e]), wy = __uint_as_float(wv[2 * e + 1]);
+              a[n1] = CP{pk(raw[n1].x * wx, raw[n1 + ROWS].x * wx), pk(raw[n1].y * wy, raw[n1 + ROWS].y * wy)};
+            }
+          }
+        } else {
+#pragma unroll
+          for (int n1 = 0; n1 < 32; n1 += 2) {
+            const float4 w = w4[(n1 >> 1) * 32];
+            a[n1] = CP{pk(raw[n1].x * w.x, raw[n1 + ROWS].x * w.x), pk(raw[n1].y * w.y, raw[n1 + ROWS].y * w.y)};
+            a[n1 + 1] = CP{pk(raw[n1 + 1].x * w.z, raw[n1 + 1 + ROWS].x * w.z),
+                           pk(raw[n1 + 1].y * w.w, raw[n1 + 1 + ROWS].y * w.w)};
+          }
         }
       } else {
         const float2* sA = reinterpret_cast<const float2*>(sSamples + 2 * warp * g.hop) + lane;
         const float2* sB = reinterpret_cast<const float2*>(sSamples + (2 * warp + 1) * g.hop) + lane;
         const float4* w4 = reinterpret_cast<const float4*>(sWindow) + lane;
+        if (TT) {
 #pragma unroll
-        for (int n1 = 0; n1 < 32; n1 += 2) {
-          const float2 a0 = sA[32 * n1], a1 = sA[32 * (n1 + 1)];
-          const float2 b0 = sB[32 * n1], b1 = sB[32 * (n1 + 1)];
-          const float4 w = w4[(n1 >> 1) * 32];
-          a[n1] = CP{pk(a0.x * w.x, b0.x * w.x), pk(a0.y * w.y, b0.y * w.y)};
-          a[n1 + 1] = CP{pk(a1.x * w.z, b1.x * w.z), pk(a1.y * w.w, b1.y * w.w)};
+          for (int q = 0; q < 4; ++q) {
+            uint32_t wv[16];
+            tmem_ld16(ttab + 16 * q, wv);
+            tmem_wait16(wv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int n1 = 8 * q + e;
+              const float2 a0 = sA[32 * n1], b0 = sB[32 * n1];
+              const float wx = __uint_as_float(wv[2 * e]), wy = __uint_as_float(wv[2 * e + 1]);
+              a[n1] = CP{pk(a0.x * wx, b0.x * wx), pk(a0.y * wy, b0.y * wy)};
+            }
+          }
+        } else {
+#pragma unroll
+          for (int n1 = 0; n1 < 32; n1 += 2) {
+            const float2 a0 = sA[32 * n1], a1 = sA[32 * (n1 + 1)];
+            const float2 b0 = sB[32 * n1], b1 = sB[32 * (n1 + 1)];
+            const float4 w = w4[(n1 >> 1) * 32];
+            a[n1] = CP{pk(a0.x * w.x, b0.x * w.x), pk(a0.y * w.y, b0.y * w.y)};
+            a[n1 + 1] = CP{pk(a1.x * w.z, b1.x * w.z), pk(a1.y * w.w, b1.y * w.w)};
+          }
         }
       }
       fft32(a);                                   // a[k1] = Y[n2 = lane][k1]
@@ -211,9 +321,20 @@ stft2048p_kernel(const Params p) {
       {
         const float4* t4 = sTwPass + lane;
         ulonglong2* st = reinterpret_cast<ulonglong2*>(ex) + lane;
+        uint32_t tv[16];
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1 += 2) {
-          const float4 t = t4[(k1 >> 1) * 32];
+          float4 t;
+          if (TT) {
+            if ((k1 & 7) == 0) {
+              tmem_ld16(ttab + 64 + 2 * k1, tv);
+              tmem_wait16(tv);
+            }
+            t = make_float4(__uint_as_float(tv[2 * (k1 & 7)]), __uint_as_float(tv[2 * (k1 & 7) + 1]),
+                            __uint_as_float(tv[2 * (k1 & 7) + 2]), __uint_as_float(tv[2 * (k1 & 7) + 3]));
+          } else {
+            t = t4[(k1 >> 1) * 32];
+          }
           const CP v0 = k1 == 0 ? a[0]
                                 : CP{pfmas(a[k1].im, -t.y, pmuls(a[k1].re, t.x)),
                                      pfmas(a[k1].im, t.x, pmuls(a[k1].re, t.y))};
@@ -236,7 +357,7 @@ stft2048p_kernel(const Params p) {
       __syncwarp();                               // the buffer becomes the power rows
       fft32(a);
 
-      if (MODE == kModeCeiling) {
+      if (MODE != kModeMel) {
         // the measurement floor: no split, no |X|^2, no mel -- one store per value
 #pragma unroll
         for (int k2 = 0; k2 < 32; ++k2)
@@ -276,11 +397,12 @@ stft2048p_kernel(const Params p) {
         }
       }
     }
-    named_sync(group + 1, kGroupThreads);
-
-    // ---- the sample buffer is free: fetch the next tile under the mel phase
-    if (tile + stride < total_tiles)
-      bulk = stage::stage_tile<kTile, kGroupThreads>(g, p.a.x, p.bulk, nb, nt, sSamples, gtid, sbar);
+    if (MODE != kModeFree) {
+      named_sync(group + 1, kGroupThreads);
+      // ---- the sample buffer is free: fetch the next tile under the mel phase
+      if (tile + stride < total_tiles)
+        bulk = stage::stage_tile<kTile, kGroupThreads>(g, p.a.x, p.bulk, nb, nt, sSamples, gtid, sbar);
+    }
 
     if (MODE == kModeMel) {
       // ---- mel projection.  lane = (filter i of the round's eight, frame pair j): one
@@ -295,41 +417,63 @@ stft2048p_kernel(const Params p) {
       const bool okA = 2 * j < nf, okB = 2 * j + 1 < nf;
       float* ob = p.a.out + (long long)b * p.a.n_mels * g.frames + p0 + 2 * j;
       const int frames = (int)g.frames;                     // n_mels * frames < 2^31 (launcher)
-      for (int r = 0; r < mel_rounds; ++r) {
-        const int2 it = mine[r * 8];                        // {weights | iterations << 24, h0 | m << 16}
-        const int iters = (int)((unsigned)it.x >> 24);      // two 4-bin steps each; the same for the whole warp
+      // Two rounds at a time, in lockstep (the host pairs rounds of equal length): the
+      // loads of one round's step are in flight under the FMAs of the other -- with two
+      // warps per scheduler the phase is latency-bound otherwise.  Every round keeps
+      // its own four accumulator chains and bin order, so the sum of a filter does not
+      // depend on which round it is paired with.
+      for (int r = 0; r < mel_rounds; r += 2) {             // mel_rounds is even
+        const int2 it0 = mine[r * 8], it1 = mine[(r + 1) * 8];   // {weights | iterations << 24, h0 | m << 16}
+        const int iters = (int)((unsigned)it0.x >> 24);     // two 4-bin steps each; warp-uniform; the pair's
         if (iters == 0) break;                              // idle rounds come last
-        const float4* wq = reinterpret_cast<const float4*>(sMelW) + (it.x & 0xFFFFFF);
-        const ulonglong2* pp = pj + (it.y & 0xFFFF);
-        // four independent accumulator chains; every step's loads are in flight under
-        // the FMAs of the step before (the last iteration reads one step past the
-        // band -- inside the tables, never used)
-        pk_t acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
-        float4 wa = wq[0];
-        ulonglong2 a01 = pp[0], a23 = pp[1];
+        const float4* wq0 = reinterpret_cast<const float4*>(sMelW) + (it0.x & 0xFFFFFF);
+        const float4* wq1 = reinterpret_cast<const float4*>(sMelW) + (it1.x & 0xFFFFFF);
+        const ulonglong2* pp0 = pj + (it0.y & 0xFFFF);
+        const ulonglong2* pp1 = pj + (it1.y & 0xFFFF);
+        pk_t c0 = 0ull, c1 = 0ull, c2 = 0ull, c3 = 0ull, d0 = 0ull, d1 = 0ull, d2 = 0ull, d3 = 0ull;
+        float4 wa0 = wq0[0], wa1 = wq1[0];
+        ulonglong2 a0 = pp0[0], a1 = pp0[1], a2 = pp1[0], a3 = pp1[1];
 #pragma unroll 1
         for (int t = 0; t < iters; ++t) {
-          const float4 wb = wq[8];
-          const ulonglong2 b01 = pp[2], b23 = pp[3];
-          acc0 = pfmas(a01.x, wa.x, acc0);
-          acc1 = pfmas(a01.y, wa.y, acc1);
-          acc2 = pfmas(a23.x, wa.z, acc2);
-          acc3 = pfmas(a23.y, wa.w, acc3);
-          wq += 16;
-          pp += 4;
-          wa = wq[0];
-          a01 = pp[0];
-          a23 = pp[1];
-          acc0 = pfmas(b01.x, wb.x, acc0);
-          acc1 = pfmas(b01.y, wb.y, acc1);
-          acc2 = pfmas(b23.x, wb.z, acc2);
-          acc3 = pfmas(b23.y, wb.w, acc3);
+          const float4 wb0 = wq0[8], wb1 = wq1[8];
+          const ulonglong2 b0 = pp0[2], b1 = pp0[3], b2 = pp1[2], b3 = pp1[3];
+          c0 = pfmas(a0.x, wa0.x, c0);
+          c1 = pfmas(a0.y, wa0.y, c1);
+          c2 = pfmas(a1.x, wa0.z, c2);
+          c3 = pfmas(a1.y, wa0.w, c3);
+          d0 = pfmas(a2.x, wa1.x, d0);
+          d1 = pfmas(a2.y, wa1.y, d1);
+          d2 = pfmas(a3.x, wa1.z, d2);
+          d3 = pfmas(a3.y, wa1.w, d3);
+          wq0 += 16;
+          wq1 += 16;
+          pp0 += 4;
+          pp1 += 4;
+          if (t + 1 < iters) {                              // nothing is fetched past the band
+            wa0 = wq0[0];
+            wa1 = wq1[0];
+            a0 = pp0[0];
+            a1 = pp0[1];
+            a2 = pp1[0];
+            a3 = pp1[1];
+          }
+          c0 = pfmas(b0.x, wb0.x, c0);
+          c1 = pfmas(b0.y, wb0.y, c1);
+          c2 = pfmas(b1.x, wb0.z, c2);
+          c3 = pfmas(b1.y, wb0.w, c3);
+          d0 = pfmas(b2.x, wb1.x, d0);
+          d1 = pfmas(b2.y, wb1.y, d1);
+          d2 = pfmas(b3.x, wb1.z, d2);
+          d3 = pfmas(b3.y, wb1.w, d3);
         }
-        const pk_t acc = padd(padd(acc0, acc1), padd(acc2, acc3));
-        const int m = it.y >> 16;
-        float* o = ob + m * frames;
-        if (m >= 0 && okA) o[0] = pk_lo(acc);
-        if (m >= 0 && okB) o[1] = pk_hi(acc);
+        const pk_t s0 = padd(padd(c0, c1), padd(c2, c3)), s1 = padd(padd(d0, d1), padd(d2, d3));
+        const int m0 = it0.y >> 16, m1 = it1.y >> 16;
+        float* o0 = ob + m0 * frames;
+        float* o1 = ob + m1 * frames;
+        if (m0 >= 0 && okA) o0[0] = pk_lo(s0);
+        if (m0 >= 0 && okB) o0[1] = pk_hi(s0);
+        if (m1 >= 0 && okA) o1[0] = pk_lo(s1);
+        if (m1 >= 0 && okB) o1[1] = pk_hi(s1);
       }
     } else {
       // ceiling mode: one value per thread and tile keeps the rows alive
@@ -337,6 +481,13 @@ stft2048p_kernel(const Params p) {
     }
     // no barrier here: the next tile's group barrier (top of the loop) orders these
     // power-row reads before the next transpositions
+  }
+  if (TT) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                   : "memory");
   }
 }
 
@@ -381,6 +532,7 @@ cudaError_t launch_stft2048p(const Stft2048PairArgs& a, bool ceiling, int sm_cou
   Params p;
   p.a = a;
   if (ceiling) { p.a.mel_w_floats = 0; p.a.mel_rounds = 0; }
+  if (getenv("SMB_PAIR_SKIP_MEL")) p.a.mel_rounds = 0;   // measurement: everything but the mel phase (no output)
   p.bulk = stage::bulk_rule(a.x, a.g, kTile, !getenv("SMB_NO_BULK"));
   p.span_bytes = span_bytes_needed(a.g);
   p.tables_bytes = tables_bytes_needed(p.a.mel_w_floats, p.a.mel_rounds);
@@ -391,21 +543,27 @@ cudaError_t launch_stft2048p(const Stft2048PairArgs& a, bool ceiling, int sm_cou
   const long long want = (p.total_tiles + kGroups - 1) / kGroups;
   const int grid = (int)(want < sm_count ? want : sm_count);
   cudaError_t e;
-#define SMB_LAUNCH2048P_R(SQ, MODE, R)                                                         \
-  e = cudaFuncSetAttribute(stft2048p_kernel<SQ, MODE, R>,                                      \
+#define SMB_LAUNCH2048P_RT(SQ, MODE, R, T)                                                     \
+  e = cudaFuncSetAttribute(stft2048p_kernel<SQ, MODE, R, T>,                                   \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
   if (e != cudaSuccess) return e;                                                              \
-  stft2048p_kernel<SQ, MODE, R><<<grid, kGroups * kGroupThreads, smem, st>>>(p);
+  stft2048p_kernel<SQ, MODE, R, T><<<grid, kGroups * kGroupThreads, smem, st>>>(p);
+  // SMB_NO_TMEM_TABLES=1: window and twiddles from shared memory (A/B measurement)
+  const bool tmem_tables = !getenv("SMB_NO_TMEM_TABLES");
+#define SMB_LAUNCH2048P_R(SQ, MODE, R)                                                         \
+  if (tmem_tables) { SMB_LAUNCH2048P_RT(SQ, MODE, R, true) } else { SMB_LAUNCH2048P_RT(SQ, MODE, R, false) }
   // hop 512 (fft / 4) and 256 (fft / 8) share sample rows between the frames of a pair
 #define SMB_LAUNCH2048P(SQ, MODE)                                                              \
   if (a.g.hop == 512 && !getenv("SMB_NO_SHARED_ROWS")) { SMB_LAUNCH2048P_R(SQ, MODE, 8) }      \
   else if (a.g.hop == 256 && !getenv("SMB_NO_SHARED_ROWS")) { SMB_LAUNCH2048P_R(SQ, MODE, 4) } \
   else { SMB_LAUNCH2048P_R(SQ, MODE, 0) }
-  if (ceiling) { SMB_LAUNCH2048P(true, kModeCeiling) }
+  if (ceiling && getenv("SMB_PAIR_FREERUN")) { SMB_LAUNCH2048P(true, kModeFree) }
+  else if (ceiling) { SMB_LAUNCH2048P(true, kModeCeiling) }
   else if (a.power == 2.0f) { SMB_LAUNCH2048P(true, kModeMel) }
   else { SMB_LAUNCH2048P(false, kModeMel) }
 #undef SMB_LAUNCH2048P
 #undef SMB_LAUNCH2048P_R
+#undef SMB_LAUNCH2048P_RT
   ++g_launch_count;
   return cudaGetLastError();
 }

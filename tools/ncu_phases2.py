@@ -30,8 +30,9 @@ def main(path, frames=441344):
     def find(prefix, start=0, last=False):
         hits = [i for i, d in enumerate(data) if d[0].startswith(prefix) and i >= start]
         return (hits[-1] if last else hits[0]) if hits else None
-    bars = [i for i, d in enumerate(data) if d[0].startswith("BAR.SYNC")]
-    b1, b2 = bars[1], bars[2]
+    # the two group barriers of the tile loop are the named ones (register operand)
+    bars = [i for i, d in enumerate(data) if d[0].startswith("BAR.SYNC") and " R" in d[0]]
+    b1, b2 = bars[0], bars[1]
     s0, s1 = find("STS.128", b1), find("STS.128", b1, last=True)
     h0 = find("SHFL", b1)
     regions = [("setup", 0, b1), ("pass 1: loads, window, fft32", b1, s0),
