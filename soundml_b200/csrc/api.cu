@@ -416,13 +416,13 @@ struct smb_mel_plan {
   // bins down, weights zero there) so that the eight 16-byte loads of a quarter-warp,
   // whose four frame pairs sit 32 bytes apart, fall in eight distinct bank groups.
   // Weights are stored [round][step][filter] x float4 = one 128-byte run per warp
-  // load.
+  // load.  Rounds go longest-first onto the lightest of the four warps.
   bool build_pair_schedule(PairSchedule& sc) const {
     sc.clear();
     const int kBins = 1032;                                  // power row incl. zeroed tail (stft2048p.cu)
     if (bins != 1025 || n_mels > 32767) return false;
     const int rounds_total = (int)((n_mels + 7) / 8);
-    struct Round { int steps; int b0[8]; int m[8]; };
+    struct Round { int steps; size_t base; int b0[8]; int m[8]; };
     std::vector<Round> built((size_t)rounds_total);
     for (int q = 0; q < rounds_total; ++q) {
       Round& rd = built[(size_t)q];
@@ -444,60 +444,46 @@ struct smb_mel_plan {
         if (rd.m[i] >= 0) rd.steps = std::max(rd.steps, (hi[i] - rd.b0[i] + 3) / 4);
       rd.steps = (rd.steps + 1) & ~1;                      // the kernel runs two steps per iteration
       if (rd.steps > 510 || 4 * rd.steps > kBins) return false;
+      // every lane runs the round's step count: keep its reads inside the row
+      for (int i = 0; i < 8; ++i) rd.b0[i] = std::min(rd.b0[i], (kBins - 4 * rd.steps) & ~1);
+      rd.base = sc.w.size();
+      sc.w.resize(rd.base + (size_t)rd.steps * 8 * 4, 0.0f);
+      for (int i = 0; i < 8; ++i) {
+        if (rd.m[i] < 0) continue;
+        for (int k = band_lo[(size_t)rd.m[i]]; k < band_hi[(size_t)rd.m[i]]; ++k) {
+          const int u = k - rd.b0[i];
+          sc.w[rd.base + ((size_t)(u >> 2) * 8 + (size_t)i) * 4 + (size_t)(u & 3)] =
+              (float)weights[(size_t)((int64_t)rd.m[i] * bins + k)];
+        }
+      }
     }
+    sc.w.resize(sc.w.size() + 8 * 4, 0.0f);                // the kernel's prefetch reads one step ahead
+    if (sc.w.size() >= (1u << 24)) return false;
     const int warps = smb::kPairTile / 2;
     std::vector<int> by_len((size_t)rounds_total);
     for (int q = 0; q < rounds_total; ++q) by_len[(size_t)q] = q;
     std::stable_sort(by_len.begin(), by_len.end(),
                      [&](int a, int b) { return built[(size_t)a].steps > built[(size_t)b].steps; });
-    // The kernel runs two rounds in lockstep: neighbours in the sorted order make a
-    // pair and run the longer one's step count (the shorter reads on through zero
-    // weights, inside its power row: b0 is clamped again for the new count).  An odd
-    // round out pairs with an idle one.  Pairs go longest-first onto the lightest warp.
-    struct Pair { int a, b, steps; };
-    std::vector<Pair> pairs;
-    for (size_t q = 0; q < by_len.size(); q += 2) {
-      Pair pr{by_len[q], q + 1 < by_len.size() ? by_len[q + 1] : -1, built[(size_t)by_len[q]].steps};
-      pairs.push_back(pr);
-    }
     std::vector<std::vector<int>> lists((size_t)warps);
     std::vector<long long> load((size_t)warps, 0);
-    for (size_t q = 0; q < pairs.size(); ++q) {
+    for (int q : by_len) {
       const size_t wi = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
-      lists[wi].push_back((int)q);
-      load[wi] += pairs[q].steps * 17 + 70;
+      lists[wi].push_back(q);
+      load[wi] += built[(size_t)q].steps * 10 + 30;
     }
-    size_t most = 0;
-    for (const auto& l : lists) most = std::max(most, l.size());
-    sc.rounds = 2 * (int)most;
+    sc.rounds = 0;
+    for (const auto& l : lists) sc.rounds = std::max(sc.rounds, (int)l.size());
     sc.items.assign((size_t)(warps * sc.rounds * 8), smb::PairMelItem{0, 0, -1});   // idle: no steps
-    std::vector<float> packed;                              // weights re-laid per pair member at its new length
     for (int wi = 0; wi < warps; ++wi)
       for (size_t r = 0; r < lists[(size_t)wi].size(); ++r) {
-        const Pair& pr = pairs[(size_t)lists[(size_t)wi][r]];
-        for (int half = 0; half < 2; ++half) {
-          const int q = half == 0 ? pr.a : pr.b;
-          const size_t base = packed.size();
-          packed.resize(base + (size_t)pr.steps * 8 * 4, 0.0f);
-          for (int i = 0; i < 8; ++i) {
-            smb::PairMelItem& it = sc.items[((size_t)wi * (size_t)sc.rounds + 2 * r + (size_t)half) * 8 + (size_t)i];
-            it.w4_steps = (int)(base / 4 + (size_t)i) | ((pr.steps / 2) << 24);
-            if (q < 0) continue;                            // idle partner: zero weights, bin 0, m = -1
-            const Round& rd = built[(size_t)q];
-            if (rd.m[i] < 0) continue;
-            const int b0 = std::min(rd.b0[i], (kBins - 4 * pr.steps) & ~1);
-            it.h0 = (unsigned short)(b0 >> 1);
-            it.m = (short)rd.m[i];
-            for (int k = band_lo[(size_t)rd.m[i]]; k < band_hi[(size_t)rd.m[i]]; ++k) {
-              const int u = k - b0;
-              packed[base + ((size_t)(u >> 2) * 8 + (size_t)i) * 4 + (size_t)(u & 3)] =
-                  (float)weights[(size_t)((int64_t)rd.m[i] * bins + k)];
-            }
-          }
+        const Round& rd = built[(size_t)lists[(size_t)wi][r]];
+        for (int i = 0; i < 8; ++i) {
+          smb::PairMelItem& it = sc.items[((size_t)wi * (size_t)sc.rounds + r) * 8 + (size_t)i];
+          it.w4_steps = (int)(rd.base / 4 + (size_t)i) | ((rd.steps / 2) << 24);
+          it.h0 = (unsigned short)(rd.b0[i] >> 1);
+          it.m = (short)rd.m[i];
         }
       }
-    sc.w.swap(packed);
-    if (sc.w.size() >= (1u << 24)) return false;
     return true;
   }
   // Mel schedule of the fused kernels.  Every filter's band, starting on a float4

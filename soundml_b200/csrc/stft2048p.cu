@@ -417,63 +417,43 @@ stft2048p_kernel(const Params p) {
       const bool okA = 2 * j < nf, okB = 2 * j + 1 < nf;
       float* ob = p.a.out + (long long)b * p.a.n_mels * g.frames + p0 + 2 * j;
       const int frames = (int)g.frames;                     // n_mels * frames < 2^31 (launcher)
-      // Two rounds at a time, in lockstep (the host pairs rounds of equal length): the
-      // loads of one round's step are in flight under the FMAs of the other -- with two
-      // warps per scheduler the phase is latency-bound otherwise.  Every round keeps
-      // its own four accumulator chains and bin order, so the sum of a filter does not
-      // depend on which round it is paired with.
-      for (int r = 0; r < mel_rounds; r += 2) {             // mel_rounds is even
-        const int2 it0 = mine[r * 8], it1 = mine[(r + 1) * 8];   // {weights | iterations << 24, h0 | m << 16}
-        const int iters = (int)((unsigned)it0.x >> 24);     // two 4-bin steps each; warp-uniform; the pair's
+      for (int r = 0; r < mel_rounds; ++r) {
+        const int2 it = mine[r * 8];                        // {weights | iterations << 24, h0 | m << 16}
+        const int iters = (int)((unsigned)it.x >> 24);      // two 4-bin steps each; the same for the whole warp
         if (iters == 0) break;                              // idle rounds come last
-        const float4* wq0 = reinterpret_cast<const float4*>(sMelW) + (it0.x & 0xFFFFFF);
-        const float4* wq1 = reinterpret_cast<const float4*>(sMelW) + (it1.x & 0xFFFFFF);
-        const ulonglong2* pp0 = pj + (it0.y & 0xFFFF);
-        const ulonglong2* pp1 = pj + (it1.y & 0xFFFF);
-        pk_t c0 = 0ull, c1 = 0ull, c2 = 0ull, c3 = 0ull, d0 = 0ull, d1 = 0ull, d2 = 0ull, d3 = 0ull;
-        float4 wa0 = wq0[0], wa1 = wq1[0];
-        ulonglong2 a0 = pp0[0], a1 = pp0[1], a2 = pp1[0], a3 = pp1[1];
+        const float4* wq = reinterpret_cast<const float4*>(sMelW) + (it.x & 0xFFFFFF);
+        const ulonglong2* pp = pj + (it.y & 0xFFFF);
+        // four independent accumulator chains; every step's loads are in flight under
+        // the FMAs of the step before (the last iteration reads one step past the
+        // band -- inside the tables, never used)
+        pk_t acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
+        float4 wa = wq[0];
+        ulonglong2 a01 = pp[0], a23 = pp[1];
 #pragma unroll 1
         for (int t = 0; t < iters; ++t) {
-          const float4 wb0 = wq0[8], wb1 = wq1[8];
-          const ulonglong2 b0 = pp0[2], b1 = pp0[3], b2 = pp1[2], b3 = pp1[3];
-          c0 = pfmas(a0.x, wa0.x, c0);
-          c1 = pfmas(a0.y, wa0.y, c1);
-          c2 = pfmas(a1.x, wa0.z, c2);
-          c3 = pfmas(a1.y, wa0.w, c3);
-          d0 = pfmas(a2.x, wa1.x, d0);
-          d1 = pfmas(a2.y, wa1.y, d1);
-          d2 = pfmas(a3.x, wa1.z, d2);
-          d3 = pfmas(a3.y, wa1.w, d3);
-          wq0 += 16;
-          wq1 += 16;
-          pp0 += 4;
-          pp1 += 4;
-          if (t + 1 < iters) {                              // nothing is fetched past the band
-            wa0 = wq0[0];
-            wa1 = wq1[0];
-            a0 = pp0[0];
-            a1 = pp0[1];
-            a2 = pp1[0];
-            a3 = pp1[1];
+          const float4 wb = wq[8];
+          const ulonglong2 b01 = pp[2], b23 = pp[3];
+          acc0 = pfmas(a01.x, wa.x, acc0);
+          acc1 = pfmas(a01.y, wa.y, acc1);
+          acc2 = pfmas(a23.x, wa.z, acc2);
+          acc3 = pfmas(a23.y, wa.w, acc3);
+          wq += 16;
+          pp += 4;
+          if (t + 1 < iters) {            // (warp-uniform) nothing is fetched past the band
+            wa = wq[0];
+            a01 = pp[0];
+            a23 = pp[1];
           }
-          c0 = pfmas(b0.x, wb0.x, c0);
-          c1 = pfmas(b0.y, wb0.y, c1);
-          c2 = pfmas(b1.x, wb0.z, c2);
-          c3 = pfmas(b1.y, wb0.w, c3);
-          d0 = pfmas(b2.x, wb1.x, d0);
-          d1 = pfmas(b2.y, wb1.y, d1);
-          d2 = pfmas(b3.x, wb1.z, d2);
-          d3 = pfmas(b3.y, wb1.w, d3);
+          acc0 = pfmas(b01.x, wb.x, acc0);
+          acc1 = pfmas(b01.y, wb.y, acc1);
+          acc2 = pfmas(b23.x, wb.z, acc2);
+          acc3 = pfmas(b23.y, wb.w, acc3);
         }
-        const pk_t s0 = padd(padd(c0, c1), padd(c2, c3)), s1 = padd(padd(d0, d1), padd(d2, d3));
-        const int m0 = it0.y >> 16, m1 = it1.y >> 16;
-        float* o0 = ob + m0 * frames;
-        float* o1 = ob + m1 * frames;
-        if (m0 >= 0 && okA) o0[0] = pk_lo(s0);
-        if (m0 >= 0 && okB) o0[1] = pk_hi(s0);
-        if (m1 >= 0 && okA) o1[0] = pk_lo(s1);
-        if (m1 >= 0 && okB) o1[1] = pk_hi(s1);
+        const pk_t acc = padd(padd(acc0, acc1), padd(acc2, acc3));
+        const int m = it.y >> 16;
+        float* o = ob + m * frames;
+        if (m >= 0 && okA) o[0] = pk_lo(acc);
+        if (m >= 0 && okB) o[1] = pk_hi(acc);
       }
     } else {
       // ceiling mode: one value per thread and tile keeps the rows alive
@@ -548,7 +528,9 @@ cudaError_t launch_stft2048p(const Stft2048PairArgs& a, bool ceiling, int sm_cou
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
   if (e != cudaSuccess) return e;                                                              \
   stft2048p_kernel<SQ, MODE, R, T><<<grid, kGroups * kGroupThreads, smem, st>>>(p);
-  // SMB_NO_TMEM_TABLES=1: window and twiddles from shared memory (A/B measurement)
+  // SMB_NO_TMEM_TABLES=1: window and twiddles from shared memory instead of tensor
+  // memory (A/B measurement: 64 more shared-memory wavefronts per frame, 0.941 against
+  // 0.937 ms on the headline workload)
   const bool tmem_tables = !getenv("SMB_NO_TMEM_TABLES");
 #define SMB_LAUNCH2048P_R(SQ, MODE, R)                                                         \
   if (tmem_tables) { SMB_LAUNCH2048P_RT(SQ, MODE, R, true) } else { SMB_LAUNCH2048P_RT(SQ, MODE, R, false) }

@@ -17,6 +17,9 @@ __device__ __forceinline__ long long src_index(const FrameGeom& g, long long q) 
   if (g.pad == 0) {
     if (g.n == 1) return 0;
     const long long period = 2 * (g.n - 1);
+    // one reflection (every border of a signal longer than the extension): no division
+    const long long once = s < 0 ? -s : period - s;
+    if (once >= 0 && once < g.n) return once;
     long long r = s % period;
     if (r < 0) r += period;
     return r < g.n ? r : period - r;
@@ -62,6 +65,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 struct BulkRule {
   int t_lo, t_hi;
   unsigned nmod, c0;
+  unsigned chunk;      // floats per bulk copy (multiple of 4), 0 = one copy per tile
 };
 
 // Brings the samples of tile t of clip b (padded stream positions t*TILE*hop .. + span)
@@ -77,9 +81,15 @@ __device__ __forceinline__ bool stage_tile(const FrameGeom& g, const float* x, c
     if (gtid == 0) {
       const uint32_t span = (uint32_t)((TILE - 1) * g.hop + 2048);
       const float* src = x + (long long)b * g.n + ((long long)t * TILE * g.hop - g.left);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // (no proxy fence: the buffer was only READ through the generic proxy, and those
+      // reads have returned -- the readers counted off or passed a barrier after using
+      // the values; a consumer release needs no more than that, as in every TMA pipeline)
       mbar_expect_tx(bar, 4u * span);
-      bulk_g2s(smem_u32(dst), src, 4u * span, bar);
+      // several copies instead of one: each keeps its own lines in flight (rule.chunk
+      // floats apiece, a multiple of 4; 0 = the whole span at once)
+      const uint32_t chunk = rule.chunk ? rule.chunk : span;
+      for (uint32_t at = 0; at < span; at += chunk)
+        bulk_g2s(smem_u32(dst + at), src + at, 4u * min(chunk, span - at), bar);
     }
     return true;
   }
@@ -92,13 +102,21 @@ __device__ __forceinline__ bool stage_tile(const FrameGeom& g, const float* x, c
   // [lo, hi): positions of the span that are real samples
   const int lo = (int)max(0LL, min((long long)span, -s0));
   const int hi = (int)max((long long)lo, min((long long)span, g.n - s0));
-  for (int i = gtid; i < lo; i += THREADS) {
-    const long long s = src_index(g, q0 + i);
-    dst[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
-  }
-  for (int i = hi + gtid; i < span; i += THREADS) {
-    const long long s = src_index(g, q0 + i);
-    dst[i] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
+  // border positions, four per thread and round so that their loads are in flight together
+  for (int side = 0; side < 2; ++side) {
+    const int from = side == 0 ? 0 : hi, to = side == 0 ? lo : span;
+    for (int i0 = from + gtid; i0 < to; i0 += 4 * THREADS) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * THREADS;
+        const long long s = i < to ? src_index(g, q0 + i) : -1;
+        v[k] = s >= 0 ? __ldg(xs + s) : (float)g.pad_value;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k * THREADS < to) dst[i0 + k * THREADS] = v[k];
+    }
   }
   const float* src = xs + s0;                       // src + i is valid for i in [lo, hi)
   const unsigned base = smem_u32(dst);
@@ -130,7 +148,7 @@ __device__ __forceinline__ bool stage_tile(const FrameGeom& g, const float* x, c
 // [t*TILE*hop - left, ... + span): inside the clip, and 16-byte aligned when
 // (x/4 + b*n - left) % 4 == 0 (TILE*hop is a multiple of 4).
 inline BulkRule bulk_rule(const float* x, const FrameGeom& g, int tile, bool enabled) {
-  BulkRule r{0, -1, 0u, 0u};
+  BulkRule r{0, -1, 0u, 0u, 0u};
   if (!enabled || (g.hop & 3) != 0 || (reinterpret_cast<size_t>(x) & 3) != 0) return r;
   const long long th = (long long)tile * g.hop, span = (long long)(tile - 1) * g.hop + 2048;
   const long long lo = (g.left + th - 1) / th;
