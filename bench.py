@@ -7,10 +7,15 @@
 A step is one pass of the hot path (Soundml.mel_spectrogram) over the batch.
 `value` is audio-seconds per second with the clips already resident in HBM,
 timed with CUDA events on the stream the kernel runs on; `e2e` is the same call
-on pinned HOST buffers (H2D + kernel + D2H inside the timed region); `roofline`
-divides the algorithmic bytes of one launch by its measured duration;
-`cpu_baseline` is the oracle (the reference's CPU arithmetic restated, see
-oracle/) timed on this box's host cores on a bounded sample.
+on pinned HOST buffers (H2D + kernel + D2H inside the timed region) with
+`copy_floor_ms`, the same buffers through cudaMemcpyAsync alone, beside it;
+`roofline` divides the algorithmic bytes of one launch by its measured duration
+and carries `compute_floor_ms`, the transform skeleton alone (staging, window,
+both FFT passes, transposition: smb_stft_fft_ceiling); `secondary` holds
+BASELINE.json configs[2..4] (FIR 511, 44.1 -> 16 kHz, resample + STFT + mel), one
+GPU's share each, with their own roofline fraction and parity; `cpu_baseline` is
+the oracle (the reference's CPU arithmetic restated, see oracle/) timed on this
+box's host cores on a bounded sample.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -44,6 +49,23 @@ WORKLOAD = ("mel_spectrogram 128 bands, 1024 x 10 s 22.05 kHz f32 clips per GPU,
 BYTES_PER_CLIP = N * 4 + N_MELS * FRAMES * 4       # 1 102 672
 ALGO_BYTES = BATCH * BYTES_PER_CLIP                # 1 129 136 128 per launch
 FALLBACK_HBM_GBS = 6650.0
+
+
+def load_synth():
+    """soundml_b200/synth.py by path: importing the package would load
+    libsoundml_b200.so, which the CPU arms must not map."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "soundml_b200_synth", os.path.join(ROOT, "soundml_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_config(world):
+    return {"workload": WORKLOAD, "global_batch_clips": world * BATCH,
+            "parallelism": f"clips sharded over {world} GPU(s), no collective",
+            "l2": "inputs (903 MB per GPU) exceed L2 (126 MB); no flush needed"}
 
 
 def peak_hbm():
@@ -123,7 +145,7 @@ def time_cpu(clips, min_seconds, workers, keep=None):
     state the GPU path's error against it next to the number."""
     os.environ["OMP_NUM_THREADS"] = str(workers)         # see run_reference
     from oracle import mel_oracle, stft_oracle
-    from soundml_b200 import synth
+    synth = load_synth()
     from threadpoolctl import threadpool_limits
     x = synth.clips_numpy(clips, N, SR)
     sc = stft_oracle.StftConfig(FFT, HOP)
@@ -155,7 +177,7 @@ def run_reference(args, rank, world):
     # library starts its pool (and see threadpool_limits below).
     os.environ["OMP_NUM_THREADS"] = str(cores)
     from oracle import mel_oracle, stft_oracle
-    from soundml_b200 import synth
+    synth = load_synth()
     x = synth.clips_numpy(clips, N, SR)
     sc = stft_oracle.StftConfig(FFT, HOP)
     mc = mel_oracle.MelConfig(N_MELS, SR, FFT)
@@ -177,13 +199,138 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": workload_config(max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def timed_ms(fn, steps, warmup, barrier, dev):
+    """CUDA-event time per call of fn on torch's current stream, max over ranks."""
+    import torch
+    from soundml_b200.parallel import max_over_ranks
+    for _ in range(warmup):
+        fn()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    barrier()
+    return max_over_ranks(a.elapsed_time(b), device=dev) / steps
+
+
+def secondary_configs(sb, dev, world, rank, barrier, peak, with_parity):
+    """BASELINE.json configs[2..4], one GPU's share each (weak scaling: every rank
+    runs its share, the step time is the max over ranks).  Each entry carries its
+    algorithmic bytes (input + output once; taps, banks and intermediates
+    excluded), the roofline fraction and -- on rank 0 at N = 1 -- the
+    error against the float64 oracle on a bounded sample of the same call."""
+    import numpy as np
+    import torch
+
+    def peak_err(got, want):
+        return float(np.abs(np.asarray(got, np.float64) - want).max() / np.abs(want).max())
+
+    def entry(workload, ms, algo_bytes, audio_s, launches, parity):
+        ach = algo_bytes / (ms * 1e-3) / 1e9
+        return {"workload": workload, "ms_per_step": ms,
+                "value": world * audio_s / (ms * 1e-3), "unit": UNIT,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                             "frac": ach / peak, "algorithmic_bytes_per_launch": algo_bytes},
+                "gpu_launches_per_step": launches, "parity": parity}
+
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def noise(shape):
+        return torch.rand(shape, device=dev, generator=gen) * 2 - 1
+
+    def launches_of(fn):
+        c0 = sb.kernel_launch_count()
+        fn()
+        return sb.kernel_launch_count() - c0
+
+    # ---- configs[2]: 511-tap FIR lowpass over 256 x 60 s stereo 48 kHz clips = 512 lines
+    lines, n = 512, 60 * 48000
+    x = noise((lines, n))
+    y = torch.empty_like(x)
+    fir = sb.Fir.lowpass(k=255, cutoff=0.25)
+    for method, steps in (("ols", 5), ("direct", 2)):
+        ms = timed_ms(lambda: fir.apply(x, method=method, out=y), steps, 1, barrier, dev)
+        parity = None
+        if with_parity:
+            from oracle import resample_oracle as R
+            m = 200000                                   # outputs [0, m) depend on x[0, m + 255] only
+            want = R.fir_apply(x[0, :m + 1024].cpu().numpy(), fir.taps)[:m]
+            parity = {"max_rel_err": peak_err(y[0, :m].cpu().numpy(), want), "tolerance": 1e-5,
+                      "sample": f"first {m} outputs of line 0 against the float64 oracle"}
+        out[f"fir511_{method}"] = entry(
+            f"511-tap FIR lowpass ({method}), {lines} lines x 60 s @48 kHz per GPU (BASELINE.json configs[2])",
+            ms, 2 * lines * n * 4, lines * 60.0,
+            launches_of(lambda: fir.apply(x, method=method, out=y)), parity)
+    del x, y
+
+    # ---- configs[3]: 44.1 -> 16 kHz, 4096 x 30 s clips over 8 GPUs = 512 clips per GPU
+    clips, n = 512, 30 * 44100
+    x = noise((clips, n))
+    cfg = sb.Resample.Config.create(sample_rate=44100, target=16000)
+    total = cfg.output_frames(n)
+    y = torch.empty((clips, total), device=dev)
+    ms = timed_ms(lambda: sb.Resample.apply(cfg, x, out=y), 5, 1, barrier, dev)
+    parity = None
+    if with_parity:
+        from oracle import resample_oracle as R
+        st = [dict(l=t["l"], m=t["m"], k=t["k"], proto=R.design_prototype(t["l"], t["k"], t["fc"], t["beta"]))
+              for t in cfg.stages()]
+        want = R.apply_plan(x[0].cpu().numpy(), st, cfg.l, cfg.m)
+        parity = {"max_rel_err": peak_err(y[0].cpu().numpy(), want), "tolerance": 1e-5,
+                  "sample": f"clip 0 at full length ({n} -> {total} samples) against the float64 oracle"}
+    out["resample_44k1_16k"] = entry(
+        f"{cfg.pp()}, {clips} clips x 30 s per GPU (BASELINE.json configs[3]: 4096 clips over 8 GPUs)",
+        ms, clips * (n + total) * 4, clips * 30.0,
+        launches_of(lambda: sb.Resample.apply(cfg, x, out=y)), parity)
+    del x, y
+
+    # ---- configs[4]: resample 44.1 -> 22.05 kHz + STFT + mel, 65536 x 10 s over 8 GPUs = 8192 per GPU
+    clips, n = 8192, 10 * 44100
+    x = noise((clips, n))
+    cfg = sb.Resample.Config.create(sample_rate=44100, target=22050)
+    mid = torch.empty((clips, cfg.output_frames(n)), device=dev)
+    sc = sb.Stft.Config.create(fft_size=FFT, hop=HOP)
+    mc = sb.Mel.Config.create(n_mels=N_MELS, sample_rate=SR, fft_size=FFT)
+    frames = sb.Stft.frames(sc, mid.shape[1])
+    y = torch.empty((clips, N_MELS, frames), device=dev)
+
+    def step():
+        sb.Resample.apply(cfg, x, out=mid)
+        sb.mel_spectrogram(sc, mc, mid, out=y)
+    ms = timed_ms(step, 5, 1, barrier, dev)
+    parity = None
+    if with_parity:
+        from oracle import mel_oracle, stft_oracle
+        from oracle import resample_oracle as R
+        st = [dict(l=t["l"], m=t["m"], k=t["k"], proto=R.design_prototype(t["l"], t["k"], t["fc"], t["beta"]))
+              for t in cfg.stages()]
+        want_mid = R.apply_plan(x[:2].cpu().numpy(), st, cfg.l, cfg.m).astype(np.float32)
+        want = mel_oracle.mel_spectrogram(stft_oracle.StftConfig(FFT, HOP),
+                                          mel_oracle.MelConfig(N_MELS, SR, FFT), want_mid)
+        got = y[:2].cpu().numpy()
+        parity = {"max_rel_err": max(peak_err(got[b], want[b]) for b in range(2)), "tolerance": 1e-4,
+                  "sample": "clips 0-1 at full length: oracle resampler (float64, rounded to float32 "
+                            "like Resample.apply's result) -> oracle STFT + mel"}
+    out["resample_stft_mel"] = entry(
+        f"{cfg.pp()} -> mel_spectrogram 128 bands, {clips} clips x 10 s @44.1 kHz per GPU "
+        "(BASELINE.json configs[4]: 65536 clips over 8 GPUs); the 22.05 kHz intermediate "
+        f"({mid.numel() * 4 / 1e9:.1f} GB) crosses HBM once each way and is not counted",
+        ms, clips * (n * 4 + N_MELS * frames * 4), clips * 10.0, launches_of(step), parity)
+    del x, mid, y
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -194,9 +341,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "fast", "tensor", "pair"],
-                    help="which fused fft-2048 kernel: auto (the library's choice), the CUDA-core "
-                         "register FFT (fast) or the tcgen05 one (tensor)")
+                    help="which fused fft-2048 kernel: auto (the library's choice: the frame-pair "
+                         "kernel), the frame-pair kernel (pair), the one-frame-per-warp register FFT "
+                         "(fast) or the tcgen05 one (tensor)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 
@@ -279,25 +428,64 @@ def main():
                "h2d_bytes_per_step": BATCH * N * 4, "d2h_bytes_per_step": BATCH * N_MELS * FRAMES * 4,
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
         assert torch.equal(oh.to(dev), out), "host and device paths disagree"
+        # the floor of that call: the same pinned buffers through cudaMemcpyAsync alone,
+        # both directions at once on two streams (what the e2e number is bound by)
+        d_in, d_out = torch.empty_like(x), torch.empty_like(out)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            with torch.cuda.stream(s_in):
+                d_in.copy_(xh, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                oh.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e["copy_floor_ms"] = 1e3 * max_over_ranks(time.perf_counter() - t0, device=dev) / e2e_steps
+        del d_in, d_out, xh, oh
+
+    # ---- the compute floor of the kernel: the transform skeleton alone (tile staging,
+    # window, both register-FFT passes, the transposition), same launch shape
+    floor_ms = None
+    if args.path in ("auto", "pair"):
+        from soundml_b200 import _lib
+        nbytes = _lib.lib.smb_stft_fft_ceiling_scratch_bytes(sc._h, BATCH, N)
+        scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib.smb_stft_plan_set_stream(sc._h, torch.cuda.current_stream(dev).cuda_stream))
+        floor_ms = timed_ms(lambda: _lib.check(_lib.lib.smb_stft_fft_ceiling(
+            sc._h, x.data_ptr(), BATCH, N, scratch.data_ptr())), 20, 3, barrier, dev)
+        del scratch
+
+    peak, peak_kind = peak_hbm()
+    parity_clips = 32
+    got_sample = out[:parity_clips].cpu().numpy() if (rank == 0 and world == 1) else None
+    del x, out
+    torch.cuda.empty_cache()
+    secondary = None
+    if not args.no_secondary:
+        secondary = secondary_configs(sb, dev, world, rank, barrier, peak, with_parity=(world == 1))
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_kind = peak_hbm()
     achieved = ALGO_BYTES / (ms_per_step * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes of one launch from the committed ncu capture of this kernel (not measured
+    # in this run: ncu replays kernels; profiles/traffic.json names the capture)
+    kernel = {"tensor": "stft2048tc_kernel<mel>", "fast": "stft2048_kernel<mel>"}.get(
+        args.path, "stft2048p_kernel<mel>")
+    traffic = traffic_source = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get("stft2048tc_mel_dram_bytes_per_launch" if args.path == "tensor"
-                           else "stft2048_mel_dram_bytes_per_launch")
+        rec = prof.get(kernel)
+        if rec:
+            traffic, traffic_source = rec["dram_bytes_per_launch"], rec["capture"]
     except Exception:
         pass
     cpu = parity = None
     if world == 1:                      # reported on rank 0 at N = 1 only
         cores = os.cpu_count() or 1
-        clips = 32
+        clips = parity_clips
         kept = []
         v, passes, dt = time_cpu(clips, args.cpu_seconds, cores, keep=kept)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -309,7 +497,7 @@ def main():
         # clips, and the elementwise pass rate at the reference's float32 gate
         import numpy as np
         want = np.asarray(kept[0], dtype=np.float64)
-        got = out[:clips].cpu().numpy().astype(np.float64)
+        got = got_sample.astype(np.float64)
         per_clip = (np.abs(got - want).max(axis=(1, 2)) / np.abs(want).max(axis=(1, 2)))
         gate = np.abs(got - want) <= 1e-7 + 1e-6 * np.abs(want)
         parity = {"max_rel_err_per_clip": float(per_clip.max()), "tolerance": 1e-4,
@@ -319,17 +507,16 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch_clips": world * BATCH,
-                   "parallelism": f"clips sharded over {world} GPU(s), no collective",
-                   "l2": "inputs (903 MB per GPU) exceed L2 (126 MB); no flush needed"},
+        "config": workload_config(world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                     "algorithmic_bytes_per_launch": ALGO_BYTES,
-                     "kernel": "stft2048tc_kernel<mel>" if args.path == "tensor"
-                               else "stft2048_kernel<mel>"},
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+                     "peak_source": peak_kind, "algorithmic_bytes_per_launch": ALGO_BYTES,
+                     "kernel": kernel, "kernel_ms": ms_per_step, "compute_floor_ms": floor_ms,
+                     "hbm_floor_ms": 1e3 * ALGO_BYTES / (peak * 1e9)},
         "cpu_baseline": cpu,
         "parity": parity,
         "e2e": e2e,
+        "secondary": secondary,
         "gpu_launches": launches,
         "clocks": clocks,
     }
