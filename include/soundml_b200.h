@@ -260,6 +260,30 @@ int smb_resample_apply(smb_resample_plan* plan, const float* x, int64_t batch,
 int smb_resample_apply_f64(smb_resample_plan* plan, const double* x, int64_t batch,
                            int64_t n, double* out, int mem);
 
+/* Resample.Kernel.prepare / step / flush / reset (resample.ml:1343-1424, 1844-1909): the
+ * chunked form of apply, what soundml-io's decode loop (soundml_io.ml:639, 768, 798) and
+ * cqt.ml:797-879 bind.  The carry (the input some future output still needs) lives in
+ * device memory.  A chunk is [channels, n] C-contiguous, dtype SMB_F32 or SMB_F64 as given
+ * at creation; step writes the samples that became computable, [channels, frames]
+ * C-contiguous with frames = smb_resample_kernel_step_frames(kernel, n) asked BEFORE the
+ * step (exact integer bookkeeping, may be 0); flush writes the delayed tail,
+ * smb_resample_kernel_flush_frames frames; everything written concatenates to
+ * smb_resample_apply's result on the concatenated input, ceil(n L / M) samples in all --
+ * bit for bit with the direct executor, to rounding (<= 1e-5 of peak) with the block
+ * executors.  Not thread-safe, single owner (resample.mli:271-273).  Errors carry the
+ * reference's wording (SMB_EINVAL: channels / max_block < 1, chunk longer than max_block,
+ * step after flush). */
+typedef struct smb_resample_kernel smb_resample_kernel;
+int smb_resample_kernel_create(smb_resample_kernel** kernel, smb_resample_plan* plan, int dtype,
+                               int64_t channels, int64_t max_block);
+int smb_resample_kernel_destroy(smb_resample_kernel* kernel);
+int smb_resample_kernel_reset(smb_resample_kernel* kernel);
+int64_t smb_resample_kernel_step_frames(const smb_resample_kernel* kernel, int64_t n);
+int64_t smb_resample_kernel_flush_frames(const smb_resample_kernel* kernel);
+int smb_resample_kernel_step(smb_resample_kernel* kernel, const void* chunk, int64_t n, void* out,
+                             int mem);
+int smb_resample_kernel_flush(smb_resample_kernel* kernel, void* out, int mem);
+
 /* ---- FIR ------------------------------------------------------------------ */
 /* y[c,i] = sum_t h[t] * x[c, i + (taps-1)/2 - t], zeros outside, taps odd.
  * method: SMB_EXEC_DIRECT, SMB_EXEC_OLS (overlap-save on the FFT kernels) or

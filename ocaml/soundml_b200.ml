@@ -1,8 +1,10 @@
 (* soundml_b200.ml — the OCaml side of the drop-in: externals over
    libsoundml_b200.so and the three functions of the reference that change.
 
-   UNVERIFIED (no OCaml toolchain in the build container).  The intent is a
-   patch to soundml/lib that leaves every signature of stft.mli / mel.mli /
+   NOT COMPILED HERE (no OCaml toolchain in the build container); the C stubs it
+   binds are syntax-checked against stand-in caml headers and every external below
+   is checked to name a CAMLprim of soundml_b200_stubs.c with the right arity
+   (tests/test_ocaml_layer.py).  The intent is a patch to soundml/lib that leaves every signature of stft.mli / mel.mli /
    resample.mli / soundml.mli untouched:
 
      Stft.power_spectrum   stft.ml:687-691   -> B200.power_spectrum
@@ -14,6 +16,8 @@
      Stft.invert           stft.ml:937-939   -> B200.invert
      Convert.power_to_db / amplitude_to_db  convert.ml:20-56 -> B200.to_db
      Soundml.mfcc          soundml.ml:50-95  -> B200.mfcc
+     Resample.Kernel.prepare / step / flush / reset
+                           resample.ml:1343-1424, 1844-1909 -> B200.Kernel
 
    Config.create stays in OCaml: the plan is built from the float64 window /
    weights the config already owns, so the two sides cannot disagree. *)
@@ -21,6 +25,7 @@
 type stft_plan
 type mel_plan
 type resample_plan
+type resample_kernel
 
 type ('a, 'b) ba = ('a, 'b, Bigarray.c_layout) Bigarray.Array1.t
 
@@ -85,6 +90,26 @@ external ingest_layout_c :
   (float, 'a) ba -> int -> int -> int -> (float, 'a) ba -> int -> int -> unit
   = "soundml_b200_ingest_layout_bc" "soundml_b200_ingest_layout"
 
+external stft_destroy : stft_plan -> unit = "soundml_b200_stft_destroy"
+external mel_destroy : mel_plan -> unit = "soundml_b200_mel_destroy"
+external resample_destroy : resample_plan -> unit = "soundml_b200_resample_destroy"
+
+(* dtype: 0 = float32, 1 = float64 *)
+external resample_kernel_create : resample_plan -> int -> int -> int -> resample_kernel
+  = "soundml_b200_resample_kernel_create"
+external resample_kernel_step_frames : resample_kernel -> int -> int
+  = "soundml_b200_resample_kernel_step_frames"
+external resample_kernel_flush_frames : resample_kernel -> int
+  = "soundml_b200_resample_kernel_flush_frames"
+external resample_kernel_step_c :
+  resample_kernel -> (float, 'a) ba -> int -> int -> (float, 'a) ba -> unit
+  = "soundml_b200_resample_kernel_step"
+external resample_kernel_flush_c : resample_kernel -> int -> (float, 'a) ba -> unit
+  = "soundml_b200_resample_kernel_flush"
+external resample_kernel_reset : resample_kernel -> unit = "soundml_b200_resample_kernel_reset"
+external resample_kernel_destroy : resample_kernel -> unit
+  = "soundml_b200_resample_kernel_destroy"
+
 (* The flat storage of a contiguous tensor, shared (resample.ml:94). *)
 let array1_of t = Nx_buffer.to_bigarray1 (Nx.to_buffer t)
 
@@ -96,13 +121,76 @@ let alignment_code = function `Centered -> 0 | `Left -> 1 | `Right -> 2
 
 let pad_code = function `Reflect -> (0, 0.) | `Constant v -> (1, v) | `Edge -> (2, 0.)
 
-(* One plan per configuration, created on first use (Config.t is immutable). *)
+(* One plan per configuration, created on first use and kept: Config.t values are
+   immutable, so physical identity keys the cache (an ephemeron table: the plan goes
+   when its configuration does; [release_plans] frees the device memory at once
+   instead of waiting for the finalizers).  Like the reference's lazies
+   (resample.ml:427, 492) the caches are not domain-safe. *)
+module Cache (K : sig type t end) = struct
+  module T = Ephemeron.K1.Make (struct
+    type t = K.t
+    let equal = ( == )
+    let hash = Hashtbl.hash
+  end)
+  let make () : 'plan T.t = T.create 8
+end
+
+module Stft_cache = Cache (struct type t = Stft.Config.t end)
+module Mel_cache = Cache (struct type t = Mel.Config.t end)
+
+let stft_plans : stft_plan Stft_cache.T.t = Stft_cache.make ()
+let mel_plans : mel_plan Mel_cache.T.t = Mel_cache.make ()
+let resample_plans : (int * int * int * float * float, resample_plan) Hashtbl.t = Hashtbl.create 8
+
 let stft_plan_of (c : Stft.Config.t) =
-  let pad, pad_value = pad_code (Stft.Config.pad c) in
-  stft_create (Stft.Config.fft_size c) (Stft.Config.hop c)
-    (alignment_code (Stft.Config.alignment c))
-    pad pad_value
-    (array1_of (Stft.Config.analysis_window c))
+  match Stft_cache.T.find_opt stft_plans c with
+  | Some p -> p
+  | None ->
+      let pad, pad_value = pad_code (Stft.Config.pad c) in
+      let p =
+        stft_create (Stft.Config.fft_size c) (Stft.Config.hop c)
+          (alignment_code (Stft.Config.alignment c))
+          pad pad_value
+          (array1_of (Stft.Config.analysis_window c))
+      in
+      Stft_cache.T.replace stft_plans c p ;
+      p
+
+let mel_plan_of (c : Mel.Config.t) =
+  match Mel_cache.T.find_opt mel_plans c with
+  | Some p -> p
+  | None ->
+      let p =
+        mel_create (Mel.Config.n_mels c) (Mel.Config.fft_size c)
+          (array1_of (Mel.filterbank Nx.float64 c))
+      in
+      Mel_cache.T.replace mel_plans c p ;
+      p
+
+let quality_code = function
+  | `Fast -> (0, 0., 0.)
+  | `High -> (1, 0., 0.)
+  | `Best -> (2, 0., 0.)
+  | `Custom (att, pb) -> (3, att, pb)
+
+let resample_plan_of ~sample_rate ~target ~quality =
+  let q, att, pb = quality_code quality in
+  let key = (sample_rate, target, q, att, pb) in
+  match Hashtbl.find_opt resample_plans key with
+  | Some p -> p
+  | None ->
+      let p = resample_create sample_rate target q att pb in
+      Hashtbl.replace resample_plans key p ;
+      p
+
+(* Free every cached plan's device memory now. *)
+let release_plans () =
+  Stft_cache.T.iter (fun _ p -> stft_destroy p) stft_plans ;
+  Stft_cache.T.reset stft_plans ;
+  Mel_cache.T.iter (fun _ p -> mel_destroy p) mel_plans ;
+  Mel_cache.T.reset mel_plans ;
+  Hashtbl.iter (fun _ p -> resample_destroy p) resample_plans ;
+  Hashtbl.reset resample_plans
 
 (* Replacement body of Stft.power_spectrum: same checks, same result shape
    [...; bins; frames]; the arithmetic is the fused B200 kernel. *)
@@ -124,35 +212,65 @@ let mel_spectrogram stft_config mel_config ?(power = 2.) x =
   let frames = Stft.frames stft_config ~n in
   let n_mels = Mel.Config.n_mels mel_config in
   let out = Nx.zeros (Nx.dtype x) (Array.append lead [|n_mels; frames|]) in
-  ( if batch > 0 && frames > 0 then
-      let mel =
-        mel_create n_mels (Mel.Config.fft_size mel_config)
-          (array1_of (Mel.filterbank Nx.float64 mel_config))
-      in
-      mel_spectrogram_c (stft_plan_of stft_config) mel
-        (array1_of (Nx.contiguous x))
-        batch n power (array1_of out) ) ;
+  if batch > 0 && frames > 0 then
+    mel_spectrogram_c (stft_plan_of stft_config) (mel_plan_of mel_config)
+      (array1_of (Nx.contiguous x))
+      batch n power (array1_of out) ;
   out
 
-let resample_apply ~sample_rate ~target ~quality x =
-  let q, att, pb =
-    match quality with
-    | `Fast -> (0, 0., 0.)
-    | `High -> (1, 0., 0.)
-    | `Best -> (2, 0., 0.)
-    | `Custom (att, pb) -> (3, att, pb)
-  in
-  let plan = resample_create sample_rate target q att pb in
+(* Replacement body of Resample.apply: the result has the dtype of [x], float32 or
+   float64 (resample.ml:72-84 carries both widths). *)
+let resample_apply (type a b) ~sample_rate ~target ~quality (x : (a, b) Nx.t) : (a, b) Nx.t =
+  let plan = resample_plan_of ~sample_rate ~target ~quality in
   let n = Nx.dim (Nx.ndim x - 1) x in
   let lead = leading_shape x in
   let batch = Array.fold_left ( * ) 1 lead in
   let g = let rec gcd a b = if b = 0 then a else gcd b (a mod b) in gcd sample_rate target in
   let l = target / g and m = sample_rate / g in
   let total = if n <= 0 then 0 else (((n * l) - 1) / m) + 1 in
-  let out = Nx.zeros Nx.float32 (Array.append lead [|total|]) in
-  if batch > 0 && n > 0 then
-    resample_apply_c plan (array1_of (Nx.contiguous x)) batch n (array1_of out) ;
+  let out = Nx.zeros (Nx.dtype x) (Array.append lead [|total|]) in
+  ( if batch > 0 && n > 0 then
+      match Nx.dtype x with
+      | Nx.Float32 -> resample_apply_c plan (array1_of (Nx.contiguous x)) batch n (array1_of out)
+      | Nx.Float64 ->
+          resample_apply_f64_c plan (array1_of (Nx.contiguous x)) batch n (array1_of out)
+      | _ -> invalid_arg "apply: cannot resample this sample type (float32 and float64 are carried)" ) ;
   out
+
+(* Replacement of Resample.Kernel (resample.ml:1343-1424, 1844-1909), the face
+   soundml-io's decode loop binds (soundml_io.ml:639, 768, 798): the carry lives on the
+   device, step returns the samples that became computable ([None] when there are
+   none), flush the delayed tail.  Single owner, not domain-safe (resample.mli:271-273). *)
+module Kernel = struct
+  type t = { k : resample_kernel; channels : int }
+
+  let prepare ~sample_rate ~target ~quality dtype ~channels ~max_block =
+    let code =
+      match dtype with
+      | `Float32 -> 0
+      | `Float64 -> 1
+    in
+    { k = resample_kernel_create (resample_plan_of ~sample_rate ~target ~quality) code channels max_block;
+      channels }
+
+  let step t chunk =
+    let n = Nx.dim (Nx.ndim chunk - 1) chunk in
+    let frames = resample_kernel_step_frames t.k n in
+    let lead = leading_shape chunk in
+    let out = Nx.zeros (Nx.dtype chunk) (Array.append lead [|frames|]) in
+    if n > 0 then
+      resample_kernel_step_c t.k (array1_of (Nx.contiguous chunk)) t.channels n (array1_of out) ;
+    if frames = 0 then None else Some out
+
+  let flush t dtype lead =
+    let frames = resample_kernel_flush_frames t.k in
+    let out = Nx.zeros dtype (Array.append lead [|frames|]) in
+    resample_kernel_flush_c t.k t.channels (array1_of out) ;
+    if frames = 0 then None else Some out
+
+  let reset t = resample_kernel_reset t.k
+  let destroy t = resample_kernel_destroy t.k
+end
 
 (* Replacement body of Stft.invert: the preconditions (check_synthesis,
    stft.ml:787) stay in OCaml; the library re-validates and raises the same
@@ -188,12 +306,9 @@ let mfcc stft_config mel_config ?(n_mfcc = 20) ?lifter x =
   let batch = Array.fold_left ( * ) 1 lead in
   let frames = Stft.frames stft_config ~n in
   let out = Nx.zeros (Nx.dtype x) (Array.append lead [|n_mfcc; frames|]) in
-  ( if batch > 0 && frames > 0 then
-      let mel =
-        mel_create (Mel.Config.n_mels mel_config) (Mel.Config.fft_size mel_config)
-          (array1_of (Mel.filterbank Nx.float64 mel_config))
-      in
-      mfcc_c (stft_plan_of stft_config) mel (array1_of (Nx.contiguous x)) batch n n_mfcc
-        (match lifter with Some l -> l | None -> 0.)
-        (array1_of out) ) ;
+  if batch > 0 && frames > 0 then
+    mfcc_c (stft_plan_of stft_config) (mel_plan_of mel_config) (array1_of (Nx.contiguous x))
+      batch n n_mfcc
+      (match lifter with Some l -> l | None -> 0.)
+      (array1_of out) ;
   out

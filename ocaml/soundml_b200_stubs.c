@@ -1,8 +1,10 @@
 /* soundml_b200_stubs.c — OCaml foreign stubs over libsoundml_b200.so.
  *
- * UNVERIFIED: the build container has no OCaml toolchain (ocaml, dune, opam all
- * absent), so this file has been reviewed by eye only; it follows the
- * conventions of the reference's own stubs:
+ * NOT LINKED HERE: the build container has no OCaml toolchain (ocaml, dune, opam all
+ * absent).  What is verified: the file compiles as C against stand-ins for
+ * the caml headers (tests/test_ocaml_layer.py: gcc -fsyntax-only -Wall -Werror with
+ * oracle/caml_shim), and every smb_* call matches include/soundml_b200.h.  It follows
+ * the conventions of the reference's own stubs:
  *   - Bigarray storage is shared, never copied      (resample.ml:94, resample_stubs.c:220-226)
  *   - every pointer is extracted before the runtime lock is released and no
  *     OCaml value is touched until it is re-acquired (resample_stubs.c:284-295)
@@ -51,11 +53,36 @@ static struct custom_operations rs_ops = {"soundml_b200.resample", rs_finalize,
   custom_compare_default, custom_hash_default, custom_serialize_default,
   custom_deserialize_default, custom_compare_ext_default, custom_fixed_length_default};
 
-static value wrap(struct custom_operations *ops, void *h) {
-  value v = caml_alloc_custom(ops, sizeof(void *), 0, 1);
+static void rk_finalize(value v) { if (HANDLE(v)) { smb_resample_kernel_destroy(HANDLE(v)); HANDLE(v) = NULL; } }
+static struct custom_operations rk_ops = {"soundml_b200.resample_kernel", rk_finalize,
+  custom_compare_default, custom_hash_default, custom_serialize_default,
+  custom_deserialize_default, custom_compare_ext_default, custom_fixed_length_default};
+
+/* `mem`: bytes the handle keeps outside the OCaml heap (device tables, staging), so
+ * that the GC's pacing sees them (caml_alloc_custom_mem, OCaml >= 4.08). */
+static value wrap(struct custom_operations *ops, void *h, uintnat mem) {
+  value v = caml_alloc_custom_mem(ops, sizeof(void *), mem);
   HANDLE(v) = h;
   return v;
 }
+
+/* Flat storage must hold `elems` elements (complex Bigarrays count complex elements).
+ * Raised while the runtime lock is held, like the reference's geometry checks
+ * (resample_stubs.c:253-276). */
+static void need(value ba, int64_t elems, const char *what) {
+  if ((int64_t)Caml_ba_array_val(ba)->dim[0] < elems) caml_failwith(what);
+}
+static void *live(value v_plan) {
+  void *h = HANDLE(v_plan);
+  if (!h) caml_invalid_argument("soundml_b200: the plan has been destroyed");
+  return h;
+}
+
+/* Explicit release (the finalizer stays as the backstop): destroy : plan -> unit */
+CAMLprim value soundml_b200_stft_destroy(value v) { stft_finalize(v); return Val_unit; }
+CAMLprim value soundml_b200_mel_destroy(value v) { mel_finalize(v); return Val_unit; }
+CAMLprim value soundml_b200_resample_destroy(value v) { rs_finalize(v); return Val_unit; }
+CAMLprim value soundml_b200_resample_kernel_destroy(value v) { rk_finalize(v); return Val_unit; }
 
 static int dtype_of(value ba) {
   int kind = Caml_ba_array_val(ba)->flags & CAML_BA_KIND_MASK;
@@ -73,12 +100,14 @@ CAMLprim value soundml_b200_stft_create(value v_fft, value v_hop, value v_align,
                                         value v_pad_value, value v_window) {
   CAMLparam1(v_window);
   smb_stft_plan *h = NULL;
+  need(v_window, Long_val(v_fft), "soundml_b200: the analysis window is shorter than fft_size");
   int st = smb_stft_plan_create_with_window(&h, Long_val(v_fft), Long_val(v_hop),
                                             Int_val(v_align), Int_val(v_pad),
                                             Double_val(v_pad_value),
                                             (const double *)Caml_ba_data_val(v_window));
   smb_ml_raise(st);
-  CAMLreturn(wrap(&stft_ops, h));
+  /* window, twiddles and fast-path tables on the device, plus host-call staging */
+  CAMLreturn(wrap(&stft_ops, h, (uintnat)Long_val(v_fft) * 64 + (1u << 20)));
 }
 CAMLprim value soundml_b200_stft_create_bc(value *argv, int argn) {
   (void)argn;
@@ -91,16 +120,15 @@ CAMLprim value soundml_b200_stft_create_bc(value *argv, int argn) {
 CAMLprim value soundml_b200_power_spectrum(value v_plan, value v_x, value v_batch, value v_n,
                                            value v_power, value v_out) {
   CAMLparam3(v_plan, v_x, v_out);
-  smb_stft_plan *h = HANDLE(v_plan);
+  smb_stft_plan *h = live(v_plan);
   const void *x = Caml_ba_data_val(v_x);
   void *out = Caml_ba_data_val(v_out);
   const int dtype = dtype_of(v_x);
   const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
   const double power = Double_val(v_power);
-  if ((int64_t)Caml_ba_array_val(v_x)->dim[0] < batch * n)
-    caml_failwith("soundml_b200: input extent disagrees with geometry");
-  if ((int64_t)Caml_ba_array_val(v_out)->dim[0] < batch * smb_stft_bins(h) * smb_stft_frames(h, n))
-    caml_failwith("soundml_b200: output extent disagrees with geometry");
+  need(v_x, batch * n, "soundml_b200: input extent disagrees with geometry");
+  need(v_out, batch * smb_stft_bins(h) * smb_stft_frames(h, n),
+       "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_stft_power_spectrum(h, x, batch, n, dtype, power, out, SMB_MEM_HOST);
   caml_acquire_runtime_system();
@@ -116,11 +144,14 @@ CAMLprim value soundml_b200_power_spectrum_bc(value *argv, int argn) {
 CAMLprim value soundml_b200_transform(value v_plan, value v_x, value v_batch, value v_n,
                                       value v_out) {
   CAMLparam3(v_plan, v_x, v_out);
-  smb_stft_plan *h = HANDLE(v_plan);
+  smb_stft_plan *h = live(v_plan);
   const void *x = Caml_ba_data_val(v_x);
   void *out = Caml_ba_data_val(v_out);
   const int dtype = dtype_of(v_x);
   const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
+  need(v_x, batch * n, "soundml_b200: input extent disagrees with geometry");
+  need(v_out, batch * smb_stft_bins(h) * smb_stft_frames(h, n),
+       "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_stft_transform(h, x, batch, n, dtype, out, SMB_MEM_HOST);
   caml_acquire_runtime_system();
@@ -132,21 +163,25 @@ CAMLprim value soundml_b200_transform(value v_plan, value v_x, value v_batch, va
 CAMLprim value soundml_b200_mel_create(value v_n_mels, value v_fft, value v_weights) {
   CAMLparam1(v_weights);
   smb_mel_plan *h = NULL;
+  need(v_weights, Long_val(v_n_mels) * (Long_val(v_fft) / 2 + 1),
+       "soundml_b200: the weight matrix is smaller than n_mels x bins");
   int st = smb_mel_plan_create_with_weights(&h, Long_val(v_n_mels), Long_val(v_fft),
                                             (const double *)Caml_ba_data_val(v_weights));
   smb_ml_raise(st);
-  CAMLreturn(wrap(&mel_ops, h));
+  CAMLreturn(wrap(&mel_ops, h, (uintnat)Long_val(v_n_mels) * (Long_val(v_fft) / 2 + 1) * 8 + (1u << 16)));
 }
 
 /* Mel.apply (mel.ml:202-231): s [batch; bins; frames] -> out [batch; n_mels; frames] */
 CAMLprim value soundml_b200_mel_apply(value v_plan, value v_s, value v_batch, value v_frames,
                                       value v_out) {
   CAMLparam3(v_plan, v_s, v_out);
-  smb_mel_plan *h = HANDLE(v_plan);
+  smb_mel_plan *h = live(v_plan);
   const void *s = Caml_ba_data_val(v_s);
   void *out = Caml_ba_data_val(v_out);
   const int dtype = dtype_of(v_s);
   const int64_t batch = Long_val(v_batch), frames = Long_val(v_frames);
+  need(v_s, batch * smb_mel_bins(h) * frames, "soundml_b200: input extent disagrees with geometry");
+  need(v_out, batch * smb_mel_n_mels(h) * frames, "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_mel_apply(h, s, batch, frames, dtype, out, SMB_MEM_HOST);
   caml_acquire_runtime_system();
@@ -158,13 +193,16 @@ CAMLprim value soundml_b200_mel_apply(value v_plan, value v_s, value v_batch, va
 CAMLprim value soundml_b200_mel_spectrogram(value v_stft, value v_mel, value v_x, value v_batch,
                                             value v_n, value v_power, value v_out) {
   CAMLparam5(v_stft, v_mel, v_x, v_out, v_power);
-  smb_stft_plan *hs = HANDLE(v_stft);
-  smb_mel_plan *hm = HANDLE(v_mel);
+  smb_stft_plan *hs = live(v_stft);
+  smb_mel_plan *hm = live(v_mel);
   const void *x = Caml_ba_data_val(v_x);
   void *out = Caml_ba_data_val(v_out);
   const int dtype = dtype_of(v_x);
   const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
   const double power = Double_val(v_power);
+  need(v_x, batch * n, "soundml_b200: input extent disagrees with geometry");
+  need(v_out, batch * smb_mel_n_mels(hm) * smb_stft_frames(hs, n),
+       "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_mel_spectrogram(hs, hm, x, batch, n, dtype, power, out, SMB_MEM_HOST);
   caml_acquire_runtime_system();
@@ -186,21 +224,22 @@ CAMLprim value soundml_b200_resample_create(value v_sr, value v_target, value v_
   int st = smb_resample_plan_create(&h, Long_val(v_sr), Long_val(v_target), Int_val(v_quality),
                                     Double_val(v_att), Double_val(v_passband));
   smb_ml_raise(st);
-  CAMLreturn(wrap(&rs_ops, h));
+  CAMLreturn(wrap(&rs_ops, h, 4u << 20));      /* banks, plan spectra, tensor-core images */
 }
 
 /* Resample.apply (resample.ml:1913-1936): x [batch; n] -> out [batch; ceil(n L / M)] */
 CAMLprim value soundml_b200_resample_apply(value v_plan, value v_x, value v_batch, value v_n,
                                            value v_out) {
   CAMLparam3(v_plan, v_x, v_out);
-  smb_resample_plan *h = HANDLE(v_plan);
+  smb_resample_plan *h = live(v_plan);
   const float *x = (const float *)Caml_ba_data_val(v_x);
   float *out = (float *)Caml_ba_data_val(v_out);
   const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
   if ((Caml_ba_array_val(v_x)->flags & CAML_BA_KIND_MASK) != CAML_BA_FLOAT32)
-    caml_invalid_argument("apply: the GPU resampler carries float32 audio");
-  if ((int64_t)Caml_ba_array_val(v_out)->dim[0] < batch * smb_resample_output_frames(h, n))
-    caml_failwith("soundml_b200: output extent disagrees with geometry");
+    caml_invalid_argument("apply: this entry carries float32 audio (float64 has its own)");
+  need(v_x, batch * n, "soundml_b200: input extent disagrees with geometry");
+  need(v_out, batch * smb_resample_output_frames(h, n),
+       "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_resample_apply(h, x, batch, n, out, SMB_MEM_HOST);
   caml_acquire_runtime_system();
@@ -212,12 +251,13 @@ CAMLprim value soundml_b200_resample_apply(value v_plan, value v_x, value v_batc
 CAMLprim value soundml_b200_resample_apply_f64(value v_plan, value v_x, value v_batch, value v_n,
                                                value v_out) {
   CAMLparam3(v_plan, v_x, v_out);
-  smb_resample_plan *h = HANDLE(v_plan);
+  smb_resample_plan *h = live(v_plan);
   const double *x = (const double *)Caml_ba_data_val(v_x);
   double *out = (double *)Caml_ba_data_val(v_out);
   const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
-  if ((int64_t)Caml_ba_array_val(v_out)->dim[0] < batch * smb_resample_output_frames(h, n))
-    caml_failwith("soundml_b200: output extent disagrees with geometry");
+  need(v_x, batch * n, "soundml_b200: input extent disagrees with geometry");
+  need(v_out, batch * smb_resample_output_frames(h, n),
+       "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_resample_apply_f64(h, x, batch, n, out, SMB_MEM_HOST);
   caml_acquire_runtime_system();
@@ -231,12 +271,15 @@ CAMLprim value soundml_b200_resample_apply_f64(value v_plan, value v_x, value v_
 CAMLprim value soundml_b200_transform_range(value v_plan, value v_x, value v_batch, value v_n,
                                             value v_p0, value v_p1, value v_out) {
   CAMLparam3(v_plan, v_x, v_out);
-  smb_stft_plan *h = HANDLE(v_plan);
+  smb_stft_plan *h = live(v_plan);
   const void *x = Caml_ba_data_val(v_x);
   void *out = Caml_ba_data_val(v_out);
   const int dtype = dtype_of(v_x);
   const int64_t batch = Long_val(v_batch), n = Long_val(v_n);
   const int64_t p0 = Long_val(v_p0), p1 = Long_val(v_p1);
+  need(v_x, batch * n, "soundml_b200: input extent disagrees with geometry");
+  if (p1 >= p0) need(v_out, batch * smb_stft_bins(h) * (p1 - p0),
+                     "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_stft_transform_range(h, x, batch, n, dtype, p0, p1, out, SMB_MEM_HOST);
   caml_acquire_runtime_system();
@@ -254,12 +297,15 @@ CAMLprim value soundml_b200_transform_range_bc(value *argv, int argn) {
 CAMLprim value soundml_b200_invert(value v_plan, value v_z, value v_batch, value v_frames,
                                    value v_length, value v_out) {
   CAMLparam3(v_plan, v_z, v_out);
-  smb_stft_plan *h = HANDLE(v_plan);
+  smb_stft_plan *h = live(v_plan);
   const void *z = Caml_ba_data_val(v_z);
   void *out = Caml_ba_data_val(v_out);
   const int in_dtype = dtype_of(v_z), out_dtype = dtype_of(v_out);
   const int64_t batch = Long_val(v_batch), frames = Long_val(v_frames);
   const int64_t length = Long_val(v_length);
+  need(v_z, batch * smb_stft_bins(h) * frames, "soundml_b200: input extent disagrees with geometry");
+  need(v_out, batch * (length >= 0 ? length : smb_stft_output_length(h, frames)),
+       "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_stft_invert(h, z, batch, frames, in_dtype, length >= 0, length >= 0 ? length : 0,
                            out_dtype, out, SMB_MEM_HOST);
@@ -284,6 +330,7 @@ CAMLprim value soundml_b200_to_db(value v_amplitude, value v_x, value v_referenc
   const double reference = Double_val(v_reference), amin = Double_val(v_amin);
   const double top_db = Double_val(v_top_db);
   const int amplitude = Bool_val(v_amplitude);
+  need(v_out, count, "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = amplitude
       ? smb_amplitude_to_db(x, count, dtype, reference, amin, top_db, out, SMB_MEM_HOST, SMB_STREAM_OWN)
@@ -302,13 +349,16 @@ CAMLprim value soundml_b200_to_db_bc(value *argv, int argn) {
 CAMLprim value soundml_b200_mfcc(value v_stft, value v_mel, value v_x, value v_batch, value v_n,
                                  value v_n_mfcc, value v_lifter, value v_out) {
   CAMLparam4(v_stft, v_mel, v_x, v_out);
-  smb_stft_plan *hs = HANDLE(v_stft);
-  smb_mel_plan *hm = HANDLE(v_mel);
+  smb_stft_plan *hs = live(v_stft);
+  smb_mel_plan *hm = live(v_mel);
   const void *x = Caml_ba_data_val(v_x);
   void *out = Caml_ba_data_val(v_out);
   const int dtype = dtype_of(v_x);
   const int64_t batch = Long_val(v_batch), n = Long_val(v_n), n_mfcc = Long_val(v_n_mfcc);
   const double lifter = Double_val(v_lifter);
+  need(v_x, batch * n, "soundml_b200: input extent disagrees with geometry");
+  need(v_out, batch * n_mfcc * smb_stft_frames(hs, n),
+       "soundml_b200: output extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_mfcc(hs, hm, x, batch, n, dtype, n_mfcc, lifter, out, SMB_MEM_HOST);
   caml_acquire_runtime_system();
@@ -335,6 +385,9 @@ CAMLprim value soundml_b200_ingest_layout(value v_staging, value v_frames, value
   const int64_t frames = Long_val(v_frames), channels = Long_val(v_channels);
   const int64_t total = Long_val(v_total), off = Long_val(v_off);
   const int mode = Int_val(v_mode);
+  need(v_staging, frames * channels, "soundml_b200: staging extent disagrees with geometry");
+  need(v_dst, (mode == 2 ? 1 : channels) * total,
+       "soundml_b200: destination extent disagrees with geometry");
   caml_release_runtime_system();
   int st = smb_ingest_layout(staging, frames, channels, mode, dtype, dst, total, off,
                              SMB_MEM_HOST, SMB_MEM_HOST, NULL);
@@ -345,4 +398,58 @@ CAMLprim value soundml_b200_ingest_layout(value v_staging, value v_frames, value
 CAMLprim value soundml_b200_ingest_layout_bc(value *argv, int argn) {
   (void)argn;
   return soundml_b200_ingest_layout(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5], argv[6]);
+}
+
+/* ---- Resample.Kernel (resample.ml:1343-1424, 1844-1909; soundml_io.ml:639, 768, 798) -----
+ * prepare : resample_plan -> dtype:int (0 = float32, 1 = float64) -> channels -> max_block -> kernel */
+CAMLprim value soundml_b200_resample_kernel_create(value v_plan, value v_dtype, value v_channels,
+                                                   value v_max_block) {
+  CAMLparam1(v_plan);
+  smb_resample_kernel *k = NULL;
+  int st = smb_resample_kernel_create(&k, live(v_plan), Int_val(v_dtype), Long_val(v_channels),
+                                      Long_val(v_max_block));
+  smb_ml_raise(st);
+  /* the carry: two rows of (max_block + cone) samples per channel, plus the window and its image */
+  CAMLreturn(wrap(&rk_ops, k, (uintnat)Long_val(v_channels) * (uintnat)Long_val(v_max_block) * 8 * 6));
+}
+/* frames the next step / the flush will emit: exact integers, asked before the call so
+ * that OCaml allocates the result (the stub allocates nothing on the OCaml heap) */
+CAMLprim value soundml_b200_resample_kernel_step_frames(value v_k, value v_n) {
+  return Val_long(smb_resample_kernel_step_frames(live(v_k), Long_val(v_n)));
+}
+CAMLprim value soundml_b200_resample_kernel_flush_frames(value v_k) {
+  return Val_long(smb_resample_kernel_flush_frames(live(v_k)));
+}
+/* step : kernel -> chunk:ba ([channels; n] flat) -> channels -> n -> out:ba ([channels; frames] flat) -> unit */
+CAMLprim value soundml_b200_resample_kernel_step(value v_k, value v_chunk, value v_channels,
+                                                 value v_n, value v_out) {
+  CAMLparam3(v_k, v_chunk, v_out);
+  smb_resample_kernel *k = live(v_k);
+  const void *chunk = Caml_ba_data_val(v_chunk);
+  void *out = Caml_ba_data_val(v_out);
+  const int64_t channels = Long_val(v_channels), n = Long_val(v_n);
+  need(v_chunk, channels * n, "soundml_b200: chunk extent disagrees with geometry");
+  need(v_out, channels * smb_resample_kernel_step_frames(k, n),
+       "soundml_b200: output extent disagrees with geometry");
+  caml_release_runtime_system();
+  int st = smb_resample_kernel_step(k, chunk, n, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value soundml_b200_resample_kernel_flush(value v_k, value v_channels, value v_out) {
+  CAMLparam2(v_k, v_out);
+  smb_resample_kernel *k = live(v_k);
+  void *out = Caml_ba_data_val(v_out);
+  need(v_out, Long_val(v_channels) * smb_resample_kernel_flush_frames(k),
+       "soundml_b200: output extent disagrees with geometry");
+  caml_release_runtime_system();
+  int st = smb_resample_kernel_flush(k, out, SMB_MEM_HOST);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value soundml_b200_resample_kernel_reset(value v_k) {
+  smb_ml_raise(smb_resample_kernel_reset(live(v_k)));
+  return Val_unit;
 }

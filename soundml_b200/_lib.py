@@ -114,6 +114,13 @@ SIGNATURES = {
     "smb_resample_output_frames": (_i64, [_vp, _i64]),
     "smb_resample_apply": (_int, [_vp, _vp, _i64, _i64, _vp, _int]),
     "smb_resample_apply_f64": (_int, [_vp, _vp, _i64, _i64, _vp, _int]),
+    "smb_resample_kernel_create": (_int, [_pvp, _vp, _int, _i64, _i64]),
+    "smb_resample_kernel_destroy": (_int, [_vp]),
+    "smb_resample_kernel_reset": (_int, [_vp]),
+    "smb_resample_kernel_step_frames": (_i64, [_vp, _i64]),
+    "smb_resample_kernel_flush_frames": (_i64, [_vp]),
+    "smb_resample_kernel_step": (_int, [_vp, _vp, _i64, _vp, _int]),
+    "smb_resample_kernel_flush": (_int, [_vp, _vp, _int]),
     "smb_fir_plan_create": (_int, [_pvp, _pd, _i64]),
     "smb_fir_plan_destroy": (_int, [_vp]),
     "smb_fir_plan_set_stream": (_int, [_vp, _vp]),

@@ -936,7 +936,7 @@ int smb_memcpy_d2h(void* dst, const void* src, size_t bytes) {
   return guarded([&] { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); });
 }
 int smb_device_synchronize(void) { return guarded([&] { CK(cudaDeviceSynchronize()); }); }
-int64_t smb_kernel_launch_count(void) { return smb::g_launch_count; }
+int64_t smb_kernel_launch_count(void) { return smb::g_launch_count.load(); }
 
 int smb_window_make(int kind, double param, int periodic, int64_t n, double* out) {
   return guarded([&] {
@@ -1893,6 +1893,201 @@ int smb_resample_apply_f64(smb_resample_plan* plan, const double* x, int64_t bat
 }
 
 // ---- FIR ----------------------------------------------------------------------
+
+// ---- Resample.Kernel: the chunked form of apply, carry resident on the device ------
+//
+// resample.ml:1343-1424 (prepare / step / flush / reset), 1844-1909; bound by soundml-io
+// (soundml_io.ml:639, 768, 798) and cqt.ml:797-879.  The reference threads per-stage
+// histories through its executors; here the state is the raw input still inside some
+// future output's dependency cone, kept in device memory, and every step runs the
+// offline stage pipeline over a window of it whose origin sits on a whole phase cycle of
+// every stage -- so each output is computed with the same phase, taps and summation
+// order as in the offline call -- and keeps the outputs whose cone lies inside the
+// samples fed so far.  With the direct executor the chunks concatenate to apply's
+// result bit for bit; the block executors (overlap-save, tcgen05) agree to rounding.
+struct smb_resample_kernel {
+  smb_resample_plan* plan = nullptr;
+  int64_t channels = 0, max_block = 0;
+  int dtype = SMB_F32;
+  size_t esz = 4;
+  int64_t l = 1, m = 1, reach = 0, grain = 1;
+  int64_t fed = 0, emitted = 0, base = 0;
+  bool drained = false;
+  int64_t cap = 0;                 // samples per channel row of the carry
+  DeviceBuffer carry[2];           // [channels][cap]: the retained input [base, fed), ping-pong
+  int cur = 0;
+  DeviceBuffer win, res;           // the contiguous window and its resampled image
+
+  static int64_t floor_div(int64_t a, int64_t b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+  int64_t avail_after(int64_t fed_now) const {           // outputs whose cone lies inside fed_now samples
+    const int64_t safe = fed_now - reach;
+    int64_t avail = safe <= 0 ? 0 : (safe * l + m - 1) / m;
+    return std::min(avail, plan->plan.output_frames(fed_now));
+  }
+  void ensure_cap(int64_t need, cudaStream_t st) {
+    if (need <= cap) return;
+    const int64_t grown = need + need / 2 + 64;
+    DeviceBuffer next;
+    next.ensure((size_t)channels * grown * esz);
+    if (fed > base)
+      CK(cudaMemcpy2DAsync(next.ptr, (size_t)grown * esz, carry[cur].ptr, (size_t)cap * esz,
+                           (size_t)(fed - base) * esz, (size_t)channels, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    carry[cur].release();
+    carry[cur] = next;
+    carry[1 - cur].release();
+    carry[1 - cur].ensure((size_t)channels * grown * esz);
+    cap = grown;
+  }
+  // outputs [emitted, upto) from a window of the retained input, written to `out`
+  // ([channels, upto - emitted], host or device)
+  void window(int64_t upto, void* out, int mem, cudaStream_t st) {
+    const int64_t first = emitted * m / l - reach;
+    const int64_t a0 = std::max<int64_t>(0, floor_div(first, grain) * grain);   // a whole number of grains
+    const int64_t len = fed - a0;
+    const int64_t total_w = plan->plan.output_frames(len);
+    char* w = (char*)win.ensure((size_t)channels * len * esz);
+    char* r = (char*)res.ensure((size_t)channels * total_w * esz);
+    CK(cudaMemcpy2DAsync(w, (size_t)len * esz, (char*)carry[cur].ptr + (size_t)(a0 - base) * esz,
+                         (size_t)cap * esz, (size_t)len * esz, (size_t)channels,
+                         cudaMemcpyDeviceToDevice, st));
+    const int rc = dtype == SMB_F32
+        ? smb_resample_apply(plan, (const float*)w, channels, len, (float*)r, SMB_MEM_DEVICE)
+        : smb_resample_apply_f64(plan, (const double*)w, channels, len, (double*)r, SMB_MEM_DEVICE);
+    if (rc != SMB_OK) throw cuda_failure(t_error);
+    const int64_t o0 = a0 * l / m;                         // a0 is a whole number of input cycles
+    const int64_t count = upto - emitted;
+    CK(cudaMemcpy2DAsync(out, (size_t)count * esz, r + (size_t)(emitted - o0) * esz,
+                         (size_t)total_w * esz, (size_t)count * esz, (size_t)channels,
+                         mem == SMB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    emitted = upto;
+    // drop what no future output can reach (kept on a grain boundary)
+    const int64_t keep = std::max<int64_t>(0, floor_div(emitted * m / l - reach, grain) * grain);
+    if (keep > base) {
+      if (fed > keep)
+        CK(cudaMemcpy2DAsync(carry[1 - cur].ptr, (size_t)cap * esz,
+                             (char*)carry[cur].ptr + (size_t)(keep - base) * esz, (size_t)cap * esz,
+                             (size_t)(fed - keep) * esz, (size_t)channels, cudaMemcpyDeviceToDevice, st));
+      cur = 1 - cur;
+      base = keep;
+    }
+  }
+};
+
+int smb_resample_kernel_create(smb_resample_kernel** kernel, smb_resample_plan* plan, int dtype,
+                               int64_t channels, int64_t max_block) {
+  return guarded([&] {
+    *kernel = nullptr;
+    // resample.ml:1346-1356, the reference's wording
+    if (channels < 1)
+      throw smb::invalid_argument(smb::format(
+          "prepare: cannot resample %lld channels (channels must be at least 1)", (long long)channels));
+    if (max_block < 1)
+      throw smb::invalid_argument(smb::format(
+          "prepare: cannot accept blocks of %lld samples (max_block must be at least 1)",
+          (long long)max_block));
+    smb_resample_kernel* k = new smb_resample_kernel;
+    k->plan = plan;
+    k->channels = channels;
+    k->max_block = max_block;
+    k->dtype = dtype;
+    k->esz = dtype_size(dtype);
+    const smb::ResamplePlan& rp = plan->plan;
+    k->l = rp.l;
+    k->m = rp.m;
+    // dependency cone of one output, in input samples either side of floor(i M / L)
+    if (rp.stages.empty()) {
+      k->reach = 0;
+      k->grain = 1;
+    } else if (rp.stages.size() == 1) {
+      k->reach = rp.stages[0].k + 1;
+      k->grain = rp.stages[0].m;
+    } else {
+      const int64_t l1 = rp.stages[0].l, m1 = rp.stages[0].m, k1 = rp.stages[0].k;
+      const int64_t m2 = rp.stages[1].m, k2 = rp.stages[1].k;
+      k->reach = k1 + ((k2 + 2) * m1 + l1 - 1) / l1 + 2;
+      int64_t g = m1;                                     // window origin: whole cycles of both stages
+      while ((g / m1 * l1) % m2) g += m1;
+      k->grain = g;
+    }
+    *kernel = k;
+  });
+}
+int smb_resample_kernel_destroy(smb_resample_kernel* k) {
+  return guarded([&] {
+    if (!k) return;
+    k->carry[0].release();
+    k->carry[1].release();
+    k->win.release();
+    k->res.release();
+    delete k;
+  });
+}
+int smb_resample_kernel_reset(smb_resample_kernel* k) {
+  return guarded([&] {
+    k->fed = k->emitted = k->base = 0;
+    k->drained = false;
+  });
+}
+int64_t smb_resample_kernel_step_frames(const smb_resample_kernel* k, int64_t n) {
+  if (k->drained || n <= 0) return 0;
+  if (k->l == k->m) return n;
+  const int64_t avail = k->avail_after(k->fed + n);
+  return avail > k->emitted ? avail - k->emitted : 0;
+}
+int64_t smb_resample_kernel_flush_frames(const smb_resample_kernel* k) {
+  if (k->drained || k->fed == 0) return 0;
+  const int64_t total = k->plan->plan.output_frames(k->fed);
+  return total > k->emitted ? total - k->emitted : 0;
+}
+int smb_resample_kernel_step(smb_resample_kernel* k, const void* chunk, int64_t n, void* out,
+                             int mem) {
+  return guarded([&] {
+    if (k->drained)
+      throw smb::invalid_argument(
+          "step: cannot feed a drained kernel (flush consumed the tail; reset before reusing)");
+    if (n < 0 || n > k->max_block)
+      throw smb::invalid_argument(smb::format(
+          "step: cannot feed a %lld-sample chunk (max_block is %lld)", (long long)n,
+          (long long)k->max_block));
+    if (mem != SMB_MEM_HOST && mem != SMB_MEM_DEVICE)
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    if (n == 0) return;
+    k->plan->ensure_device();
+    cudaStream_t st = k->plan->stream.use;
+    const cudaMemcpyKind in_kind = mem == SMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (k->l == k->m) {                                   // identity: forward a copy
+      CK(cudaMemcpyAsync(out, chunk, (size_t)k->channels * n * k->esz,
+                         mem == SMB_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToDevice, st));
+      k->fed += n;
+      k->emitted = k->base = k->fed;
+      if (mem == SMB_MEM_HOST) CK(cudaStreamSynchronize(st));
+      return;
+    }
+    k->ensure_cap(k->fed - k->base + n, st);
+    CK(cudaMemcpy2DAsync((char*)k->carry[k->cur].ptr + (size_t)(k->fed - k->base) * k->esz,
+                         (size_t)k->cap * k->esz, chunk, (size_t)n * k->esz, (size_t)n * k->esz,
+                         (size_t)k->channels, in_kind, st));
+    k->fed += n;
+    const int64_t avail = k->avail_after(k->fed);
+    if (avail > k->emitted) k->window(avail, out, mem, st);
+    if (mem == SMB_MEM_HOST) CK(cudaStreamSynchronize(st));
+  });
+}
+int smb_resample_kernel_flush(smb_resample_kernel* k, void* out, int mem) {
+  return guarded([&] {
+    if (k->drained) return;
+    k->drained = true;
+    if (mem != SMB_MEM_HOST && mem != SMB_MEM_DEVICE)
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    const int64_t total = k->fed ? k->plan->plan.output_frames(k->fed) : 0;
+    if (total <= k->emitted) return;
+    k->plan->ensure_device();
+    cudaStream_t st = k->plan->stream.use;
+    k->window(total, out, mem, st);
+    if (mem == SMB_MEM_HOST) CK(cudaStreamSynchronize(st));
+  });
+}
 
 int smb_fir_plan_create(smb_fir_plan** plan, const double* h, int64_t taps) {
   return guarded([&] {

@@ -1,6 +1,7 @@
 // Launch wrappers of the CUDA kernels (internal to the library).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 
 namespace smb {
@@ -16,7 +17,7 @@ struct FrameGeom {
 
 enum SpecMode { kModeComplex = 0, kModePower = 1 };
 
-extern long long g_launch_count;   // kernels launched by this library
+extern std::atomic<long long> g_launch_count;   // kernels launched by this library (plans may run on several host threads)
 
 // ---- generic path: any fft size, float64 interior ---------------------------
 // x [batch, n] (f32 or f64) -> out [batch, bins, frames]; complex mode writes

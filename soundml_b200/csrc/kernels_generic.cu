@@ -10,7 +10,7 @@
 
 namespace smb {
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 __device__ __forceinline__ long long source_index(const FrameGeom& g, long long q) {
   // padded position q -> source sample, -1 for a constant fill.

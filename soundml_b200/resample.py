@@ -143,6 +143,11 @@ class Kernel:
     the result is bit-identical to ``apply`` for every partition; block executors
     (overlap-save, tensor-core) agree to rounding, their block grids being
     anchored to the window.
+
+    The product path is the library's ``smb_resample_kernel_*`` (C ABI, carry
+    resident on the device): this class binds it.  The same state machine is also
+    written out below in Python for one purpose -- ``_apply`` lets the CPU tests
+    run it over the oracle's ``apply`` where no GPU is present.
     """
 
     def __init__(self, c, channels, max_block, _apply=None):
@@ -154,7 +159,8 @@ class Kernel:
                 f"prepare: cannot accept blocks of {max_block} samples "
                 "(max_block must be at least 1)")
         self.cfg, self.channels, self.max_block = c, channels, max_block
-        self._apply = _apply if _apply is not None else (lambda x: apply(c, x))
+        self._apply = _apply
+        self._k = None                 # the library's kernel, created with the first chunk (its dtype)
         self.l, self.m = c.l, c.m
         st = c.stages()
         # dependency cone of one output, in input samples either side of floor(i M / L)
@@ -182,6 +188,48 @@ class Kernel:
         self.fed = self.emitted = self.base = 0
         self.buf = []
         self.drained = False
+        if getattr(self, "_k", None):
+            _lib.check(_lib.lib.smb_resample_kernel_reset(self._k))
+
+    def __del__(self):
+        k, self._k = getattr(self, "_k", None), None
+        if k and getattr(_lib, "lib", None) is not None:
+            _lib.lib.smb_resample_kernel_destroy(k)
+
+    def _native(self, chunk):
+        """The library's kernel for chunks of this dtype."""
+        _, _, dtype = _lib.describe(chunk)
+        if self._k is None:
+            self._k = C.c_void_p()
+            self._dtype = dtype
+            _lib.check(_lib.lib.smb_resample_kernel_create(
+                C.byref(self._k), self.cfg._h, dtype, self.channels, self.max_block))
+        elif dtype != self._dtype:
+            raise ValueError("step: cannot change the sample type between chunks")
+        return self._k
+
+    def _native_step(self, chunk):
+        chunk = _lib.contiguous(chunk)
+        ptr, mem, _ = _lib.describe(chunk)
+        k = self._native(chunk)
+        n = int(chunk.shape[-1])
+        frames = int(_lib.lib.smb_resample_kernel_step_frames(k, n))
+        out = _lib.empty_like_kind(chunk, tuple(chunk.shape[:-1]) + (frames,))
+        stream = _lib.current_stream(chunk)
+        if stream is not None:
+            _lib.check(_lib.lib.smb_resample_plan_set_stream(self.cfg._h, stream))
+        _lib.check(_lib.lib.smb_resample_kernel_step(k, ptr, n, _lib.out_pointer(out), mem))
+        self._like = chunk[..., :0]
+        return out if frames else None
+
+    def _native_flush(self):
+        if self._k is None:
+            return None
+        frames = int(_lib.lib.smb_resample_kernel_flush_frames(self._k))
+        out = _lib.empty_like_kind(self._like, tuple(self._like.shape[:-1]) + (frames,))
+        _, mem, _ = _lib.describe(self._like) if not _lib.is_torch(self._like) else (0, _lib.MEM_DEVICE, 0)
+        _lib.check(_lib.lib.smb_resample_kernel_flush(self._k, _lib.out_pointer(out), mem))
+        return out if frames else None
 
     def _window(self, upto):
         """Outputs [emitted, upto) from a window of the retained input."""
@@ -222,6 +270,9 @@ class Kernel:
                              f"prepared for {self.channels} {unit})")
         if n == 0:
             return None
+        if self._apply is None:
+            self.fed += n
+            return self._native_step(chunk)
         self.buf.append(chunk.clone() if _lib.is_torch(chunk) else np.array(chunk, copy=True))
         self.fed += n
         if self.l == self.m:                                  # identity: forward a copy
@@ -241,6 +292,8 @@ class Kernel:
         if self.drained:
             return None
         self.drained = True
+        if self._apply is None:
+            return self._native_flush()
         total = self.cfg.output_frames(self.fed) if self.fed else 0
         if total <= self.emitted:
             self.buf = []
