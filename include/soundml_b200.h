@@ -183,6 +183,7 @@ int smb_mel_plan_destroy(smb_mel_plan* plan);
 int smb_mel_plan_set_stream(smb_mel_plan* plan, void* cuda_stream);
 int64_t smb_mel_n_mels(const smb_mel_plan* plan);
 int64_t smb_mel_bins(const smb_mel_plan* plan);
+int64_t smb_mel_fft_size(const smb_mel_plan* plan);   /* as given at creation (odd sizes too) */
 /* Mel.filterbank Nx.float64: out [n_mels, bins]. */
 int smb_mel_filterbank(const smb_mel_plan* plan, double* out);
 /* Mel.apply: s [batch, bins, frames] -> out [batch, n_mels, frames]. */
@@ -205,7 +206,9 @@ int smb_stft_fft_ceiling(smb_stft_plan* stft, const void* x, int64_t batch, int6
 /* Convert.power_to_db / amplitude_to_db ?reference ?amin ?top_db (convert.ml:20-56):
  * elementwise over `count` values in the input's dtype; top_db = NaN means "no
  * clamp", otherwise the clamp sits top_db below the maximum of the whole tensor.
- * Runs on `cuda_stream` (NULL = default stream) and returns when done. */
+ * Runs on `cuda_stream` (NULL or SMB_STREAM_OWN = the default stream): a host-memory
+ * call returns when the result is in `out`, a device-memory call is asynchronous on the
+ * stream like every other device-memory entry (no hidden synchronisation). */
 int smb_power_to_db(const void* x, int64_t count, int dtype, double reference, double amin,
                     double top_db, void* out, int mem, void* cuda_stream);
 int smb_amplitude_to_db(const void* x, int64_t count, int dtype, double reference, double amin,

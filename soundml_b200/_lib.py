@@ -90,6 +90,7 @@ SIGNATURES = {
     "smb_mel_plan_set_stream": (_int, [_vp, _vp]),
     "smb_mel_n_mels": (_i64, [_vp]),
     "smb_mel_bins": (_i64, [_vp]),
+    "smb_mel_fft_size": (_i64, [_vp]),
     "smb_mel_filterbank": (_int, [_vp, _pd]),
     "smb_mel_apply": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _int]),
     "smb_mel_spectrogram": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _dbl, _vp, _int]),
@@ -220,9 +221,18 @@ def out_pointer(y):
     return y.ctypes.data
 
 
+STREAM_OWN = (1 << (8 * C.sizeof(C.c_void_p))) - 1      # SMB_STREAM_OWN: (void*)-1
+
+
 def current_stream(x):
-    """torch's current CUDA stream handle for device tensors, else None."""
+    """The stream a call on ``x`` runs on: torch's current CUDA stream for device
+    tensors (which must live on the current device: a plan is bound to one), the
+    plan's own stream for host arrays -- a plan that last ran on a torch stream must
+    not keep that handle for a host call (the stream may be gone by then)."""
     if is_torch(x):
         import torch
+        if x.device.index != torch.cuda.current_device():
+            raise ValueError(f"the tensor lives on {x.device} but cuda:{torch.cuda.current_device()} "
+                             "is current (one plan per device; torch.cuda.set_device first)")
         return torch.cuda.current_stream(x.device).cuda_stream
-    return None
+    return STREAM_OWN

@@ -97,8 +97,24 @@ struct StreamOwner {
     use = own;
   }
   // SMB_STREAM_OWN restores the plan's stream; anything else (NULL = the CUDA
-  // default stream) is used as given.
-  void set(void* external) { use = external == SMB_STREAM_OWN ? own : (cudaStream_t)external; }
+  // default stream) is used as given.  Plans own scratch (the generic mel path's power
+  // spectrogram, the cascade's hand-off buffer, the dB maximum, host-call staging) that
+  // the next call reuses without an event, which is safe on ONE stream: when the stream
+  // changes, work queued on the previous one is drained first, so the scratch is never
+  // shared by two streams in flight.  The previous stream must still exist -- or have
+  // been synchronised before it was destroyed (cudaErrorInvalidResourceHandle from a
+  // stream already gone is swallowed: nothing can be pending on it).
+  void set(void* external) {
+    cudaStream_t next = external == SMB_STREAM_OWN ? own : (cudaStream_t)external;
+    if (next != use) {
+      const cudaError_t e = cudaStreamSynchronize(use);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (e != cudaErrorInvalidResourceHandle && e != cudaErrorContextIsDestroyed) CK(e);
+      }
+    }
+    use = next;
+  }
   void destroy() {
     if (own) cudaStreamDestroy(own);
     own = use = nullptr;
@@ -128,13 +144,15 @@ struct HostPipe {
     ready = true;
   }
   void release() {
+    for (int i = 0; i < 2; ++i) {      // the buffers may have been used without the streams (smb_mfcc)
+      in[i].release();
+      out[i].release();
+    }
     if (!ready) return;
     for (int i = 0; i < 2; ++i) {
       cudaEventDestroy(ev_in[i]);
       cudaEventDestroy(ev_run[i]);
       cudaEventDestroy(ev_out[i]);
-      in[i].release();
-      out[i].release();
     }
     cudaStreamDestroy(h2d);
     cudaStreamDestroy(d2h);
@@ -182,6 +200,18 @@ const double kTwoPi = 6.283185307179586476925286766559;
 
 }  // namespace
 
+// A plan's tables, scratch and stream belong to the device that was current when it was
+// first used; a later call under another current device would hand kernels pointers of
+// the wrong device.
+void same_device(int bound) {
+  int now = -1;
+  CK(cudaGetDevice(&now));
+  if (now != bound)
+    throw smb::invalid_argument(smb::format(
+        "soundml_b200: the plan is bound to CUDA device %d but device %d is current "
+        "(one plan per device; cudaSetDevice before the call)", bound, now));
+}
+
 // ============================ plan types =====================================
 
 struct smb_stft_plan {
@@ -203,7 +233,7 @@ struct smb_stft_plan {
   DeviceBuffer cepstral;   // mel spectrogram (+ host-call output) of the MFCC path
 
   void ensure_device() {
-    if (device_ready) return;
+    if (device_ready) return same_device(device);
     require_device();
     CK(cudaGetDevice(&device));
     CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -309,6 +339,7 @@ struct smb_stft_plan {
 };
 
 struct smb_mel_plan {
+  int bound_device = 0;              // the device the tables live on (first use)
   int64_t n_mels = 0, fft = 0, bins = 0, sample_rate = 0;
   double f_min = 0, f_max = 0;
   int scale = 0, norm = 0;
@@ -618,8 +649,9 @@ struct smb_mel_plan {
     return true;
   }
   void ensure_device() {
-    if (device_ready) return;
+    if (device_ready) return same_device(bound_device);
     require_device();
+    CK(cudaGetDevice(&bound_device));
     stream.create();
     d_weights = upload(weights);
     d_band_lo = upload(band_lo);
@@ -809,6 +841,7 @@ struct GemmDevice {
 };
 
 struct smb_resample_plan {
+  int bound_device = 0;              // the device the tables live on (first use)
   smb::ResamplePlan plan;
   bool device_ready = false;
   StreamOwner stream;
@@ -819,8 +852,9 @@ struct smb_resample_plan {
   int executor = SMB_EXEC_PLANNED;   // SMB_EXEC_DIRECT forces the dot-product kernel everywhere
   DeviceBuffer in, out, mid;
   void ensure_device() {
-    if (device_ready) return;
+    if (device_ready) return same_device(bound_device);
     require_device();
+    CK(cudaGetDevice(&bound_device));
     stream.create();
     for (const auto& s : plan.stages) {
       std::vector<float> b(s.bank.size());
@@ -879,6 +913,7 @@ struct smb_resample_plan {
 };
 
 struct smb_fir_plan {
+  int bound_device = 0;              // the device the tables live on (first use)
   std::vector<double> h;
   int64_t k = 0;
   bool device_ready = false;
@@ -887,8 +922,9 @@ struct smb_fir_plan {
   OlsDevice ols;
   DeviceBuffer in, out;
   void ensure_device() {
-    if (device_ready) return;
+    if (device_ready) return same_device(bound_device);
     require_device();
+    CK(cudaGetDevice(&bound_device));
     stream.create();
     std::vector<float> b(h.size());
     for (size_t s = 0; s < h.size(); ++s) b[s] = (float)h[h.size() - 1 - s];  // row reversed
@@ -1478,6 +1514,7 @@ int smb_mel_plan_set_stream(smb_mel_plan* plan, void* s) {
 }
 int64_t smb_mel_n_mels(const smb_mel_plan* plan) { return plan->n_mels; }
 int64_t smb_mel_bins(const smb_mel_plan* plan) { return plan->bins; }
+int64_t smb_mel_fft_size(const smb_mel_plan* plan) { return plan->fft; }
 int smb_mel_filterbank(const smb_mel_plan* plan, double* out) {
   return guarded([&] {
     std::memcpy(out, plan->weights.data(), plan->weights.size() * sizeof(double));
@@ -1622,18 +1659,26 @@ void to_db_call(const char* fn, double gain, int magnitude, const void* x, int64
   const size_t esz = dtype_size(dtype);
   if (count == 0) return;
   require_device();
-  cudaStream_t st = (cudaStream_t)stream;
+  // there is no plan here, hence no plan stream: SMB_STREAM_OWN means the default stream
+  cudaStream_t st = stream == SMB_STREAM_OWN ? nullptr : (cudaStream_t)stream;
   const double scale = gain / 10.0 * kDecade;
   const double offset = scale * std::log(std::max(amin, reference));
+  // the maximum's slot and the host call's staging are stream-ordered allocations:
+  // no device-wide synchronisation, and a device-memory call stays asynchronous
   unsigned long long* slot = nullptr;
-  CK(cudaMalloc(&slot, sizeof(unsigned long long)));
   void *din = nullptr, *dout = nullptr;
+  auto release = [&] {
+    if (slot) cudaFreeAsync(slot, st);
+    if (din) cudaFreeAsync(din, st);
+    if (dout) cudaFreeAsync(dout, st);
+  };
   try {
+    CK(cudaMallocAsync((void**)&slot, sizeof(unsigned long long), st));
     const void* src = x;
     void* dst = out;
     if (mem == SMB_MEM_HOST) {
-      CK(cudaMalloc(&din, (size_t)count * esz));
-      CK(cudaMalloc(&dout, (size_t)count * esz));
+      CK(cudaMallocAsync(&din, (size_t)count * esz, st));
+      CK(cudaMallocAsync(&dout, (size_t)count * esz, st));
       CK(cudaMemcpyAsync(din, x, (size_t)count * esz, cudaMemcpyHostToDevice, st));
       src = din;
       dst = dout;
@@ -1644,16 +1689,12 @@ void to_db_call(const char* fn, double gain, int magnitude, const void* x, int64
                          clamp ? top_db : 0.0, slot, dst, st));
     if (mem == SMB_MEM_HOST)
       CK(cudaMemcpyAsync(out, dout, (size_t)count * esz, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
   } catch (...) {
-    cudaFree(slot);
-    cudaFree(din);
-    cudaFree(dout);
+    release();
     throw;
   }
-  cudaFree(slot);
-  cudaFree(din);
-  cudaFree(dout);
+  release();
+  if (mem == SMB_MEM_HOST) CK(cudaStreamSynchronize(st));   // the host buffer is the caller's again
 }
 
 }  // namespace

@@ -48,7 +48,7 @@ class Config:
 
     n_mels = property(lambda self: int(_lib.lib.smb_mel_n_mels(self._h)))
     bins = property(lambda self: int(_lib.lib.smb_mel_bins(self._h)))
-    fft_size = property(lambda self: 2 * (self.bins - 1) if self.bins > 1 else 1)
+    fft_size = property(lambda self: int(_lib.lib.smb_mel_fft_size(self._h)))
 
 
 def filterbank(c, dtype=np.float64):
