@@ -133,7 +133,8 @@ def main():
         mc = sb.Mel.Config.create(n_mels=128, sample_rate=22050, fft_size=2048)
         frames = sb.Stft.frames(sc, n)
         for name, fn, out_rows in (("mfcc20", lambda: sb.mfcc(sc, mc, x, n_mfcc=20), 20),
-                                   ("logmel_db", lambda: sb.Convert.power_to_db(
+                                   ("logmel_db", lambda: sb.log_mel_spectrogram(sc, mc, x, top_db=80.0), 128),
+                                   ("logmel_db_two_calls", lambda: sb.Convert.power_to_db(
                                        sb.mel_spectrogram(sc, mc, x), top_db=80.0), 128)):
             c0 = sb.kernel_launch_count()
             ms = timed(fn, args.steps, 2)

@@ -218,6 +218,15 @@ int smb_amplitude_to_db(const void* x, int64_t count, int dtype, double referenc
  * 80 dB clamp below the whole-tensor maximum, orthonormal DCT-II, in double. */
 int smb_mfcc(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batch, int64_t n,
              int dtype, int64_t n_mfcc, double lifter, void* out, int mem);
+/* Convert.power_to_db ?reference ?amin ?top_db (Soundml.mel_spectrogram ?power stft mel x)
+ * (convert.ml:20-56 over soundml.ml:12-24) -- the log-mel spectrogram, in the input's
+ * dtype, out [batch, n_mels, frames].  top_db = NaN means "no clamp".  For fft 2048
+ * float32 the mel kernel leaves the whole-tensor maximum behind as it writes, so the
+ * decibel map and its clamp are one pass in place: two launches.  Errors: the mel
+ * spectrogram's, then power_to_db's, in the reference's wording. */
+int smb_mel_spectrogram_db(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batch,
+                           int64_t n, int dtype, double power, double reference, double amin,
+                           double top_db, void* out, int mem);
 
 /* ---- resampler ------------------------------------------------------------ */
 /* Resample.Config.create ?quality ~sample_rate ~target; attenuation/passband

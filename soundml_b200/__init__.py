@@ -21,7 +21,8 @@ Resample = _resample_mod
 Fir = _resample_mod.Fir
 Io = io
 
-__all__ = ["Stft", "Mel", "Window", "Convert", "Resample", "Fir", "Io", "mel_spectrogram", "mfcc",
+__all__ = ["Stft", "Mel", "Window", "Convert", "Resample", "Fir", "Io", "mel_spectrogram",
+           "log_mel_spectrogram", "mfcc",
            "resample",
            "kernel_launch_count", "SoundmlError"]
 
@@ -52,6 +53,29 @@ def mel_spectrogram(stft_config, mel_config, x, power=2.0, out=None):
         _lib.check(_lib.lib.smb_stft_plan_set_stream(stft_config._h, stream))
     _lib.check(_lib.lib.smb_mel_spectrogram(stft_config._h, mel_config._h, ptr, batch, n, dtype,
                                             float(power), _lib.out_pointer(out), mem))
+    return out
+
+
+def log_mel_spectrogram(stft_config, mel_config, x, power=2.0, reference=1.0, amin=1e-10,
+                        top_db=80.0, out=None):
+    """``Convert.power_to_db ?reference ?amin ?top_db (Soundml.mel_spectrogram ?power stft mel
+    x)`` in one call (convert.ml:20-56 over soundml.ml:12-24): the mel kernel leaves the
+    whole-tensor maximum behind, so the decibel map with its ``top_db`` clamp is one pass
+    in place.  ``[..., n]`` -> ``[..., n_mels, frames]``; ``top_db=None`` for no clamp."""
+    if x.ndim < 1:
+        raise ValueError("power_spectrum: cannot analyse a rank-zero tensor "
+                         "(the time axis must exist)")
+    x = _lib.contiguous(x)
+    ptr, mem, dtype = _lib.describe(x)
+    n = int(x.shape[-1])
+    lead = tuple(int(d) for d in x.shape[:-1])
+    batch = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    count = stft.frames(stft_config, n) if stft_config.fft_size == mel_config.fft_size else 0
+    out = _lib.empty_like_kind(x, lead + (mel_config.n_mels, count), out=out)
+    _lib.check(_lib.lib.smb_stft_plan_set_stream(stft_config._h, _lib.current_stream(x)))
+    _lib.check(_lib.lib.smb_mel_spectrogram_db(
+        stft_config._h, mel_config._h, ptr, batch, n, dtype, float(power), float(reference),
+        float(amin), math.nan if top_db is None else float(top_db), _lib.out_pointer(out), mem))
     return out
 
 

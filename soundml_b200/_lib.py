@@ -96,6 +96,7 @@ SIGNATURES = {
     "smb_mel_spectrogram": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _dbl, _vp, _int]),
     "smb_stft_fft_ceiling_scratch_bytes": (_i64, [_vp, _i64, _i64]),
     "smb_stft_fft_ceiling": (_int, [_vp, _vp, _i64, _i64, _vp]),
+    "smb_mel_spectrogram_db": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _dbl, _dbl, _dbl, _dbl, _vp, _int]),
     "smb_power_to_db": (_int, [_vp, _i64, _int, _dbl, _dbl, _dbl, _vp, _int, _vp]),
     "smb_amplitude_to_db": (_int, [_vp, _i64, _int, _dbl, _dbl, _dbl, _vp, _int, _vp]),
     "smb_mfcc": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _i64, _dbl, _vp, _int]),

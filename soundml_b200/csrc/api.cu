@@ -1545,9 +1545,16 @@ int smb_mel_apply(smb_mel_plan* plan, const void* s, int64_t batch, int64_t fram
   });
 }
 
-int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batch,
-                        int64_t n, int dtype, double power, void* out, int mem) {
-  return guarded([&] {
+}  // extern "C"
+
+// Soundml.mel_spectrogram.  max_slot (device, zeroed by the caller, may be null): where
+// the kernel leaves the maximum of what it writes; the return value says whether it did
+// (only the frame-pair kernel does; slices of a host batch accumulate into the one slot).
+static bool mel_spectrogram_impl(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batch,
+                                 int64_t n, int dtype, double power, void* out, int mem,
+                                 unsigned long long* max_slot) {
+  bool max_known = false;
+  {
     // soundml.ml:12-20
     if (stft->geom.fft != mel->fft)
       throw smb::invalid_argument(smb::format(
@@ -1557,15 +1564,17 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
     check_signal("power_spectrum", batch, n);
     const size_t esz = dtype_size(dtype);
     const smb::FrameGeom g = stft->frame_geom(n);
-    if (batch == 0 || g.frames == 0) return;
+    if (batch == 0 || g.frames == 0) return false;
     stft->ensure_device();
     mel->ensure_device();
     cudaStream_t st = stft->stream.use;
     const int fast = want_fast(stft, dtype, g, smb::kFastMel, mel);
+    max_known = fast == SMB_PATH_PAIR && max_slot != nullptr;
     auto run = [&](const void* din, void* dout, int64_t nb) {
       if (fast == SMB_PATH_PAIR) {
-        CK(smb::launch_stft2048p(pair_args(stft, mel, din, dout, nb, g, power), false,
-                                 stft->sm_count, st));
+        smb::Stft2048PairArgs a = pair_args(stft, mel, din, dout, nb, g, power);
+        a.max_slot = max_slot;
+        CK(smb::launch_stft2048p(a, false, stft->sm_count, st));
       } else if (fast) {
         smb::Stft2048Args a{};
         a.x = (const float*)din;
@@ -1606,7 +1615,15 @@ int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, i
     } else {
       throw smb::invalid_argument("soundml_b200: unknown memory kind");
     }
-  });
+  }
+  return max_known;
+}
+
+extern "C" {
+
+int smb_mel_spectrogram(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batch,
+                        int64_t n, int dtype, double power, void* out, int mem) {
+  return guarded([&] { mel_spectrogram_impl(stft, mel, x, batch, n, dtype, power, out, mem, nullptr); });
 }
 
 // Measurement only: the transform alone on the frame-pair kernel's skeleton (tile
@@ -1755,14 +1772,71 @@ int smb_mfcc(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batc
     } else if (mem != SMB_MEM_DEVICE) {
       throw smb::invalid_argument("soundml_b200: unknown memory kind");
     }
-    if (smb_mel_spectrogram(stft, mel, din, batch, n, dtype, 2.0, dmel, SMB_MEM_DEVICE) != SMB_OK)
-      throw cuda_failure(t_error);
+    // the frame-pair kernel leaves the mel spectrogram's maximum in the slot as it writes
+    CK(cudaMemsetAsync(mel->d_max, 0, sizeof(unsigned long long), st));
+    const bool max_known = mel_spectrogram_impl(stft, mel, din, batch, n, dtype, 2.0, dmel,
+                                                SMB_MEM_DEVICE, mel->d_max);
     const double scale = kDecade, offset = scale * std::log(1.0);   // reference 1, amin 1e-10
     CK(smb::launch_mfcc(dmel, dtype, batch, (int)mel->n_mels, g.frames, (int)n_mfcc,
-                        mel->dct_table(n_mfcc, has_lifter ? lifter : 0.0), mel->d_max, 1e-10,
-                        scale, offset, 80.0, dout, st));
+                        mel->dct_table(n_mfcc, has_lifter ? lifter : 0.0), mel->d_max, max_known,
+                        1e-10, scale, offset, 80.0, dout, st));
     if (mem == SMB_MEM_HOST) {
       CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  });
+}
+
+// Convert.power_to_db ?reference ?amin ?top_db (Soundml.mel_spectrogram ?power stft mel x):
+// the log-mel spectrogram ML front ends ingest, as the reference composes it
+// (convert.ml:20-56 over soundml.ml:12-24).  The mel kernel leaves the whole-tensor
+// maximum behind as it writes, so the decibel map with its top_db clamp is ONE pass in
+// place over the 128-band output: two launches in all.
+int smb_mel_spectrogram_db(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batch,
+                           int64_t n, int dtype, double power, double reference, double amin,
+                           double top_db, void* out, int mem) {
+  return guarded([&] {
+    const char* fn = "power_to_db";
+    if (!(std::isfinite(reference) && reference > 0.0))
+      throw smb::invalid_argument(smb::format("Soundml.Convert.%s: reference must be finite and positive", fn));
+    if (!(std::isfinite(amin) && amin > 0.0))
+      throw smb::invalid_argument(smb::format("Soundml.Convert.%s: amin must be finite and positive", fn));
+    const bool clamp = !std::isnan(top_db);
+    if (clamp && !(std::isfinite(top_db) && top_db >= 0.0))
+      throw smb::invalid_argument(smb::format("Soundml.Convert.%s: top_db must be finite and non-negative", fn));
+    if (mem != SMB_MEM_HOST && mem != SMB_MEM_DEVICE)
+      throw smb::invalid_argument("soundml_b200: unknown memory kind");
+    if (stft->geom.fft != mel->fft || batch < 0 || n < 0) {   // the composition's first checks, its wording
+      mel_spectrogram_impl(stft, mel, x, batch, n, dtype, power, out, mem, nullptr);
+      return;
+    }
+    const size_t esz = dtype_size(dtype);
+    const smb::FrameGeom g = stft->frame_geom(n);
+    if (batch == 0 || g.frames == 0) return;
+    stft->ensure_device();
+    mel->ensure_device();
+    cudaStream_t st = stft->stream.use;
+    const int64_t count = batch * mel->n_mels * g.frames;
+    void* dmel = mem == SMB_MEM_HOST ? stft->cepstral.ensure((size_t)count * esz) : out;
+    CK(cudaMemsetAsync(mel->d_max, 0, sizeof(unsigned long long), st));
+    const void* din = x;
+    if (mem == SMB_MEM_HOST) {          // the result stays on the device until it is in decibels
+      void* stage = stft->pipe.in[0].ensure((size_t)batch * n * esz);
+      CK(cudaMemcpyAsync(stage, x, (size_t)batch * n * esz, cudaMemcpyHostToDevice, st));
+      din = stage;
+    }
+    const bool max_known = mel_spectrogram_impl(stft, mel, din, batch, n, dtype, power, dmel,
+                                                SMB_MEM_DEVICE, mel->d_max);
+    const double scale = kDecade;                                   // gain 10: powers
+    const double offset = scale * std::log(std::max(amin, reference));
+    if (max_known)
+      CK(smb::launch_db_known_max(dmel, count, dtype, amin, scale, offset, clamp, clamp ? top_db : 0.0,
+                                  mel->d_max, st));
+    else
+      CK(smb::launch_to_db(dmel, count, dtype, 0, amin, scale, offset, clamp, clamp ? top_db : 0.0,
+                           mel->d_max, dmel, st));
+    if (mem == SMB_MEM_HOST) {
+      CK(cudaMemcpyAsync(out, dmel, (size_t)count * esz, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
     }
   });

@@ -7,29 +7,13 @@
 //           the mel axis, orthonormal scales, lifter -- double interior, one
 //           rounding
 #include "kernels.h"
+#include "max_key.cuh"
 
 namespace smb {
 
 namespace {
 
-// order-preserving map of doubles onto unsigned 64-bit keys (for atomicMax)
-__device__ __forceinline__ unsigned long long key_of(double v) {
-  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double value_of(unsigned long long k) {
-  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
-  return __longlong_as_double((long long)b);
-}
-
-__device__ __forceinline__ void block_max_to(double v, unsigned long long* slot) {
-  unsigned long long k = key_of(v);
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
-    k = other > k ? other : k;
-  }
-  if ((threadIdx.x & 31) == 0) atomicMax(slot, k);
-}
+__device__ __forceinline__ void block_max_to(double v, unsigned long long* slot) { warp_max_to(v, slot); }
 
 template <typename T> __device__ __forceinline__ T log_t(T v);
 template <> __device__ __forceinline__ float log_t<float>(float v) { return logf(v); }
@@ -77,17 +61,20 @@ __global__ void max_value_kernel(const T* __restrict__ x, long long count,
 
 constexpr int kMfccFrames = 32;     // frame columns per CTA
 constexpr int kMfccThreads = 256;
+constexpr int kMfccPer = 3;         // coefficients per thread (the log-mel value is loaded once for them)
 
 // mel [batch, n_mels, frames] (T) -> out [batch, n_mfcc, frames] (T).  One CTA per
-// (32-frame tile, signal): the log-mel tile is built once in shared memory in
-// double (with the 80 dB clamp below the whole-tensor maximum), then thread
-// (coefficient, frame) walks the mel axis against the DCT table.
+// (32-frame tile, signal): the log-mel tile is built once in shared memory in double
+// (with the 80 dB clamp below the whole-tensor maximum) next to the DCT rows, then
+// thread (coefficient group, frame) walks the mel axis: one log-mel load feeds up to
+// three coefficients.
 template <typename T>
 __global__ void __launch_bounds__(kMfccThreads)
 mfcc_kernel(const T* __restrict__ mel, int n_mels, long long frames, int n_mfcc,
             const double* __restrict__ dct, const unsigned long long* max_mel_slot, double amin,
             double scale, double offset, double range, T* __restrict__ out) {
-  extern __shared__ __align__(8) double sDb[];           // [n_mels][kMfccFrames]
+  extern __shared__ __align__(8) double sDb[];           // [n_mels][kMfccFrames], then the DCT rows
+  double* sDct = sDb + n_mels * kMfccFrames;              // [n_mfcc][n_mels]
   const long long b = blockIdx.y;
   const long long p0 = (long long)blockIdx.x * kMfccFrames;
   const int nf = (int)min((long long)kMfccFrames, frames - p0);
@@ -95,6 +82,7 @@ mfcc_kernel(const T* __restrict__ mel, int n_mels, long long frames, int n_mfcc,
   const double vmax = fmax(value_of(*max_mel_slot), amin);
   const double floor_db = (log(vmax) * scale - offset) - range;
   const T* src = mel + b * n_mels * frames + p0;
+  for (int i = threadIdx.x; i < n_mfcc * n_mels; i += blockDim.x) sDct[i] = __ldg(dct + i);
   for (int i = threadIdx.x; i < n_mels * kMfccFrames; i += blockDim.x) {
     const int m = i / kMfccFrames, f = i - m * kMfccFrames;
     double db = 0.0;
@@ -106,12 +94,41 @@ mfcc_kernel(const T* __restrict__ mel, int n_mels, long long frames, int n_mfcc,
   }
   __syncthreads();
   const int f = threadIdx.x & (kMfccFrames - 1);
+  constexpr int kGroups = kMfccThreads / kMfccFrames;     // coefficient c = g + kGroups * j
   T* dst = out + b * n_mfcc * frames + p0 + f;
-  for (int c = threadIdx.x / kMfccFrames; c < n_mfcc; c += kMfccThreads / kMfccFrames) {
-    const double* row = dct + (long long)c * n_mels;
-    double acc = 0.0;
-    for (int m = 0; m < n_mels; ++m) acc = fma(__ldg(row + m), sDb[m * kMfccFrames + f], acc);
-    if (f < nf) dst[(long long)c * frames] = (T)acc;
+  for (int c0 = threadIdx.x / kMfccFrames; c0 < n_mfcc; c0 += kGroups * kMfccPer) {
+    double acc[kMfccPer];
+    const double* row[kMfccPer];
+#pragma unroll
+    for (int j = 0; j < kMfccPer; ++j) {
+      acc[j] = 0.0;
+      row[j] = sDct + (long long)min(c0 + kGroups * j, n_mfcc - 1) * n_mels;
+    }
+    for (int m = 0; m < n_mels; ++m) {
+      const double v = sDb[m * kMfccFrames + f];
+#pragma unroll
+      for (int j = 0; j < kMfccPer; ++j) acc[j] = fma(row[j][m], v, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kMfccPer; ++j)
+      if (f < nf && c0 + kGroups * j < n_mfcc) dst[(long long)(c0 + kGroups * j) * frames] = (T)acc[j];
+  }
+}
+
+// db in place over values whose maximum is already in the slot (the fused mel kernel
+// left it there): the reference's arithmetic in T, clamp included, one pass
+template <typename T>
+__global__ void db_with_known_max_kernel(T* __restrict__ x, long long count, T amin, T scale, T offset,
+                                         const unsigned long long* max_slot, bool clamp, T range) {
+  T vmax = (T)value_of(*max_slot);
+  vmax = vmax > amin ? vmax : amin;
+  const T floor_db = (log_t<T>(vmax) * scale - offset) - range;     // max of db = db of the max
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    T v = x[i];
+    v = v > amin ? v : amin;
+    const T db = log_t<T>(v) * scale - offset;
+    x[i] = clamp && db < floor_db ? floor_db : db;
   }
 }
 
@@ -147,17 +164,35 @@ cudaError_t launch_to_db(const void* x, long long count, int dtype, int magnitud
   return cudaGetLastError();
 }
 
-cudaError_t launch_mfcc(const void* mel, int dtype, long long batch, int n_mels, long long frames,
-                        int n_mfcc, const double* dct, unsigned long long* max_slot, double amin,
-                        double scale, double offset, double range, void* out, cudaStream_t st) {
-  if (batch == 0 || frames == 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(max_slot, 0, sizeof(unsigned long long), st);
-  if (e != cudaSuccess) return e;
-  const long long count = batch * n_mels * frames;
-  if (dtype == 0) max_value_kernel<float><<<grid_for(count), 256, 0, st>>>((const float*)mel, count, max_slot);
-  else max_value_kernel<double><<<grid_for(count), 256, 0, st>>>((const double*)mel, count, max_slot);
+cudaError_t launch_db_known_max(void* x, long long count, int dtype, double amin, double scale,
+                                double offset, bool clamp, double range,
+                                const unsigned long long* max_slot, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  if (dtype == 0)
+    db_with_known_max_kernel<float><<<grid_for(count), 256, 0, st>>>(
+        (float*)x, count, (float)amin, (float)scale, (float)offset, max_slot, clamp, (float)range);
+  else
+    db_with_known_max_kernel<double><<<grid_for(count), 256, 0, st>>>(
+        (double*)x, count, amin, scale, offset, max_slot, clamp, range);
   ++g_launch_count;
-  const size_t smem = (size_t)n_mels * kMfccFrames * sizeof(double);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mfcc(const void* mel, int dtype, long long batch, int n_mels, long long frames,
+                        int n_mfcc, const double* dct, unsigned long long* max_slot, bool max_known,
+                        double amin, double scale, double offset, double range, void* out,
+                        cudaStream_t st) {
+  if (batch == 0 || frames == 0) return cudaSuccess;
+  cudaError_t e;
+  if (!max_known) {                      // else the kernel that wrote `mel` left its maximum in the slot
+    e = cudaMemsetAsync(max_slot, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    const long long count = batch * n_mels * frames;
+    if (dtype == 0) max_value_kernel<float><<<grid_for(count), 256, 0, st>>>((const float*)mel, count, max_slot);
+    else max_value_kernel<double><<<grid_for(count), 256, 0, st>>>((const double*)mel, count, max_slot);
+    ++g_launch_count;
+  }
+  const size_t smem = (size_t)(n_mels * kMfccFrames + n_mfcc * n_mels) * sizeof(double);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   const long long tiles = (frames + kMfccFrames - 1) / kMfccFrames;
   for (long long b0 = 0; b0 < batch; b0 += 65535) {

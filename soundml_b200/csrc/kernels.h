@@ -119,8 +119,12 @@ struct Stft2048PairArgs {
   const float* mel_w;               // [round][step][8 filters] x float4 band weights
   int mel_w_floats;                 // multiple of 4
   const PairMelItem* mel_items;     // [4 warps][mel_rounds][8 filters]
-  int mel_rounds;                   // even: rounds 2q, 2q + 1 of a warp run in lockstep, same step count
+  int mel_rounds;
   float power;
+  // optional: the maximum of everything written goes here (atomicMax on the
+  // order-preserving key of db_kernels.cu), so that power_to_db's whole-tensor clamp
+  // and the MFCC epilogue need no reduction pass of their own
+  unsigned long long* max_slot;
 };
 bool stft2048p_supports(const FrameGeom& g, int n_mels, int mel_w_floats, int mel_rounds);
 // ceiling = true: the measurement floor of the transform alone (stage + window + both
@@ -150,9 +154,15 @@ cudaError_t launch_polyphase_direct_f64(const double* x, long long batch, long l
 cudaError_t launch_to_db(const void* x, long long count, int dtype, int magnitude, double amin,
                          double scale, double offset, bool clamp, double range,
                          unsigned long long* max_slot, void* out, cudaStream_t st);
+// max_known: the slot already holds the maximum of `mel` (left by the fused mel kernel)
 cudaError_t launch_mfcc(const void* mel, int dtype, long long batch, int n_mels, long long frames,
-                        int n_mfcc, const double* dct, unsigned long long* max_slot, double amin,
-                        double scale, double offset, double range, void* out, cudaStream_t st);
+                        int n_mfcc, const double* dct, unsigned long long* max_slot, bool max_known,
+                        double amin, double scale, double offset, double range, void* out,
+                        cudaStream_t st);
+// power_to_db in place over values whose whole-tensor maximum is in the slot
+cudaError_t launch_db_known_max(void* x, long long count, int dtype, double amin, double scale,
+                                double offset, bool clamp, double range,
+                                const unsigned long long* max_slot, cudaStream_t st);
 
 // soundml-io's layout pass (soundml_io_stubs.c:832-872): interleaved [frames][channels]
 // -> planar (channel c at out + c * out_total) or the mono downmix.

@@ -38,6 +38,7 @@
 
 #include "fft32x2.cuh"
 #include "kernels.h"
+#include "max_key.cuh"
 #include "stft_stage.cuh"
 
 namespace smb {
@@ -230,6 +231,7 @@ stft2048p_kernel(const Params p) {
   // (clip, tile of the clip) walk the round-robin deal without a division per tile
   const int step_b = stride / tiles_per_signal, step_t = stride - step_b * tiles_per_signal;
   int nb = slot / tiles_per_signal, nt = slot - nb * tiles_per_signal;
+  float vmax = 0.0f;                       // maximum of what this thread writes (mel values are >= 0)
   bool bulk = false;
   if (slot < total_tiles)
     bulk = stage::stage_tile<kTile, kGroupThreads>(g, p.a.x, p.bulk, nb, nt, sSamples, gtid, sbar);
@@ -452,8 +454,8 @@ stft2048p_kernel(const Params p) {
         const pk_t acc = padd(padd(acc0, acc1), padd(acc2, acc3));
         const int m = it.y >> 16;
         float* o = ob + m * frames;
-        if (m >= 0 && okA) o[0] = pk_lo(acc);
-        if (m >= 0 && okB) o[1] = pk_hi(acc);
+        if (m >= 0 && okA) { o[0] = pk_lo(acc); vmax = fmaxf(vmax, pk_lo(acc)); }
+        if (m >= 0 && okB) { o[1] = pk_hi(acc); vmax = fmaxf(vmax, pk_hi(acc)); }
       }
     } else {
       // ceiling mode: one value per thread and tile keeps the rows alive
@@ -462,6 +464,7 @@ stft2048p_kernel(const Params p) {
     // no barrier here: the next tile's group barrier (top of the loop) orders these
     // power-row reads before the next transpositions
   }
+  if (MODE == kModeMel && p.a.max_slot) warp_max_to((double)vmax, p.a.max_slot);
   if (TT) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -85,3 +85,35 @@ def test_db_large_and_errors(sb):
     with pytest.raises(ValueError, match=r"mfcc: cannot lifter with a coefficient of -1"):
         sb.mfcc(sc, mc, np.zeros(1000, np.float32), lifter=-1.0)
     assert sb.mfcc(sc, mc, np.zeros((2, 0), np.float32), n_mfcc=13).shape == (2, 13, 0)
+
+
+@pytest.mark.parametrize("fft,hop,top_db", [(2048, 512, 80.0), (2048, 512, None), (2048, 500, 60.0),
+                                            (1024, 256, 80.0), (400, 160, 80.0)])
+def test_log_mel_spectrogram_is_the_composition(sb, fft, hop, top_db):
+    """Convert.power_to_db (Soundml.mel_spectrogram ...) in one call: for fft 2048 the
+    frame-pair kernel leaves the whole-tensor maximum behind (one decibel pass in place),
+    other geometries reduce separately -- the same numbers as the two calls, held to the
+    oracle's composition like them."""
+    import torch
+    from soundml_b200 import synth
+    x = synth.clips_numpy(5, 30000, first_clip=11)
+    x[2] *= 1e-5                                      # a quiet clip: the global clamp bites
+    n_mels = 128 if fft == 2048 else 40
+    sc = sb.Stft.Config.create(fft_size=fft, hop=hop)
+    mc = sb.Mel.Config.create(n_mels=n_mels, sample_rate=22050, fft_size=fft)
+    mel = mel_oracle.mel_spectrogram(stft_oracle.StftConfig(fft, hop),
+                                     mel_oracle.MelConfig(n_mels, 22050, fft), x).astype(np.float32)
+    want = convert_oracle.power_to_db(mel, top_db=top_db)
+    got = sb.log_mel_spectrogram(sc, mc, x, top_db=top_db)
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert_close(got, want, 1e-5, 2e-4, "log mel")        # decibels: 2e-4 dB absolute
+    two = sb.Convert.power_to_db(sb.mel_spectrogram(sc, mc, x), top_db=top_db)
+    assert np.abs(got - two).max() <= 1e-5                # one float32 rounding of the clamp floor apart at most
+    before = sb.kernel_launch_count()
+    dev = sb.log_mel_spectrogram(sc, mc, torch.from_numpy(x).cuda(), top_db=top_db)
+    torch.cuda.synchronize()
+    if fft == 2048 and hop == 512:
+        assert sb.kernel_launch_count() - before == 2     # mel kernel (+ maximum) and one decibel pass
+    assert np.array_equal(dev.cpu().numpy(), got)
+    with pytest.raises(ValueError, match=r"Soundml.Convert.power_to_db: top_db must be finite and non-negative"):
+        sb.log_mel_spectrogram(sc, mc, x, top_db=-3.0)

@@ -210,3 +210,44 @@ def test_planned_ols_stages_match_direct_and_oracle(sb, sr, target):
         scale = max(np.abs(want).max(), 1e-3)
         assert np.abs(planned - want).max() / scale <= RESAMPLE_TOL, (sr, target, n)
         assert np.abs(direct - want).max() / scale <= RESAMPLE_TOL, (sr, target, n)
+
+
+# ---- BASELINE.json configs[3] and configs[4] at their full clip lengths ----------------
+
+def test_config_length_resample_44k1_to_16k(sb):
+    """One 30 s clip of configs[3] (1 323 000 samples, 44.1 -> 16 kHz, the tcgen05
+    executor) against the float64 oracle at the FIR/resample bar."""
+    cfg = sb.Resample.Config.create(sample_rate=44100, target=16000)
+    n = 30 * 44100
+    x = noise((2, n), 4416)
+    got = sb.Resample.apply(cfg, x)
+    want = R.apply_plan(x, oracle_stages(cfg), cfg.l, cfg.m)
+    assert got.shape == want.shape == (2, 480000)
+    for c in range(2):
+        assert peak_rel_err(got[c], want[c]) <= RESAMPLE_TOL, c
+
+
+def test_config5_resample_then_mel_spectrogram(sb):
+    """configs[4] composed: Resample.apply(44.1 -> 22.05 kHz) -> Soundml.mel_spectrogram on
+    four 10 s clips (441 000 samples) against oracle resampler -> oracle STFT + mel, at the
+    spectrogram bar (max |got - ref| / max |ref| <= 1e-4 per clip); soundml.thumper:151,161
+    is the reference's closest benchmark of the pair."""
+    from oracle import mel_oracle, stft_oracle
+    from soundml_b200 import synth
+    x = synth.clips_numpy(4, 441000, sample_rate=44100, first_clip=21)
+    cfg = sb.Resample.Config.create(sample_rate=44100, target=22050)
+    sc = sb.Stft.Config.create(fft_size=2048, hop=512)
+    mc = sb.Mel.Config.create(n_mels=128, sample_rate=22050, fft_size=2048)
+    mid = sb.Resample.apply(cfg, x)
+    assert mid.shape == (4, 220500)
+    got = sb.mel_spectrogram(sc, mc, mid)
+    want_mid = R.apply_plan(x, oracle_stages(cfg), cfg.l, cfg.m)
+    for c in range(4):
+        assert peak_rel_err(mid[c], want_mid[c]) <= RESAMPLE_TOL, c
+    # the reference's Resample.apply returns float32 audio: the oracle chain rounds there too
+    want = mel_oracle.mel_spectrogram(stft_oracle.StftConfig(2048, 512),
+                                      mel_oracle.MelConfig(128, 22050, 2048),
+                                      want_mid.astype(np.float32))
+    assert got.shape == want.shape == (4, 128, 431)
+    for c in range(4):
+        assert peak_rel_err(got[c], want[c]) <= 1e-4, c
