@@ -851,6 +851,7 @@ struct smb_resample_plan {
   std::vector<GemmDevice> gemm;      // per stage; ok only for GEMM-tagged stages
   int executor = SMB_EXEC_PLANNED;   // SMB_EXEC_DIRECT forces the dot-product kernel everywhere
   DeviceBuffer in, out, mid;
+  HostPipe pipe;                     // host-memory calls: sliced, copies under kernels
   void ensure_device() {
     if (device_ready) return same_device(bound_device);
     require_device();
@@ -908,6 +909,7 @@ struct smb_resample_plan {
     in.release();
     out.release();
     mid.release();
+    pipe.release();
     stream.destroy();
   }
 };
@@ -921,6 +923,7 @@ struct smb_fir_plan {
   float* d_bank = nullptr;
   OlsDevice ols;
   DeviceBuffer in, out;
+  HostPipe pipe;                     // host-memory calls: sliced, copies under kernels
   void ensure_device() {
     if (device_ready) return same_device(bound_device);
     require_device();
@@ -938,6 +941,7 @@ struct smb_fir_plan {
     ols.release();
     in.release();
     out.release();
+    pipe.release();
     stream.destroy();
   }
 };
@@ -1931,34 +1935,28 @@ int smb_resample_apply(smb_resample_plan* plan, const float* x, int64_t batch, i
     if (batch == 0 || n == 0 || total == 0) return;
     plan->ensure_device();
     cudaStream_t st = plan->stream.use;
-    const size_t in_bytes = (size_t)batch * n * 4, out_bytes = (size_t)batch * total * 4;
-    const float* din = x;
-    float* dout = out;
-    if (mem == SMB_MEM_HOST) {
-      float* stage = (float*)plan->in.ensure(in_bytes);
-      dout = (float*)plan->out.ensure(out_bytes);
-      CK(cudaMemcpyAsync(stage, x, in_bytes, cudaMemcpyHostToDevice, st));
-      din = stage;
-    } else if (mem != SMB_MEM_DEVICE) {
-      throw smb::invalid_argument("soundml_b200: unknown memory kind");
-    }
-    if (rp.identity()) {
-      CK(cudaMemcpyAsync(dout, din, in_bytes, cudaMemcpyDeviceToDevice, st));
-    } else if (rp.stages.size() == 1) {
-      plan->run_stage(0, din, batch, n, total, dout, st);
-    } else {
-      // cascade (resample.ml:1819-1842): stage 1 emits its exact ceil tail,
-      // stage 2 runs over it with zeros beyond and is cut to output_frames.
-      const smb::ResampleStage& s1 = rp.stages[0];
-      const int64_t n1 = (n * s1.l + s1.m - 1) / s1.m;
-      float* mid = (float*)plan->mid.ensure((size_t)batch * n1 * 4);
-      plan->run_stage(0, din, batch, n, n1, mid, st);
-      plan->run_stage(1, mid, batch, n1, total, dout, st);
-    }
-    if (mem == SMB_MEM_HOST) {
-      CK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-    }
+    // signals are independent: a host batch goes through in slices, the copies of one
+    // slice under the kernels of its neighbours (HostPipe)
+    auto run = [&](const void* din_v, void* dout_v, int64_t nb) {
+      const float* din = (const float*)din_v;
+      float* dout = (float*)dout_v;
+      if (rp.identity()) {
+        CK(cudaMemcpyAsync(dout, din, (size_t)nb * n * 4, cudaMemcpyDeviceToDevice, st));
+      } else if (rp.stages.size() == 1) {
+        plan->run_stage(0, din, nb, n, total, dout, st);
+      } else {
+        // cascade (resample.ml:1819-1842): stage 1 emits its exact ceil tail,
+        // stage 2 runs over it with zeros beyond and is cut to output_frames.
+        const smb::ResampleStage& s1 = rp.stages[0];
+        const int64_t n1 = (n * s1.l + s1.m - 1) / s1.m;
+        float* mid = (float*)plan->mid.ensure((size_t)nb * n1 * 4);
+        plan->run_stage(0, din, nb, n, n1, mid, st);
+        plan->run_stage(1, mid, nb, n1, total, dout, st);
+      }
+    };
+    if (mem == SMB_MEM_DEVICE) run(x, out, batch);
+    else if (mem == SMB_MEM_HOST) plan->pipe.execute(st, x, out, batch, (size_t)n * 4, (size_t)total * 4, run);
+    else throw smb::invalid_argument("soundml_b200: unknown memory kind");
   });
 }
 
@@ -2236,25 +2234,16 @@ int smb_fir_apply(smb_fir_plan* plan, const float* x, int64_t batch, int64_t n, 
       throw smb::invalid_argument(
           "fir: this filter is too long for the overlap-save kernel (use the direct method)");
     cudaStream_t st = plan->stream.use;
-    const size_t bytes = (size_t)batch * n * 4;
-    const float* din = x;
-    float* dout = out;
-    if (mem == SMB_MEM_HOST) {
-      float* stage = (float*)plan->in.ensure(bytes);
-      dout = (float*)plan->out.ensure(bytes);
-      CK(cudaMemcpyAsync(stage, x, bytes, cudaMemcpyHostToDevice, st));
-      din = stage;
-    } else if (mem != SMB_MEM_DEVICE) {
-      throw smb::invalid_argument("soundml_b200: unknown memory kind");
-    }
-    if (method == SMB_EXEC_OLS)
-      plan->ols.run(din, batch, n, n, dout, st);
-    else
-      CK(smb::launch_polyphase_direct(din, batch, n, plan->d_bank, 1, 1, (int)plan->k, n, dout, st));
-    if (mem == SMB_MEM_HOST) {
-      CK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-    }
+    auto run = [&](const void* din, void* dout, int64_t nb) {
+      if (method == SMB_EXEC_OLS)
+        plan->ols.run((const float*)din, nb, n, n, (float*)dout, st);
+      else
+        CK(smb::launch_polyphase_direct((const float*)din, nb, n, plan->d_bank, 1, 1, (int)plan->k, n,
+                                        (float*)dout, st));
+    };
+    if (mem == SMB_MEM_DEVICE) run(x, out, batch);
+    else if (mem == SMB_MEM_HOST) plan->pipe.execute(st, x, out, batch, (size_t)n * 4, (size_t)n * 4, run);
+    else throw smb::invalid_argument("soundml_b200: unknown memory kind");
   });
 }
 // ---- soundml-io device ingest ------------------------------------------------------
