@@ -153,6 +153,7 @@ stft2048p_kernel(const Params p) {
   float* sMelW = reinterpret_cast<float*>(smem_raw + 16640);
   PairMelItem* sItems = reinterpret_cast<PairMelItem*>(sMelW + p.a.mel_w_floats);
   __shared__ __align__(8) uint64_t sbars[kGroups];
+  __shared__ __align__(8) uint64_t sfree[kGroups];     // a group's power rows have been read (4 warps arrive)
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
@@ -215,13 +216,17 @@ stft2048p_kernel(const Params p) {
     for (int i = tid; i < kGroupWarps * p.a.mel_rounds * 8; i += blockDim.x) sItems[i] = p.a.mel_items[i];
   }
   if (tid == 0) {
-    for (int gI = 0; gI < kGroups; ++gI) stage::mbar_init(smem_u32(&sbars[gI]), 1);
+    for (int gI = 0; gI < kGroups; ++gI) {
+      stage::mbar_init(smem_u32(&sbars[gI]), 1);
+      stage::mbar_init(smem_u32(&sfree[gI]), kGroupWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (TT) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t sbar = smem_u32(&sbars[group]);
-  uint32_t sphase = 0;
+  const uint32_t fbar = smem_u32(&sfree[group]);
+  uint32_t sphase = 0, tiles_done = 0;
 
   const FrameGeom g = p.a.g;
   const int mel_rounds = p.a.mel_rounds;
@@ -246,13 +251,17 @@ stft2048p_kernel(const Params p) {
 
     // ---- the tile's samples were requested one iteration ago
     if (MODE != kModeFree || tile == slot) {
+      // no group barrier here when the tile came by bulk copy: every thread sees the
+      // samples through the mbarrier, and the only other thing the barrier ordered -- the
+      // previous tile's mel reads of the power rows against this tile's transposition
+      // stores -- is waited for where it matters, just before those stores (sfree)
       if (bulk) {
         stage::mbar_wait(sbar, sphase & 1);
         ++sphase;
       } else {
         asm volatile("cp.async.wait_all;" ::: "memory");
+        named_sync(group + 1, kGroupThreads);
       }
-      named_sync(group + 1, kGroupThreads);
     }
 
     {
@@ -319,6 +328,8 @@ stft2048p_kernel(const Params p) {
         }
       }
       fft32(a);                                   // a[k1] = Y[n2 = lane][k1]
+      // ---- the previous tile's power rows (this buffer) have been read by all four warps
+      if (MODE != kModeFree && tiles_done > 0) stage::mbar_wait(fbar, (tiles_done - 1) & 1);
       // ---- twiddle W1024^(k1 n2), transpose through the warp's padded buffer
       {
         const float4* t4 = sTwPass + lane;
@@ -461,8 +472,11 @@ stft2048p_kernel(const Params p) {
       // ceiling mode: one value per thread and tile keeps the rows alive
       if (p.a.out) p.a.out[(long long)tile * kGroupThreads + gtid] = prow[2 * gtid];
     }
-    // no barrier here: the next tile's group barrier (top of the loop) orders these
-    // power-row reads before the next transpositions
+    // this warp has read the power rows it needs: count off (the next tile's
+    // transposition stores wait for all four warps, see above)
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fbar) : "memory");
+    ++tiles_done;
   }
   if (MODE == kModeMel && p.a.max_slot) warp_max_to((double)vmax, p.a.max_slot);
   if (TT) {
