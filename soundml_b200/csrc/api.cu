@@ -759,9 +759,134 @@ struct GemmDevice {
   };
   bool ok = false;
   std::vector<Group> groups;
+  // Row form (resample_rows_kernel): stages whose L columns are one launch and whose
+  // shift accumulators fit tensor memory.
+  bool rows_ok = false;
+  int rows_sm_count = 0;
+  smb::GemmRowsArgs rows{};
+  float* d_rows_images = nullptr;
+  int4 *d_rows_chunks = nullptr, *d_rows_slices = nullptr;
+  void build_rows(const smb::ResampleStage& s) {
+    const int64_t l = s.l, m = s.m, k = s.k, taps = 2 * k + 1;
+    if (l > 160 || m < 32) return;
+    std::vector<int64_t> d((size_t)l);
+    for (int64_t r = 0; r < l; ++r) d[(size_t)r] = (r * m) / l;
+    const int64_t p_len = taps + d[(size_t)(l - 1)];
+    const int shifts = (int)((p_len + m - 1) / m);
+    const int chunks = (int)((m + 31) / 32);
+    const int n_pad = (int)((l + 15) / 16 * 16);
+    if (shifts > 4) return;
+    // columns of G_q with a nonzero in rows [j0, j1] of the shift's block: d_r <= q m + j <= d_r + taps - 1
+    auto active = [&](int q, int64_t j0, int64_t j1, int* lo, int* hi) {
+      *lo = n_pad;
+      *hi = -1;
+      for (int64_t r = 0; r < l; ++r) {
+        const int64_t first = d[(size_t)r] - (int64_t)q * m, last = first + taps - 1;
+        if (first <= j1 && last >= j0) {
+          *lo = std::min(*lo, (int)r);
+          *hi = std::max(*hi, (int)r);
+        }
+      }
+      return *hi >= 0;
+    };
+    smb::GemmRowsArgs a{};
+    int total_cols = 0;
+    // accumulators side by side in DESCENDING q: the active columns of D_q are a suffix
+    // and those of D_(q-1) a prefix, so a chunk's nonzeros form one run of TMEM columns
+    for (int q = shifts - 1; q >= 0; --q) {
+      int lo, hi;
+      if (!active(q, 0, m - 1, &lo, &hi)) return;
+      a.acc_lo[q] = q == 0 ? 0 : lo / 16 * 16;
+      a.acc_w[q] = q == 0 ? n_pad : (hi + 1 - a.acc_lo[q] + 15) / 16 * 16;
+      a.acc_col[q] = total_cols;
+      total_cols += a.acc_w[q];
+    }
+    if (total_cols > 512 || chunks > 32) return;
+    struct Slice { int tmem0, width, bytes_at; };
+    std::vector<int4> chunk_meta((size_t)chunks), slice_meta;
+    // per chunk: TMEM column -> (slice, row inside the slice), -1 where nothing is stored
+    std::vector<std::vector<int>> slice_at((size_t)chunks, std::vector<int>((size_t)total_cols, -1));
+    size_t total_bytes = 0;
+    int stage_bytes = 0;
+    for (int ch = 0; ch < chunks; ++ch) {
+      std::vector<char> on((size_t)total_cols, 0);
+      for (int q = 0; q < shifts; ++q) {
+        int lo, hi;
+        if (!active(q, 32 * (int64_t)ch, std::min<int64_t>(32 * (int64_t)ch + 31, m - 1), &lo, &hi)) continue;
+        const int col0 = lo / 16 * 16, ncols = (hi + 1 - col0 + 15) / 16 * 16;
+        for (int cc = col0; cc < col0 + ncols; ++cc) on[(size_t)(a.acc_col[q] + cc - a.acc_lo[q])] = 1;
+      }
+      const int first_slice = (int)slice_meta.size();
+      int bytes = 0;
+      for (int t0 = 0; t0 < total_cols;) {
+        if (!on[(size_t)t0]) { ++t0; continue; }
+        int t1 = t0;
+        while (t1 < total_cols && on[(size_t)t1] && t1 - t0 < 256) ++t1;   // runs are multiples of 16 wide
+        for (int t = t0; t < t1; ++t) slice_at[(size_t)ch][(size_t)t] = (int)slice_meta.size();
+        slice_meta.push_back(make_int4(bytes, t0, t1 - t0, 0));
+        bytes += 2 * (t1 - t0) * 128;
+        t0 = t1;
+      }
+      chunk_meta[(size_t)ch] = make_int4((int)total_bytes, bytes, first_slice, (int)slice_meta.size() - first_slice);
+      total_bytes += (size_t)bytes;
+      stage_bytes = std::max(stage_bytes, bytes);
+    }
+    if (slice_meta.size() > 64) return;
+    stage_bytes = (stage_bytes + 1023) / 1024 * 1024;
+    if (smb::resample_rows_smem_bytes(stage_bytes) > 227 * 1024) return;
+    int device = 0;
+    CK(cudaGetDevice(&device));
+    CK(cudaDeviceGetAttribute(&rows_sm_count, cudaDevAttrMultiProcessorCount, device));
+    std::vector<float> img(total_bytes / 4, 0.0f);
+    for (int64_t r = 0; r < l; ++r) {
+      const int64_t ph = (r * m) % l;
+      for (int64_t t = 0; t < taps; ++t) {
+        const int64_t j = d[(size_t)r] + t;
+        const int q = (int)(j / m);
+        const int64_t jj = j % m;
+        const int ch = (int)(jj / 32), kk = (int)(jj % 32);
+        const int tcol = a.acc_col[q] + (int)r - a.acc_lo[q];
+        const int sl = slice_at[(size_t)ch][(size_t)tcol];
+        if (sl < 0) return;                                     // (cannot happen: the runs cover every nonzero)
+        const int4 sm = slice_meta[(size_t)sl];
+        const double gv = s.bank[(size_t)(ph * taps + t)];
+        const float gf = (float)gv;
+        uint32_t bits;
+        std::memcpy(&bits, &gf, 4);
+        bits &= 0xFFFFE000u;
+        float hi;
+        std::memcpy(&hi, &bits, 4);
+        const float lo = (float)(gv - (double)hi);
+        const int64_t rr = tcol - sm.y;                          // row inside the slice
+        const size_t cell = (size_t)(rr * 32 + ((((kk >> 2) ^ (rr & 7)) << 2) | (kk & 3)));
+        const size_t base = ((size_t)chunk_meta[(size_t)ch].x + (size_t)sm.x) / 4;
+        img[base + cell] = hi;
+        img[base + (size_t)sm.z * 32 + cell] = lo;
+      }
+    }
+    a.slices = (int)slice_meta.size();
+    a.l = (int)l;
+    a.m = (int)m;
+    a.k = (int)k;
+    a.n_pad = n_pad;
+    a.shifts = shifts;
+    a.chunks = chunks;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < total_cols) a.tmem_cols *= 2;
+    a.b_stage_bytes = stage_bytes;
+    d_rows_images = upload(img);
+    d_rows_chunks = upload(chunk_meta);
+    d_rows_slices = upload(slice_meta);
+    a.b_images = d_rows_images;
+    a.chunk_meta = d_rows_chunks;
+    a.slice_meta = d_rows_slices;
+    rows = a;
+    rows_ok = true;
+  }
   void build(const smb::ResampleStage& s) {
     const int64_t l = s.l, m = s.m, k = s.k, taps = 2 * k + 1;
     if (s.exec != smb::kExecGemm || l > 1024) return;
+    build_rows(s);
     const int n_groups = (int)((l + 159) / 160);
     const int base_width = (int)(((l + n_groups - 1) / n_groups + 15) / 16 * 16);
     for (int c0 = 0; c0 < l; c0 += base_width) {
@@ -837,6 +962,12 @@ struct GemmDevice {
       cudaFree(g.d_meta);
     }
     groups.clear();
+    cudaFree(d_rows_images);
+    cudaFree(d_rows_chunks);
+    cudaFree(d_rows_slices);
+    d_rows_images = nullptr;
+    d_rows_chunks = d_rows_slices = nullptr;
+    rows_ok = false;
   }
 };
 
@@ -877,6 +1008,14 @@ struct smb_resample_plan {
     const smb::ResampleStage& s = plan.stages[i];
     if (executor != SMB_EXEC_DIRECT && ols[i].plan.ok) {
       ols[i].run(x, batch, n, n_out, out, st);
+    } else if (executor != SMB_EXEC_DIRECT && gemm[i].rows_ok && !getenv("SMB_GEMM_WINDOWS")) {
+      // (SMB_GEMM_WINDOWS=1: the overlapping-window form below, for A/B measurement)
+      smb::GemmRowsArgs a = gemm[i].rows;
+      a.x = x;
+      a.out = out;
+      a.n = n;
+      a.n_out = n_out;
+      CK(smb::launch_resample_rows(a, batch, gemm[i].rows_sm_count, st));
     } else if (executor != SMB_EXEC_DIRECT && gemm[i].ok) {
       for (const GemmDevice::Group& g : gemm[i].groups) {
         smb::GemmResampleArgs a{};

@@ -201,6 +201,34 @@ struct GemmResampleArgs {
   const int4* chunk_meta;  // per chunk: {byte offset into b_images, first column, columns, 0}
 };
 size_t resample_gemm_smem_bytes(int n_pad);
+
+// The same stage in row form (resample_gemm.cu, resample_rows_kernel): the input is read
+// as non-overlapping rows X[i][j'] = xz[i M + j' - K], j' < M, and block-row rho of the
+// output is sum_q X[rho + q] G_q with G_q = rows [q M, (q + 1) M) of G -- one accumulator
+// per shift q, added with the row shift in the epilogue.  Every input sample is gathered
+// and split once per tile instead of P / M times.
+struct GemmRowsArgs {
+  const float* x;          // [batch, n]
+  float* out;              // [batch, n_out]
+  long long n, n_out;
+  int l, m, k;             // stage L (all columns in one launch), M, group delay
+  int n_pad;               // l rounded up to a multiple of 16
+  int shifts;              // accumulators: ceil(P / M), at most 4
+  int chunks;              // ceil(M / 32) K-chunks (at most 32)
+  int slices;              // entries of slice_meta (at most 64)
+  int tmem_cols;           // power of two >= sum of acc_w
+  int b_stage_bytes;       // largest chunk image (multiple of 1024)
+  int acc_col[4];          // TMEM column of accumulator q (laid out in descending q)
+  int acc_lo[4];           // first G column accumulator q holds (multiple of 16; 0 for q = 0)
+  int acc_w[4];            // its width (multiple of 16; n_pad for q = 0)
+  const float* b_images;   // per chunk, per slice: [hi, lo][columns][32] pre-swizzled K-major tiles; a slice is a
+                           // contiguous run of TMEM columns (the end of D_q followed by the start of D_(q-1))
+  const int4* chunk_meta;  // per chunk: {byte offset into b_images, bytes, first slice, slices}
+  const int4* slice_meta;  // per slice: {byte offset inside the chunk image, TMEM column, columns, 0}
+  int debug;               // measurement only (SMB_ROWS_DEBUG): 1 no MMAs, 2 no B loads, 4 no A gather, 8 no epilogue
+};
+size_t resample_rows_smem_bytes(int b_stage_bytes);
+cudaError_t launch_resample_rows(const GemmRowsArgs& a, long long batch, int sm_count, cudaStream_t st);
 cudaError_t launch_resample_gemm(const GemmResampleArgs& a, long long batch, cudaStream_t st);
 
 }  // namespace smb

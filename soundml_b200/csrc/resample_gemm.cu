@@ -30,7 +30,9 @@
 //      row-contiguous (a block-row is L consecutive outputs).
 #include "kernels.h"
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 namespace smb {
 
@@ -331,7 +333,351 @@ teardown:
                  "r"(a.tmem_cols) : "memory");
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Row form of the same product (GemmRowsArgs, kernels.h).  The window form above gathers
+// row rho of A as the P consecutive inputs from rho M - K: consecutive rows overlap, so
+// every input sample is fetched, split and stored P / M times (2.18 x for 44.1 -> 16 kHz),
+// a tile walks ceil(P / 32) K-chunks, and each chunk is 12 small products.  Here A is
+// the input cut into NON-overlapping rows X[i][j'] = xz[i M + j' - K], j' < M; with
+// G_q = rows [q M, (q + 1) M) of G
+//
+//     out[rho][r] = sum_q  ( X[rho + q] . G_q[:, r] )
+//
+// so the CTA keeps one accumulator D_q = X G_q per shift q (q < ceil(P / M) <= 4; the later
+// ones only hold the few columns whose taps reach that far) and the epilogue adds
+// D_q[i + q] into output row i.  The accumulators sit side by side in tensor memory in
+// DESCENDING q: the band of G makes the active columns of D_q a suffix and those of
+// D_(q-1) a prefix, so a chunk's nonzeros are one contiguous run of TMEM columns -- ONE
+// product of N ~ 200 per K-step and split term where the window form issues several of
+// N ~ 16 .. 160 (the tensor core retires a small product faster than one thread can issue
+// the next: measured ~ 94 cycles per tcgen05.mma).
+//
+// A tile is 128 rows of A = four groups of 32 X-rows, one per epilogue warp (a warp can
+// only read its own 32 TMEM lanes); consecutive groups overlap by shifts - 1 X-rows, so
+// that every warp finds D_q[i + q] in its own lanes (a warp shuffle) and finishes
+// 32 - (shifts - 1) output rows on its own: no exchange, no barrier in the epilogue.
+//
+// One persistent CTA per SM, warp-specialised, every hand-over an mbarrier:
+//   warps 0-7   producers: gather, split and store the A chunks, running ahead of the
+//               tensor core by the three A stages, across tile boundaries;
+//   warp  8     one lane streams the B images (two stages, refilled one chunk behind the
+//               issue point) and issues the MMAs; after a tile's last chunk it commits
+//               acc_full and waits for acc_free before the next tile's first product;
+//   warps 9-12  epilogue: drain the accumulators, shift, write 64-byte runs per row
+//               straight to global memory, zero the accumulators with tcgen05.st (every
+//               product accumulates) and arrive on acc_free.  Meanwhile the producers and
+//               the B loader are already filling the next tile's stages.
+constexpr int kAStages = 3;
+constexpr int kBStages = 2;
+constexpr int kEpiWarp0 = kMmaWarp + 1;
+constexpr int kRowsThreads = kThreads + 128;       // + 4 epilogue warps
+constexpr int kMaxRowsChunks = 32, kMaxRowsSlices = 64;
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(0u) : "memory");
+}
+// load without the wait: several are put in flight, then one tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kRowsThreads, 1)
+resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* b_smem = smem + kAStages * 2 * kABytes;
+  __shared__ __align__(8) uint64_t bars[2 * kAStages + 2 * kBStages + 2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ int4 s_chunk[kMaxRowsChunks], s_slice[kMaxRowsSlices];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int group_rows = 32 - (a.shifts - 1);               // finished output rows per epilogue warp
+  const int rows_out = 4 * group_rows;                      // ... per tile
+
+  const uint32_t bar_a = smem_u32(&bars[0]);                         // [A stage]: tile written
+  const uint32_t bar_a_empty = smem_u32(&bars[kAStages]);            // [A stage]: its MMAs done
+  const uint32_t bar_b = smem_u32(&bars[2 * kAStages]);              // [B stage]: bytes landed
+  const uint32_t bar_b_empty = smem_u32(&bars[2 * kAStages + kBStages]);
+  const uint32_t bar_acc_full = smem_u32(&bars[2 * kAStages + 2 * kBStages]);      // a tile's MMAs done
+  const uint32_t bar_acc_free = smem_u32(&bars[2 * kAStages + 2 * kBStages + 1]);  // accumulators drained and zeroed
+  if (tid == 0) {
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(bar_a + 8 * s, kProducers);
+      mbar_init(bar_a_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(bar_b + 8 * s, 1);
+      mbar_init(bar_b_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_acc_free, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < a.chunks; i += kRowsThreads) s_chunk[i] = a.chunk_meta[i];
+  for (int i = tid; i < a.slices; i += kRowsThreads) s_slice[i] = a.slice_meta[i];
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_slot)), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_slot;
+
+  // this CTA's tiles: blockIdx.x, + gridDim.x, ...
+  const int my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int my_chunks = my_tiles * a.chunks;                 // (the launcher keeps this below 2^31)
+
+  if (warp == kMmaWarp) {
+    // ===== B loader + MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24);
+      const uint8_t* images = reinterpret_cast<const uint8_t*>(a.b_images);
+      int lb_stage = 0, lb_chunk = 0;                        // next B load: stage, chunk of the tile
+      auto load_b = [&]() {
+        const int4 meta = s_chunk[lb_chunk];
+        if (a.debug & 2) {
+          mbar_arrive(bar_b + 8 * lb_stage);
+        } else {
+          mbar_expect_tx(bar_b + 8 * lb_stage, (uint32_t)meta.y);
+          bulk_g2s(smem_u32(b_smem + (size_t)lb_stage * a.b_stage_bytes), images + meta.x, (uint32_t)meta.y,
+                   bar_b + 8 * lb_stage);
+        }
+        if (++lb_stage == kBStages) lb_stage = 0;
+        if (++lb_chunk == a.chunks) lb_chunk = 0;
+      };
+      int loaded = 0;
+      for (; loaded < kBStages && loaded < my_chunks; ++loaded) load_b();
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;                               // parities of the stages' current use
+      int prev_sb = 0;
+      uint32_t prev_pb = 0;
+      int g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(bar_acc_free, (uint32_t)(it & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ch = 0; ch < a.chunks; ++ch, ++g) {
+          mbar_wait(bar_a + 8 * sa, pa);
+          mbar_wait(bar_b + 8 * sb, pb);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int4 meta = s_chunk[ch];
+          // descriptors differ from their base only in the start-address field
+          const uint64_t a_hi = umma_desc(smem_u32(smem + sa * 2 * kABytes));
+          const uint64_t a_lo = a_hi + (uint64_t)(kABytes >> 4);
+          const uint32_t b_base = smem_u32(b_smem + (size_t)sb * a.b_stage_bytes);
+          for (int sl = meta.z; sl < meta.z + ((a.debug & 1) ? 0 : meta.w); ++sl) {
+            const int4 sm = s_slice[sl];
+            const uint32_t idesc = idesc0 | ((uint32_t)(sm.z >> 3) << 17);
+            const uint64_t b_hi = umma_desc(b_base + (uint32_t)sm.x);
+            const uint64_t b_lo = b_hi + (uint64_t)((sm.z * 128) >> 4);
+            const uint32_t acc = tmem + (uint32_t)sm.y;
+#pragma unroll
+            for (int ks = 0; ks < kChunk / 8; ++ks) {
+              const uint64_t off = (uint64_t)(ks * 2);                 // 8 tf32 = 32 bytes = 2 units along K
+              umma_tf32(acc, a_hi + off, b_hi + off, idesc, 1);
+              umma_tf32(acc, a_hi + off, b_lo + off, idesc, 1);
+              umma_tf32(acc, a_lo + off, b_hi + off, idesc, 1);
+            }
+          }
+          umma_commit(bar_a_empty + 8 * sa);
+          umma_commit(bar_b_empty + 8 * sb);
+          if (ch == a.chunks - 1) umma_commit(bar_acc_full);
+          // refill the B stage of the chunk BEFORE this one: its MMAs drain while this
+          // chunk's are queued, so the issuing thread does not sit out a whole chunk
+          if (g >= 1 && loaded < my_chunks) {
+            mbar_wait(bar_b_empty + 8 * prev_sb, prev_pb);
+            load_b();
+            ++loaded;
+          }
+          prev_sb = sb;
+          prev_pb = pb;
+          if (++sa == kAStages) { sa = 0; pa ^= 1; }
+          if (++sb == kBStages) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < kProducerWarps) {
+    // ===== producers: a warp gathers 16 rows of the tile, lane = sample within the chunk
+    // (one 128-byte request per row); loads run two chunks ahead of the stores in registers.
+    // Tile row i is X-row  row0 + group_rows (i / 32) + i % 32  (the groups overlap).
+    float v0[kRowsPerWarp] = {}, v1[kRowsPerWarp] = {};
+    const int row_in_tile = group_rows * (warp >> 1) + kRowsPerWarp * (warp & 1);
+    int ld_it = 0, ld_ch = 0;                                // next chunk to load: tile iteration, chunk
+    auto load_chunk = [&](float (&v)[kRowsPerWarp]) {
+      if (ld_it >= my_tiles) return;
+      if (!(a.debug & 4)) {
+        const int tile = (int)blockIdx.x + ld_it * (int)gridDim.x;
+        const int c = tile / tiles_per_clip;
+        const long long first_row = (long long)(tile - c * tiles_per_clip) * rows_out + row_in_tile;
+        const float* xs = a.x + (long long)c * a.n;
+        const long long b0 = first_row * a.m + lane - a.k + (long long)ld_ch * kChunk;
+        // the warp's rows of this chunk are interior for most tiles: no bounds checks then
+        if (b0 - lane >= 0 && b0 - lane + (long long)(kRowsPerWarp - 1) * a.m + kChunk <= a.n) {
+          const float* p = xs + b0;
+#pragma unroll
+          for (int rr = 0; rr < kRowsPerWarp; ++rr) v[rr] = __ldg(p + rr * a.m);
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+            const long long si = b0 + (long long)rr * a.m;
+            v[rr] = (si >= 0 && si < a.n) ? __ldg(xs + si) : 0.0f;
+          }
+        }
+      }
+      if (++ld_ch == a.chunks) { ld_ch = 0; ++ld_it; }
+    };
+    int st_stage = 0;
+    uint32_t st_parity = 1;                                  // (first use of a stage: nothing to wait for)
+    int stored = 0;
+    auto store_chunk = [&](const float (&v)[kRowsPerWarp]) {
+      if (stored >= kAStages) mbar_wait(bar_a_empty + 8 * st_stage, st_parity);
+      // element (row, k) lands at 16-byte chunk (k/4) XOR (row mod 8) of its 128-byte row
+      float* ahi = reinterpret_cast<float*>(smem + st_stage * 2 * kABytes) + warp * kRowsPerWarp * 32;
+      float* alo = ahi + kABytes / 4;
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const float h = __uint_as_float(__float_as_uint(v[rr]) & 0xFFFFE000u);
+        const int cell = rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3));
+        ahi[cell] = h;
+        alo[cell] = v[rr] - h;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> async proxy
+      mbar_arrive(bar_a + 8 * st_stage);
+      ++stored;
+      if (++st_stage == kAStages) { st_stage = 0; st_parity ^= 1; }
+    };
+    load_chunk(v0);
+    load_chunk(v1);
+    for (int g = 0; g < my_chunks; g += 2) {
+      store_chunk(v0);
+      load_chunk(v0);
+      if (g + 1 < my_chunks) {
+        store_chunk(v1);
+        load_chunk(v1);
+      }
+    }
+  } else {
+    // ===== epilogue warps: w4 = the TMEM lane quarter this warp may read = its row group
+    const int w4 = warp & 3;
+    const uint32_t lane_base = ((uint32_t)(w4 * 32)) << 16;
+    int total_cols = 0;
+    for (int q = 0; q < a.shifts; ++q) total_cols += a.acc_w[q];
+    auto zero_accumulators = [&]() {
+      for (int col = 0; col < total_cols; col += 16) tmem_st16_zero(tmem + lane_base + col);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_acc_free);
+    };
+    zero_accumulators();
+    const long long rows_total = (a.n_out + a.l - 1) / a.l;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int c = tile / tiles_per_clip;
+      const long long out_row = (long long)(tile - c * tiles_per_clip) * rows_out + group_rows * w4 + lane;
+      mbar_wait(bar_acc_full, (uint32_t)(it & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (!(a.debug & 8)) {
+        // out[row] = (D_0[row] + D_1[row + 1]) + D_2[row + 2] ..., 16 columns at a time
+        float* obase = a.out + (long long)c * a.n_out;
+        float* orow = obase + out_row * a.l;
+        const bool row_ok = lane < group_rows && out_row < rows_total;
+        const bool vec = (a.l & 3) == 0 && (reinterpret_cast<size_t>(obase) & 15) == 0;
+        for (int col = 0; col < a.acc_w[0]; col += 16) {
+          uint32_t d[4][16];
+          bool have[4];
+          tmem_ld16_async(tmem + lane_base + (uint32_t)(a.acc_col[0] + col), d[0]);
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            have[q] = q < a.shifts && col >= a.acc_lo[q] && col < a.acc_lo[q] + a.acc_w[q];
+            if (have[q]) tmem_ld16_async(tmem + lane_base + (uint32_t)(a.acc_col[q] + col - a.acc_lo[q]), d[q]);
+          }
+          tmem_ld_wait();
+          float o[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(d[0][e]);
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            if (have[q]) {                                         // (uniform)
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] += __shfl_down_sync(0xffffffffu, __uint_as_float(d[q][e]), q);
+            }
+          }
+          if (row_ok) {
+            const long long g0 = out_row * a.l + col;              // index inside the clip
+            if (vec && col + 16 <= a.l && g0 + 16 <= a.n_out) {
+              float4* dst = reinterpret_cast<float4*>(orow + col);
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) dst[e >> 2] = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (col + e < a.l && g0 + e < a.n_out) orow[col + e] = o[e];
+            }
+          }
+        }
+      }
+      zero_accumulators();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kMmaWarp)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
+                 "r"(a.tmem_cols) : "memory");
+}
+
 }  // namespace
+
+size_t resample_rows_smem_bytes(int b_stage_bytes) {
+  return (size_t)kAStages * 2 * kABytes + (size_t)kBStages * b_stage_bytes + 1024;
+}
+
+cudaError_t launch_resample_rows(const GemmRowsArgs& a, long long batch, int sm_count, cudaStream_t st) {
+  if (batch == 0 || a.n_out == 0) return cudaSuccess;
+  const size_t smem = resample_rows_smem_bytes(a.b_stage_bytes);
+  if (smem > 227 * 1024 || a.shifts < 1 || a.shifts > 4 || a.chunks > kMaxRowsChunks || a.slices > kMaxRowsSlices)
+    return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(resample_rows_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long rows = (a.n_out + a.l - 1) / a.l;
+  const int rows_out = 4 * (32 - (a.shifts - 1));
+  const long long tiles = (rows + rows_out - 1) / rows_out;
+  // tile and chunk counters are 32-bit inside the kernel: split the batch
+  const long long max_clips = std::max<long long>(1, ((1LL << 31) - 1) / (tiles * a.chunks) - 1);
+  if (tiles * a.chunks >= (1LL << 30)) return cudaErrorInvalidConfiguration;
+  for (long long b0 = 0; b0 < batch; b0 += max_clips) {
+    const long long nb = std::min(max_clips, batch - b0);
+    GemmRowsArgs s = a;
+    s.x = a.x + b0 * a.n;
+    s.out = a.out + b0 * a.n_out;
+    s.debug = getenv("SMB_ROWS_DEBUG") ? atoi(getenv("SMB_ROWS_DEBUG")) : 0;
+    const long long total = tiles * nb;
+    const int grid = (int)(total < sm_count ? total : sm_count);
+    resample_rows_kernel<<<grid, kRowsThreads, smem, st>>>(s, (int)tiles, (int)total);
+    ++g_launch_count;
+  }
+  return cudaGetLastError();
+}
 
 size_t resample_gemm_smem_bytes(int n_pad) {
   return (size_t)kStages * (2 * kABytes + 2 * (size_t)n_pad * 128) + 1024;
