@@ -802,30 +802,41 @@ struct GemmDevice {
       total_cols += a.acc_w[q];
     }
     if (total_cols > 512 || chunks > 32) return;
-    struct Slice { int tmem0, width, bytes_at; };
+    int tmem_alloc = 32;
+    while (tmem_alloc < total_cols) tmem_alloc *= 2;
+    const int kSliceAlign = getenv("SMB_ROWS_ALIGN") ? atoi(getenv("SMB_ROWS_ALIGN")) : 8;
     std::vector<int4> chunk_meta((size_t)chunks), slice_meta;
     // per chunk: TMEM column -> (slice, row inside the slice), -1 where nothing is stored
-    std::vector<std::vector<int>> slice_at((size_t)chunks, std::vector<int>((size_t)total_cols, -1));
+    std::vector<std::vector<int>> slice_at((size_t)chunks, std::vector<int>((size_t)tmem_alloc, -1));
     size_t total_bytes = 0;
     int stage_bytes = 0;
     for (int ch = 0; ch < chunks; ++ch) {
-      std::vector<char> on((size_t)total_cols, 0);
+      // exact active columns (TMEM coordinates); a run may start on any column -- only its
+      // width is a multiple of 16 -- so a chunk stores ceil16(band) columns, not the
+      // band widened to 16-column boundaries on both sides
+      std::vector<char> on((size_t)tmem_alloc, 0);
       for (int q = 0; q < shifts; ++q) {
         int lo, hi;
         if (!active(q, 32 * (int64_t)ch, std::min<int64_t>(32 * (int64_t)ch + 31, m - 1), &lo, &hi)) continue;
-        const int col0 = lo / 16 * 16, ncols = (hi + 1 - col0 + 15) / 16 * 16;
-        for (int cc = col0; cc < col0 + ncols; ++cc) on[(size_t)(a.acc_col[q] + cc - a.acc_lo[q])] = 1;
+        for (int cc = lo; cc <= hi; ++cc) on[(size_t)(a.acc_col[q] + cc - a.acc_lo[q])] = 1;
       }
       const int first_slice = (int)slice_meta.size();
       int bytes = 0;
-      for (int t0 = 0; t0 < total_cols;) {
+      for (int t0 = 0; t0 < tmem_alloc;) {
         if (!on[(size_t)t0]) { ++t0; continue; }
-        int t1 = t0;
-        while (t1 < total_cols && on[(size_t)t1] && t1 - t0 < 256) ++t1;   // runs are multiples of 16 wide
-        for (int t = t0; t < t1; ++t) slice_at[(size_t)ch][(size_t)t] = (int)slice_meta.size();
-        slice_meta.push_back(make_int4(bytes, t0, t1 - t0, 0));
-        bytes += 2 * (t1 - t0) * 128;
-        t0 = t1;
+        int t1 = t0 + 1;                                          // one past the run's last active column
+        for (int t = t0 + 1; t < tmem_alloc && t - t0 < 256; ++t) {
+          if (on[(size_t)t]) t1 = t + 1;
+          else if (t - t1 >= 16) break;                           // a gap of 16 columns ends the run
+        }
+        int start = t0 / kSliceAlign * kSliceAlign;              // the accumulator address of a product
+        int width = (t1 - start + 15) / 16 * 16;
+        if (width > 256) { width = 256; t1 = start + 256; }
+        if (start + width > tmem_alloc) start = tmem_alloc - width;
+        for (int t = start; t < start + width; ++t) slice_at[(size_t)ch][(size_t)t] = (int)slice_meta.size();
+        slice_meta.push_back(make_int4(bytes, start, width, 0));
+        bytes += 2 * width * 128;
+        t0 = std::max(t1, start + width);
       }
       chunk_meta[(size_t)ch] = make_int4((int)total_bytes, bytes, first_slice, (int)slice_meta.size() - first_slice);
       total_bytes += (size_t)bytes;
@@ -833,7 +844,12 @@ struct GemmDevice {
     }
     if (slice_meta.size() > 64) return;
     stage_bytes = (stage_bytes + 1023) / 1024 * 1024;
-    if (smb::resample_rows_smem_bytes(stage_bytes) > 227 * 1024) return;
+    // static shared memory of the kernel (barriers, metadata) comes out of the same 227 KB
+    const size_t budget = 227 * 1024 - 2048;
+    if (smb::resample_rows_smem_bytes(2, 3, stage_bytes) <= budget) { a.a_stages = 2; a.b_stages = 3; }
+    else if (smb::resample_rows_smem_bytes(3, 2, stage_bytes) <= budget) { a.a_stages = 3; a.b_stages = 2; }
+    else if (smb::resample_rows_smem_bytes(2, 2, stage_bytes) <= budget) { a.a_stages = 2; a.b_stages = 2; }
+    else return;
     int device = 0;
     CK(cudaGetDevice(&device));
     CK(cudaDeviceGetAttribute(&rows_sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -871,8 +887,7 @@ struct GemmDevice {
     a.n_pad = n_pad;
     a.shifts = shifts;
     a.chunks = chunks;
-    a.tmem_cols = 32;
-    while (a.tmem_cols < total_cols) a.tmem_cols *= 2;
+    a.tmem_cols = tmem_alloc;
     a.b_stage_bytes = stage_bytes;
     d_rows_images = upload(img);
     d_rows_chunks = upload(chunk_meta);

@@ -218,6 +218,7 @@ struct GemmRowsArgs {
   int slices;              // entries of slice_meta (at most 64)
   int tmem_cols;           // power of two >= sum of acc_w
   int b_stage_bytes;       // largest chunk image (multiple of 1024)
+  int a_stages, b_stages;  // pipeline depth of the A tiles and of the B images (2 or 3 each)
   int acc_col[4];          // TMEM column of accumulator q (laid out in descending q)
   int acc_lo[4];           // first G column accumulator q holds (multiple of 16; 0 for q = 0)
   int acc_w[4];            // its width (multiple of 16; n_pad for q = 0)
@@ -227,7 +228,7 @@ struct GemmRowsArgs {
   const int4* slice_meta;  // per slice: {byte offset inside the chunk image, TMEM column, columns, 0}
   int debug;               // measurement only (SMB_ROWS_DEBUG): 1 no MMAs, 2 no B loads, 4 no A gather, 8 no epilogue
 };
-size_t resample_rows_smem_bytes(int b_stage_bytes);
+size_t resample_rows_smem_bytes(int a_stages, int b_stages, int b_stage_bytes);
 cudaError_t launch_resample_rows(const GemmRowsArgs& a, long long batch, int sm_count, cudaStream_t st);
 cudaError_t launch_resample_gemm(const GemmResampleArgs& a, long long batch, cudaStream_t st);
 

@@ -360,18 +360,20 @@ teardown:
 //
 // One persistent CTA per SM, warp-specialised, every hand-over an mbarrier:
 //   warps 0-7   producers: gather, split and store the A chunks, running ahead of the
-//               tensor core by the three A stages, across tile boundaries;
-//   warp  8     one lane streams the B images (two stages, refilled one chunk behind the
-//               issue point) and issues the MMAs; after a tile's last chunk it commits
-//               acc_full and waits for acc_free before the next tile's first product;
-//   warps 9-12  epilogue: drain the accumulators, shift, write 64-byte runs per row
+//               tensor core by the two A stages (and two more chunks in registers), across tiles;
+//   warp  8     one lane issues the MMAs and nothing else (a chunk is 12 products; whatever
+//               else that thread does is time the tensor core's queue runs dry); after a
+//               tile's last chunk it commits acc_full and waits for acc_free;
+//   warp  9     one lane streams the B images (cp.async.bulk), stage by stage as they drain;
+//   warps 10-17 epilogue (two per TMEM lane quarter, alternate 16-column groups): drain the accumulators, shift, write 64-byte runs per row
 //               straight to global memory, zero the accumulators with tcgen05.st (every
 //               product accumulates) and arrive on acc_free.  Meanwhile the producers and
 //               the B loader are already filling the next tile's stages.
-constexpr int kAStages = 3;
-constexpr int kBStages = 2;
-constexpr int kEpiWarp0 = kMmaWarp + 1;
-constexpr int kRowsThreads = kThreads + 128;       // + 4 epilogue warps
+constexpr int kMaxStages = 3;                       // A and B stages: (2, 3) when that fits shared memory, else (3, 2)
+constexpr int kLoadWarp = kMmaWarp + 1;             // streams the B images
+constexpr int kEpiWarp0 = kMmaWarp + 2;
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, alternate 16-column groups
+constexpr int kRowsThreads = kThreads + 32 + 32 * kEpiWarps;
 constexpr int kMaxRowsChunks = 32, kMaxRowsSlices = 64;
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
@@ -400,8 +402,9 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
+  const int kAStages = a.a_stages, kBStages = a.b_stages;
   uint8_t* b_smem = smem + kAStages * 2 * kABytes;
-  __shared__ __align__(8) uint64_t bars[2 * kAStages + 2 * kBStages + 2];
+  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ int4 s_chunk[kMaxRowsChunks], s_slice[kMaxRowsSlices];
 
@@ -412,11 +415,11 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
   const int rows_out = 4 * group_rows;                      // ... per tile
 
   const uint32_t bar_a = smem_u32(&bars[0]);                         // [A stage]: tile written
-  const uint32_t bar_a_empty = smem_u32(&bars[kAStages]);            // [A stage]: its MMAs done
-  const uint32_t bar_b = smem_u32(&bars[2 * kAStages]);              // [B stage]: bytes landed
-  const uint32_t bar_b_empty = smem_u32(&bars[2 * kAStages + kBStages]);
-  const uint32_t bar_acc_full = smem_u32(&bars[2 * kAStages + 2 * kBStages]);      // a tile's MMAs done
-  const uint32_t bar_acc_free = smem_u32(&bars[2 * kAStages + 2 * kBStages + 1]);  // accumulators drained and zeroed
+  const uint32_t bar_a_empty = smem_u32(&bars[kMaxStages]);          // [A stage]: its MMAs done
+  const uint32_t bar_b = smem_u32(&bars[2 * kMaxStages]);            // [B stage]: bytes landed
+  const uint32_t bar_b_empty = smem_u32(&bars[3 * kMaxStages]);
+  const uint32_t bar_acc_full = smem_u32(&bars[4 * kMaxStages]);     // a tile's MMAs done
+  const uint32_t bar_acc_free = smem_u32(&bars[4 * kMaxStages + 1]); // accumulators drained and zeroed
   if (tid == 0) {
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(bar_a + 8 * s, kProducers);
@@ -427,7 +430,7 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
       mbar_init(bar_b_empty + 8 * s, 1);
     }
     mbar_init(bar_acc_full, 1);
-    mbar_init(bar_acc_free, 128);
+    mbar_init(bar_acc_free, 32 * kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < a.chunks; i += kRowsThreads) s_chunk[i] = a.chunk_meta[i];
@@ -450,31 +453,12 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
     // ===== B loader + MMA issuer (one elected lane) =====
     if (lane == 0) {
       const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24);
-      const uint8_t* images = reinterpret_cast<const uint8_t*>(a.b_images);
-      int lb_stage = 0, lb_chunk = 0;                        // next B load: stage, chunk of the tile
-      auto load_b = [&]() {
-        const int4 meta = s_chunk[lb_chunk];
-        if (a.debug & 2) {
-          mbar_arrive(bar_b + 8 * lb_stage);
-        } else {
-          mbar_expect_tx(bar_b + 8 * lb_stage, (uint32_t)meta.y);
-          bulk_g2s(smem_u32(b_smem + (size_t)lb_stage * a.b_stage_bytes), images + meta.x, (uint32_t)meta.y,
-                   bar_b + 8 * lb_stage);
-        }
-        if (++lb_stage == kBStages) lb_stage = 0;
-        if (++lb_chunk == a.chunks) lb_chunk = 0;
-      };
-      int loaded = 0;
-      for (; loaded < kBStages && loaded < my_chunks; ++loaded) load_b();
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;                               // parities of the stages' current use
-      int prev_sb = 0;
-      uint32_t prev_pb = 0;
-      int g = 0;
       for (int it = 0; it < my_tiles; ++it) {
         mbar_wait(bar_acc_free, (uint32_t)(it & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int ch = 0; ch < a.chunks; ++ch, ++g) {
+        for (int ch = 0; ch < a.chunks; ++ch) {
           mbar_wait(bar_a + 8 * sa, pa);
           mbar_wait(bar_b + 8 * sb, pb);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -500,18 +484,30 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
           umma_commit(bar_a_empty + 8 * sa);
           umma_commit(bar_b_empty + 8 * sb);
           if (ch == a.chunks - 1) umma_commit(bar_acc_full);
-          // refill the B stage of the chunk BEFORE this one: its MMAs drain while this
-          // chunk's are queued, so the issuing thread does not sit out a whole chunk
-          if (g >= 1 && loaded < my_chunks) {
-            mbar_wait(bar_b_empty + 8 * prev_sb, prev_pb);
-            load_b();
-            ++loaded;
-          }
-          prev_sb = sb;
-          prev_pb = pb;
           if (++sa == kAStages) { sa = 0; pa ^= 1; }
           if (++sb == kBStages) { sb = 0; pb ^= 1; }
         }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kLoadWarp) {
+    // ===== B loader: the chunk images in order, round and round, as stages drain
+    if (lane == 0) {
+      const uint8_t* images = reinterpret_cast<const uint8_t*>(a.b_images);
+      int stage = 0, ch = 0;
+      uint32_t parity = 1;                                   // (first use of a stage: nothing to wait for)
+      for (int g = 0; g < my_chunks; ++g) {
+        if (g >= kBStages) mbar_wait(bar_b_empty + 8 * stage, parity);
+        const int4 meta = s_chunk[ch];
+        if (a.debug & 2) {
+          mbar_arrive(bar_b + 8 * stage);
+        } else {
+          mbar_expect_tx(bar_b + 8 * stage, (uint32_t)meta.y);
+          bulk_g2s(smem_u32(b_smem + (size_t)stage * a.b_stage_bytes), images + meta.x, (uint32_t)meta.y,
+                   bar_b + 8 * stage);
+        }
+        if (++stage == kBStages) { stage = 0; parity ^= 1; }
+        if (++ch == a.chunks) ch = 0;
       }
     }
     __syncwarp();
@@ -519,6 +515,7 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
     // ===== producers: a warp gathers 16 rows of the tile, lane = sample within the chunk
     // (one 128-byte request per row); loads run two chunks ahead of the stores in registers.
     // Tile row i is X-row  row0 + group_rows (i / 32) + i % 32  (the groups overlap).
+    // (the loads run TWO chunks ahead in registers whatever the number of A stages)
     float v0[kRowsPerWarp] = {}, v1[kRowsPerWarp] = {};
     const int row_in_tile = group_rows * (warp >> 1) + kRowsPerWarp * (warp & 1);
     int ld_it = 0, ld_ch = 0;                                // next chunk to load: tile iteration, chunk
@@ -578,11 +575,12 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
   } else {
     // ===== epilogue warps: w4 = the TMEM lane quarter this warp may read = its row group
     const int w4 = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;                 // which 16-column groups: even or odd
     const uint32_t lane_base = ((uint32_t)(w4 * 32)) << 16;
     int total_cols = 0;
     for (int q = 0; q < a.shifts; ++q) total_cols += a.acc_w[q];
     auto zero_accumulators = [&]() {
-      for (int col = 0; col < total_cols; col += 16) tmem_st16_zero(tmem + lane_base + col);
+      for (int col = 16 * half; col < total_cols; col += 32) tmem_st16_zero(tmem + lane_base + col);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar_acc_free);
@@ -601,7 +599,7 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
         float* orow = obase + out_row * a.l;
         const bool row_ok = lane < group_rows && out_row < rows_total;
         const bool vec = (a.l & 3) == 0 && (reinterpret_cast<size_t>(obase) & 15) == 0;
-        for (int col = 0; col < a.acc_w[0]; col += 16) {
+        for (int col = 16 * half; col < a.acc_w[0]; col += 32) {
           uint32_t d[4][16];
           bool have[4];
           tmem_ld16_async(tmem + lane_base + (uint32_t)(a.acc_col[0] + col), d[0]);
@@ -647,13 +645,14 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
 
 }  // namespace
 
-size_t resample_rows_smem_bytes(int b_stage_bytes) {
-  return (size_t)kAStages * 2 * kABytes + (size_t)kBStages * b_stage_bytes + 1024;
+size_t resample_rows_smem_bytes(int a_stages, int b_stages, int b_stage_bytes) {
+  return (size_t)a_stages * 2 * kABytes + (size_t)b_stages * b_stage_bytes + 1024;
 }
 
 cudaError_t launch_resample_rows(const GemmRowsArgs& a, long long batch, int sm_count, cudaStream_t st) {
   if (batch == 0 || a.n_out == 0) return cudaSuccess;
-  const size_t smem = resample_rows_smem_bytes(a.b_stage_bytes);
+  const size_t smem = resample_rows_smem_bytes(a.a_stages, a.b_stages, a.b_stage_bytes);
+  if (a.a_stages < 2 || a.a_stages > kMaxStages || a.b_stages < 2 || a.b_stages > kMaxStages) return cudaErrorInvalidConfiguration;
   if (smem > 227 * 1024 || a.shifts < 1 || a.shifts > 4 || a.chunks > kMaxRowsChunks || a.slices > kMaxRowsSlices)
     return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(resample_rows_kernel,
