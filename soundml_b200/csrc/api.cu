@@ -801,7 +801,7 @@ struct GemmDevice {
       a.acc_col[q] = total_cols;
       total_cols += a.acc_w[q];
     }
-    if (total_cols > 512 || chunks > 32) return;
+    if (total_cols > 512 || chunks > 32 || chunks < 3) return;   // (chunks >= stages: the loader's scratch hand-over)
     int tmem_alloc = 32;
     while (tmem_alloc < total_cols) tmem_alloc *= 2;
     const int kSliceAlign = getenv("SMB_ROWS_ALIGN") ? atoi(getenv("SMB_ROWS_ALIGN")) : 8;

@@ -251,3 +251,36 @@ def test_config5_resample_then_mel_spectrogram(sb):
     assert got.shape == want.shape == (4, 128, 431)
     for c in range(4):
         assert peak_rel_err(got[c], want[c]) <= 1e-4, c
+
+
+# resample.ml:1608-1698 (gemm_run) — the row form of the tensor-core stage (one persistent
+# CTA per SM walking many tiles) against the window form, at a size where every CTA runs
+# dozens of tiles back to back: the hand-overs between tiles (accumulators drained and
+# zeroed by two warps per lane quarter, the borrowed B stage) only show under load.
+@pytest.mark.parametrize("sr,target", [(44100, 16000), (44100, 48000), (48000, 44100)])
+def test_row_form_of_the_tensor_core_stage_at_scale(sb, sr, target, monkeypatch):
+    import torch
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
+    assert any(s["exec"] == "gemm" and s["l"] <= 160 for s in cfg.stages()), cfg.pp()
+    clips, n = 96, 12 * sr
+    x = torch.rand((clips, n), device="cuda", generator=torch.Generator("cuda").manual_seed(sr + target)) * 2 - 1
+    rows = torch.empty((clips, cfg.output_frames(n)), device="cuda")
+    windows = torch.empty_like(rows)
+    monkeypatch.delenv("SMB_GEMM_WINDOWS", raising=False)
+    for _ in range(3):                                     # a race does not show every time
+        rows.zero_()
+        sb.Resample.apply(cfg, x, out=rows)
+        torch.cuda.synchronize()
+        monkeypatch.setenv("SMB_GEMM_WINDOWS", "1")
+        sb.Resample.apply(cfg, x, out=windows)
+        torch.cuda.synchronize()
+        monkeypatch.delenv("SMB_GEMM_WINDOWS")
+        peak = float(windows.abs().max())
+        assert float((rows - windows).abs().max()) / peak <= RESAMPLE_TOL, (sr, target)
+    # and both against the oracle on a few clips (float64, CPU)
+    st = oracle_stages(cfg)
+    pick = [0, clips // 2, clips - 1]
+    want = R.apply_plan(x[pick].cpu().numpy(), st, cfg.l, cfg.m)
+    got = rows[pick].cpu().numpy()
+    for c in range(len(pick)):
+        assert peak_rel_err(got[c], want[c]) <= RESAMPLE_TOL, (sr, target, c)
