@@ -763,19 +763,35 @@ struct GemmDevice {
   // shift accumulators fit tensor memory.
   bool rows_ok = false;
   int rows_sm_count = 0;
-  smb::GemmRowsArgs rows{};
-  float* d_rows_images = nullptr;
-  int4 *d_rows_chunks = nullptr, *d_rows_slices = nullptr;
-  void build_rows(const smb::ResampleStage& s) {
-    const int64_t l = s.l, m = s.m, k = s.k, taps = 2 * k + 1;
-    if (l > 160 || m < 32) return;
+  struct RowsGroup {
+    smb::GemmRowsArgs a{};
+    float* d_images = nullptr;
+    int4 *d_chunks = nullptr, *d_slices = nullptr;
+  };
+  std::vector<RowsGroup> rows_groups;            // one launch per group of <= 160 columns
+  void release_rows() {
+    for (RowsGroup& g : rows_groups) {
+      cudaFree(g.d_images);
+      cudaFree(g.d_chunks);
+      cudaFree(g.d_slices);
+    }
+    rows_groups.clear();
+    rows_ok = false;
+  }
+  // columns [c0, c0 + l) of the stage's L (l_total below)
+  bool build_rows_group(const smb::ResampleStage& s, int64_t c0, int64_t l) {
+    const int64_t l_total = s.l, m = s.m, taps = 2 * s.k + 1;
+    if (l > 160 || m < 32) return false;
+    // the group's first column starts q0 whole input rows in: fold them into the delay
+    const int64_t q0 = ((c0 * m) / l_total) / m;
+    const int64_t k = s.k - q0 * m;
     std::vector<int64_t> d((size_t)l);
-    for (int64_t r = 0; r < l; ++r) d[(size_t)r] = (r * m) / l;
+    for (int64_t r = 0; r < l; ++r) d[(size_t)r] = ((c0 + r) * m) / l_total - q0 * m;
     const int64_t p_len = taps + d[(size_t)(l - 1)];
     const int shifts = (int)((p_len + m - 1) / m);
     const int chunks = (int)((m + 31) / 32);
     const int n_pad = (int)((l + 15) / 16 * 16);
-    if (shifts > 4) return;
+    if (shifts > 4) return false;
     // columns of G_q with a nonzero in rows [j0, j1] of the shift's block: d_r <= q m + j <= d_r + taps - 1
     auto active = [&](int q, int64_t j0, int64_t j1, int* lo, int* hi) {
       *lo = n_pad;
@@ -795,13 +811,13 @@ struct GemmDevice {
     // and those of D_(q-1) a prefix, so a chunk's nonzeros form one run of TMEM columns
     for (int q = shifts - 1; q >= 0; --q) {
       int lo, hi;
-      if (!active(q, 0, m - 1, &lo, &hi)) return;
+      if (!active(q, 0, m - 1, &lo, &hi)) return false;
       a.acc_lo[q] = q == 0 ? 0 : lo / 16 * 16;
       a.acc_w[q] = q == 0 ? n_pad : (hi + 1 - a.acc_lo[q] + 15) / 16 * 16;
       a.acc_col[q] = total_cols;
       total_cols += a.acc_w[q];
     }
-    if (total_cols > 512 || chunks > 32 || chunks < 3) return;   // (chunks >= stages: the loader's scratch hand-over)
+    if (total_cols > 512 || chunks > 32 || chunks < 3) return false;   // (chunks >= stages: the loader's scratch hand-over)
     int tmem_alloc = 32;
     while (tmem_alloc < total_cols) tmem_alloc *= 2;
     const int kSliceAlign = getenv("SMB_ROWS_ALIGN") ? atoi(getenv("SMB_ROWS_ALIGN")) : 8;
@@ -842,20 +858,20 @@ struct GemmDevice {
       total_bytes += (size_t)bytes;
       stage_bytes = std::max(stage_bytes, bytes);
     }
-    if (slice_meta.size() > 64) return;
+    if (slice_meta.size() > 64) return false;
     stage_bytes = (stage_bytes + 1023) / 1024 * 1024;
     // static shared memory of the kernel (barriers, metadata) comes out of the same 227 KB
     const size_t budget = 227 * 1024 - 2048;
     if (smb::resample_rows_smem_bytes(2, 3, stage_bytes) <= budget) { a.a_stages = 2; a.b_stages = 3; }
     else if (smb::resample_rows_smem_bytes(3, 2, stage_bytes) <= budget) { a.a_stages = 3; a.b_stages = 2; }
     else if (smb::resample_rows_smem_bytes(2, 2, stage_bytes) <= budget) { a.a_stages = 2; a.b_stages = 2; }
-    else return;
+    else return false;
     int device = 0;
     CK(cudaGetDevice(&device));
     CK(cudaDeviceGetAttribute(&rows_sm_count, cudaDevAttrMultiProcessorCount, device));
     std::vector<float> img(total_bytes / 4, 0.0f);
     for (int64_t r = 0; r < l; ++r) {
-      const int64_t ph = (r * m) % l;
+      const int64_t ph = ((c0 + r) * m) % l_total;
       for (int64_t t = 0; t < taps; ++t) {
         const int64_t j = d[(size_t)r] + t;
         const int q = (int)(j / m);
@@ -863,7 +879,7 @@ struct GemmDevice {
         const int ch = (int)(jj / 32), kk = (int)(jj % 32);
         const int tcol = a.acc_col[q] + (int)r - a.acc_lo[q];
         const int sl = slice_at[(size_t)ch][(size_t)tcol];
-        if (sl < 0) return;                                     // (cannot happen: the runs cover every nonzero)
+        if (sl < 0) return false;                               // (cannot happen: the runs cover every nonzero)
         const int4 sm = slice_meta[(size_t)sl];
         const double gv = s.bank[(size_t)(ph * taps + t)];
         const float gf = (float)gv;
@@ -889,13 +905,27 @@ struct GemmDevice {
     a.chunks = chunks;
     a.tmem_cols = tmem_alloc;
     a.b_stage_bytes = stage_bytes;
-    d_rows_images = upload(img);
-    d_rows_chunks = upload(chunk_meta);
-    d_rows_slices = upload(slice_meta);
-    a.b_images = d_rows_images;
-    a.chunk_meta = d_rows_chunks;
-    a.slice_meta = d_rows_slices;
-    rows = a;
+    a.l_total = (int)l_total;
+    a.col_begin = (int)c0;
+    RowsGroup g;
+    g.d_images = upload(img);
+    g.d_chunks = upload(chunk_meta);
+    g.d_slices = upload(slice_meta);
+    a.b_images = g.d_images;
+    a.chunk_meta = g.d_chunks;
+    a.slice_meta = g.d_slices;
+    g.a = a;
+    rows_groups.push_back(g);
+    return true;
+  }
+  void build_rows(const smb::ResampleStage& s) {
+    const int n_groups = (int)((s.l + 159) / 160);
+    const int64_t base_width = ((s.l + n_groups - 1) / n_groups + 15) / 16 * 16;
+    for (int64_t c0 = 0; c0 < s.l; c0 += base_width)
+      if (!build_rows_group(s, c0, std::min<int64_t>(base_width, s.l - c0))) {
+        release_rows();
+        return;
+      }
     rows_ok = true;
   }
   void build(const smb::ResampleStage& s) {
@@ -977,12 +1007,7 @@ struct GemmDevice {
       cudaFree(g.d_meta);
     }
     groups.clear();
-    cudaFree(d_rows_images);
-    cudaFree(d_rows_chunks);
-    cudaFree(d_rows_slices);
-    d_rows_images = nullptr;
-    d_rows_chunks = d_rows_slices = nullptr;
-    rows_ok = false;
+    release_rows();
   }
 };
 
@@ -1025,12 +1050,14 @@ struct smb_resample_plan {
       ols[i].run(x, batch, n, n_out, out, st);
     } else if (executor != SMB_EXEC_DIRECT && gemm[i].rows_ok && !getenv("SMB_GEMM_WINDOWS")) {
       // (SMB_GEMM_WINDOWS=1: the overlapping-window form below, for A/B measurement)
-      smb::GemmRowsArgs a = gemm[i].rows;
-      a.x = x;
-      a.out = out;
-      a.n = n;
-      a.n_out = n_out;
-      CK(smb::launch_resample_rows(a, batch, gemm[i].rows_sm_count, st));
+      for (const GemmDevice::RowsGroup& g : gemm[i].rows_groups) {
+        smb::GemmRowsArgs a = g.a;
+        a.x = x;
+        a.out = out;
+        a.n = n;
+        a.n_out = n_out;
+        CK(smb::launch_resample_rows(a, batch, gemm[i].rows_sm_count, st));
+      }
     } else if (executor != SMB_EXEC_DIRECT && gemm[i].ok) {
       for (const GemmDevice::Group& g : gemm[i].groups) {
         smb::GemmResampleArgs a{};

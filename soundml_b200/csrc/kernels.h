@@ -211,7 +211,8 @@ struct GemmRowsArgs {
   const float* x;          // [batch, n]
   float* out;              // [batch, n_out]
   long long n, n_out;
-  int l, m, k;             // stage L (all columns in one launch), M, group delay
+  int l, m, k;             // columns of this launch (at most 160), stage M, group delay less the whole input rows skipped
+  int l_total, col_begin;  // stage L (outputs per block-row) and this launch's first column
   int n_pad;               // l rounded up to a multiple of 16
   int shifts;              // accumulators: ceil(P / M), at most 4
   int chunks;              // ceil(M / 32) K-chunks (at most 32)

@@ -595,7 +595,7 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
     };
     for (int col = 16 * half; col < total_cols; col += 32) tmem_st16_zero(tmem + lane_base + col);
     release_accumulators();
-    const long long rows_total = (a.n_out + a.l - 1) / a.l;
+    const long long rows_total = (a.n_out + a.l_total - 1) / a.l_total;
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int c = tile / tiles_per_clip;
@@ -611,7 +611,7 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
         // completed).
         float* obase = a.out + (long long)c * a.n_out;
         const long long base_row = out_row - lane;              // the warp's first output row
-        const bool vec = (a.l & 3) == 0 && (reinterpret_cast<size_t>(obase) & 15) == 0;
+        const bool vec = ((a.l | a.l_total | a.col_begin) & 3) == 0 && (reinterpret_cast<size_t>(obase) & 15) == 0;
         const int last_stage = (int)(((long long)it * a.chunks + a.chunks - 1) % kBStages);
         float* tr = reinterpret_cast<float*>(b_smem + (size_t)last_stage * a.b_stage_bytes) +
                     (warp - kEpiWarp0) * (32 * 17);
@@ -640,14 +640,14 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
             }
           }
           __syncwarp();                                            // the previous group has been read out
-          const long long idx0 = base_row * a.l + col;             // index of (the warp's row 0, col) in the clip
+          const long long idx0 = base_row * a.l_total + a.col_begin + col;   // index of (the warp's row 0, col) in the clip
           const int rows_ok = (int)min((long long)group_rows, rows_total - base_row);
           if (vec && col + 16 <= a.l) {
             // L a multiple of 4: a lane writes its row's 64 bytes itself, four 16-byte
             // stores (measured faster than turning the block through shared memory:
             // 1.97 against 2.14 ms on the 44.1 -> 16 kHz workload -- the tensor core waits
             // for the epilogue, so its latency counts more than its sector efficiency)
-            const long long idx = idx0 + lane * a.l;
+            const long long idx = idx0 + lane * a.l_total;
             if (lane < rows_ok) {
               if (idx + 16 <= a.n_out) {
                 float4* dst = reinterpret_cast<float4*>(obase + idx);
@@ -668,7 +668,7 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int r = 2 * i + (lane >> 4);
-                const long long idx = idx0 + r * a.l + cc;
+                const long long idx = idx0 + r * a.l_total + cc;
                 if (r < rows_ok && idx < a.n_out) obase[idx] = tr[r * 17 + cc];
               }
             }
@@ -703,7 +703,7 @@ cudaError_t launch_resample_rows(const GemmRowsArgs& a, long long batch, int sm_
   cudaError_t e = cudaFuncSetAttribute(resample_rows_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const long long rows = (a.n_out + a.l - 1) / a.l;
+  const long long rows = (a.n_out + a.l_total - 1) / a.l_total;
   const int rows_out = 4 * (32 - (a.shifts - 1));
   const long long tiles = (rows + rows_out - 1) / rows_out;
   // tile and chunk counters are 32-bit inside the kernel: split the batch

@@ -27,7 +27,7 @@ def run(cfg, x, out, reps=5):
 
 def main():
     peak, _ = peak_hbm()
-    for sr, target, clips in [(44100, 16000, 512), (44100, 48000, 128), (48000, 44100, 128)]:
+    for sr, target, clips in [(44100, 16000, 512), (44100, 48000, 128), (48000, 44100, 128), (44100, 32000, 128), (16000, 44100, 128)]:
         n = 30 * sr
         x = torch.rand((clips, n), device="cuda") * 2 - 1
         cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
