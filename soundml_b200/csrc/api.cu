@@ -779,7 +779,7 @@ struct GemmDevice {
     rows_ok = false;
   }
   // columns [c0, c0 + l) of the stage's L (l_total below)
-  bool build_rows_group(const smb::ResampleStage& s, int64_t c0, int64_t l) {
+  bool build_rows_group(const smb::ResampleStage& s, int64_t c0, int64_t l, bool single_group) {
     const int64_t l_total = s.l, m = s.m, taps = 2 * s.k + 1;
     if (l > 160 || m < 32) return false;
     // the group's first column starts q0 whole input rows in: fold them into the delay
@@ -818,8 +818,15 @@ struct GemmDevice {
       total_cols += a.acc_w[q];
     }
     if (total_cols > 512 || chunks > 32 || chunks < 3) return false;   // (chunks >= stages: the loader's scratch hand-over)
+    // the A tiles go to tensor memory when two stages of 64 columns fit beside the accumulators
+    // (the products then read only B from shared memory: 1.99 -> 1.90 ms on configs[3]); a stage
+    // cut into column groups gathers A once per group and is better off with the cheaper
+    // shared-memory producers (44.1 -> 32 kHz: 0.88 against 0.93 ms).  SMB_ROWS_SMEM_A=1 /
+    // SMB_ROWS_TMEM_A=1 force either.
+    const bool a_tmem = total_cols + 128 <= 512 && !getenv("SMB_ROWS_SMEM_A") &&
+                        (single_group || getenv("SMB_ROWS_TMEM_A"));
     int tmem_alloc = 32;
-    while (tmem_alloc < total_cols) tmem_alloc *= 2;
+    while (tmem_alloc < total_cols + (a_tmem ? 128 : 0)) tmem_alloc *= 2;
     const int kSliceAlign = getenv("SMB_ROWS_ALIGN") ? atoi(getenv("SMB_ROWS_ALIGN")) : 8;
     std::vector<int4> chunk_meta((size_t)chunks), slice_meta;
     // per chunk: TMEM column -> (slice, row inside the slice), -1 where nothing is stored
@@ -830,7 +837,7 @@ struct GemmDevice {
       // exact active columns (TMEM coordinates); a run may start on any column -- only its
       // width is a multiple of 16 -- so a chunk stores ceil16(band) columns, not the
       // band widened to 16-column boundaries on both sides
-      std::vector<char> on((size_t)tmem_alloc, 0);
+      std::vector<char> on((size_t)total_cols, 0);
       for (int q = 0; q < shifts; ++q) {
         int lo, hi;
         if (!active(q, 32 * (int64_t)ch, std::min<int64_t>(32 * (int64_t)ch + 31, m - 1), &lo, &hi)) continue;
@@ -838,17 +845,17 @@ struct GemmDevice {
       }
       const int first_slice = (int)slice_meta.size();
       int bytes = 0;
-      for (int t0 = 0; t0 < tmem_alloc;) {
+      for (int t0 = 0; t0 < total_cols;) {
         if (!on[(size_t)t0]) { ++t0; continue; }
         int t1 = t0 + 1;                                          // one past the run's last active column
-        for (int t = t0 + 1; t < tmem_alloc && t - t0 < 256; ++t) {
+        for (int t = t0 + 1; t < total_cols && t - t0 < 256; ++t) {
           if (on[(size_t)t]) t1 = t + 1;
           else if (t - t1 >= 16) break;                           // a gap of 16 columns ends the run
         }
         int start = t0 / kSliceAlign * kSliceAlign;              // the accumulator address of a product
         int width = (t1 - start + 15) / 16 * 16;
         if (width > 256) { width = 256; t1 = start + 256; }
-        if (start + width > tmem_alloc) start = tmem_alloc - width;
+        if (start + width > total_cols) start = total_cols - width;   // (never past the accumulators: A tiles may follow)
         for (int t = start; t < start + width; ++t) slice_at[(size_t)ch][(size_t)t] = (int)slice_meta.size();
         slice_meta.push_back(make_int4(bytes, start, width, 0));
         bytes += 2 * width * 128;
@@ -862,7 +869,15 @@ struct GemmDevice {
     stage_bytes = (stage_bytes + 1023) / 1024 * 1024;
     // static shared memory of the kernel (barriers, metadata) comes out of the same 227 KB
     const size_t budget = 227 * 1024 - 2048;
-    if (smb::resample_rows_smem_bytes(2, 3, stage_bytes) <= budget) { a.a_stages = 2; a.b_stages = 3; }
+    a.a_tmem = a_tmem ? 1 : 0;
+    a.a_tmem_col = total_cols;
+    if (a_tmem) {
+      a.a_stages = 2;
+      a.b_stages = 4;
+      const size_t turn = 8 * 32 * 17 * 4;                      // the producers' transposition tiles
+      while (a.b_stages > 2 && smb::resample_rows_smem_bytes(0, a.b_stages, stage_bytes) + turn > budget) --a.b_stages;
+      if (smb::resample_rows_smem_bytes(0, a.b_stages, stage_bytes) + turn > budget) return false;
+    } else if (smb::resample_rows_smem_bytes(2, 3, stage_bytes) <= budget) { a.a_stages = 2; a.b_stages = 3; }
     else if (smb::resample_rows_smem_bytes(3, 2, stage_bytes) <= budget) { a.a_stages = 3; a.b_stages = 2; }
     else if (smb::resample_rows_smem_bytes(2, 2, stage_bytes) <= budget) { a.a_stages = 2; a.b_stages = 2; }
     else return false;
@@ -922,7 +937,7 @@ struct GemmDevice {
     const int n_groups = (int)((s.l + 159) / 160);
     const int64_t base_width = ((s.l + n_groups - 1) / n_groups + 15) / 16 * 16;
     for (int64_t c0 = 0; c0 < s.l; c0 += base_width)
-      if (!build_rows_group(s, c0, std::min<int64_t>(base_width, s.l - c0))) {
+      if (!build_rows_group(s, c0, std::min<int64_t>(base_width, s.l - c0), n_groups == 1)) {
         release_rows();
         return;
       }

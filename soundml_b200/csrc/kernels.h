@@ -219,7 +219,8 @@ struct GemmRowsArgs {
   int slices;              // entries of slice_meta (at most 64)
   int tmem_cols;           // power of two >= sum of acc_w
   int b_stage_bytes;       // largest chunk image (multiple of 1024)
-  int a_stages, b_stages;  // pipeline depth of the A tiles and of the B images (2 or 3 each)
+  int a_stages, b_stages;  // pipeline depth of the A tiles and of the B images (2 .. 4)
+  int a_tmem, a_tmem_col;  // A tiles in tensor memory (64 columns per stage from a_tmem_col) instead of shared memory
   int acc_col[4];          // TMEM column of accumulator q (laid out in descending q)
   int acc_lo[4];           // first G column accumulator q holds (multiple of 16; 0 for q = 0)
   int acc_w[4];            // its width (multiple of 16; n_pad for q = 0)

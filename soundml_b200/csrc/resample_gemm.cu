@@ -370,12 +370,13 @@ teardown:
 //               64-byte runs to global memory, zero the accumulators with tcgen05.st (every
 //               product accumulates) and arrive on acc_free.  Meanwhile the producers and
 //               the B loader are already filling the next tile's stages.
-constexpr int kMaxStages = 3;                       // A and B stages: (2, 3) when that fits shared memory, else (3, 2)
+constexpr int kMaxStages = 4;                       // A / B stages: shared-memory A (2, 3) or (3, 2); tensor-memory A (2, up to 4)
 constexpr int kLoadWarp = kMmaWarp + 1;             // streams the B images
 constexpr int kEpiWarp0 = kMmaWarp + 2;
 constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, alternate 16-column groups
 constexpr int kRowsThreads = kThreads + 32 + 32 * kEpiWarps;
 constexpr int kMaxRowsChunks = 32, kMaxRowsSlices = 64;
+constexpr int kRowsTurnBytes = kProducerWarps * 32 * 17 * 4;   // the producers' transposition tiles (A in tensor memory)
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
   asm volatile(
@@ -394,6 +395,24 @@ __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16
       : "r"(taddr)
       : "memory");
 }
+// A operand from tensor memory (lane = row, consecutive columns = consecutive K)
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+        "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -404,7 +423,8 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   const int kAStages = a.a_stages, kBStages = a.b_stages;
-  uint8_t* b_smem = smem + kAStages * 2 * kABytes;
+  const bool a_in_tmem = a.a_tmem != 0;                     // A tiles in tensor memory: 64 columns per stage
+  uint8_t* b_smem = smem + (a_in_tmem ? 0 : kAStages * 2 * kABytes);
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 3];
   __shared__ uint32_t tmem_base_slot;
   __shared__ int4 s_chunk[kMaxRowsChunks], s_slice[kMaxRowsSlices];
@@ -476,12 +496,23 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
             const uint64_t b_hi = umma_desc(b_base + (uint32_t)sm.x);
             const uint64_t b_lo = b_hi + (uint64_t)((sm.z * 128) >> 4);
             const uint32_t acc = tmem + (uint32_t)sm.y;
+            if (a_in_tmem) {
+              const uint32_t ta_hi = tmem + (uint32_t)(a.a_tmem_col + 64 * sa), ta_lo = ta_hi + 32;
 #pragma unroll
-            for (int ks = 0; ks < kChunk / 8; ++ks) {
-              const uint64_t off = (uint64_t)(ks * 2);                 // 8 tf32 = 32 bytes = 2 units along K
-              umma_tf32(acc, a_hi + off, b_hi + off, idesc, 1);
-              umma_tf32(acc, a_hi + off, b_lo + off, idesc, 1);
-              umma_tf32(acc, a_lo + off, b_hi + off, idesc, 1);
+              for (int ks = 0; ks < kChunk / 8; ++ks) {
+                const uint64_t off = (uint64_t)(ks * 2);               // 8 tf32 = 32 bytes = 2 units along K
+                umma_tf32_ta(acc, ta_hi + 8 * ks, b_hi + off, idesc);
+                umma_tf32_ta(acc, ta_hi + 8 * ks, b_lo + off, idesc);
+                umma_tf32_ta(acc, ta_lo + 8 * ks, b_hi + off, idesc);
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < kChunk / 8; ++ks) {
+                const uint64_t off = (uint64_t)(ks * 2);               // 8 tf32 = 32 bytes = 2 units along K
+                umma_tf32(acc, a_hi + off, b_hi + off, idesc, 1);
+                umma_tf32(acc, a_hi + off, b_lo + off, idesc, 1);
+                umma_tf32(acc, a_lo + off, b_hi + off, idesc, 1);
+              }
             }
           }
           umma_commit(bar_a_empty + 8 * sa);
@@ -517,6 +548,81 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
       }
     }
     __syncwarp();
+  } else if (warp < kProducerWarps && a_in_tmem) {
+    // ===== producers, A in tensor memory.  A warp may only write its own TMEM lane quarter
+    // (w4 = warp % 4: rows 32 w4 .. + 31 of the tile) and a thread writes a row, so warp
+    // (w4, kh) owns the block [32 rows] x [16 samples: half kh of the chunk].  It is loaded
+    // coalesced -- a load instruction reads two 64-byte row segments, lane = (row parity,
+    // sample) -- two chunks ahead in registers, turned through a [32][17] shared-memory
+    // tile so that lane = row, split, and written with two tcgen05.st (hi | lo).
+    const int w4 = warp & 3, kh = warp >> 2;
+    const uint32_t lane_base = ((uint32_t)(w4 * 32)) << 16;
+    float* turn = reinterpret_cast<float*>(b_smem + (size_t)kBStages * a.b_stage_bytes) + warp * (32 * 17);
+    const int sub = lane >> 4, cc = lane & 15;               // row parity and sample of the loads
+    float v0[16] = {}, v1[16] = {};
+    int ld_it = 0, ld_ch = 0;
+    auto load_chunk = [&](float (&v)[16]) {
+      if (ld_it >= my_tiles) return;
+      if (!(a.debug & 4)) {
+        const int tile = (int)blockIdx.x + ld_it * (int)gridDim.x;
+        const int c = tile / tiles_per_clip;
+        const long long row = (long long)(tile - c * tiles_per_clip) * rows_out + group_rows * w4 + sub;
+        const float* xs = a.x + (long long)c * a.n;
+        const long long b0 = row * a.m - a.k + (long long)ld_ch * kChunk + 16 * kh + cc;   // row `sub` of the block
+        const long long first = b0 - cc - (long long)sub * a.m;                          // the block's first sample
+        if (first >= 0 && first + 31LL * a.m + 16 <= a.n) {
+          const float* p = xs + b0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __ldg(p + 2 * i * a.m);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const long long si = b0 + 2LL * i * a.m;
+            v[i] = (si >= 0 && si < a.n) ? __ldg(xs + si) : 0.0f;
+          }
+        }
+      }
+      if (++ld_ch == a.chunks) { ld_ch = 0; ++ld_it; }
+    };
+    int st_stage = 0;
+    uint32_t st_parity = 1;
+    int stored = 0;
+    auto store_chunk = [&](const float (&v)[16]) {
+      // v[i] = (row 2 i + sub, sample cc)  ->  lane = row, 16 samples
+#pragma unroll
+      for (int i = 0; i < 16; ++i) turn[(2 * i + sub) * 17 + cc] = v[i];
+      __syncwarp();
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float x = turn[lane * 17 + e];
+        hi[e] = __float_as_uint(x) & 0xFFFFE000u;
+        lo[e] = __float_as_uint(x - __uint_as_float(hi[e]));
+      }
+      __syncwarp();                                          // the tile may be overwritten
+      if (stored >= kAStages) {
+        mbar_wait(bar_a_empty + 8 * st_stage, st_parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const uint32_t col = tmem + lane_base + (uint32_t)(a.a_tmem_col + 64 * st_stage + 16 * kh);
+      tmem_st16(col, hi);
+      tmem_st16(col + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_a + 8 * st_stage);
+      ++stored;
+      if (++st_stage == kAStages) { st_stage = 0; st_parity ^= 1; }
+    };
+    load_chunk(v0);
+    load_chunk(v1);
+    for (int g = 0; g < my_chunks; g += 2) {
+      store_chunk(v0);
+      load_chunk(v0);
+      if (g + 1 < my_chunks) {
+        store_chunk(v1);
+        load_chunk(v1);
+      }
+    }
   } else if (warp < kProducerWarps) {
     // ===== producers: a warp gathers 16 rows of the tile, lane = sample within the chunk
     // (one 128-byte request per row); loads run two chunks ahead of the stores in registers.
@@ -690,13 +796,15 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
 
 }  // namespace
 
+// (a_stages = 0 when the A tiles live in tensor memory)
 size_t resample_rows_smem_bytes(int a_stages, int b_stages, int b_stage_bytes) {
   return (size_t)a_stages * 2 * kABytes + (size_t)b_stages * b_stage_bytes + 1024;
 }
 
 cudaError_t launch_resample_rows(const GemmRowsArgs& a, long long batch, int sm_count, cudaStream_t st) {
   if (batch == 0 || a.n_out == 0) return cudaSuccess;
-  const size_t smem = resample_rows_smem_bytes(a.a_stages, a.b_stages, a.b_stage_bytes);
+  const size_t smem = resample_rows_smem_bytes(a.a_tmem ? 0 : a.a_stages, a.b_stages, a.b_stage_bytes) +
+                      (a.a_tmem ? kRowsTurnBytes : 0);
   if (a.a_stages < 2 || a.a_stages > kMaxStages || a.b_stages < 2 || a.b_stages > kMaxStages) return cudaErrorInvalidConfiguration;
   if (smem > 227 * 1024 || a.shifts < 1 || a.shifts > 4 || a.chunks > kMaxRowsChunks || a.slices > kMaxRowsSlices)
     return cudaErrorInvalidConfiguration;
