@@ -257,11 +257,19 @@ def test_config5_resample_then_mel_spectrogram(sb):
 # CTA per SM walking many tiles) against the window form, at a size where every CTA runs
 # dozens of tiles back to back: the hand-overs between tiles (accumulators drained and
 # zeroed by two warps per lane quarter, the borrowed B stage) only show under load.
-@pytest.mark.parametrize("sr,target", [(44100, 16000), (44100, 48000), (48000, 44100)])
-def test_row_form_of_the_tensor_core_stage_at_scale(sb, sr, target, monkeypatch):
+@pytest.mark.parametrize("a_tiles", ["default", "shared", "tensor"])
+@pytest.mark.parametrize("sr,target", [(44100, 16000), (44100, 48000), (48000, 44100), (44100, 32000)])
+def test_row_form_of_the_tensor_core_stage_at_scale(sb, sr, target, a_tiles, monkeypatch):
     import torch
+    # where the A tiles live is decided when the plan's device tables are built (first apply)
+    monkeypatch.delenv("SMB_ROWS_SMEM_A", raising=False)
+    monkeypatch.delenv("SMB_ROWS_TMEM_A", raising=False)
+    if a_tiles == "shared":
+        monkeypatch.setenv("SMB_ROWS_SMEM_A", "1")
+    elif a_tiles == "tensor":
+        monkeypatch.setenv("SMB_ROWS_TMEM_A", "1")
     cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
-    assert any(s["exec"] == "gemm" and s["l"] <= 160 for s in cfg.stages()), cfg.pp()
+    assert any(s["exec"] == "gemm" for s in cfg.stages()), cfg.pp()
     clips, n = 96, 12 * sr
     x = torch.rand((clips, n), device="cuda", generator=torch.Generator("cuda").manual_seed(sr + target)) * 2 - 1
     rows = torch.empty((clips, cfg.output_frames(n)), device="cuda")
