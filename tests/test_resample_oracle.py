@@ -100,3 +100,33 @@ def test_dc_is_alive_at_sample_zero(lib):
     cfg = lib.Resample.Config.create(sample_rate=44100, target=48000)
     y = R.apply_plan(np.ones(500), oracle_stages(cfg), cfg.l, cfg.m)
     assert 0.4 < y[0] < 1.05 and abs(y[200] - 1.0) < 1e-6
+
+
+# resample_stubs.c:329-408 (soundml_resample_shape, compiled unmodified into oracle/_ref) inside
+# the reference's overlap-save orchestration (oracle/ref_ols.py restates resample.ml:279-300,
+# 856-867, 1313-1315, 1456-1598): the reference's OLS surface must equal the oracle's stage
+# filter -- which is what every GPU overlap-save kernel is tested against.
+@needs_ref
+@pytest.mark.parametrize("sr,target", [(44100, 22050), (22050, 44100), (48000, 8000), (8000, 48000),
+                                       (32000, 16000), (96000, 48000), (16000, 48000)])
+def test_reference_ols_shaping_matches_the_oracle_stage_filter(lib, sr, target):
+    from oracle import ref_ols
+    cfg = lib.Resample.Config.create(sample_rate=sr, target=target)
+    rate = sr
+    seen = 0
+    for s, st in zip(cfg.stages(), oracle_stages(cfg)):
+        if s["exec"] == "ols":
+            # the planner's block rule is the reference's (plan strings carry N; here also B, delta)
+            geom = ref_ols.ols_geom(rate, s["l"], s["m"], s["k"])
+            assert geom == (s["ols_n"], s["ols_b"], s["ols_delta"]), (sr, target, geom, s)
+            rng = np.random.default_rng(sr + target + s["k"])
+            for n in (1, 333, 5 * s["ols_n"] + 17):
+                x = rng.uniform(-1, 1, n)
+                n_out = R.ceil_div(n * s["l"], s["m"])
+                want = R.stage_apply(x[None], st["proto"], s["l"], s["m"], s["k"], n_out)[0]
+                got = ref_ols.stage_apply(x, st["proto"], s["l"], s["m"], s["k"], n_out, geom)
+                peak = max(np.abs(want).max(), 1e-300)
+                assert np.abs(got - want).max() / peak <= 1e-12, (sr, target, n)
+            seen += 1
+        rate = rate * s["l"] // s["m"]
+    assert seen >= 1, cfg.pp()
