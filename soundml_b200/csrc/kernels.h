@@ -221,13 +221,20 @@ struct GemmRowsArgs {
   int b_stage_bytes;       // largest chunk image (multiple of 1024)
   int a_stages, b_stages;  // pipeline depth of the A tiles and of the B images (2 .. 4)
   int a_tmem, a_tmem_col;  // A tiles in tensor memory (64 columns per stage from a_tmem_col) instead of shared memory
-  int acc_col[4];          // TMEM column of accumulator q (laid out in descending q)
-  int acc_lo[4];           // first G column accumulator q holds (multiple of 16; 0 for q = 0)
-  int acc_w[4];            // its width (multiple of 16; n_pad for q = 0)
+  // accumulators: one per shift q (index q), and optionally one more that takes the two small
+  // split terms of the shift holding the filters' main lobes (so that accumulator is a short
+  // chain of exact hi x hi products only: what keeps a 14-chunk stage at -132 dB THD+N)
+  int n_acc;               // shifts, or shifts + 1
+  int acc_shift[5];        // the row shift the accumulator's rows carry
+  int acc_col[5];          // its TMEM column (the shifts laid out in descending q)
+  int acc_lo[5];           // first G column it holds (multiple of 16)
+  int acc_w[5];            // its width (multiple of 16)
   const float* b_images;   // per chunk, per slice: [hi, lo][columns][32] pre-swizzled K-major tiles; a slice is a
                            // contiguous run of TMEM columns (the end of D_q followed by the start of D_(q-1))
   const int4* chunk_meta;  // per chunk: {byte offset into b_images, bytes, first slice, slices}
-  const int4* slice_meta;  // per slice: {byte offset inside the chunk image, TMEM column, columns, 0}
+  const int4* slice_meta;  // per slice: {byte offset of its hi rows inside the chunk image, TMEM column, columns,
+                           //  kind | byte distance from the hi rows to the lo rows << 2}; kind 0: all three
+                           //  products, 1: hi x hi only, 2: the two small terms only
   int debug;               // measurement only (SMB_ROWS_DEBUG): 1 no MMAs, 2 no B loads, 4 no A gather, 8 no epilogue
 };
 size_t resample_rows_smem_bytes(int a_stages, int b_stages, int b_stage_bytes);

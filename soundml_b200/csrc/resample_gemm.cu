@@ -373,9 +373,11 @@ teardown:
 constexpr int kMaxStages = 4;                       // A / B stages: shared-memory A (2, 3) or (3, 2); tensor-memory A (2, up to 4)
 constexpr int kLoadWarp = kMmaWarp + 1;             // streams the B images
 constexpr int kEpiWarp0 = kMmaWarp + 2;
-constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, alternate 16-column groups
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, alternate 16-column groups (four cost the
+                                                    // five-chunk stages 15 %: 0.84 -> 0.96 ms)
+constexpr int kEpiPerQuarter = kEpiWarps / 4;
 constexpr int kRowsThreads = kThreads + 32 + 32 * kEpiWarps;
-constexpr int kMaxRowsChunks = 32, kMaxRowsSlices = 64;
+constexpr int kMaxRowsChunks = 32, kMaxRowsSlices = 80;
 constexpr int kRowsTurnBytes = kProducerWarps * 32 * 17 * 4;   // the producers' transposition tiles (A in tensor memory)
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
@@ -494,24 +496,29 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
             const int4 sm = s_slice[sl];
             const uint32_t idesc = idesc0 | ((uint32_t)(sm.z >> 3) << 17);
             const uint64_t b_hi = umma_desc(b_base + (uint32_t)sm.x);
-            const uint64_t b_lo = b_hi + (uint64_t)((sm.z * 128) >> 4);
+            const uint64_t b_lo = b_hi + (uint64_t)((sm.w >> 2) >> 4);
+            const int kind = sm.w & 3;                                   // 0 all, 1 hi x hi, 2 the small terms
             const uint32_t acc = tmem + (uint32_t)sm.y;
             if (a_in_tmem) {
               const uint32_t ta_hi = tmem + (uint32_t)(a.a_tmem_col + 64 * sa), ta_lo = ta_hi + 32;
 #pragma unroll
               for (int ks = 0; ks < kChunk / 8; ++ks) {
                 const uint64_t off = (uint64_t)(ks * 2);               // 8 tf32 = 32 bytes = 2 units along K
-                umma_tf32_ta(acc, ta_hi + 8 * ks, b_hi + off, idesc);
-                umma_tf32_ta(acc, ta_hi + 8 * ks, b_lo + off, idesc);
-                umma_tf32_ta(acc, ta_lo + 8 * ks, b_hi + off, idesc);
+                if (kind != 2) umma_tf32_ta(acc, ta_hi + 8 * ks, b_hi + off, idesc);
+                if (kind != 1) {
+                  umma_tf32_ta(acc, ta_hi + 8 * ks, b_lo + off, idesc);
+                  umma_tf32_ta(acc, ta_lo + 8 * ks, b_hi + off, idesc);
+                }
               }
             } else {
 #pragma unroll
               for (int ks = 0; ks < kChunk / 8; ++ks) {
                 const uint64_t off = (uint64_t)(ks * 2);               // 8 tf32 = 32 bytes = 2 units along K
-                umma_tf32(acc, a_hi + off, b_hi + off, idesc, 1);
-                umma_tf32(acc, a_hi + off, b_lo + off, idesc, 1);
-                umma_tf32(acc, a_lo + off, b_hi + off, idesc, 1);
+                if (kind != 2) umma_tf32(acc, a_hi + off, b_hi + off, idesc, 1);
+                if (kind != 1) {
+                  umma_tf32(acc, a_hi + off, b_lo + off, idesc, 1);
+                  umma_tf32(acc, a_lo + off, b_hi + off, idesc, 1);
+                }
               }
             }
           }
@@ -690,7 +697,7 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
     const int half = (warp - kEpiWarp0) >> 2;                 // which 16-column groups: even or odd
     const uint32_t lane_base = ((uint32_t)(w4 * 32)) << 16;
     int total_cols = 0;
-    for (int q = 0; q < a.shifts; ++q) total_cols += a.acc_w[q];
+    for (int q = 0; q < a.n_acc; ++q) total_cols += a.acc_w[q];
     // the accumulators start every tile at zero.  A warp zeroes exactly the columns it
     // drained (right after reading them): the other warp of its lane quarter may still be
     // reading its own.
@@ -699,7 +706,7 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar_acc_free);
     };
-    for (int col = 16 * half; col < total_cols; col += 32) tmem_st16_zero(tmem + lane_base + col);
+    for (int col = 16 * half; col < total_cols; col += 16 * kEpiPerQuarter) tmem_st16_zero(tmem + lane_base + col);
     release_accumulators();
     const long long rows_total = (a.n_out + a.l_total - 1) / a.l_total;
     for (int it = 0; it < my_tiles; ++it) {
@@ -721,28 +728,33 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
         const int last_stage = (int)(((long long)it * a.chunks + a.chunks - 1) % kBStages);
         float* tr = reinterpret_cast<float*>(b_smem + (size_t)last_stage * a.b_stage_bytes) +
                     (warp - kEpiWarp0) * (32 * 17);
-        for (int col = 16 * half; col < a.acc_w[0]; col += 32) {
-          uint32_t d[4][16];
-          bool have[4];
-          tmem_ld16_async(tmem + lane_base + (uint32_t)(a.acc_col[0] + col), d[0]);
-#pragma unroll
-          for (int q = 1; q < 4; ++q) {
-            have[q] = q < a.shifts && col >= a.acc_lo[q] && col < a.acc_lo[q] + a.acc_w[q];
-            if (have[q]) tmem_ld16_async(tmem + lane_base + (uint32_t)(a.acc_col[q] + col - a.acc_lo[q]), d[q]);
-          }
-          tmem_ld_wait();
-          tmem_st16_zero(tmem + lane_base + (uint32_t)(a.acc_col[0] + col));
-#pragma unroll
-          for (int q = 1; q < 4; ++q)
-            if (have[q]) tmem_st16_zero(tmem + lane_base + (uint32_t)(a.acc_col[q] + col - a.acc_lo[q]));
+        for (int col = 16 * half; col < a.n_pad; col += 16 * kEpiPerQuarter) {
+          // every accumulator that holds these 16 columns, in a fixed order
+          // ((acc0 + acc1) + acc2) + ..., three loads in flight at a time (registers)
           float o[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(d[0][e]);
+          for (int e = 0; e < 16; ++e) o[e] = 0.0f;
 #pragma unroll
-          for (int q = 1; q < 4; ++q) {
-            if (have[q]) {                                         // (uniform)
+          for (int q0 = 0; q0 < 6; q0 += 3) {
+            if (q0 >= a.n_acc) break;
+            uint32_t d[3][16];
+            bool have[3];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) o[e] += __shfl_down_sync(0xffffffffu, __uint_as_float(d[q][e]), q);
+            for (int u = 0; u < 3; ++u) {
+              const int q = q0 + u;
+              have[u] = q < a.n_acc && col >= a.acc_lo[q < 5 ? q : 4] && col < a.acc_lo[q < 5 ? q : 4] + a.acc_w[q < 5 ? q : 4];
+              if (have[u]) tmem_ld16_async(tmem + lane_base + (uint32_t)(a.acc_col[q < 5 ? q : 4] + col - a.acc_lo[q < 5 ? q : 4]), d[u]);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              const int q = q0 + u < 5 ? q0 + u : 4;
+              if (have[u]) {                                       // (uniform)
+                tmem_st16_zero(tmem + lane_base + (uint32_t)(a.acc_col[q] + col - a.acc_lo[q]));
+                const int sh = a.acc_shift[q];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o[e] += __shfl_down_sync(0xffffffffu, __uint_as_float(d[u][e]), sh);
+              }
             }
           }
           __syncwarp();                                            // the previous group has been read out
@@ -806,7 +818,7 @@ cudaError_t launch_resample_rows(const GemmRowsArgs& a, long long batch, int sm_
   const size_t smem = resample_rows_smem_bytes(a.a_tmem ? 0 : a.a_stages, a.b_stages, a.b_stage_bytes) +
                       (a.a_tmem ? kRowsTurnBytes : 0);
   if (a.a_stages < 2 || a.a_stages > kMaxStages || a.b_stages < 2 || a.b_stages > kMaxStages) return cudaErrorInvalidConfiguration;
-  if (smem > 227 * 1024 || a.shifts < 1 || a.shifts > 4 || a.chunks > kMaxRowsChunks || a.slices > kMaxRowsSlices)
+  if (smem > 227 * 1024 || a.shifts < 1 || a.shifts > 4 || a.n_acc < a.shifts || a.n_acc > 5 || a.chunks > kMaxRowsChunks || a.slices > kMaxRowsSlices)
     return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(resample_rows_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
