@@ -330,6 +330,35 @@ int smb_ingest_layout(const void* interleaved, int64_t frames, int64_t channels,
  * per decode block of the fused read. */
 int64_t smb_ingest_block_frames(int64_t channels, int64_t elt, int64_t advertised);
 
+/* The fused read's decode loop on the device (soundml_io.ml:742-807 decode_step /
+ * resolve_eof; the staging block of soundml_io_stubs.c:1175-1239): two PINNED interleaved
+ * staging blocks of max_block frames.  The decoder (sf_readf_* on the CPU) fills the block
+ * smb_ingest_staging hands out; smb_ingest_submit(frames) only ENQUEUES -- the upload on a
+ * copy stream, then, behind an event, the layout pass and the streaming resampler's step on
+ * the compute stream, writing [width, released] C-contiguous straight into `out_device`
+ * (width = channels, or 1 with SMB_INGEST_DOWNMIX) -- and flips to the other block, so block
+ * i + 1 is being decoded while block i is uploaded and resampled.  `released` is integer
+ * bookkeeping known beforehand: smb_ingest_submit_frames(frames), asked BEFORE the submit;
+ * smb_ingest_finish writes the resampler's tail (smb_ingest_finish_frames) at decoder EOF.
+ * target = 0 (or = sample_rate) delivers the native rate: submit is the layout pass alone.
+ * smb_ingest_staging blocks only until the upload that last read that block (two submits
+ * ago) has left the host.  max_block = 0 takes decode_block_frames' rule.  Everything
+ * written concatenates to smb_resample_apply of the whole laid-out signal (bit for bit with
+ * the direct executor, <= 1e-5 of peak with the block executors).  Single owner. */
+typedef struct smb_ingest smb_ingest;
+int smb_ingest_create(smb_ingest** reader, int64_t channels, int64_t sample_rate, int64_t target,
+                      int mode, int quality, int64_t max_block, int dtype);
+int smb_ingest_destroy(smb_ingest* reader);
+int64_t smb_ingest_max_block(const smb_ingest* reader);
+int smb_ingest_staging(smb_ingest* reader, void** block);
+int64_t smb_ingest_submit_frames(const smb_ingest* reader, int64_t frames);
+int smb_ingest_submit(smb_ingest* reader, int64_t frames, void* out_device);
+int64_t smb_ingest_finish_frames(const smb_ingest* reader);
+int smb_ingest_finish(smb_ingest* reader, void* out_device);
+int smb_ingest_sync(smb_ingest* reader);
+/* the compute stream (a cudaStream_t): what a consumer of out_device must order itself behind */
+void* smb_ingest_stream(smb_ingest* reader);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,23 @@ external resample_kernel_destroy : resample_kernel -> unit
   = "soundml_b200_resample_kernel_destroy"
 
 (* The flat storage of a contiguous tensor, shared (resample.ml:94). *)
+type ingest
+
+external ingest_create : int -> int -> int -> int -> int -> int -> ingest
+  = "soundml_b200_ingest_create_bc" "soundml_b200_ingest_create"
+external ingest_destroy : ingest -> unit = "soundml_b200_ingest_destroy"
+external ingest_max_block : ingest -> int = "soundml_b200_ingest_max_block"
+external ingest_staging : ingest -> int -> (float, Bigarray.float32_elt) ba
+  = "soundml_b200_ingest_staging"
+external ingest_submit_frames : ingest -> int -> int = "soundml_b200_ingest_submit_frames"
+external ingest_finish_frames : ingest -> int = "soundml_b200_ingest_finish_frames"
+external device_alloc : int -> nativeint = "soundml_b200_device_alloc"
+external device_free : nativeint -> unit = "soundml_b200_device_free"
+external ingest_submit : ingest -> int -> nativeint -> int -> unit = "soundml_b200_ingest_submit"
+external ingest_finish : ingest -> nativeint -> int -> unit = "soundml_b200_ingest_finish"
+external ingest_result_read : ingest -> nativeint -> int -> (float, Bigarray.float32_elt) ba -> unit
+  = "soundml_b200_ingest_result_read"
+
 let array1_of t = Nx_buffer.to_bigarray1 (Nx.to_buffer t)
 
 let leading_shape t =
@@ -312,3 +329,57 @@ let mfcc stft_config mel_config ?(n_mfcc = 20) ?lifter x =
       (match lifter with Some l -> l | None -> 0.)
       (array1_of out) ;
   out
+
+(* The fused read of soundml-io (Soundml_io.read ~sample_rate, soundml_io.ml:742-807) on the
+   device: [decode] is the caller's sf_readf_float -- it fills the staging block it is handed
+   and returns the frames it wrote (0 at EOF).  Block i + 1 is decoded while block i is
+   uploaded, laid out and resampled; pieces land in a device buffer and come back once, as
+   planar [width; total] float32 ([total] = ceil (frames * L / M), from the file's frame
+   count as Soundml_io knows it). *)
+module Reader = struct
+  let read ~channels ~sample_rate ~target ~mono ~quality ~frames
+      ~(decode : (float, Bigarray.float32_elt) ba -> int -> int) =
+    let width = if mono then 1 else channels in
+    let r =
+      ingest_create channels sample_rate (if target = sample_rate then 0 else target)
+        (if mono then 2 else 1) (quality_code quality) 0
+    in
+    let block = ingest_max_block r in
+    (* an upper bound of what the pieces can add up to: every piece is [width; released] *)
+    let total =
+      if target = sample_rate then frames
+      else
+        let g = let rec gcd a b = if b = 0 then a else gcd b (a mod b) in gcd sample_rate target in
+        ((frames * (target / g)) + (sample_rate / g) - 1) / (sample_rate / g)
+    in
+    let dev = device_alloc (Stdlib.max 1 (4 * width * total)) in
+    Fun.protect
+      ~finally:(fun () -> device_free dev ; ingest_destroy r)
+      (fun () ->
+        let pieces = ref [] and at = ref 0 in
+        let rec loop () =
+          let got = decode (ingest_staging r channels) block in
+          if got > 0 then begin
+            let released = ingest_submit_frames r got in
+            ingest_submit r got dev (4 * width * !at) ;
+            if released > 0 then pieces := (!at, released) :: !pieces ;
+            at := !at + released ;
+            loop ()
+          end
+        in
+        loop () ;
+        let tail = ingest_finish_frames r in
+        ingest_finish r dev (4 * width * !at) ;
+        if tail > 0 then pieces := (!at, tail) :: !pieces ;
+        at := !at + tail ;
+        (* pieces are [width; n_i] blocks one after the other: stride them into [width; total] *)
+        let flat = Nx.zeros Nx.float32 [|width * !at|] in
+        ingest_result_read r dev (4 * width * !at) (array1_of flat) ;
+        let out = Nx.zeros Nx.float32 [|width; !at|] in
+        List.iter
+          (fun (p, n) ->
+            let piece = Nx.reshape [|width; n|] (Nx.slice [Nx.R (width * p, width * (p + n))] flat) in
+            Nx.set_slice [Nx.A; Nx.R (p, p + n)] out piece )
+          (List.rev !pieces) ;
+        out )
+end

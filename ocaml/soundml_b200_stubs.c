@@ -453,3 +453,86 @@ CAMLprim value soundml_b200_resample_kernel_reset(value v_k) {
   smb_ml_raise(smb_resample_kernel_reset(live(v_k)));
   return Val_unit;
 }
+
+/* ---- the fused read's decode loop on the device (soundml_io.ml:742-807) ------------------
+ * reader = two pinned staging blocks + the streaming resampler; the OCaml side decodes with
+ * sf_readf_* straight into the Bigarray `ingest_staging` returns (it aliases the pinned
+ * block: CAML_BA_EXTERNAL, nothing for the GC to free), submits, and collects the planar
+ * result from a device buffer it owns (`ingest_result_*`). */
+static void ing_finalize(value v) { if (HANDLE(v)) { smb_ingest_destroy(HANDLE(v)); HANDLE(v) = NULL; } }
+static struct custom_operations ing_ops = {"soundml_b200.ingest", ing_finalize,
+  custom_compare_default, custom_hash_default, custom_serialize_default,
+  custom_deserialize_default, custom_compare_ext_default, custom_fixed_length_default};
+
+/* channels -> sample_rate -> target (0 = native) -> mode -> quality -> max_block (0 = rule) -> reader
+ * (float32 frames: what sf_readf_float delivers) */
+CAMLprim value soundml_b200_ingest_create(value v_channels, value v_sr, value v_target, value v_mode,
+                                          value v_quality, value v_max_block) {
+  CAMLparam0();
+  smb_ingest *r = NULL;
+  smb_ml_raise(smb_ingest_create(&r, Long_val(v_channels), Long_val(v_sr), Long_val(v_target),
+                                 Int_val(v_mode), Int_val(v_quality), Long_val(v_max_block), SMB_F32));
+  const int64_t block = smb_ingest_max_block(r) * Long_val(v_channels) * 4;
+  CAMLreturn(wrap(&ing_ops, r, (uintnat)(4 * block)));   /* two pinned blocks, two device copies */
+}
+CAMLprim value soundml_b200_ingest_create_bc(value *argv, int argn) {
+  (void)argn;
+  return soundml_b200_ingest_create(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5]);
+}
+CAMLprim value soundml_b200_ingest_destroy(value v) { ing_finalize(v); return Val_unit; }
+CAMLprim value soundml_b200_ingest_max_block(value v) { return Val_long(smb_ingest_max_block(live(v))); }
+/* reader -> channels -> (float, float32_elt) Array1.t over the block to decode into next */
+CAMLprim value soundml_b200_ingest_staging(value v_r, value v_channels) {
+  CAMLparam1(v_r);
+  smb_ingest *r = live(v_r);
+  void *block = NULL;
+  caml_release_runtime_system();               /* may wait for the upload of two submits ago */
+  int st = smb_ingest_staging(r, &block);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  intnat dim[1] = {(intnat)(smb_ingest_max_block(r) * Long_val(v_channels))};
+  CAMLreturn(caml_ba_alloc(CAML_BA_FLOAT32 | CAML_BA_C_LAYOUT | CAML_BA_EXTERNAL, 1, block, dim));
+}
+CAMLprim value soundml_b200_ingest_submit_frames(value v_r, value v_frames) {
+  return Val_long(smb_ingest_submit_frames(live(v_r), Long_val(v_frames)));
+}
+CAMLprim value soundml_b200_ingest_finish_frames(value v_r) {
+  return Val_long(smb_ingest_finish_frames(live(v_r)));
+}
+/* The planar result lives in a device buffer [width, total] the OCaml side allocates once
+ * (it knows the file's frame count): a piece of `released` frames is written as
+ * [width, released] C-contiguous at `at`; ingest_result_read strides them back into place. */
+CAMLprim value soundml_b200_device_alloc(value v_bytes) {
+  void *p = NULL;
+  smb_ml_raise(smb_device_alloc(&p, (size_t)Long_val(v_bytes)));
+  return caml_copy_nativeint((intnat)p);
+}
+CAMLprim value soundml_b200_device_free(value v_ptr) {
+  smb_ml_raise(smb_device_free((void *)Nativeint_val(v_ptr)));
+  return Val_unit;
+}
+/* reader -> frames -> device base -> byte offset -> unit (only enqueues) */
+CAMLprim value soundml_b200_ingest_submit(value v_r, value v_frames, value v_dev, value v_off) {
+  smb_ingest *r = live(v_r);
+  smb_ml_raise(smb_ingest_submit(r, Long_val(v_frames), (char *)Nativeint_val(v_dev) + Long_val(v_off)));
+  return Val_unit;
+}
+CAMLprim value soundml_b200_ingest_finish(value v_r, value v_dev, value v_off) {
+  smb_ingest *r = live(v_r);
+  smb_ml_raise(smb_ingest_finish(r, (char *)Nativeint_val(v_dev) + Long_val(v_off)));
+  return Val_unit;
+}
+/* reader -> device base -> bytes -> dst:ba -> unit: waits for the reader, then one copy down */
+CAMLprim value soundml_b200_ingest_result_read(value v_r, value v_dev, value v_bytes, value v_dst) {
+  CAMLparam2(v_r, v_dst);
+  smb_ingest *r = live(v_r);
+  void *dst = Caml_ba_data_val(v_dst);
+  const size_t bytes = (size_t)Long_val(v_bytes);
+  need(v_dst, (int64_t)(bytes / 4), "soundml_b200: output extent disagrees with geometry");
+  caml_release_runtime_system();
+  int st = smb_ingest_sync(r);
+  if (st == SMB_OK) st = smb_memcpy_d2h(dst, (const void *)Nativeint_val(v_dev), bytes);
+  caml_acquire_runtime_system();
+  smb_ml_raise(st);
+  CAMLreturn(Val_unit);
+}

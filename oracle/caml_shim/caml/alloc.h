@@ -5,4 +5,5 @@
 #include "mlvalues.h"
 value caml_copy_double(double d);
 value caml_alloc_tuple(uintnat n);
+value caml_copy_nativeint(intnat i);
 #endif

@@ -22,4 +22,5 @@ struct custom_operations {
 value caml_alloc_custom(struct custom_operations *ops, uintnat size, uintnat mem, uintnat max);
 value caml_alloc_custom_mem(struct custom_operations *ops, uintnat size, uintnat mem);
 #define Data_custom_val(v) ((void *)((value *)(v) + 1))
+#define Nativeint_val(v) (*((intnat *)Data_custom_val(v)))
 #endif

@@ -130,6 +130,16 @@ SIGNATURES = {
     "smb_fir_design_lowpass": (_int, [_i64, _dbl, _dbl, _pd]),
     "smb_ingest_layout": (_int, [_vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _int, _int, _vp]),
     "smb_ingest_block_frames": (_i64, [_i64, _i64, _i64]),
+    "smb_ingest_create": (_int, [_pvp, _i64, _i64, _i64, _int, _int, _i64, _int]),
+    "smb_ingest_destroy": (_int, [_vp]),
+    "smb_ingest_max_block": (_i64, [_vp]),
+    "smb_ingest_staging": (_int, [_vp, _pvp]),
+    "smb_ingest_submit_frames": (_i64, [_vp, _i64]),
+    "smb_ingest_submit": (_int, [_vp, _i64, _vp]),
+    "smb_ingest_finish_frames": (_i64, [_vp]),
+    "smb_ingest_finish": (_int, [_vp, _vp]),
+    "smb_ingest_sync": (_int, [_vp]),
+    "smb_ingest_stream": (_vp, [_vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

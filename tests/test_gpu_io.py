@@ -98,3 +98,40 @@ def test_ingest_argument_checks(sb):
     rd.finish()
     with pytest.raises(ValueError):
         rd.feed(np.zeros((10, 2), np.float32))
+
+
+def test_reader_decodes_into_pinned_staging_blocks(sb):
+    """The decode loop as soundml-io runs it (soundml_io.ml:742-807): the decoder writes block
+    i + 1 into the other pinned staging block while block i is uploaded and resampled; nothing
+    but ``submit`` touches the data.  The pieces concatenate to the offline result."""
+    import torch
+    sr, target, channels, frames = 44100, 16000, 2, 150000
+    rng = np.random.default_rng(3)
+    sig = rng.uniform(-1, 1, (frames, channels)).astype(np.float32)
+    rd = sb.Io.Ingest(channels=channels, sample_rate=sr, target=target, mode="mono", max_block=8192)
+    assert rd.max_block == 8192
+    pieces, blocks = [], []
+    for i in range(0, frames, 8192):
+        blk = rd.staging()
+        blocks.append(blk.ctypes.data)
+        n = min(8192, frames - i)
+        blk[:n] = sig[i:i + n]                                 # "sf_readf_float" into pinned memory
+        p = rd.submit(n)
+        if p is not None:
+            pieces.append(p)
+    assert len(set(blocks)) == 2 and blocks[0] != blocks[1] and blocks[0] == blocks[2]   # two blocks, alternating
+    tail = rd.finish()
+    if tail is not None:
+        pieces.append(tail)
+    got = torch.cat(pieces, dim=-1).cpu().numpy()
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
+    off = sb.Resample.apply(cfg, io_oracle.layout(sig, "mono"))
+    assert got.shape == off.shape == (1, -(-frames * cfg.l // cfg.m))
+    assert peak_rel_err(got, off) <= 1e-5
+    with pytest.raises(ValueError):
+        rd.submit(10)
+    # native rate, float64, planar: the layout pass alone, bit for bit
+    rd = sb.Io.Ingest(channels=3, sample_rate=48000, target=None, max_block=5000, dtype=np.float64)
+    sig64 = rng.uniform(-1, 1, (12345, 3))
+    got = rd.read(sig64[i:i + 5000] for i in range(0, 12345, 5000)).cpu().numpy()
+    assert np.array_equal(got, io_oracle.layout(sig64, "planar"))
