@@ -77,7 +77,23 @@ enum { SMB_EXEC_DIRECT = 0, SMB_EXEC_OLS = 1, SMB_EXEC_GEMM = 2, SMB_EXEC_PLANNE
  * fused tcgen05 kernel (both 32-point FFT passes as split-fp16 products in TMEM),
  * PAIR the frame-pair kernel (two frames per warp in float32x2 lanes; mel output of
  * fft 2048, what AUTO picks for smb_mel_spectrogram when it applies);
- * a forced kernel that does not cover the call is SMB_EINVAL. */
+ * a forced kernel that does not cover the call is SMB_EINVAL.
+ *
+ * NUMERICAL CONTRACT.  The reference computes every float32 call in a double interior
+ * and rounds once (stft.ml:61-142, mel.ml:202-231; its gate is per element, rtol 1e-6 /
+ * atol 1e-7).  SMB_PATH_GENERIC does exactly that, at any size.  The fused kernels
+ * (FAST, PAIR, TENSOR: what AUTO picks for float32 audio and fft_size in 128 .. 2048)
+ * keep a FLOAT32 interior -- window, twiddles, mel weights and the transform itself
+ * rounded to float32 -- and hold a weaker, peak-relative contract: every output is within
+ * 1e-6 of its clip's largest output (measured 5e-7; tests gate 1e-4, the bar
+ * BASELINE.json states for this path), so values more than ~120 dB below the clip's
+ * peak are noise.  In decibels with the reference's default 80 dB floor that is within
+ * 0.01 dB (tests/test_gpu_pair_kernel.py::test_high_dynamic_range_elementwise; log-mel
+ * and MFCC through the fused path are gated on the reference's goldens and the oracle in
+ * tests/test_gpu_db_mfcc.py).  smb_stft_invert's fused kernel likewise runs its
+ * transforms in float32 but divides by the overlap envelope in double, including the
+ * partially covered head and tail.  Float64 audio always takes the double interior.
+ * A caller that needs the per-element contract forces SMB_PATH_GENERIC. */
 enum { SMB_PATH_AUTO = 0, SMB_PATH_GENERIC = 1, SMB_PATH_FAST = 2, SMB_PATH_TENSOR = 3,
        SMB_PATH_PAIR = 4 };
 
