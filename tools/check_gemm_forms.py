@@ -1,3 +1,6 @@
+"""Row form against window form of the tensor-core resampler stage on random input, small and at
+scale, three times over (a race does not show every time): max difference and where the bad
+values sit (clip, block-row, column).  python tools/check_gemm_forms.py"""
 import os, sys, torch, numpy as np
 sys.path.insert(0, ".")
 import soundml_b200 as sb

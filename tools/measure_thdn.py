@@ -1,4 +1,8 @@
-"""THD+N / SFDR of the float32 planned path for a few pairs, row form against window form."""
+"""SFDR and THD+N (resample_quality.ml Q1/Q2: gate 125 dB / -125 dB in float32) of the
+float32 planned path for the tensor-core pairs: the row form as shipped, the row form with
+the A tiles in shared memory, and round 1's window form.  One JSON-ish line per (pair, form):
+(tone Hz, SFDR dB, THD+N dB).  python tools/measure_thdn.py   (SMB_ROWS_SPLIT=0 shows the
+out-of-gate single-accumulator variant)"""
 import os, sys
 import numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tests")

@@ -15,5 +15,8 @@ timeout 400 python bench_extra.py > $O/r2_bench_extra.jsonl 2>> $O/r2_bench_err.
 timeout 300 python tools/bench_resample_pairs.py > $O/r2_resample_pairs.jsonl 2>> $O/r2_bench_err.log
 timeout 300 python tools/bench_direct.py > $O/r2_direct_kernel.jsonl 2>> $O/r2_bench_err.log
 timeout 200 python tools/bench_host_paths.py > $O/r2_host_paths.jsonl 2>> $O/r2_bench_err.log
+timeout 200 python tools/bench_gemm_forms.py > $O/r2_gemm_forms.jsonl 2>> $O/r2_bench_err.log
+timeout 200 python tools/measure_thdn.py > $O/r2_thdn.txt 2>> $O/r2_bench_err.log
+timeout 200 python tools/bench_mel_gemm.py > $O/r2_mel_gemm.json 2>> $O/r2_bench_err.log
 tail -c 400 $O/r2_bench_err.log
 cut -c1-300 $O/r2_bench_line.json
