@@ -827,9 +827,18 @@ struct GemmDevice {
     int total_cols = 0;
     // accumulators side by side in DESCENDING q: the active columns of D_q are a suffix
     // and those of D_(q-1) a prefix, so a chunk's nonzeros form one run of TMEM columns
-    for (int q = shifts - 1; q >= 0; --q) {
+    // (split_main: the outer shifts first, then the main shift, then its small-term accumulator:
+    // the main shift and the tails are dealt to different issuing threads)
+    std::vector<int> order;
+    for (int q = shifts - 1; q >= 0; --q)
+      if (!split_main || q != qc) order.push_back(q);
+    if (split_main && qc >= shifts) return false;
+    if (split_main) order.push_back(qc);
+    int tails_cols = 0;
+    for (int q : order) {
       int lo, hi;
       if (!active(q, 0, m - 1, &lo, &hi)) return false;
+      if (split_main && q == qc) tails_cols = total_cols;
       a.acc_shift[q] = q;
       a.acc_lo[q] = (q == 0 && !split_main) ? 0 : lo / 16 * 16;
       a.acc_w[q] = (q == 0 && !split_main) ? n_pad : (hi + 1 - a.acc_lo[q] + 15) / 16 * 16;
@@ -839,7 +848,6 @@ struct GemmDevice {
     const int d_cols = total_cols;                                // the shifts' accumulators: what a run may cover
     a.n_acc = shifts;
     if (split_main) {
-      if (qc >= shifts) return false;
       a.acc_shift[shifts] = qc;
       a.acc_lo[shifts] = a.acc_lo[qc];
       a.acc_w[shifts] = a.acc_w[qc];
@@ -880,7 +888,8 @@ struct GemmDevice {
       for (int t0 = 0; t0 < d_cols;) {
         if (!on[(size_t)t0]) { ++t0; continue; }
         int t1 = t0 + 1;                                          // one past the run's last active column
-        for (int t = t0 + 1; t < d_cols && t - t0 < 256; ++t) {
+        const int t_end = split_main && t0 < tails_cols ? tails_cols : d_cols;   // a run stays with one owner
+        for (int t = t0 + 1; t < t_end && t - t0 < 256; ++t) {
           if (on[(size_t)t]) t1 = t + 1;
           else if (t - t1 >= 16) break;                           // a gap of 16 columns ends the run
         }
@@ -888,22 +897,21 @@ struct GemmDevice {
         int width = (t1 - start + 15) / 16 * 16;
         if (width > 256) { width = 256; t1 = start + 256; }
         if (start + width > d_cols) start = d_cols - width;      // (never past the shifts' accumulators)
+        if (split_main && t0 < tails_cols && start + width > tails_cols) start = tails_cols - width;
+        if (split_main && t0 >= tails_cols && start < tails_cols) start = tails_cols;   // (a 16-column boundary)
         if (start < 0) return false;
         for (int t = start; t < start + width; ++t) run_at[(size_t)ch][(size_t)t] = (int)runs.size();
         runs.push_back(Run{bytes, start, width});
         const int lo_delta = width * 128;                         // from a row's hi image to its lo image
         if (!split_main) {
-          slice_meta.push_back(make_int4(bytes, start, width, 0 | (lo_delta << 2)));
+          slice_meta.push_back(make_int4(bytes, start, width, 0 | (lo_delta << 3)));
+        } else if (start < tails_cols) {
+          // the outer shifts: all three products in their own accumulators, second issuer
+          slice_meta.push_back(make_int4(bytes, start, width, 0 | 4 | (lo_delta << 3)));
         } else {
-          // hi x hi over the whole run; the small terms piece by piece: shift qc's columns go to
-          // the extra accumulator, the others stay with their shift
-          slice_meta.push_back(make_int4(bytes, start, width, 1 | (lo_delta << 2)));
-          for (int q = shifts - 1; q >= 0; --q) {
-            const int p0 = std::max(start, a.acc_col[q]), p1 = std::min(start + width, a.acc_col[q] + a.acc_w[q]);
-            if (p1 <= p0) continue;
-            const int target = q == qc ? a.acc_col[shifts] + (p0 - a.acc_col[qc]) : p0;
-            slice_meta.push_back(make_int4(bytes + (p0 - start) * 128, target, p1 - p0, 2 | (lo_delta << 2)));
-          }
+          // the main shift: hi x hi into its accumulator, the small terms into the extra one
+          slice_meta.push_back(make_int4(bytes, start, width, 1 | (lo_delta << 3)));
+          slice_meta.push_back(make_int4(bytes, a.acc_col[shifts] + (start - a.acc_col[qc]), width, 2 | (lo_delta << 3)));
         }
         bytes += 2 * width * 128;
         t0 = std::max(t1, start + width);
@@ -959,6 +967,7 @@ struct GemmDevice {
       }
     }
     a.slices = (int)slice_meta.size();
+    a.two_issuers = split_main ? 1 : 0;
     a.l = (int)l;
     a.m = (int)m;
     a.k = (int)k;

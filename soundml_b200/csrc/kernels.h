@@ -233,8 +233,10 @@ struct GemmRowsArgs {
                            // contiguous run of TMEM columns (the end of D_q followed by the start of D_(q-1))
   const int4* chunk_meta;  // per chunk: {byte offset into b_images, bytes, first slice, slices}
   const int4* slice_meta;  // per slice: {byte offset of its hi rows inside the chunk image, TMEM column, columns,
-                           //  kind | byte distance from the hi rows to the lo rows << 2}; kind 0: all three
-                           //  products, 1: hi x hi only, 2: the two small terms only
+                           //  kind | owner << 2 | byte distance from the hi rows to the lo rows << 3}; kind 0: all
+                           //  three products, 1: hi x hi only, 2: the two small terms only; owner: which of the
+                           //  two issuing threads takes the slice
+  int two_issuers;         // slices are dealt to two MMA-issuing threads (every accumulator to one of them)
   int debug;               // measurement only (SMB_ROWS_DEBUG): 1 no MMAs, 2 no B loads, 4 no A gather, 8 no epilogue
 };
 size_t resample_rows_smem_bytes(int a_stages, int b_stages, int b_stage_bytes);

@@ -365,6 +365,7 @@ teardown:
 //               else that thread does is time the tensor core's queue runs dry); after a
 //               tile's last chunk it commits acc_full and waits for acc_free;
 //   warp  9     one lane streams the B images (cp.async.bulk), stage by stage as they drain;
+//   warp  18    a second MMA issuer for plans that deal their slices to two owners;
 //   warps 10-17 epilogue (two per TMEM lane quarter, alternate 16-column groups): drain the accumulators, shift,
 //               turn 32 x 16 blocks through shared memory (a drained B stage) and write whole
 //               64-byte runs to global memory, zero the accumulators with tcgen05.st (every
@@ -376,7 +377,8 @@ constexpr int kEpiWarp0 = kMmaWarp + 2;
 constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, alternate 16-column groups (four cost the
                                                     // five-chunk stages 15 %: 0.84 -> 0.96 ms)
 constexpr int kEpiPerQuarter = kEpiWarps / 4;
-constexpr int kRowsThreads = kThreads + 32 + 32 * kEpiWarps;
+constexpr int kIssue2Warp = kEpiWarp0 + kEpiWarps;    // the second MMA issuer (plans with two owners)
+constexpr int kRowsThreads = kThreads + 32 + 32 * kEpiWarps + 32;
 constexpr int kMaxRowsChunks = 32, kMaxRowsSlices = 80;
 constexpr int kRowsTurnBytes = kProducerWarps * 32 * 17 * 4;   // the producers' transposition tiles (A in tensor memory)
 
@@ -447,13 +449,13 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
   if (tid == 0) {
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(bar_a + 8 * s, kProducers);
-      mbar_init(bar_a_empty + 8 * s, 1);
+      mbar_init(bar_a_empty + 8 * s, 1 + a.two_issuers);
     }
     for (int s = 0; s < kBStages; ++s) {
       mbar_init(bar_b + 8 * s, 1);
-      mbar_init(bar_b_empty + 8 * s, 1);
+      mbar_init(bar_b_empty + 8 * s, 1 + a.two_issuers);
     }
-    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_acc_full, 1 + a.two_issuers);
     mbar_init(bar_acc_free, 32 * kEpiWarps);
     mbar_init(bar_scratch, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -474,8 +476,12 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
   const int my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int my_chunks = my_tiles * a.chunks;                 // (the launcher keeps this below 2^31)
 
-  if (warp == kMmaWarp) {
-    // ===== B loader + MMA issuer (one elected lane) =====
+  if (warp == kMmaWarp || (warp == kIssue2Warp && a.two_issuers)) {
+    // ===== MMA issuer (one elected lane).  A plan may deal its slices to two issuers: one
+    // thread issues a tcgen05.mma every ~80 cycles whatever its size, so the separated small
+    // terms (twice the pieces) go through two threads side by side -- each accumulator is
+    // only ever touched by one of them, which keeps the summation order fixed.
+    const int owner = warp == kIssue2Warp ? 1 : 0;
     if (lane == 0) {
       const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24);
       int sa = 0, sb = 0;
@@ -494,9 +500,10 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
           const uint32_t b_base = smem_u32(b_smem + (size_t)sb * a.b_stage_bytes);
           for (int sl = meta.z; sl < meta.z + ((a.debug & 1) ? 0 : meta.w); ++sl) {
             const int4 sm = s_slice[sl];
+            if (((sm.w >> 2) & 1) != owner) continue;
             const uint32_t idesc = idesc0 | ((uint32_t)(sm.z >> 3) << 17);
             const uint64_t b_hi = umma_desc(b_base + (uint32_t)sm.x);
-            const uint64_t b_lo = b_hi + (uint64_t)((sm.w >> 2) >> 4);
+            const uint64_t b_lo = b_hi + (uint64_t)((sm.w >> 3) >> 4);
             const int kind = sm.w & 3;                                   // 0 all, 1 hi x hi, 2 the small terms
             const uint32_t acc = tmem + (uint32_t)sm.y;
             if (a_in_tmem) {
@@ -691,7 +698,7 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
         load_chunk(v1);
       }
     }
-  } else {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
     // ===== epilogue warps: w4 = the TMEM lane quarter this warp may read = its row group
     const int w4 = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;                 // which 16-column groups: even or odd
