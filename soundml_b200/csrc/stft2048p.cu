@@ -82,6 +82,7 @@ struct Params {
   int span_bytes;            // bytes reserved per group for samples (multiple of 128)
   int tables_bytes;          // window, twiddles, mel tables (multiple of 128)
   int tiles_per_signal, total_tiles;
+  int skip_b;                // measurement only (SMB_PAIR_NO_B=1): no group barrier before the mel phase (results are wrong)
 };
 
 // ---- TMEM as a per-lane table store.  The window and the inter-pass twiddles are
@@ -411,7 +412,7 @@ stft2048p_kernel(const Params p) {
       }
     }
     if (MODE != kModeFree) {
-      named_sync(group + 1, kGroupThreads);
+      if (!p.skip_b) named_sync(group + 1, kGroupThreads);
       // ---- the sample buffer is free: fetch the next tile under the mel phase
       if (tile + stride < total_tiles)
         bulk = stage::stage_tile<kTile, kGroupThreads>(g, p.a.x, p.bulk, nb, nt, sSamples, gtid, sbar);
@@ -535,6 +536,7 @@ cudaError_t launch_stft2048p(const Stft2048PairArgs& a, bool ceiling, int sm_cou
   p.tables_bytes = tables_bytes_needed(p.a.mel_w_floats, p.a.mel_rounds);
   p.tiles_per_signal = (int)tiles_per_signal;
   p.total_tiles = (int)(tiles_per_signal * a.batch);
+  p.skip_b = getenv("SMB_PAIR_NO_B") ? 1 : 0;
   const size_t smem = smem_needed(a.g, p.a.mel_w_floats, p.a.mel_rounds);
   if (smem + 64 > kSmemLimit) return cudaErrorInvalidConfiguration;
   const long long want = (p.total_tiles + kGroups - 1) / kGroups;

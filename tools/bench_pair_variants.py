@@ -48,6 +48,12 @@ os.environ["SMB_PAIR_FREERUN"] = "1"
 res["fft_ceiling_free_running_ms"] = timed(lambda: _lib.check(_lib.lib.smb_stft_fft_ceiling(
     sc._h, x.data_ptr(), B, N, scratch.data_ptr())))
 del os.environ["SMB_PAIR_FREERUN"]
+# timing only (results are wrong): what the group barrier before the mel phase costs
+os.environ["SMB_PAIR_NO_B"] = "1"
+res["mel_without_group_barrier_ms"] = timed(lambda: sb.mel_spectrogram(sc, mc, x, out=out))
+res["fft_ceiling_without_group_barrier_ms"] = timed(lambda: _lib.check(_lib.lib.smb_stft_fft_ceiling(
+    sc._h, x.data_ptr(), B, N, scratch.data_ptr())))
+del os.environ["SMB_PAIR_NO_B"]
 res["fast_kernel_ms"] = timed(lambda: sb.mel_spectrogram(sc.set_path("fast"), mc, x, out=out))
 res["hbm_floor_ms"] = 1e3 * 1129136128 / 6542.7e9
 print(json.dumps(res))
