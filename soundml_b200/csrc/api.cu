@@ -453,43 +453,44 @@ struct smb_mel_plan {
     sc.clear();
     const int kBins = 1032;                                  // power row incl. zeroed tail (stft2048p.cu)
     if (bins != 1025 || n_mels > 32767) return false;
-    const int rounds_total = (int)((n_mels + 7) / 8);
-    struct Round { int steps; size_t base; int b0[8]; int m[8]; };
+    constexpr int F = smb::kPairFilters;                     // filters per round (lane = filter, frame pair)
+    const int rounds_total = (int)((n_mels + F - 1) / F);
+    struct Round { int steps; size_t base; int b0[F]; int m[F]; };
     std::vector<Round> built((size_t)rounds_total);
     for (int q = 0; q < rounds_total; ++q) {
       Round& rd = built[(size_t)q];
-      int hi[8];
-      for (int i = 0; i < 8; ++i) {
-        const int64_t m = (int64_t)q * 8 + i;
+      int hi[F];
+      for (int i = 0; i < F; ++i) {
+        const int64_t m = (int64_t)q * F + i;
         rd.m[i] = m < n_mels ? (int)m : -1;
         rd.b0[i] = m < n_mels ? band_lo[(size_t)m] & ~1 : 0;
         hi[i] = m < n_mels ? std::max(band_hi[(size_t)m], rd.b0[i]) : 0;
       }
-      for (int i = 0; i < 8; i += 2) {
+      for (int i = 0; i < F; i += 2) {
         if (rd.m[i] < 0 || rd.m[i + 1] < 0) continue;
         if ((((rd.b0[i] >> 1) + (rd.b0[i + 1] >> 1)) & 1) != 0) continue;
         if (rd.b0[i + 1] >= 2) rd.b0[i + 1] -= 2;
         else if (rd.b0[i] >= 2) rd.b0[i] -= 2;
       }
       rd.steps = 1;                                        // 0 marks an idle round in the kernel
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < F; ++i)
         if (rd.m[i] >= 0) rd.steps = std::max(rd.steps, (hi[i] - rd.b0[i] + 3) / 4);
       rd.steps = (rd.steps + 1) & ~1;                      // the kernel runs two steps per iteration
       if (rd.steps > 510 || 4 * rd.steps > kBins) return false;
       // every lane runs the round's step count: keep its reads inside the row
-      for (int i = 0; i < 8; ++i) rd.b0[i] = std::min(rd.b0[i], (kBins - 4 * rd.steps) & ~1);
+      for (int i = 0; i < F; ++i) rd.b0[i] = std::min(rd.b0[i], (kBins - 4 * rd.steps) & ~1);
       rd.base = sc.w.size();
-      sc.w.resize(rd.base + (size_t)rd.steps * 8 * 4, 0.0f);
-      for (int i = 0; i < 8; ++i) {
+      sc.w.resize(rd.base + (size_t)rd.steps * F * 4, 0.0f);
+      for (int i = 0; i < F; ++i) {
         if (rd.m[i] < 0) continue;
         for (int k = band_lo[(size_t)rd.m[i]]; k < band_hi[(size_t)rd.m[i]]; ++k) {
           const int u = k - rd.b0[i];
-          sc.w[rd.base + ((size_t)(u >> 2) * 8 + (size_t)i) * 4 + (size_t)(u & 3)] =
+          sc.w[rd.base + ((size_t)(u >> 2) * F + (size_t)i) * 4 + (size_t)(u & 3)] =
               (float)weights[(size_t)((int64_t)rd.m[i] * bins + k)];
         }
       }
     }
-    sc.w.resize(sc.w.size() + 8 * 4, 0.0f);                // the kernel's prefetch reads one step ahead
+    sc.w.resize(sc.w.size() + F * 4, 0.0f);                // the kernel's prefetch reads one step ahead
     if (sc.w.size() >= (1u << 24)) return false;
     const int warps = smb::kPairTile / 2;
     std::vector<int> by_len((size_t)rounds_total);
@@ -505,12 +506,12 @@ struct smb_mel_plan {
     }
     sc.rounds = 0;
     for (const auto& l : lists) sc.rounds = std::max(sc.rounds, (int)l.size());
-    sc.items.assign((size_t)(warps * sc.rounds * 8), smb::PairMelItem{0, 0, -1});   // idle: no steps
+    sc.items.assign((size_t)(warps * sc.rounds * F), smb::PairMelItem{0, 0, -1});   // idle: no steps
     for (int wi = 0; wi < warps; ++wi)
       for (size_t r = 0; r < lists[(size_t)wi].size(); ++r) {
         const Round& rd = built[(size_t)lists[(size_t)wi][r]];
-        for (int i = 0; i < 8; ++i) {
-          smb::PairMelItem& it = sc.items[((size_t)wi * (size_t)sc.rounds + r) * 8 + (size_t)i];
+        for (int i = 0; i < F; ++i) {
+          smb::PairMelItem& it = sc.items[((size_t)wi * (size_t)sc.rounds + r) * F + (size_t)i];
           it.w4_steps = (int)(rd.base / 4 + (size_t)i) | ((rd.steps / 2) << 24);
           it.h0 = (unsigned short)(rd.b0[i] >> 1);
           it.m = (short)rd.m[i];

@@ -98,7 +98,11 @@ bool stft2048_supports(const FrameGeom& g, int out_kind, int n_mels, int nnz, in
                        int mpad);
 cudaError_t launch_stft2048(const Stft2048Args& a, int out_kind, int sm_count, cudaStream_t st);
 // ---- frame-pair kernel (stft2048p.cu): two frames per warp in float32x2 lanes -----
-constexpr int kPairTile = 8;           // frames per group tile, two per warp
+#ifndef SMB_PAIR_TILE
+#define SMB_PAIR_TILE 8
+#endif
+constexpr int kPairTile = SMB_PAIR_TILE;   // frames per group tile, two per warp (8: two groups of four warps; 4: four of two)
+constexpr int kPairFilters = 32 / (kPairTile / 2);   // filters per mel round: lane = (filter, frame pair)
 // One filter of a mel round of the frame-pair kernel: lane (filter i, frame pair j)
 // walks `steps` 4-bin steps from bin b0 (even) of warp j's power rows.
 struct PairMelItem {

@@ -52,7 +52,8 @@ using stage::smem_u32;
 constexpr int kTile = kPairTile;            // frames per group tile
 constexpr int kGroupWarps = kTile / 2;      // a warp carries two frames
 constexpr int kGroupThreads = 32 * kGroupWarps;
-constexpr int kGroups = 2;
+constexpr int kGroups = 16 / kTile;          // eight warps in all
+constexpr int kF = kPairFilters;             // filters per mel round
 constexpr int kExPitch = 33;                // 16-byte elements per transposition row (conflict-free both ways)
 constexpr int kWarpBuf = 32 * kExPitch * 16;   // bytes: [32][33] x (re A, re B, im A, im B)
 constexpr int kPowerBins = 1032;            // bins per power row incl. the zeroed tail the mel steps may read
@@ -214,7 +215,7 @@ stft2048p_kernel(const Params p) {
   if (tid < 32) sTwPost[tid] = p.a.tw_post[tid];
   if (MODE == kModeMel) {
     for (int i = tid; i < p.a.mel_w_floats; i += blockDim.x) sMelW[i] = p.a.mel_w[i];
-    for (int i = tid; i < kGroupWarps * p.a.mel_rounds * 8; i += blockDim.x) sItems[i] = p.a.mel_items[i];
+    for (int i = tid; i < kGroupWarps * p.a.mel_rounds * kF; i += blockDim.x) sItems[i] = p.a.mel_items[i];
   }
   if (tid == 0) {
     for (int gI = 0; gI < kGroups; ++gI) {
@@ -425,14 +426,14 @@ stft2048p_kernel(const Params p) {
       // quarter-warp's loads in distinct bank groups); one FFMA2 per weight.  Bin
       // k = b0 + u of the band goes to accumulator u mod 4, in ascending order; the
       // four are added pairwise at the end -- a fixed summation tree.
-      const int i = lane >> 2, j = lane & 3;
+      const int i = lane / kGroupWarps, j = lane % kGroupWarps;
       const ulonglong2* pj = reinterpret_cast<const ulonglong2*>(sBufs + j * kWarpBuf + 32 * j);
-      const int2* mine = reinterpret_cast<const int2*>(sItems + warp * p.a.mel_rounds * 8 + i);
+      const int2* mine = reinterpret_cast<const int2*>(sItems + warp * p.a.mel_rounds * kF + i);
       const bool okA = 2 * j < nf, okB = 2 * j + 1 < nf;
       float* ob = p.a.out + (long long)b * p.a.n_mels * g.frames + p0 + 2 * j;
       const int frames = (int)g.frames;                     // n_mels * frames < 2^31 (launcher)
       for (int r = 0; r < mel_rounds; ++r) {
-        const int2 it = mine[r * 8];                        // {weights | iterations << 24, h0 | m << 16}
+        const int2 it = mine[r * kF];                       // {weights | iterations << 24, h0 | m << 16}
         const int iters = (int)((unsigned)it.x >> 24);      // two 4-bin steps each; the same for the whole warp
         if (iters == 0) break;                              // idle rounds come last
         const float4* wq = reinterpret_cast<const float4*>(sMelW) + (it.x & 0xFFFFFF);
@@ -445,13 +446,13 @@ stft2048p_kernel(const Params p) {
         ulonglong2 a01 = pp[0], a23 = pp[1];
 #pragma unroll 1
         for (int t = 0; t < iters; ++t) {
-          const float4 wb = wq[8];
+          const float4 wb = wq[kF];
           const ulonglong2 b01 = pp[2], b23 = pp[3];
           acc0 = pfmas(a01.x, wa.x, acc0);
           acc1 = pfmas(a01.y, wa.y, acc1);
           acc2 = pfmas(a23.x, wa.z, acc2);
           acc3 = pfmas(a23.y, wa.w, acc3);
-          wq += 16;
+          wq += 2 * kF;
           pp += 4;
           if (t + 1 < iters) {            // (warp-uniform) nothing is fetched past the band
             wa = wq[0];
@@ -497,7 +498,7 @@ static int span_bytes_needed(const FrameGeom& g) {
   return ((((kTile - 1) * g.hop + 2048) * 4) + 127) & ~127;
 }
 static int tables_bytes_needed(int mel_w_floats, int mel_rounds) {
-  return (16640 + mel_w_floats * 4 + kGroupWarps * mel_rounds * 8 * (int)sizeof(PairMelItem) + 127) & ~127;
+  return (16640 + mel_w_floats * 4 + kGroupWarps * mel_rounds * kF * (int)sizeof(PairMelItem) + 127) & ~127;
 }
 static size_t smem_needed(const FrameGeom& g, int mel_w_floats, int mel_rounds) {
   return (size_t)tables_bytes_needed(mel_w_floats, mel_rounds) +
