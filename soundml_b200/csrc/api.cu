@@ -2028,18 +2028,28 @@ int smb_mfcc(smb_stft_plan* stft, smb_mel_plan* mel, const void* x, int64_t batc
     void* dmel = stft->cepstral.ensure(mel_bytes + out_bytes);
     void* dout = mem == SMB_MEM_HOST ? (void*)((char*)dmel + mel_bytes) : out;
     const int inner_mem = mem == SMB_MEM_HOST ? SMB_MEM_HOST : SMB_MEM_DEVICE;
-    const void* din = x;
-    if (inner_mem == SMB_MEM_HOST) {
-      void* stage = stft->pipe.in[0].ensure((size_t)batch * n * esz);
-      CK(cudaMemcpyAsync(stage, x, (size_t)batch * n * esz, cudaMemcpyHostToDevice, st));
-      din = stage;
-    } else if (mem != SMB_MEM_DEVICE) {
+    if (inner_mem != SMB_MEM_HOST && mem != SMB_MEM_DEVICE)
       throw smb::invalid_argument("soundml_b200: unknown memory kind");
-    }
     // the frame-pair kernel leaves the mel spectrogram's maximum in the slot as it writes
     CK(cudaMemsetAsync(mel->d_max, 0, sizeof(unsigned long long), st));
-    const bool max_known = mel_spectrogram_impl(stft, mel, din, batch, n, dtype, 2.0, dmel,
-                                                SMB_MEM_DEVICE, mel->d_max);
+    bool max_known = true;
+    if (inner_mem == SMB_MEM_HOST) {
+      // host audio goes up in slices of about 64 MB (the whole-tensor maximum needs every
+      // slice's mel values before the first cepstral coefficient, so those stay on the
+      // device -- a quarter of the audio's size -- but the audio never does at once)
+      const int64_t per = std::max<int64_t>(1, (int64_t)(64u << 20) / std::max<int64_t>(1, n * (int64_t)esz));
+      for (int64_t b0 = 0; b0 < batch; b0 += per) {
+        const int64_t nb = std::min(per, batch - b0);
+        void* stage = stft->pipe.in[0].ensure((size_t)std::min(per, batch) * n * esz);
+        CK(cudaMemcpyAsync(stage, (const char*)x + (size_t)b0 * n * esz, (size_t)nb * n * esz,
+                           cudaMemcpyHostToDevice, st));
+        max_known = mel_spectrogram_impl(stft, mel, stage, nb, n, dtype, 2.0,
+                                         (char*)dmel + (size_t)b0 * mel->n_mels * g.frames * esz,
+                                         SMB_MEM_DEVICE, mel->d_max) && max_known;
+      }
+    } else {
+      max_known = mel_spectrogram_impl(stft, mel, x, batch, n, dtype, 2.0, dmel, SMB_MEM_DEVICE, mel->d_max);
+    }
     const double scale = kDecade, offset = scale * std::log(1.0);   // reference 1, amin 1e-10
     CK(smb::launch_mfcc(dmel, dtype, batch, (int)mel->n_mels, g.frames, (int)n_mfcc,
                         mel->dct_table(n_mfcc, has_lifter ? lifter : 0.0), mel->d_max, max_known,

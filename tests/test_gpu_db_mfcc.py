@@ -117,3 +117,24 @@ def test_log_mel_spectrogram_is_the_composition(sb, fft, hop, top_db):
     assert np.array_equal(dev.cpu().numpy(), got)
     with pytest.raises(ValueError, match=r"Soundml.Convert.power_to_db: top_db must be finite and non-negative"):
         sb.log_mel_spectrogram(sc, mc, x, top_db=-3.0)
+
+
+def test_mfcc_host_batches_go_up_in_slices(sb):
+    """Host audio larger than one 64 MB slice: the mel values of every slice stay on the device
+    until the whole-tensor maximum is known, so the 80 dB clamp is still global over the batch --
+    bit for bit the device-memory call (which takes the batch at once)."""
+    import torch
+    from soundml_b200 import synth
+    x = synth.clips_numpy(40, 500000, first_clip=11)           # 80 MB: two slices of 33 and 7 clips
+    x[2] *= 1e-4                                                # quiet clip in the first slice ...
+    x[37] *= 4.0                                                # ... the maximum in the second
+    sc = sb.Stft.Config.create(fft_size=2048, hop=512)
+    mc = sb.Mel.Config.create(n_mels=128, sample_rate=22050, fft_size=2048)
+    host = sb.mfcc(sc, mc, x, n_mfcc=13)
+    dev = sb.mfcc(sc, mc, torch.from_numpy(x).cuda(), n_mfcc=13)
+    torch.cuda.synchronize()
+    assert host.shape == (40, 13, 977)
+    assert np.array_equal(dev.cpu().numpy(), host)
+    # the clamp really is global: clip 2's floor sits 80 dB under clip 37's peak, not its own
+    alone = sb.mfcc(sc, mc, x[2:3], n_mfcc=13)
+    assert not np.array_equal(alone[0], host[2])
