@@ -22,7 +22,8 @@ KEEP = [
     "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "smsp__inst_executed.sum", "launch__grid_size", "launch__block_size",
     "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct",
-    "lts__t_bytes.sum",
+    "lts__t_bytes.sum", "lts__t_sectors.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+    "lts__t_sectors_srcunit_tex_op_write.sum",
 ]
 
 
