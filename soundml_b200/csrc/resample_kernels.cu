@@ -78,8 +78,14 @@ polyphase_direct_kernel(const T* __restrict__ x, long long n,
 // accumulator chain over ascending s, whatever tile or call it falls in.  The staged
 // inputs carry 16 bytes of padding per 128 so that the 32 lanes, whose windows start
 // kCycles * M samples apart, load from distinct bank groups.
-constexpr int kCycles = 8;
-constexpr int kBlockThreads = 128;
+#ifndef SMB_BLOCK_CYCLES
+#define SMB_BLOCK_CYCLES 8
+#endif
+#ifndef SMB_BLOCK_THREADS
+#define SMB_BLOCK_THREADS 128
+#endif
+constexpr int kCycles = SMB_BLOCK_CYCLES;
+constexpr int kBlockThreads = SMB_BLOCK_THREADS;
 
 template <typename T>
 struct alignas(16) Vec16 { T v[16 / sizeof(T)]; };
