@@ -1,0 +1,70 @@
+"""Batches past the 65 535 limit of a grid's second dimension (and past one launch's tile
+counters): every launcher that walks the batch in launches must hand clip 65 535 and its
+neighbours to the right place.  The reference has no such limit (its batch is a leading
+axis of an Nx tensor, stft.mli:216-218); a clip's result must equal the standalone call on
+that clip, bit for bit (stft_grid.ml:180-205).  ``pytest -m gpu``."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BATCH = 66000
+PICK = [0, 1, 65534, 65535, 65536, BATCH - 1]
+
+
+@pytest.fixture(scope="module")
+def sb(lib):
+    import torch
+    assert torch.cuda.is_available()
+    return lib
+
+
+def clips(n, seed=0):
+    import torch
+    g = torch.Generator("cuda").manual_seed(seed)
+    return torch.rand((BATCH, n), device="cuda", generator=g) * 2 - 1
+
+
+@pytest.mark.parametrize("sr,target", [(48000, 16000), (44100, 22050), (22050, 44100), (44100, 48000),
+                                       (48000, 8000), (3, 2)])
+def test_resample_batches_past_the_grid_limit(sb, sr, target):
+    import torch
+    x = clips(700, sr + target)
+    cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
+    y = sb.Resample.apply(cfg, x)
+    assert y.shape == (BATCH, cfg.output_frames(700))
+    for b in PICK:
+        alone = sb.Resample.apply(cfg, x[b:b + 1])
+        assert torch.equal(alone[0], y[b]), (sr, target, b)
+    direct = sb.Resample.apply(cfg.set_executor("direct"), x)
+    scale = float(y.abs().max())
+    assert float((direct - y).abs().max()) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("method", ["direct", "ols"])
+def test_fir_batches_past_the_grid_limit(sb, method):
+    import torch
+    x = clips(900, 7)
+    fir = sb.Fir.lowpass(k=20, cutoff=0.3)
+    y = fir.apply(x, method=method)
+    for b in PICK:
+        assert torch.equal(fir.apply(x[b:b + 1], method=method)[0], y[b]), (method, b)
+
+
+def test_stft_family_batches_past_the_grid_limit(sb):
+    import torch
+    x = clips(3000, 11)
+    sc = sb.Stft.Config.create(fft_size=2048, hop=512)
+    mc = sb.Mel.Config.create(n_mels=128, sample_rate=22050, fft_size=2048)
+    m = sb.mel_spectrogram(sc, mc, x)
+    assert m.shape == (BATCH, 128, sb.Stft.frames(sc, 3000))
+    p = sb.Stft.power_spectrum(sc, x[:, :2048 + 512])         # 1025 x 6 floats per clip: keep it small
+    for b in PICK:
+        assert torch.equal(sb.mel_spectrogram(sc, mc, x[b:b + 1])[0], m[b]), b
+        assert torch.equal(sb.Stft.power_spectrum(sc, x[b:b + 1, :2048 + 512])[0], p[b]), b
+    small = sb.Stft.Config.create(fft_size=64, hop=16)          # the generic (double interior) kernels
+    z = sb.Stft.transform(small, x[:, :400])
+    back = sb.Stft.invert(small, z, length=400)
+    for b in PICK:
+        assert torch.equal(sb.Stft.transform(small, x[b:b + 1, :400])[0], z[b]), b
+    assert float((back - x[:, :400]).abs().max()) <= 1e-5
