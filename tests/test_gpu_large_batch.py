@@ -68,3 +68,32 @@ def test_stft_family_batches_past_the_grid_limit(sb):
     for b in PICK:
         assert torch.equal(sb.Stft.transform(small, x[b:b + 1, :400])[0], z[b]), b
     assert float((back - x[:, :400]).abs().max()) <= 1e-5
+
+
+def test_empty_and_tiny_inputs_through_the_newer_entry_points(sb):
+    """Zero-size leading axes, zero-length signals and signals shorter than anything the block
+    executors need (resample_kernel.ml:28-52: output length is ceil(n L / M) also for tiny inputs;
+    stft.ml:217-223: no frames when the padded signal is shorter than a frame)."""
+    import torch
+    sc = sb.Stft.Config.create(fft_size=2048, hop=512)
+    mc = sb.Mel.Config.create(n_mels=128, sample_rate=22050, fft_size=2048)
+    assert sb.log_mel_spectrogram(sc, mc, np.zeros((0, 5000), np.float32)).shape == (0, 128, 10)
+    assert sb.log_mel_spectrogram(sc, mc, np.zeros((3, 0), np.float32)).shape == (3, 128, 0)
+    one = sb.log_mel_spectrogram(sc, mc, np.ones((1, 1), np.float32))       # one sample, reflect-extended
+    assert one.shape == (1, 128, 1) and np.isfinite(one).all()
+    for sr, target in [(44100, 16000), (44100, 48000), (44100, 32000), (44100, 22050), (48000, 8000)]:
+        cfg = sb.Resample.Config.create(sample_rate=sr, target=target)
+        for n in (0, 1, 2, 17):
+            x = torch.ones((2, n), device="cuda")
+            y = sb.Resample.apply(cfg, x)
+            assert y.shape == (2, -(-n * cfg.l // cfg.m)), (sr, target, n)
+            if n:
+                ref = sb.Resample.apply(cfg.set_executor("direct"), x)
+                assert float((y - ref).abs().max()) <= 1e-5, (sr, target, n)
+                cfg.set_executor("planned")
+        assert sb.Resample.apply(cfg, torch.ones((0, 300), device="cuda")).shape == (0, cfg.output_frames(300))
+    rd = sb.Io.Ingest(channels=2, sample_rate=44100, target=16000, max_block=1000)
+    assert tuple(rd.read([]).shape) == (2, 0)
+    rd = sb.Io.Ingest(channels=2, sample_rate=44100, target=16000, max_block=1000)
+    out = rd.read([np.ones((1, 2), np.float32)])                           # a one-frame file
+    assert tuple(out.shape) == (2, 1)
