@@ -688,15 +688,18 @@ resample_rows_kernel(const GemmRowsArgs a, const int tiles_per_clip, const int t
       ++stored;
       if (++st_stage == kAStages) { st_stage = 0; st_parity ^= 1; }
     };
+    // loads run THREE chunks ahead of the stores in registers: a chunk's rows come from HBM
+    // (the input is read once), and two chunk-times do not cover that latency (four deep
+    // spills at this block size)
+    float v2[kRowsPerWarp] = {};
     load_chunk(v0);
     load_chunk(v1);
-    for (int g = 0; g < my_chunks; g += 2) {
+    load_chunk(v2);
+    for (int g = 0; g < my_chunks; g += 3) {
       store_chunk(v0);
       load_chunk(v0);
-      if (g + 1 < my_chunks) {
-        store_chunk(v1);
-        load_chunk(v1);
-      }
+      if (g + 1 < my_chunks) { store_chunk(v1); load_chunk(v1); }
+      if (g + 2 < my_chunks) { store_chunk(v2); load_chunk(v2); }
     }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
     // ===== epilogue warps: w4 = the TMEM lane quarter this warp may read = its row group
